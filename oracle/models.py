@@ -1,0 +1,124 @@
+"""Oracle (TEST INFRASTRUCTURE): float64 NumPy restatement of the model log-likelihoods and of
+the black-box projection that builds the N x S matrix.
+
+References (relative to the reference repository root):
+  bayesiancoresets/projector.py:19-29            BlackBoxProjector.project (row-centring)
+  examples/common/model_lr.py:25-32, 50-57       logistic regression
+  examples/common/model_gaussian.py:4-15         Gaussian location model
+  examples/common/model_poiss.py:25-38, 58-67    Poisson regression (softplus link)
+"""
+import numpy as np
+from scipy.special import gammaln
+
+
+# ---------------------------------------------------------------- logistic regression
+def lr_loglik(z, th):
+  """model_lr.py:25-32: ll[n,s] = -log(1+exp(-z_n.th_s)), linear branch when -z.th >= 100."""
+  z = np.atleast_2d(z)
+  th = np.atleast_2d(th)
+  m = -z.dot(th.T)
+  small = m < 100
+  m[small] = -np.log1p(np.exp(m[small]))
+  m[np.logical_not(small)] = -m[np.logical_not(small)]
+  return m
+
+
+def lr_grad_z_loglik(z, th):
+  """model_lr.py:50-57: d ll[n,s] / d z_n = sigma(-z_n.th_s) * th_s  -> (n, S, d)."""
+  z = np.atleast_2d(z)
+  th = np.atleast_2d(th)
+  m = -z.dot(th.T)
+  small = m < 100
+  m[small] = np.exp(m[small])/(1.+np.exp(m[small]))
+  m[np.logical_not(small)] = 1.
+  return m[:, :, np.newaxis]*th[np.newaxis, :, :]
+
+
+# ---------------------------------------------------------------- Gaussian location model
+def gaussian_loglik(x, th, Siginv, logdetSig):
+  """model_gaussian.py:4-10"""
+  x = np.atleast_2d(x)
+  th = np.atleast_2d(th)
+  xSx = (x*(x.dot(Siginv))).sum(axis=1)
+  tSt = (th*(th.dot(Siginv))).sum(axis=1)
+  xSt = x.dot(Siginv.dot(th.T))
+  return -x.shape[1]/2*np.log(2*np.pi) - 1./2.*logdetSig - 1./2.*(xSx[:, np.newaxis] + tSt - 2*xSt)
+
+
+def gaussian_grad_x_loglik(x, th, Siginv):
+  """model_gaussian.py:12-15"""
+  x = np.atleast_2d(x)
+  th = np.atleast_2d(th)
+  return th.dot(Siginv)[np.newaxis, :, :] - x.dot(Siginv)[:, np.newaxis, :]
+
+
+# ---------------------------------------------------------------- Poisson regression
+def poisson_log_rate(th, x):
+  """model_poiss.py:25-30: s = log(softplus(x.th)), with s ~= x.th when x.th <= -100."""
+  s = x.dot(th.T)
+  big = s > -100
+  s[big] = np.log(np.maximum(s[big], 0) + np.log1p(np.exp(-np.fabs(s[big]))))
+  return s
+
+
+def poisson_loglik(z, th):
+  """model_poiss.py:32-38: z = [x, y]; ll = y*s - gammaln(y+1) - exp(s)."""
+  th = np.atleast_2d(th)
+  z = np.atleast_2d(z)
+  x = z[:, :-1]
+  y = np.tile(z[:, -1][:, np.newaxis], (1, th.shape[0]))
+  s = poisson_log_rate(th, x)
+  return y*s - gammaln(y+1) - np.exp(s)
+
+
+def poisson_grad_z_loglik_fixed(z, th):
+  """model_poiss.py:58-67 with the broadcast defect repaired.
+
+  DEVIATION (documented in SURVEY.md section 8c): the reference multiplies by
+  ``th[:, np.newaxis, :]`` (model_poiss.py:67), which raises a broadcast ValueError for n != S,
+  and returns no derivative for the response column.  This oracle uses ``th[np.newaxis,:,:]``
+  and appends a zero d/dy column so the result has the (n, S, d+1) shape BatchPSVI needs.
+  """
+  th = np.atleast_2d(th)
+  z = np.atleast_2d(z)
+  x = z[:, :-1]
+  y = np.tile(z[:, -1][:, np.newaxis], (1, th.shape[0]))
+  s = poisson_log_rate(th, x)
+  g = y - np.exp(s)
+  nz = np.exp(s) > 1e-15
+  g[nz] = (y[nz]*np.exp(-s[nz]) - 1.)*(1. - np.exp(-np.exp(s[nz])))
+  gx = g[:, :, np.newaxis]*th[np.newaxis, :, :]
+  return np.concatenate((gx, np.zeros(gx.shape[:2] + (1,))), axis=2)
+
+
+# ---------------------------------------------------------------- projection
+def project(loglik, pts, samples, grad_loglik=None):
+  """projector.py:19-29: evaluate and centre each row over the S samples.  The gradient branch
+  centres over the LAST axis (d), as the reference does (projector.py:26)."""
+  lls = loglik(pts, samples)
+  lls -= lls.mean(axis=1)[:, np.newaxis]
+  if grad_loglik is None:
+    return lls
+  glls = grad_loglik(pts, samples)
+  glls -= glls.mean(axis=2)[:, :, np.newaxis]
+  return lls, glls
+
+
+class OracleProjector(object):
+  """projector.py:11-32 (BlackBoxProjector) restated: sampler(n, wts, pts) -> (n, D)."""
+  def __init__(self, sampler, projection_dimension, loglik, grad_loglik=None):
+    self.projection_dimension = projection_dimension
+    self.sampler = sampler
+    self.loglik = loglik
+    self.grad_loglik = grad_loglik
+    self.update(np.array([]), np.array([]))
+
+  def update(self, wts, pts):
+    self.samples = self.sampler(self.projection_dimension, wts, pts)
+
+  def project(self, pts, grad=False):
+    if grad:
+      if self.grad_loglik is None:
+        raise ValueError('grad_loglikelihood was requested but not initialized')
+      return project(self.loglik, pts, self.samples, self.grad_loglik)
+    return project(self.loglik, pts, self.samples)
