@@ -1,0 +1,343 @@
+"""ctypes binding of the C-ABI shared library (include/bcg.h -> lib/libbcg_b200.so).
+
+There is deliberately NO fallback: if the library is missing, or no CUDA device is visible,
+every constructor raises.  The CPU oracle under /oracle is test infrastructure and is never
+imported from here.
+"""
+import ctypes
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libbcg_b200.so')
+
+BCG_OK = 0
+ERR_NAMES = {1: 'BCG_ERR_CUDA', 2: 'BCG_ERR_ARG', 3: 'BCG_ERR_NO_DEVICE', 4: 'BCG_ERR_ZERO_B', 5: 'BCG_ERR_STATE',
+             6: 'BCG_ERR_COMM', 7: 'BCG_ERR_UNSUPPORTED'}
+ERR_ZERO_B = 4
+ALG_GIGA, ALG_FW, ALG_OMP = 0, 1, 2
+IT_OK, IT_FAIL_CDIR, IT_FAIL_GEODESIC, IT_FAIL_GAMMA, IT_FAIL_MONOTONE = 0, 1, 2, 3, 4
+
+
+class BcgError(RuntimeError):
+  def __init__(self, code, msg):
+    super().__init__('%s: %s' % (ERR_NAMES.get(code, 'BCG_ERR_%d' % code), msg))
+    self.code = code
+
+
+class IterEvent(ctypes.Structure):
+  """struct bcg_iter_event"""
+  _fields_ = [('code', ctypes.c_int32), ('nact', ctypes.c_int32), ('f', ctypes.c_int64), ('error', ctypes.c_double),
+              ('aux0', ctypes.c_double), ('aux1', ctypes.c_double)]
+
+
+_c = ctypes
+_P = ctypes.c_void_p
+_PP = ctypes.POINTER(ctypes.c_void_p)
+_PROTOTYPES = {
+  'bcg_abi_version': (_c.c_int, []),
+  'bcg_last_error': (_c.c_char_p, []),
+  'bcg_device_count': (_c.c_int, [_c.POINTER(_c.c_int)]),
+  'bcg_ctx_create': (_c.c_int, [_c.c_int, _PP]),
+  'bcg_ctx_destroy': (_c.c_int, [_P]),
+  'bcg_ctx_info': (_c.c_int, [_P, _c.c_char_p, _c.c_int, _c.POINTER(_c.c_int), _c.POINTER(_c.c_int),
+                              _c.POINTER(_c.c_int), _c.POINTER(_c.c_int64)]),
+  'bcg_ctx_synchronize': (_c.c_int, [_P]),
+  'bcg_ctx_flush_l2': (_c.c_int, [_P, _c.c_int64]),
+  'bcg_vecs_from_host_f64': (_c.c_int, [_P, _P, _c.c_int64, _c.c_int32, _c.c_int64, _PP]),
+  'bcg_vecs_project_lr': (_c.c_int, [_P, _P, _c.c_int64, _c.c_int32, _P, _c.c_int32, _PP]),
+  'bcg_vecs_project_gaussian': (_c.c_int, [_P, _P, _c.c_int64, _c.c_int32, _P, _c.c_int32, _P, _PP]),
+  'bcg_vecs_project_poisson': (_c.c_int, [_P, _P, _c.c_int64, _c.c_int32, _P, _c.c_int32, _PP]),
+  'bcg_vecs_shape': (_c.c_int, [_P, _c.POINTER(_c.c_int64), _c.POINTER(_c.c_int32), _c.POINTER(_c.c_int32)]),
+  'bcg_vecs_colsum': (_c.c_int, [_P, _P]),
+  'bcg_vecs_norm_sum': (_c.c_int, [_P, _c.POINTER(_c.c_double)]),
+  'bcg_vecs_zero_rows': (_c.c_int, [_P, _c.POINTER(_c.c_int64)]),
+  'bcg_vecs_norms': (_c.c_int, [_P, _c.c_int64, _c.c_int64, _P]),
+  'bcg_vecs_rows_f64': (_c.c_int, [_P, _c.c_int64, _c.c_int64, _P]),
+  'bcg_vecs_destroy': (_c.c_int, [_P]),
+  'bcg_solver_create': (_c.c_int, [_P, _P, _c.c_int32, _P, _c.c_double, _c.c_int64, _c.c_int64, _PP]),
+  'bcg_solver_destroy': (_c.c_int, [_P]),
+  'bcg_solver_comm_handle': (_c.c_int, [_P, _P]),
+  'bcg_solver_comm_connect': (_c.c_int, [_P, _c.c_int32, _c.c_int32, _P]),
+  'bcg_solver_build': (_c.c_int, [_P, _c.c_int32, _c.c_double, _c.POINTER(IterEvent), _c.POINTER(_c.c_int32)]),
+  'bcg_solver_omp_select': (_c.c_int, [_P, _c.POINTER(_c.c_int64)]),
+  'bcg_solver_error': (_c.c_int, [_P, _c.POINTER(_c.c_double)]),
+  'bcg_solver_size': (_c.c_int, [_P, _c.POINTER(_c.c_int64), _c.POINTER(_c.c_int64)]),
+  'bcg_solver_halted': (_c.c_int, [_P, _c.POINTER(_c.c_int32)]),
+  'bcg_solver_active': (_c.c_int, [_P, _c.c_int64, _P, _P, _c.POINTER(_c.c_int64)]),
+  'bcg_solver_active_rows': (_c.c_int, [_P, _c.c_int64, _c.c_int64, _P]),
+  'bcg_solver_set_weights': (_c.c_int, [_P, _P, _c.c_int64]),
+  'bcg_solver_reset': (_c.c_int, [_P]),
+  'bcg_solver_timing': (_c.c_int, [_P, _c.POINTER(_c.c_float), _c.POINTER(_c.c_float), _c.POINTER(_c.c_int32),
+                                   _c.POINTER(_c.c_int32)]),
+  'bcg_solver_set_profiling': (_c.c_int, [_P, _c.c_int32]),
+}
+EXPORTED_SYMBOLS = sorted(_PROTOTYPES)
+
+_lib = None
+
+
+def lib():
+  """Load the shared library (once).  Raises if it has not been built."""
+  global _lib
+  if _lib is None:
+    if not os.path.exists(LIB_PATH):
+      raise ImportError('%s is missing: build it with `make -C bayesian-coresets_b200` (nvcc, sm_100a). '
+                        'There is no CPU fallback.' % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _PROTOTYPES.items():
+      fn = getattr(L, name)
+      fn.restype = res
+      fn.argtypes = args
+    if L.bcg_abi_version() != 1:
+      raise ImportError('libbcg_b200.so ABI version mismatch')
+    _lib = L
+  return _lib
+
+
+def check(rc):
+  if rc != BCG_OK:
+    raise BcgError(rc, lib().bcg_last_error().decode('utf-8', 'replace'))
+
+
+def _f64(a):
+  return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a):
+  return ctypes.c_void_p(a.ctypes.data)
+
+
+class Context(object):
+  """bcg_ctx: one CUDA device + private stream.  Fails loudly when no B200 is visible."""
+  _default = {}
+
+  def __init__(self, device=0):
+    self.handle = ctypes.c_void_p()
+    check(lib().bcg_ctx_create(int(device), ctypes.byref(self.handle)))
+    self.device = int(device)
+
+  @classmethod
+  def default(cls, device=None):
+    if device is None:
+      device = int(os.environ.get('LOCAL_RANK', '0'))
+    if device not in cls._default:
+      cls._default[device] = cls(device)
+    return cls._default[device]
+
+  def info(self):
+    name = ctypes.create_string_buffer(256)
+    sm, maj, mnr, mem = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int64()
+    check(lib().bcg_ctx_info(self.handle, name, 256, ctypes.byref(sm), ctypes.byref(maj), ctypes.byref(mnr),
+                             ctypes.byref(mem)))
+    return {'name': name.value.decode(), 'sm_count': sm.value, 'cc': (maj.value, mnr.value), 'total_mem': mem.value}
+
+  def synchronize(self):
+    check(lib().bcg_ctx_synchronize(self.handle))
+
+  def flush_l2(self, nbytes=256 << 20):
+    check(lib().bcg_ctx_flush_l2(self.handle, int(nbytes)))
+
+
+class DeviceVecs(object):
+  """bcg_vecs: device-resident (n, S) projection -- unit float32 rows + float64 norms.
+
+  Stands in for the ndarray returned by Projector.project in the reference: supports `.shape`,
+  `.T`, `.sum(axis=0)` (the three things coreset/hilbert.py:24 uses) and `.to_numpy()`."""
+
+  def __init__(self, ctx, handle):
+    self.ctx = ctx
+    self.handle = handle
+    n, S, ld = ctypes.c_int64(), ctypes.c_int32(), ctypes.c_int32()
+    check(lib().bcg_vecs_shape(handle, ctypes.byref(n), ctypes.byref(S), ctypes.byref(ld)))
+    self.shape = (n.value, S.value)
+    self.ld = ld.value
+    self.ndim = 2
+    self.size = n.value*S.value
+
+  # ---- constructors -----------------------------------------------------------------------
+  @classmethod
+  def from_host(cls, rows, ctx=None):
+    ctx = ctx or Context.default()
+    rows = np.asarray(rows)
+    if rows.ndim != 2:
+      raise ValueError('expected an (n, S) array')
+    if rows.dtype != np.float64 or rows.strides[1] != 8 or rows.strides[0] % 8 != 0 or rows.strides[0] < 8*rows.shape[1]:
+      rows = _f64(rows)
+    h = ctypes.c_void_p()
+    check(lib().bcg_vecs_from_host_f64(ctx.handle, _ptr(rows), rows.shape[0], rows.shape[1], rows.strides[0]//8,
+                                       ctypes.byref(h)))
+    return cls(ctx, h)
+
+  @classmethod
+  def project_lr(cls, Z, theta, ctx=None):
+    ctx = ctx or Context.default()
+    Z, theta = _f64(np.atleast_2d(Z)), _f64(np.atleast_2d(theta))
+    if Z.shape[1] != theta.shape[1]:
+      raise ValueError('Z and theta disagree on the feature dimension')
+    h = ctypes.c_void_p()
+    check(lib().bcg_vecs_project_lr(ctx.handle, _ptr(Z), Z.shape[0], Z.shape[1], _ptr(theta), theta.shape[0],
+                                    ctypes.byref(h)))
+    return cls(ctx, h)
+
+  @classmethod
+  def project_gaussian(cls, x, theta, Siginv, ctx=None):
+    ctx = ctx or Context.default()
+    x, theta, Siginv = _f64(np.atleast_2d(x)), _f64(np.atleast_2d(theta)), _f64(Siginv)
+    h = ctypes.c_void_p()
+    check(lib().bcg_vecs_project_gaussian(ctx.handle, _ptr(x), x.shape[0], x.shape[1], _ptr(theta), theta.shape[0],
+                                          _ptr(Siginv), ctypes.byref(h)))
+    return cls(ctx, h)
+
+  @classmethod
+  def project_poisson(cls, Z, theta, ctx=None):
+    ctx = ctx or Context.default()
+    Z, theta = _f64(np.atleast_2d(Z)), _f64(np.atleast_2d(theta))
+    if Z.shape[1] != theta.shape[1] + 1:
+      raise ValueError('Z must be [x, y] with one more column than theta')
+    h = ctypes.c_void_p()
+    check(lib().bcg_vecs_project_poisson(ctx.handle, _ptr(Z), Z.shape[0], theta.shape[1], _ptr(theta), theta.shape[0],
+                                         ctypes.byref(h)))
+    return cls(ctx, h)
+
+  # ---- ndarray-like surface -----------------------------------------------------------------
+  @property
+  def T(self):
+    return DeviceVecsT(self)
+
+  def sum(self, axis=None):
+    if axis != 0:
+      raise NotImplementedError('DeviceVecs.sum supports axis=0 only (hilbert.py:24)')
+    out = np.empty(self.shape[1])
+    check(lib().bcg_vecs_colsum(self.handle, _ptr(out)))
+    return out
+
+  def norm_sum(self):
+    v = ctypes.c_double()
+    check(lib().bcg_vecs_norm_sum(self.handle, ctypes.byref(v)))
+    return v.value
+
+  def zero_rows(self):
+    v = ctypes.c_int64()
+    check(lib().bcg_vecs_zero_rows(self.handle, ctypes.byref(v)))
+    return v.value
+
+  def norms(self, row0=0, nrows=None):
+    nrows = self.shape[0] - row0 if nrows is None else nrows
+    out = np.empty(nrows)
+    check(lib().bcg_vecs_norms(self.handle, row0, nrows, _ptr(out)))
+    return out
+
+  def to_numpy(self, row0=0, nrows=None):
+    """(nrows, S) float64 = norm * unit row; the host view of what the device holds."""
+    nrows = self.shape[0] - row0 if nrows is None else nrows
+    out = np.empty((nrows, self.shape[1]))
+    check(lib().bcg_vecs_rows_f64(self.handle, row0, nrows, _ptr(out)))
+    return out
+
+  def __array__(self, dtype=None, copy=None):
+    a = self.to_numpy()
+    return a if dtype is None else a.astype(dtype)
+
+  def __del__(self):
+    try:
+      if self.handle:
+        lib().bcg_vecs_destroy(self.handle)
+        self.handle = None
+    except Exception:
+      pass
+
+
+class DeviceVecsT(object):
+  """`vecs.T`: the (S, N) view the reference hands to the snnls constructors (hilbert.py:24)."""
+  def __init__(self, vecs):
+    self.vecs = vecs
+    self.shape = (vecs.shape[1], vecs.shape[0])
+    self.size = vecs.size
+
+  @property
+  def T(self):
+    return self.vecs
+
+
+class NativeSolver(object):
+  """bcg_solver"""
+  def __init__(self, vecs, alg, b, norm_sum, row_offset=0, n_global=None):
+    self.vecs = vecs           # keep the matrix alive
+    b = _f64(b)
+    if b.shape != (vecs.shape[1],):
+      raise ValueError('b must have shape (S,)')
+    self.handle = ctypes.c_void_p()
+    n_global = vecs.shape[0] if n_global is None else n_global
+    check(lib().bcg_solver_create(vecs.ctx.handle, vecs.handle, alg, _ptr(b), float(norm_sum), int(row_offset),
+                                  int(n_global), ctypes.byref(self.handle)))
+
+  def comm_handle(self):
+    buf = ctypes.create_string_buffer(64)
+    check(lib().bcg_solver_comm_handle(self.handle, buf))
+    return buf.raw
+
+  def comm_connect(self, world, rank, handles):
+    blob = b''.join(handles)
+    assert len(blob) == 64*world
+    check(lib().bcg_solver_comm_connect(self.handle, world, rank, ctypes.c_char_p(blob)))
+
+  def build(self, itrs, tol):
+    ev = (IterEvent*max(int(itrs), 1))()
+    n = ctypes.c_int32()
+    check(lib().bcg_solver_build(self.handle, int(itrs), float(tol), ev, ctypes.byref(n)))
+    return [ev[i] for i in range(n.value)]
+
+  def omp_select(self):
+    f = ctypes.c_int64()
+    check(lib().bcg_solver_omp_select(self.handle, ctypes.byref(f)))
+    return f.value
+
+  def error(self):
+    v = ctypes.c_double()
+    check(lib().bcg_solver_error(self.handle, ctypes.byref(v)))
+    return v.value
+
+  def halted(self):
+    v = ctypes.c_int32()
+    check(lib().bcg_solver_halted(self.handle, ctypes.byref(v)))
+    return bool(v.value)
+
+  def active(self):
+    k = ctypes.c_int64()
+    check(lib().bcg_solver_active(self.handle, 0, None, None, ctypes.byref(k)))
+    idx = np.empty(k.value, dtype=np.int64)
+    w = np.empty(k.value)
+    if k.value:
+      check(lib().bcg_solver_active(self.handle, k.value, _ptr(idx), _ptr(w), ctypes.byref(k)))
+    return idx, w
+
+  def active_rows(self, first, count):
+    out = np.empty((count, self.vecs.shape[1]))
+    if count:
+      check(lib().bcg_solver_active_rows(self.handle, first, count, _ptr(out)))
+    return out
+
+  def set_weights(self, w):
+    w = _f64(w)
+    check(lib().bcg_solver_set_weights(self.handle, _ptr(w), w.shape[0]))
+
+  def reset(self):
+    check(lib().bcg_solver_reset(self.handle))
+
+  def set_profiling(self, on):
+    check(lib().bcg_solver_set_profiling(self.handle, 1 if on else 0))
+
+  def timing(self):
+    b, s = ctypes.c_float(), ctypes.c_float()
+    ns, nt = ctypes.c_int32(), ctypes.c_int32()
+    check(lib().bcg_solver_timing(self.handle, ctypes.byref(b), ctypes.byref(s), ctypes.byref(ns), ctypes.byref(nt)))
+    return {'build_ms': b.value, 'scan_ms': s.value, 'scan_launches': ns.value, 'step_launches': nt.value}
+
+  def __del__(self):
+    try:
+      if self.handle:
+        lib().bcg_solver_destroy(self.handle)
+        self.handle = None
+    except Exception:
+      pass

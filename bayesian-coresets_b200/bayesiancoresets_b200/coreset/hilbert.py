@@ -1,0 +1,66 @@
+"""HilbertCoreset on the device (reference: coreset/hilbert.py:7-48).
+
+The projection is evaluated once -- on the device when the projector offers `project_device` --
+and handed to the sparse-NNLS solver exactly as the reference does: `snnls(vecs.T, vecs.sum(0))`.
+With a communicator the rows of `data` are this rank's shard of the N axis: b is all-reduced
+once, the greedy loop exchanges candidates over NVLink inside the step kernel, and every rank
+ends with the same (wts, idcs, pts)."""
+import numpy as np
+from ..snnls.giga import GIGA
+from ..comm import SerialComm, gather_rows
+from .. import _native as nat
+from .coreset import Coreset
+
+
+class HilbertCoreset(Coreset):
+  def __init__(self, data, ll_projector, n_subsample=None, snnls=GIGA, comm=None, **kw):
+    self.comm = comm or SerialComm()
+    project = getattr(ll_projector, 'project_device', ll_projector.project)
+    if n_subsample is None:
+      sub_idcs = np.arange(data.shape[0])
+      vecs = project(data)
+    else:
+      if self.comm.world > 1:
+        raise NotImplementedError('n_subsample with N-sharding is not supported')
+      # hilbert.py:13-22: sorted, de-duplicated subsample from the global RNG, zero rows removed
+      sub_idcs = np.unique(np.random.randint(data.shape[0], size=n_subsample))
+      vecs = project(data[sub_idcs])
+      nonzero = (vecs.norms() > 0.) if isinstance(vecs, nat.DeviceVecs) else (np.sqrt((vecs**2).sum(axis=1)) > 0.)
+      if not nonzero.all():
+        sub_idcs = sub_idcs[nonzero]
+        vecs = project(data[sub_idcs])
+    b = vecs.sum(axis=0)
+    extra = {}
+    if self.comm.world > 1:
+      b = self.comm.allreduce_sum(b)
+      extra['comm'] = self.comm
+    self.snnls = snnls(vecs.T, b, **extra)
+    self.sub_idcs = sub_idcs
+    self.data = data
+    super().__init__(**kw)
+
+  def reset(self):
+    self.snnls.reset()
+    super().reset()
+
+  def _export(self):
+    # hilbert.py:35-38: ascending index order, strictly positive weights
+    idx, w = self.snnls.weights_sparse()
+    self.wts = w
+    if self.comm.world > 1:
+      self.idcs = idx
+      self.pts = gather_rows(self.comm, self.data, self.snnls.row_offset, idx)
+    else:
+      self.idcs = self.sub_idcs[idx]
+      self.pts = self.data[self.idcs]
+
+  def _build(self, itrs):
+    self.snnls.build(itrs)
+    self._export()
+
+  def _optimize(self):
+    self.snnls.optimize()
+    self._export()
+
+  def error(self):
+    return self.snnls.error()

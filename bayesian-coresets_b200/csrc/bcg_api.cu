@@ -1,0 +1,896 @@
+// C-ABI implementation (include/bcg.h) of the B200-native coreset engine.
+// Host side: handle management, uploads, kernel launches on a private stream.  There is no CPU
+// compute path: without a CUDA device every entry point fails with BCG_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/bcg.h"
+#include "bcg_state.h"
+#include "project_kernels.cuh"
+#include "scan_kernel.cuh"
+#include "step_kernels.cuh"
+
+using namespace bcg;
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return fail(BCG_ERR_CUDA, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+#define RET(call)                  \
+  do {                             \
+    int r__ = (call);              \
+    if (r__ != BCG_OK) return r__; \
+  } while (0)
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+static int pow2ceil(int x) {
+  int p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+// ------------------------------------------------------------------------------------------
+// handles
+// ------------------------------------------------------------------------------------------
+struct bcg_ctx {
+  int device;
+  int sm_count;
+  cudaDeviceProp prop;
+  cudaStream_t stream;
+  float* flush_buf;
+  int64_t flush_bytes;
+};
+
+struct bcg_vecs {
+  bcg_ctx* ctx;
+  int64_t n;
+  int32_t S, ld;
+  float* An;
+  double* norms;
+  std::vector<double> colsum;   // S sums + [S] = sum of norms
+  uint64_t zero_rows;
+};
+
+struct ScanConfig {
+  int ch, ndir, lpr, rps, stages, wpb, grid, evict_first;
+  size_t smem;
+};
+
+struct bcg_solver {
+  bcg_ctx* ctx;
+  bcg_vecs* v;
+  SolverState h;      // host mirror (valid after every synchronising call)
+  SolverState* d;
+  ScanConfig sc;
+  bool scan_attr_set;
+  int64_t* d_fout;
+  unsigned char* mail;      // this rank's mailbox allocation
+  int64_t mail_bytes;
+  void* peer_ptrs[kMaxWorld];
+  bool peers_open;
+  // timing
+  int profiling;
+  cudaEvent_t ev0, ev1;
+  std::vector<cudaEvent_t> scan_ev;
+  float build_ms, scan_ms;
+  int scan_launches, step_launches;
+};
+
+static int use_device(bcg_ctx* ctx) {
+  if (!ctx) return fail(BCG_ERR_ARG, "null context");
+  CK(cudaSetDevice(ctx->device));
+  return BCG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// library / context
+// ------------------------------------------------------------------------------------------
+extern "C" int bcg_abi_version(void) { return BCG_ABI_VERSION; }
+extern "C" const char* bcg_last_error(void) { return g_err; }
+
+extern "C" int bcg_device_count(int* count) {
+  if (!count) return fail(BCG_ERR_ARG, "null count");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    *count = 0;
+    return fail(BCG_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  }
+  *count = n;
+  return BCG_OK;
+}
+
+extern "C" int bcg_ctx_create(int device, bcg_ctx** out) {
+  if (!out) return fail(BCG_ERR_ARG, "null out");
+  *out = nullptr;
+  int n = 0;
+  RET(bcg_device_count(&n));
+  if (device < 0 || device >= n) return fail(BCG_ERR_ARG, "device %d out of range [0,%d)", device, n);
+  bcg_ctx* c = new bcg_ctx();
+  c->device = device;
+  c->flush_buf = nullptr;
+  c->flush_bytes = 0;
+  CK(cudaSetDevice(device));
+  CK(cudaGetDeviceProperties(&c->prop, device));
+  if (c->prop.major < 10)
+    return fail(BCG_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                c->prop.major, c->prop.minor);
+  c->sm_count = c->prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  *out = c;
+  return BCG_OK;
+}
+
+extern "C" int bcg_ctx_destroy(bcg_ctx* ctx) {
+  if (!ctx) return BCG_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return BCG_OK;
+}
+
+extern "C" int bcg_ctx_info(bcg_ctx* ctx, char* name, int name_cap, int* sm_count, int* cc_major, int* cc_minor,
+                            int64_t* total_mem_bytes) {
+  if (!ctx) return fail(BCG_ERR_ARG, "null context");
+  if (name && name_cap > 0) {
+    strncpy(name, ctx->prop.name, name_cap - 1);
+    name[name_cap - 1] = 0;
+  }
+  if (sm_count) *sm_count = ctx->sm_count;
+  if (cc_major) *cc_major = ctx->prop.major;
+  if (cc_minor) *cc_minor = ctx->prop.minor;
+  if (total_mem_bytes) *total_mem_bytes = (int64_t)ctx->prop.totalGlobalMem;
+  return BCG_OK;
+}
+
+extern "C" int bcg_ctx_synchronize(bcg_ctx* ctx) {
+  RET(use_device(ctx));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return BCG_OK;
+}
+
+extern "C" int bcg_ctx_flush_l2(bcg_ctx* ctx, int64_t bytes) {
+  RET(use_device(ctx));
+  if (bytes <= 0) return BCG_OK;
+  if (ctx->flush_bytes < bytes) {
+    if (ctx->flush_buf) CK(cudaFree(ctx->flush_buf));
+    ctx->flush_buf = nullptr;
+    CK(cudaMalloc(&ctx->flush_buf, bytes));
+    ctx->flush_bytes = bytes;
+  }
+  fill_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(ctx->flush_buf, bytes / 4, 0.f);
+  CK(cudaGetLastError());
+  return BCG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// projection matrix
+// ------------------------------------------------------------------------------------------
+static int j_for_ld(int ld) {
+  int j = pow2ceil((ld + 31) / 32);
+  return j;
+}
+
+static int vecs_alloc(bcg_ctx* ctx, int64_t n, int32_t S, bcg_vecs** out) {
+  if (n < 0 || S <= 0) return fail(BCG_ERR_ARG, "bad shape n=%lld S=%d", (long long)n, S);
+  if (S > 1024) return fail(BCG_ERR_UNSUPPORTED, "S=%d > 1024 is not supported", S);
+  if (n >= (1ll << 32) - 1) return fail(BCG_ERR_UNSUPPORTED, "more than 2^32-2 local rows");
+  bcg_vecs* v = new bcg_vecs();
+  v->ctx = ctx;
+  v->n = n;
+  v->S = S;
+  v->ld = (S + 3) / 4 * 4;
+  v->An = nullptr;
+  v->norms = nullptr;
+  v->zero_rows = 0;
+  v->colsum.assign(S + 1, 0.);
+  if (n > 0) {
+    CK(cudaMalloc(&v->An, (size_t)n * v->ld * sizeof(float)));
+    CK(cudaMalloc(&v->norms, (size_t)n * sizeof(double)));
+  }
+  *out = v;
+  return BCG_OK;
+}
+
+// reduce `nparts` partial column-sum rows on the device and fetch them
+static int finish_colsum(bcg_vecs* v, const double* d_partial, int nparts, unsigned long long* d_zero) {
+  bcg_ctx* ctx = v->ctx;
+  const int S1 = v->S + 1;
+  double* d_out = nullptr;
+  CK(cudaMalloc(&d_out, S1 * sizeof(double)));
+  colsum_reduce_kernel<<<(S1 + 127) / 128, 128, 0, ctx->stream>>>(d_partial, nparts, S1, d_out);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(v->colsum.data(), d_out, S1 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  unsigned long long z = 0;
+  CK(cudaMemcpyAsync(&z, d_zero, sizeof(z), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  v->zero_rows = z;
+  CK(cudaFree(d_out));
+  return BCG_OK;
+}
+
+template <int J>
+static int launch_ingest(bcg_ctx* ctx, const double* src, int64_t src_ld, int64_t n, bcg_vecs* v, int64_t row0,
+                         double* partial, int grid, unsigned long long* d_zero) {
+  const size_t smem = (size_t)kProjWarps * (v->S + 1) * sizeof(double);
+  CK(cudaFuncSetAttribute(ingest_kernel<J>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ingest_kernel<J><<<grid, kProjWarps * 32, smem, ctx->stream>>>(src, src_ld, n, v->S, v->ld,
+                                                                  v->An + (size_t)row0 * v->ld, v->norms + row0,
+                                                                  partial, d_zero);
+  CK(cudaGetLastError());
+  return BCG_OK;
+}
+
+static int dispatch_ingest(bcg_ctx* ctx, const double* src, int64_t src_ld, int64_t n, bcg_vecs* v, int64_t row0,
+                           double* partial, int grid, unsigned long long* d_zero) {
+  switch (j_for_ld(v->ld)) {
+    case 1: return launch_ingest<1>(ctx, src, src_ld, n, v, row0, partial, grid, d_zero);
+    case 2: return launch_ingest<2>(ctx, src, src_ld, n, v, row0, partial, grid, d_zero);
+    case 4: return launch_ingest<4>(ctx, src, src_ld, n, v, row0, partial, grid, d_zero);
+    case 8: return launch_ingest<8>(ctx, src, src_ld, n, v, row0, partial, grid, d_zero);
+    case 16: return launch_ingest<16>(ctx, src, src_ld, n, v, row0, partial, grid, d_zero);
+    default: return launch_ingest<32>(ctx, src, src_ld, n, v, row0, partial, grid, d_zero);
+  }
+}
+
+extern "C" int bcg_vecs_from_host_f64(bcg_ctx* ctx, const double* rows, int64_t n, int32_t S, int64_t ld_host,
+                                      bcg_vecs** out) {
+  RET(use_device(ctx));
+  if (!out || (n > 0 && !rows) || ld_host < S) return fail(BCG_ERR_ARG, "bad arguments");
+  *out = nullptr;
+  bcg_vecs* v = nullptr;
+  RET(vecs_alloc(ctx, n, S, &v));
+  if (n == 0) { *out = v; return BCG_OK; }
+
+  // double-buffered pinned staging: host memcpy of chunk c+1 overlaps H2D + ingest of chunk c
+  const int64_t chunk_rows = std::max<int64_t>(1, std::min<int64_t>(n, (32ll << 20) / ((int64_t)S * 8)));
+  const int nchunks = (int)((n + chunk_rows - 1) / chunk_rows);
+  const int grid = (int)std::min<int64_t>((chunk_rows + kProjWarps - 1) / kProjWarps, (int64_t)ctx->sm_count * 2);
+  double* pin[2] = {nullptr, nullptr};
+  double* dev[2] = {nullptr, nullptr};
+  cudaEvent_t done[2];
+  double* d_partial = nullptr;
+  unsigned long long* d_zero = nullptr;
+  const size_t cbytes = (size_t)chunk_rows * S * sizeof(double);
+  for (int i = 0; i < 2; ++i) {
+    CK(cudaMallocHost(&pin[i], cbytes));
+    CK(cudaMalloc(&dev[i], cbytes));
+    CK(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+  }
+  CK(cudaMalloc(&d_partial, (size_t)nchunks * grid * (S + 1) * sizeof(double)));
+  CK(cudaMalloc(&d_zero, sizeof(unsigned long long)));
+  CK(cudaMemsetAsync(d_zero, 0, sizeof(unsigned long long), ctx->stream));
+  for (int c = 0; c < nchunks; ++c) {
+    const int i = c & 1;
+    const int64_t r0 = (int64_t)c * chunk_rows;
+    const int64_t nr = std::min<int64_t>(chunk_rows, n - r0);
+    if (c >= 2) CK(cudaEventSynchronize(done[i]));
+    if (ld_host == S) {
+      memcpy(pin[i], rows + r0 * ld_host, (size_t)nr * S * sizeof(double));
+    } else {
+      for (int64_t r = 0; r < nr; ++r) memcpy(pin[i] + r * S, rows + (r0 + r) * ld_host, (size_t)S * sizeof(double));
+    }
+    CK(cudaMemcpyAsync(dev[i], pin[i], (size_t)nr * S * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    RET(dispatch_ingest(ctx, dev[i], S, nr, v, r0, d_partial + (size_t)c * grid * (S + 1), grid, d_zero));
+    CK(cudaEventRecord(done[i], ctx->stream));
+  }
+  RET(finish_colsum(v, d_partial, nchunks * grid, d_zero));
+  for (int i = 0; i < 2; ++i) {
+    cudaFreeHost(pin[i]);
+    cudaFree(dev[i]);
+    cudaEventDestroy(done[i]);
+  }
+  cudaFree(d_partial);
+  cudaFree(d_zero);
+  *out = v;
+  return BCG_OK;
+}
+
+template <int J>
+static int launch_project(bcg_ctx* ctx, const ProjectArgs& a, int grid, size_t smem, int ktile) {
+  (void)ktile;
+  CK(cudaFuncSetAttribute(project_kernel<J>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  project_kernel<J><<<grid, kProjWarps * 32, smem, ctx->stream>>>(a);
+  CK(cudaGetLastError());
+  return BCG_OK;
+}
+
+// common driver: Z (n x zld) host, thetaT (d x S) host (already transposed), coff (S) host or null
+static int project_common(bcg_ctx* ctx, const double* Z, int64_t n, int32_t zld, int32_t d, const double* thetaT,
+                          const double* coff, int32_t S, int model, bcg_vecs** out) {
+  *out = nullptr;
+  if (d <= 0) return fail(BCG_ERR_ARG, "d must be positive");
+  bcg_vecs* v = nullptr;
+  RET(vecs_alloc(ctx, n, S, &v));
+  if (n == 0) { *out = v; return BCG_OK; }
+  const size_t cs_bytes = (size_t)kProjWarps * (S + 1) * sizeof(double);
+  const size_t budget = 200 * 1024;
+  if (cs_bytes + (size_t)S * sizeof(double) > budget)
+    return fail(BCG_ERR_UNSUPPORTED, "projection tile does not fit shared memory for S=%d", S);
+  const int ktile = (int)std::min<size_t>(std::min<size_t>(kProjKTile, (size_t)d), (budget - cs_bytes) / ((size_t)S * sizeof(double)));
+  const size_t smem = (size_t)ktile * S * sizeof(double) + cs_bytes;
+  double *dZ = nullptr, *dT = nullptr, *dC = nullptr, *d_partial = nullptr;
+  unsigned long long* d_zero = nullptr;
+  const int64_t nbatch = (n + kProjWarps - 1) / kProjWarps;
+  const int grid = (int)std::min<int64_t>(nbatch, (int64_t)ctx->sm_count);
+  CK(cudaMalloc(&dZ, (size_t)n * zld * sizeof(double)));
+  CK(cudaMalloc(&dT, (size_t)d * S * sizeof(double)));
+  CK(cudaMalloc(&d_partial, (size_t)grid * (S + 1) * sizeof(double)));
+  CK(cudaMalloc(&d_zero, sizeof(unsigned long long)));
+  CK(cudaMemsetAsync(d_zero, 0, sizeof(unsigned long long), ctx->stream));
+  CK(cudaMemcpyAsync(dZ, Z, (size_t)n * zld * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(dT, thetaT, (size_t)d * S * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (coff) {
+    CK(cudaMalloc(&dC, (size_t)S * sizeof(double)));
+    CK(cudaMemcpyAsync(dC, coff, (size_t)S * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  ProjectArgs a;
+  a.Z = dZ; a.theta = dT; a.coff = dC; a.An = v->An; a.norms = v->norms; a.partial = d_partial;
+  a.zero_rows = d_zero; a.n = n; a.zld = zld; a.d = d; a.S = S; a.ld = v->ld; a.model = model; a.ktile = ktile;
+  int rc;
+  switch (j_for_ld(v->ld)) {
+    case 1: rc = launch_project<1>(ctx, a, grid, smem, ktile); break;
+    case 2: rc = launch_project<2>(ctx, a, grid, smem, ktile); break;
+    case 4: rc = launch_project<4>(ctx, a, grid, smem, ktile); break;
+    case 8: rc = launch_project<8>(ctx, a, grid, smem, ktile); break;
+    case 16: rc = launch_project<16>(ctx, a, grid, smem, ktile); break;
+    default: rc = launch_project<32>(ctx, a, grid, smem, ktile); break;
+  }
+  RET(rc);
+  RET(finish_colsum(v, d_partial, grid, d_zero));
+  cudaFree(dZ); cudaFree(dT); cudaFree(d_partial); cudaFree(d_zero);
+  if (dC) cudaFree(dC);
+  *out = v;
+  return BCG_OK;
+}
+
+static std::vector<double> transpose_sd(const double* theta, int S, int d) {
+  std::vector<double> t((size_t)S * d);
+  for (int s = 0; s < S; ++s)
+    for (int k = 0; k < d; ++k) t[(size_t)k * S + s] = theta[(size_t)s * d + k];
+  return t;
+}
+
+extern "C" int bcg_vecs_project_lr(bcg_ctx* ctx, const double* Z, int64_t n, int32_t d, const double* theta,
+                                   int32_t S, bcg_vecs** out) {
+  RET(use_device(ctx));
+  if (!out || !theta || (n > 0 && !Z)) return fail(BCG_ERR_ARG, "null argument");
+  std::vector<double> tT = transpose_sd(theta, S, d);
+  return project_common(ctx, Z, n, d, d, tT.data(), nullptr, S, MODEL_LR, out);
+}
+
+extern "C" int bcg_vecs_project_gaussian(bcg_ctx* ctx, const double* x, int64_t n, int32_t d, const double* theta,
+                                         int32_t S, const double* Siginv, bcg_vecs** out) {
+  RET(use_device(ctx));
+  if (!out || !theta || !Siginv || (n > 0 && !x)) return fail(BCG_ERR_ARG, "null argument");
+  // after row-centring only  x . (Siginv theta_s) - 0.5 theta_s . Siginv theta_s  survives (model_gaussian.py:4-10)
+  std::vector<double> tT((size_t)S * d), coff(S);
+  for (int s = 0; s < S; ++s) {
+    double q = 0.;
+    for (int i = 0; i < d; ++i) {
+      double m = 0.;
+      for (int j = 0; j < d; ++j) m += Siginv[(size_t)i * d + j] * theta[(size_t)s * d + j];
+      tT[(size_t)i * S + s] = m;
+      q += theta[(size_t)s * d + i] * m;
+    }
+    coff[s] = -0.5 * q;
+  }
+  return project_common(ctx, x, n, d, d, tT.data(), coff.data(), S, MODEL_LINEAR, out);
+}
+
+extern "C" int bcg_vecs_project_poisson(bcg_ctx* ctx, const double* Z, int64_t n, int32_t d, const double* theta,
+                                        int32_t S, bcg_vecs** out) {
+  RET(use_device(ctx));
+  if (!out || !theta || (n > 0 && !Z)) return fail(BCG_ERR_ARG, "null argument");
+  std::vector<double> tT = transpose_sd(theta, S, d);
+  return project_common(ctx, Z, n, d + 1, d, tT.data(), nullptr, S, MODEL_POISSON, out);
+}
+
+extern "C" int bcg_vecs_shape(bcg_vecs* v, int64_t* n, int32_t* S, int32_t* ld) {
+  if (!v) return fail(BCG_ERR_ARG, "null vecs");
+  if (n) *n = v->n;
+  if (S) *S = v->S;
+  if (ld) *ld = v->ld;
+  return BCG_OK;
+}
+
+extern "C" int bcg_vecs_colsum(bcg_vecs* v, double* out_S) {
+  if (!v || !out_S) return fail(BCG_ERR_ARG, "null argument");
+  memcpy(out_S, v->colsum.data(), (size_t)v->S * sizeof(double));
+  return BCG_OK;
+}
+
+extern "C" int bcg_vecs_norm_sum(bcg_vecs* v, double* out) {
+  if (!v || !out) return fail(BCG_ERR_ARG, "null argument");
+  *out = v->colsum[v->S];
+  return BCG_OK;
+}
+
+extern "C" int bcg_vecs_zero_rows(bcg_vecs* v, int64_t* count) {
+  if (!v || !count) return fail(BCG_ERR_ARG, "null argument");
+  *count = (int64_t)v->zero_rows;
+  return BCG_OK;
+}
+
+extern "C" int bcg_vecs_norms(bcg_vecs* v, int64_t row0, int64_t nrows, double* out) {
+  if (!v || !out) return fail(BCG_ERR_ARG, "null argument");
+  if (row0 < 0 || nrows < 0 || row0 + nrows > v->n) return fail(BCG_ERR_ARG, "row range out of bounds");
+  RET(use_device(v->ctx));
+  if (nrows == 0) return BCG_OK;
+  CK(cudaMemcpyAsync(out, v->norms + row0, (size_t)nrows * sizeof(double), cudaMemcpyDeviceToHost, v->ctx->stream));
+  CK(cudaStreamSynchronize(v->ctx->stream));
+  return BCG_OK;
+}
+
+extern "C" int bcg_vecs_rows_f64(bcg_vecs* v, int64_t row0, int64_t nrows, double* out) {
+  if (!v || !out) return fail(BCG_ERR_ARG, "null argument");
+  if (row0 < 0 || nrows < 0 || row0 + nrows > v->n) return fail(BCG_ERR_ARG, "row range out of bounds");
+  RET(use_device(v->ctx));
+  const int64_t chunk = std::max<int64_t>(1, (64ll << 20) / ((int64_t)v->S * 8));
+  double* tmp = nullptr;
+  CK(cudaMalloc(&tmp, (size_t)std::min(chunk, std::max<int64_t>(nrows, 1)) * v->S * sizeof(double)));
+  for (int64_t r = 0; r < nrows; r += chunk) {
+    const int64_t nr = std::min(chunk, nrows - r);
+    const int64_t tot = nr * v->S;
+    expand_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, v->ctx->stream>>>(v->An, v->norms, row0 + r, nr, v->S,
+                                                                               v->ld, tmp);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out + r * v->S, tmp, (size_t)tot * sizeof(double), cudaMemcpyDeviceToHost, v->ctx->stream));
+    CK(cudaStreamSynchronize(v->ctx->stream));
+  }
+  CK(cudaFree(tmp));
+  return BCG_OK;
+}
+
+extern "C" int bcg_vecs_destroy(bcg_vecs* v) {
+  if (!v) return BCG_OK;
+  cudaSetDevice(v->ctx->device);
+  if (v->An) cudaFree(v->An);
+  if (v->norms) cudaFree(v->norms);
+  delete v;
+  return BCG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// solver
+// ------------------------------------------------------------------------------------------
+static int choose_scan_config(bcg_solver* s) {
+  const int ld = s->v->ld;
+  ScanConfig& c = s->sc;
+  const int nchunk = ld / 4;
+  c.lpr = std::min(32, pow2ceil(nchunk));
+  const int need = (nchunk + c.lpr - 1) / c.lpr;
+  c.ch = pow2ceil(need);
+  if (c.ch > 8) return fail(BCG_ERR_UNSUPPORTED, "S=%d needs more than 8 float4 chunks per lane", s->v->S);
+  c.ndir = (s->h.alg == BCG_ALG_GIGA) ? 2 : 1;
+  const int ngrp = 32 / c.lpr;
+  const int row_bytes = ld * 4;
+  const int stage_bytes = env_int("BCG_SCAN_STAGE_BYTES", 4096);
+  c.rps = std::max(1, stage_bytes / row_bytes);
+  c.rps = std::max(ngrp, c.rps / ngrp * ngrp);
+  c.wpb = std::max(1, std::min(16, env_int("BCG_SCAN_WARPS", 16)));
+  c.stages = std::max(1, env_int("BCG_SCAN_STAGES", 3));
+  const int ctas = std::max(1, env_int("BCG_SCAN_CTAS_PER_SM", 1));
+  c.evict_first = env_int("BCG_SCAN_EVICT_FIRST", 0);
+  const size_t budget = (size_t)(220 * 1024) / ctas;
+  auto smem_for = [&](int stages) { return (size_t)c.wpb * stages * c.rps * row_bytes + (size_t)c.wpb * stages * 8; };
+  while (c.stages > 1 && smem_for(c.stages) > budget) --c.stages;
+  while (c.rps > ngrp && smem_for(c.stages) > budget) c.rps -= ngrp;
+  c.smem = smem_for(c.stages);
+  if (c.smem > budget) return fail(BCG_ERR_UNSUPPORTED, "scan tile does not fit shared memory (ld=%d)", ld);
+  c.grid = s->ctx->sm_count * ctas;
+  return BCG_OK;
+}
+
+template <int CH, int NDIR>
+static int launch_scan_t(bcg_solver* s, const ScanArgs& a) {
+  if (!s->scan_attr_set) {
+    CK(cudaFuncSetAttribute(scan_kernel<CH, NDIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->sc.smem));
+    s->scan_attr_set = true;
+  }
+  scan_kernel<CH, NDIR><<<s->sc.grid, s->sc.wpb * 32, s->sc.smem, s->ctx->stream>>>(a);
+  CK(cudaGetLastError());
+  return BCG_OK;
+}
+
+static int launch_scan(bcg_solver* s) {
+  ScanArgs a;
+  a.An = s->v->An;
+  a.dir = s->h.dir32;
+  a.cands = s->h.cands;
+  a.skip0 = &s->d->halted;
+  a.skip1 = &s->d->select_failed;
+  a.n_rows = s->v->n;
+  a.ld = s->v->ld;
+  a.lpr = s->sc.lpr;
+  a.rps = s->sc.rps;
+  a.stages = s->sc.stages;
+  a.evict_first = s->sc.evict_first;
+  const int key = s->sc.ch * 10 + s->sc.ndir;
+  switch (key) {
+    case 11: return launch_scan_t<1, 1>(s, a);
+    case 12: return launch_scan_t<1, 2>(s, a);
+    case 21: return launch_scan_t<2, 1>(s, a);
+    case 22: return launch_scan_t<2, 2>(s, a);
+    case 41: return launch_scan_t<4, 1>(s, a);
+    case 42: return launch_scan_t<4, 2>(s, a);
+    case 81: return launch_scan_t<8, 1>(s, a);
+    case 82: return launch_scan_t<8, 2>(s, a);
+  }
+  return fail(BCG_ERR_UNSUPPORTED, "no scan kernel for ch=%d ndir=%d", s->sc.ch, s->sc.ndir);
+}
+
+static int push_state(bcg_solver* s) {
+  CK(cudaMemcpyAsync(s->d, &s->h, sizeof(SolverState), cudaMemcpyHostToDevice, s->ctx->stream));
+  return BCG_OK;
+}
+static int pull_state(bcg_solver* s) {
+  CK(cudaMemcpyAsync(&s->h, s->d, sizeof(SolverState), cudaMemcpyDeviceToHost, s->ctx->stream));
+  CK(cudaStreamSynchronize(s->ctx->stream));
+  return BCG_OK;
+}
+
+template <typename T>
+static int grow(T** p, size_t old_n, size_t new_n, cudaStream_t st) {
+  T* q = nullptr;
+  CK(cudaMalloc(&q, new_n * sizeof(T)));
+  CK(cudaMemsetAsync(q, 0, new_n * sizeof(T), st));
+  if (*p && old_n) CK(cudaMemcpyAsync(q, *p, old_n * sizeof(T), cudaMemcpyDeviceToDevice, st));
+  CK(cudaStreamSynchronize(st));
+  if (*p) CK(cudaFree(*p));
+  *p = q;
+  return BCG_OK;
+}
+
+// make room for `extra` more stored active rows (host mirror must be current)
+static int ensure_capacity(bcg_solver* s, int extra) {
+  SolverState& h = s->h;
+  const int need = h.nact + extra;
+  if (need <= h.cap) return BCG_OK;
+  const int ncap = std::max(need, std::max(64, h.cap * 2));
+  cudaStream_t st = s->ctx->stream;
+  RET(grow(&h.act_idx, (size_t)h.cap, (size_t)ncap, st));
+  RET(grow(&h.act_w, (size_t)h.cap, (size_t)ncap, st));
+  RET(grow(&h.act_w_new, (size_t)h.cap, (size_t)ncap, st));
+  RET(grow(&h.act_norm, (size_t)h.cap, (size_t)ncap, st));
+  RET(grow(&h.act_rows, (size_t)h.cap * h.ld, (size_t)ncap * h.ld, st));
+  h.cap = ncap;
+  return BCG_OK;
+}
+
+extern "C" int bcg_solver_create(bcg_ctx* ctx, bcg_vecs* v, int32_t alg, const double* b, double norm_sum,
+                                 int64_t row_offset, int64_t n_global, bcg_solver** out) {
+  RET(use_device(ctx));
+  if (!out || !v || !b) return fail(BCG_ERR_ARG, "null argument");
+  if (alg != BCG_ALG_GIGA && alg != BCG_ALG_FW && alg != BCG_ALG_OMP) return fail(BCG_ERR_ARG, "unknown alg %d", alg);
+  *out = nullptr;
+  const int S = v->S, ld = v->ld;
+  double bnorm = 0.;
+  for (int i = 0; i < S; ++i) bnorm += b[i] * b[i];
+  bnorm = sqrt(bnorm);
+  if (alg == BCG_ALG_GIGA && bnorm == 0.) return fail(BCG_ERR_ZERO_B, "norm of b must be > 0");
+  bcg_solver* s = new bcg_solver();
+  memset(&s->h, 0, sizeof(SolverState));
+  s->ctx = ctx;
+  s->v = v;
+  s->mail = nullptr;
+  s->mail_bytes = 0;
+  s->peers_open = false;
+  s->scan_attr_set = false;
+  s->profiling = 0;
+  s->build_ms = s->scan_ms = 0.f;
+  s->scan_launches = s->step_launches = 0;
+  for (int i = 0; i < kMaxWorld; ++i) s->peer_ptrs[i] = nullptr;
+  SolverState& h = s->h;
+  h.alg = alg; h.S = S; h.ld = ld; h.world = 1; h.rank = 0;
+  h.n_local = v->n; h.row_offset = row_offset; h.n_global = n_global;
+  h.tol = 1e-12; h.bnorm = bnorm; h.nsum = norm_sum;
+  h.An = v->An; h.norms = v->norms;
+  h.err = bnorm;
+  RET(choose_scan_config(s));
+  h.n_cands = s->sc.grid * s->sc.wpb;
+  cudaStream_t st = ctx->stream;
+  std::vector<double> bn(S);
+  for (int i = 0; i < S; ++i) bn[i] = bnorm > 0. ? b[i] / bnorm : 0.;
+  CK(cudaMalloc(&h.b, S * sizeof(double)));
+  CK(cudaMalloc(&h.bn, S * sizeof(double)));
+  CK(cudaMalloc(&h.xw, S * sizeof(double)));
+  CK(cudaMalloc(&h.xw_new, S * sizeof(double)));
+  CK(cudaMalloc(&h.xf, S * sizeof(double)));
+  CK(cudaMalloc(&h.dir64, 2 * S * sizeof(double)));
+  CK(cudaMalloc(&h.dir32, 2 * ld * sizeof(float)));
+  CK(cudaMalloc(&h.wrow, ld * sizeof(float)));
+  CK(cudaMalloc(&h.cands, (size_t)h.n_cands * sizeof(ScanCand)));
+  CK(cudaMalloc(&s->d_fout, sizeof(int64_t)));
+  CK(cudaMalloc(&s->d, sizeof(SolverState)));
+  CK(cudaMemcpyAsync(h.b, b, S * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h.bn, bn.data(), S * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(h.xw, 0, S * sizeof(double), st));
+  CK(cudaMemsetAsync(h.dir32, 0, 2 * ld * sizeof(float), st));
+  CK(cudaMemsetAsync(h.dir64, 0, 2 * S * sizeof(double), st));
+  CK(cudaMemsetAsync(h.cands, 0xff, (size_t)h.n_cands * sizeof(ScanCand), st));
+  CK(cudaStreamSynchronize(st));
+  RET(ensure_capacity(s, 64));
+  RET(push_state(s));
+  CK(cudaEventCreate(&s->ev0));
+  CK(cudaEventCreate(&s->ev1));
+  CK(cudaStreamSynchronize(st));
+  *out = s;
+  return BCG_OK;
+}
+
+extern "C" int bcg_solver_destroy(bcg_solver* s) {
+  if (!s) return BCG_OK;
+  cudaSetDevice(s->ctx->device);
+  cudaStreamSynchronize(s->ctx->stream);
+  SolverState& h = s->h;
+  if (s->peers_open)
+    for (int p = 0; p < h.world; ++p)
+      if (p != h.rank && s->peer_ptrs[p]) cudaIpcCloseMemHandle(s->peer_ptrs[p]);
+  void* bufs[] = {h.b, h.bn, h.xw, h.xw_new, h.xf, h.dir64, h.dir32, h.wrow, h.cands, h.act_idx, h.act_w,
+                  h.act_w_new, h.act_norm, h.act_rows, h.events, s->d_fout, s->d, s->mail};
+  for (void* p : bufs)
+    if (p) cudaFree(p);
+  for (cudaEvent_t e : s->scan_ev) cudaEventDestroy(e);
+  cudaEventDestroy(s->ev0);
+  cudaEventDestroy(s->ev1);
+  delete s;
+  return BCG_OK;
+}
+
+static int ensure_mailbox(bcg_solver* s, int world) {
+  const int64_t sb = mail_slot_bytes_for(s->h.ld);
+  const int64_t bytes = 2 * (int64_t)world * sb;
+  if (s->mail && s->mail_bytes >= bytes) return BCG_OK;
+  if (s->mail) CK(cudaFree(s->mail));
+  CK(cudaMalloc(&s->mail, bytes));
+  CK(cudaMemset(s->mail, 0, bytes));
+  s->mail_bytes = bytes;
+  return BCG_OK;
+}
+
+extern "C" int bcg_solver_comm_handle(bcg_solver* s, void* handle64) {
+  if (!s || !handle64) return fail(BCG_ERR_ARG, "null argument");
+  RET(use_device(s->ctx));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle must be 64 bytes");
+  RET(ensure_mailbox(s, kMaxWorld));
+  cudaIpcMemHandle_t hnd;
+  CK(cudaIpcGetMemHandle(&hnd, s->mail));
+  memcpy(handle64, &hnd, 64);
+  return BCG_OK;
+}
+
+extern "C" int bcg_solver_comm_connect(bcg_solver* s, int32_t world, int32_t rank, const void* handles64) {
+  if (!s || !handles64) return fail(BCG_ERR_ARG, "null argument");
+  if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world)
+    return fail(BCG_ERR_ARG, "bad world/rank %d/%d (max world %d)", world, rank, kMaxWorld);
+  RET(use_device(s->ctx));
+  RET(ensure_mailbox(s, kMaxWorld));
+  SolverState& h = s->h;
+  for (int p = 0; p < world; ++p) {
+    if (p == rank) {
+      s->peer_ptrs[p] = s->mail;
+    } else {
+      cudaIpcMemHandle_t hnd;
+      memcpy(&hnd, (const char*)handles64 + 64 * p, 64);
+      void* ptr = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&ptr, hnd, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess)
+        return fail(BCG_ERR_COMM, "cudaIpcOpenMemHandle(rank %d) failed: %s", p, cudaGetErrorString(e));
+      s->peer_ptrs[p] = ptr;
+    }
+    h.mail_peer[p] = (unsigned char*)s->peer_ptrs[p];
+  }
+  s->peers_open = true;
+  h.world = world;
+  h.rank = rank;
+  h.mail_local = s->mail;
+  h.mail_slot_bytes = mail_slot_bytes_for(h.ld);
+  h.seq = 0;
+  RET(push_state(s));
+  CK(cudaStreamSynchronize(s->ctx->stream));
+  return BCG_OK;
+}
+
+extern "C" int bcg_solver_build(bcg_solver* s, int32_t itrs, double tol, bcg_iter_event* events, int32_t* n_events) {
+  if (!s) return fail(BCG_ERR_ARG, "null solver");
+  RET(use_device(s->ctx));
+  if (n_events) *n_events = 0;
+  if (s->h.alg == BCG_ALG_OMP) return fail(BCG_ERR_STATE, "OMP iterations are driven with bcg_solver_omp_select");
+  if (itrs <= 0 || s->h.halted || (s->v->n == 0 && s->h.world == 1)) return BCG_OK;
+  cudaStream_t st = s->ctx->stream;
+  SolverState& h = s->h;
+  RET(ensure_capacity(s, itrs + 1));
+  if (h.events) CK(cudaFree(h.events));
+  h.events = nullptr;
+  CK(cudaMalloc(&h.events, (size_t)itrs * sizeof(bcg_iter_event)));
+  CK(cudaMemsetAsync(h.events, 0, (size_t)itrs * sizeof(bcg_iter_event), st));
+  h.n_events = 0;
+  h.tol = tol;
+  h.comm_error = 0;
+  RET(push_state(s));
+  if (s->profiling) {
+    while ((int)s->scan_ev.size() < 2 * itrs) {
+      cudaEvent_t e;
+      CK(cudaEventCreate(&e));
+      s->scan_ev.push_back(e);
+    }
+  }
+  CK(cudaEventRecord(s->ev0, st));
+  step_kernel<<<1, kStepThreads, 0, st>>>(s->d, 0, 1, 1);
+  for (int i = 0; i < itrs; ++i) {
+    if (s->profiling) CK(cudaEventRecord(s->scan_ev[2 * i], st));
+    RET(launch_scan(s));
+    if (s->profiling) CK(cudaEventRecord(s->scan_ev[2 * i + 1], st));
+    step_kernel<<<1, kStepThreads, 0, st>>>(s->d, 1, (i + 1 < itrs) ? 1 : 0, 0);
+  }
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(s->ev1, st));
+  RET(pull_state(s));
+  CK(cudaEventElapsedTime(&s->build_ms, s->ev0, s->ev1));
+  s->scan_launches = itrs;
+  s->step_launches = itrs + 1;
+  s->scan_ms = 0.f;
+  if (s->profiling) {
+    for (int i = 0; i < itrs; ++i) {
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, s->scan_ev[2 * i], s->scan_ev[2 * i + 1]));
+      s->scan_ms += ms;
+    }
+  }
+  const int ne = h.n_events;
+  if (events && ne > 0) CK(cudaMemcpy(events, h.events, (size_t)ne * sizeof(bcg_iter_event), cudaMemcpyDeviceToHost));
+  if (n_events) *n_events = ne;
+  if (h.comm_error) return fail(BCG_ERR_COMM, "peer-memory candidate exchange timed out (a rank is missing)");
+  return BCG_OK;
+}
+
+extern "C" int bcg_solver_omp_select(bcg_solver* s, int64_t* f) {
+  if (!s || !f) return fail(BCG_ERR_ARG, "null argument");
+  RET(use_device(s->ctx));
+  if (s->h.alg != BCG_ALG_OMP) return fail(BCG_ERR_STATE, "solver was not created with BCG_ALG_OMP");
+  cudaStream_t st = s->ctx->stream;
+  RET(ensure_capacity(s, 1));
+  s->h.comm_error = 0;
+  RET(push_state(s));
+  step_kernel<<<1, kStepThreads, 0, st>>>(s->d, 0, 1, 0);
+  RET(launch_scan(s));
+  omp_select_kernel<<<1, kStepThreads, 0, st>>>(s->d, s->d_fout);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(f, s->d_fout, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  RET(pull_state(s));
+  if (s->h.comm_error) return fail(BCG_ERR_COMM, "peer-memory candidate exchange timed out (a rank is missing)");
+  return BCG_OK;
+}
+
+extern "C" int bcg_solver_error(bcg_solver* s, double* err) {
+  if (!s || !err) return fail(BCG_ERR_ARG, "null argument");
+  *err = s->h.err;
+  return BCG_OK;
+}
+
+extern "C" int bcg_solver_halted(bcg_solver* s, int32_t* reached) {
+  if (!s || !reached) return fail(BCG_ERR_ARG, "null argument");
+  *reached = s->h.halted;
+  return BCG_OK;
+}
+
+extern "C" int bcg_solver_active(bcg_solver* s, int64_t cap, int64_t* idx, double* w, int64_t* k) {
+  if (!s || !k) return fail(BCG_ERR_ARG, "null argument");
+  RET(use_device(s->ctx));
+  const int64_t n = s->h.nact;
+  *k = n;
+  if (n == 0 || (!idx && !w)) return BCG_OK;
+  if (cap < n) return fail(BCG_ERR_ARG, "capacity %lld < %lld stored rows", (long long)cap, (long long)n);
+  cudaStream_t st = s->ctx->stream;
+  if (idx) CK(cudaMemcpyAsync(idx, s->h.act_idx, (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  if (w) CK(cudaMemcpyAsync(w, s->h.act_w, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return BCG_OK;
+}
+
+extern "C" int bcg_solver_size(bcg_solver* s, int64_t* n_positive, int64_t* n_stored) {
+  if (!s) return fail(BCG_ERR_ARG, "null solver");
+  const int64_t n = s->h.nact;
+  if (n_stored) *n_stored = n;
+  if (n_positive) {
+    std::vector<double> w((size_t)std::max<int64_t>(n, 1));
+    int64_t k = 0;
+    RET(bcg_solver_active(s, n, nullptr, w.data(), &k));
+    int64_t c = 0;
+    for (int64_t i = 0; i < n; ++i) c += w[i] > 0.;
+    *n_positive = c;
+  }
+  return BCG_OK;
+}
+
+extern "C" int bcg_solver_active_rows(bcg_solver* s, int64_t first, int64_t count, double* out) {
+  if (!s || !out) return fail(BCG_ERR_ARG, "null argument");
+  if (first < 0 || count < 0 || first + count > s->h.nact) return fail(BCG_ERR_ARG, "active row range out of bounds");
+  RET(use_device(s->ctx));
+  if (count == 0) return BCG_OK;
+  cudaStream_t st = s->ctx->stream;
+  const int64_t tot = count * s->h.S;
+  double* tmp = nullptr;
+  CK(cudaMalloc(&tmp, (size_t)tot * sizeof(double)));
+  expand_active_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(s->h.act_rows, s->h.act_norm, first, count, s->h.S,
+                                                                   s->h.ld, tmp);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, tmp, (size_t)tot * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaFree(tmp));
+  return BCG_OK;
+}
+
+extern "C" int bcg_solver_set_weights(bcg_solver* s, const double* w, int64_t k) {
+  if (!s || (k > 0 && !w)) return fail(BCG_ERR_ARG, "null argument");
+  if (k != s->h.nact) return fail(BCG_ERR_ARG, "expected %d weights, got %lld", s->h.nact, (long long)k);
+  RET(use_device(s->ctx));
+  cudaStream_t st = s->ctx->stream;
+  if (k > 0) CK(cudaMemcpyAsync(s->h.act_w, w, (size_t)k * sizeof(double), cudaMemcpyHostToDevice, st));
+  refresh_kernel<<<1, kStepThreads, 0, st>>>(s->d);
+  CK(cudaGetLastError());
+  RET(pull_state(s));
+  return BCG_OK;
+}
+
+extern "C" int bcg_solver_reset(bcg_solver* s) {
+  if (!s) return fail(BCG_ERR_ARG, "null solver");
+  RET(use_device(s->ctx));
+  SolverState& h = s->h;
+  h.nact = 0;
+  h.halted = 0;
+  h.retried = 0;
+  h.select_failed = 0;
+  h.err = h.bnorm;
+  CK(cudaMemsetAsync(h.xw, 0, h.S * sizeof(double), s->ctx->stream));
+  RET(push_state(s));
+  CK(cudaStreamSynchronize(s->ctx->stream));
+  return BCG_OK;
+}
+
+extern "C" int bcg_solver_timing(bcg_solver* s, float* build_ms, float* scan_ms, int32_t* scan_launches,
+                                 int32_t* step_launches) {
+  if (!s) return fail(BCG_ERR_ARG, "null solver");
+  if (build_ms) *build_ms = s->build_ms;
+  if (scan_ms) *scan_ms = s->scan_ms;
+  if (scan_launches) *scan_launches = s->scan_launches;
+  if (step_launches) *step_launches = s->step_launches;
+  return BCG_OK;
+}
+
+extern "C" int bcg_solver_set_profiling(bcg_solver* s, int32_t per_kernel_events) {
+  if (!s) return fail(BCG_ERR_ARG, "null solver");
+  s->profiling = per_kernel_events ? 1 : 0;
+  return BCG_OK;
+}

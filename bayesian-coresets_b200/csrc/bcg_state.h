@@ -1,0 +1,72 @@
+// Device-resident solver state shared by the scan kernel (K1), the step kernel (K2) and the host
+// API.  Plain C++ (no CUDA types) so that step_logic.h can also be compiled for the host by the
+// logic check in tests/hostcheck (test-only; the product library never runs solver math on CPU).
+#pragma once
+#include <stdint.h>
+#include "../../include/bcg.h"
+
+namespace bcg {
+
+// one candidate per scan warp: best fp32 score and the LOCAL row it belongs to
+struct ScanCand {
+  float score;
+  uint32_t row;   // 0xffffffff = warp saw no rows
+};
+
+constexpr int kMaxWorld = 8;        // GPUs of one NVSwitch node
+constexpr int kRescoreMax = 8;      // near-tie candidates re-scored in float64 per iteration
+
+// mailbox slot written by one peer for one iteration parity (lives in IPC-shared device memory)
+struct MailHeader {
+  unsigned long long seq;           // iteration sequence number, written last (release)
+  double score;                     // float64 re-scored best local score
+  int64_t gidx;                     // global row index (-1: rank has no rows)
+  double norm;                      // row norm
+};
+
+struct SolverState {
+  // ---- problem -------------------------------------------------------------------------
+  int32_t alg, S, ld;
+  int32_t world, rank;
+  int64_t n_local, row_offset, n_global;
+  double tol, bnorm, nsum;
+  const float* An;                  // n_local x ld unit rows
+  const double* norms;              // n_local
+  double* b;                        // S
+  double* bn;                       // S   b / ||b||  (GIGA)
+  // ---- iterate -------------------------------------------------------------------------
+  double* xw;                       // S   A w
+  double* xw_new;                   // S   candidate
+  double* xf;                       // S   unnormalised selected row
+  double* dir64;                    // 2 x S   float64 scan directions (re-scoring)
+  float* dir32;                     // 2 x ld  float32 scan directions (K1 input)
+  float* wrow;                      // ld      winner's unit row (copied out of the mailbox)
+  double err;                       // ||A w - b||
+  // ---- active set (replicated on every rank), selection order ----------------------------
+  int32_t nact, cap;
+  int64_t* act_idx;                 // cap       global indices
+  double* act_w;                    // cap
+  double* act_w_new;                // cap
+  double* act_norm;                 // cap
+  float* act_rows;                  // cap x ld  copies of the unit rows
+  // ---- loop control ----------------------------------------------------------------------
+  int32_t retried, halted, select_failed, n_events;
+  double sel_aux;
+  bcg_iter_event* events;
+  unsigned long long seq;           // iteration sequence number (mailbox protocol)
+  // ---- scan output -------------------------------------------------------------------------
+  ScanCand* cands;
+  int32_t n_cands;
+  int32_t comm_error;
+  // ---- N-sharding mailboxes ----------------------------------------------------------------
+  unsigned char* mail_local;        // this rank's mailbox: [2][world] slots
+  unsigned char* mail_peer[kMaxWorld];  // mapped mailboxes of all ranks (self included)
+  int64_t mail_slot_bytes;
+};
+
+inline int64_t mail_slot_bytes_for(int ld) {
+  int64_t raw = (int64_t)sizeof(MailHeader) + (int64_t)ld * 4;
+  return (raw + 127) / 128 * 128;
+}
+
+}  // namespace bcg

@@ -1,0 +1,145 @@
+/*
+ * bcg.h -- C ABI of the B200-native coreset-construction engine (libbcg_b200.so).
+ *
+ * Drop-in boundary for ONE hot path of trevorcampbell/bayesian-coresets: the projection of N
+ * datapoints into an N x S matrix of centred log-likelihood vectors and the greedy sparse-NNLS
+ * loop (GIGA / Frank-Wolfe / OrthoPursuit) that runs over that matrix.  Plain pointers and
+ * sizes only; every call returns an int status (0 = BCG_OK) and bcg_last_error() returns a
+ * human-readable message for the last failure on the calling thread.  Host pointers are
+ * borrowed for the duration of a call only.  Not re-entrant per handle.
+ *
+ * Reference interfaces replaced (paths relative to the reference repository root):
+ *   bcg_vecs_from_host_f64     bayesiancoresets/snnls/giga.py:10-13 (column norms, An = A/norms)
+ *                              + coreset/hilbert.py:24 (b = vecs.sum(axis=0))
+ *   bcg_vecs_project_lr        bayesiancoresets/projector.py:19-21 with
+ *                              examples/common/model_lr.py:25-32 as the log-likelihood
+ *   bcg_vecs_project_gaussian  projector.py:19-21 with examples/common/model_gaussian.py:4-10
+ *   bcg_vecs_project_poisson   projector.py:19-21 with examples/common/model_poiss.py:25-38
+ *   bcg_vecs_colsum / _rows    hilbert.py:24 / the ndarray returned by Projector.project
+ *   bcg_solver_create          snnls/snnls.py:9-16 + giga.py:8-18 / frankwolfe.py:7-13 /
+ *                              orthopursuit.py:9-15
+ *   bcg_solver_build           snnls/snnls.py:31-79 driving giga.py:20-64 / frankwolfe.py:15-40
+ *   bcg_solver_omp_select      orthopursuit.py:17-35 (+ the w[f] = 1 of :38)
+ *   bcg_solver_error           snnls/snnls.py:28-29
+ *   bcg_solver_active / size   snnls/snnls.py:22-26 (sparse form of w)
+ *   bcg_solver_set_weights     the write-back of snnls.py:88 / orthopursuit.py:41
+ *   bcg_solver_reset           snnls/snnls.py:18-20
+ *
+ * Storage: the N x S matrix is kept as unit-norm float32 rows (row stride `ld` floats, a
+ * multiple of 4, zero padded) plus one float64 norm per row; all S-vector and scalar state of
+ * the solvers is float64.
+ */
+#ifndef BCG_H
+#define BCG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BCG_ABI_VERSION 1
+
+/* status codes */
+#define BCG_OK             0
+#define BCG_ERR_CUDA       1   /* a CUDA runtime call or kernel failed */
+#define BCG_ERR_ARG        2   /* invalid argument */
+#define BCG_ERR_NO_DEVICE  3   /* no usable CUDA device: there is NO CPU fallback */
+#define BCG_ERR_ZERO_B     4   /* ||b|| == 0 (giga.py:16-17) */
+#define BCG_ERR_STATE      5   /* call not valid in the current solver state */
+#define BCG_ERR_COMM       6   /* peer-memory exchange failed or timed out */
+#define BCG_ERR_UNSUPPORTED 7  /* shape outside the supported range (e.g. S > 1024) */
+
+/* algorithms (bcg_solver_create) */
+#define BCG_ALG_GIGA 0
+#define BCG_ALG_FW   1
+#define BCG_ALG_OMP  2
+
+/* per-iteration event codes (bcg_iter_event.code) */
+#define BCG_IT_OK            0
+#define BCG_IT_FAIL_CDIR     1  /* giga.py:28-29     aux0 = cdirnrm */
+#define BCG_IT_FAIL_GEODESIC 2  /* giga.py:50-51     aux0 = gA, aux1 = gB */
+#define BCG_IT_FAIL_GAMMA    3  /* frankwolfe.py:33  aux0 = gammanum, aux1 = gammadenom */
+#define BCG_IT_FAIL_MONOTONE 4  /* snnls.py:58-61    aux0 = new error, aux1 = previous error */
+
+typedef struct bcg_iter_event {
+  int32_t code;      /* BCG_IT_* */
+  int32_t nact;      /* number of stored active rows after the iteration */
+  int64_t f;         /* selected GLOBAL row index (-1 when selection itself failed) */
+  double  error;     /* ||A w - b||_2 after the iteration (unchanged state on failure) */
+  double  aux0;
+  double  aux1;
+} bcg_iter_event;
+
+typedef struct bcg_ctx    bcg_ctx;     /* one CUDA device + stream */
+typedef struct bcg_vecs   bcg_vecs;    /* device-resident N_local x S projection */
+typedef struct bcg_solver bcg_solver;  /* greedy sparse-NNLS state over a bcg_vecs */
+
+/* ---- library / context ------------------------------------------------------------------ */
+int         bcg_abi_version(void);
+const char* bcg_last_error(void);
+int  bcg_device_count(int* count);
+int  bcg_ctx_create(int device, bcg_ctx** out);
+int  bcg_ctx_destroy(bcg_ctx* ctx);
+int  bcg_ctx_info(bcg_ctx* ctx, char* name, int name_cap, int* sm_count, int* cc_major, int* cc_minor,
+                  int64_t* total_mem_bytes);
+int  bcg_ctx_synchronize(bcg_ctx* ctx);
+/* write `bytes` of device scratch (evicts L2 between timed iterations) */
+int  bcg_ctx_flush_l2(bcg_ctx* ctx, int64_t bytes);
+
+/* ---- projection matrix ------------------------------------------------------------------ */
+/* rows: host, row-major, n x S float64 with row stride ld_host (elements) */
+int  bcg_vecs_from_host_f64(bcg_ctx* ctx, const double* rows, int64_t n, int32_t S, int64_t ld_host,
+                            bcg_vecs** out);
+/* Z: host n x d float64 (z_n = y_n x_n); theta: host S x d float64 */
+int  bcg_vecs_project_lr(bcg_ctx* ctx, const double* Z, int64_t n, int32_t d, const double* theta, int32_t S,
+                         bcg_vecs** out);
+/* x: host n x d; theta: host S x d; Siginv: host d x d (symmetric) */
+int  bcg_vecs_project_gaussian(bcg_ctx* ctx, const double* x, int64_t n, int32_t d, const double* theta,
+                               int32_t S, const double* Siginv, bcg_vecs** out);
+/* Z: host n x (d+1) = [x, y]; theta: host S x d */
+int  bcg_vecs_project_poisson(bcg_ctx* ctx, const double* Z, int64_t n, int32_t d, const double* theta,
+                              int32_t S, bcg_vecs** out);
+int  bcg_vecs_shape(bcg_vecs* v, int64_t* n, int32_t* S, int32_t* ld);
+int  bcg_vecs_colsum(bcg_vecs* v, double* out_S);          /* sum over local rows of the centred vectors */
+int  bcg_vecs_norm_sum(bcg_vecs* v, double* out);          /* sum of local row norms */
+int  bcg_vecs_zero_rows(bcg_vecs* v, int64_t* count);      /* rows whose norm is exactly 0 */
+int  bcg_vecs_norms(bcg_vecs* v, int64_t row0, int64_t nrows, double* out);
+int  bcg_vecs_rows_f64(bcg_vecs* v, int64_t row0, int64_t nrows, double* out); /* norm * unit row */
+int  bcg_vecs_destroy(bcg_vecs* v);
+
+/* ---- greedy solver ---------------------------------------------------------------------- */
+/* b: host S float64 (GLOBAL target); norm_sum: GLOBAL sum of row norms (used by FW);
+ * row_offset: global index of local row 0; n_global: total rows over all ranks */
+int  bcg_solver_create(bcg_ctx* ctx, bcg_vecs* v, int32_t alg, const double* b, double norm_sum,
+                       int64_t row_offset, int64_t n_global, bcg_solver** out);
+int  bcg_solver_destroy(bcg_solver* s);
+/* N-sharding over GPUs of one node: every rank exports a 64-byte handle of its mailbox, the
+ * host exchanges them (any transport), then every rank connects to all `world` handles. */
+int  bcg_solver_comm_handle(bcg_solver* s, void* handle64);
+int  bcg_solver_comm_connect(bcg_solver* s, int32_t world, int32_t rank, const void* handles64);
+/* run up to `itrs` greedy iterations entirely on the device (GIGA, FW).  events: host array of
+ * `itrs` entries; n_events receives how many iterations were attempted. */
+int  bcg_solver_build(bcg_solver* s, int32_t itrs, double tol, bcg_iter_event* events, int32_t* n_events);
+/* OMP selection step: residual scan + negative direction over the active set; the selected row
+ * joins the active set with weight 1 (orthopursuit.py:17-38).  *f = selected global index. */
+int  bcg_solver_omp_select(bcg_solver* s, int64_t* f);
+int  bcg_solver_error(bcg_solver* s, double* err);
+int  bcg_solver_size(bcg_solver* s, int64_t* n_positive, int64_t* n_stored);
+int  bcg_solver_halted(bcg_solver* s, int32_t* reached_numeric_limit);
+/* stored active set in selection order: global indices, weights (may contain zeros) */
+int  bcg_solver_active(bcg_solver* s, int64_t cap, int64_t* idx, double* w, int64_t* k);
+/* unnormalised float64 active rows, k x S, same order as bcg_solver_active */
+int  bcg_solver_active_rows(bcg_solver* s, int64_t first, int64_t count, double* out);
+/* overwrite the weights of the stored active rows (k must equal n_stored); recomputes A w and error */
+int  bcg_solver_set_weights(bcg_solver* s, const double* w, int64_t k);
+int  bcg_solver_reset(bcg_solver* s);
+/* device time of the last bcg_solver_build: total, and summed over the scan kernel launches */
+int  bcg_solver_timing(bcg_solver* s, float* build_ms, float* scan_ms, int32_t* scan_launches,
+                       int32_t* step_launches);
+int  bcg_solver_set_profiling(bcg_solver* s, int32_t per_kernel_events);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BCG_H */

@@ -1,0 +1,136 @@
+// TEST-ONLY logic check (never part of the product library): compiles the single-block step logic
+// of bayesian-coresets_b200/csrc/step_logic.h for the host (one "thread", Blk{0,1}) and drives it
+// with a plain-loop float32 stand-in for the scan kernel, so the iteration state machine (winner
+// resolution, reweight, monotone check, retry / latch) can be compared with the oracle on a box
+// without a GPU.  The CUDA kernels themselves are only ever validated on the GPU (tests -m gpu).
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "../../bayesian-coresets_b200/csrc/step_logic.h"
+
+using namespace bcg;
+
+namespace {
+struct Host {
+  SolverState st;
+  std::vector<float> An, dir32, wrow, act_rows;
+  std::vector<double> norms, b, bn, xw, xw_new, xf, dir64, act_w, act_w_new, act_norm;
+  std::vector<int64_t> act_idx;
+  std::vector<ScanCand> cands;
+  std::vector<bcg_iter_event> events;
+  double sred[256];
+};
+
+// float32 scan stand-in: same per-row arithmetic as scan_kernel.cuh (fmaf accumulation, float32
+// GIGA epilogue), candidates bucketed over `nb` interleaved row groups, first maximum wins
+void scan(Host& H, int nb) {
+  SolverState& st = H.st;
+  H.cands.assign(nb, ScanCand{-INFINITY, kNoRow});
+  if (st.halted || st.select_failed) return;
+  for (int64_t r = 0; r < st.n_local; ++r) {
+    const float* row = &H.An[(size_t)r * st.ld];
+    float a0 = 0.f, a1 = 0.f;
+    for (int s = 0; s < st.ld; ++s) {
+      a0 = fmaf(row[s], H.dir32[s], a0);
+      if (st.alg == BCG_ALG_GIGA) a1 = fmaf(row[s], H.dir32[st.ld + s], a1);
+    }
+    float score = a0;
+    if (st.alg == BCG_ALG_GIGA) {
+      const float den = 1.f - a1 * a1;
+      score = (a1 > -1.f && den > 0.f) ? a0 / sqrtf(den) : 0.f;
+    }
+    ScanCand& c = H.cands[r % nb];
+    if (c.row == kNoRow || score > c.score) { c.score = score; c.row = (uint32_t)r; }
+  }
+}
+}  // namespace
+
+extern "C" int hostcheck_run(int alg, const float* An, const double* norms, const double* b, int S, int ld,
+                             int64_t N, double nsum, int itrs, int builds, double tol, bcg_iter_event* events_out,
+                             int* n_events_out, int64_t* idx_out, double* w_out, int* k_out, double* err_out,
+                             int* halted_out) {
+  Host H;
+  memset(&H.st, 0, sizeof(SolverState));
+  SolverState& st = H.st;
+  const int cap = itrs * builds + 8;
+  H.An.assign(An, An + (size_t)N * ld);
+  H.norms.assign(norms, norms + N);
+  H.b.assign(b, b + S);
+  double bnorm = 0.;
+  for (int i = 0; i < S; ++i) bnorm += b[i] * b[i];
+  bnorm = sqrt(bnorm);
+  H.bn.resize(S);
+  for (int i = 0; i < S; ++i) H.bn[i] = bnorm > 0 ? b[i] / bnorm : 0.;
+  H.xw.assign(S, 0.); H.xw_new.assign(S, 0.); H.xf.assign(S, 0.); H.dir64.assign(2 * S, 0.);
+  H.dir32.assign(2 * ld, 0.f); H.wrow.assign(ld, 0.f);
+  H.act_rows.assign((size_t)cap * ld, 0.f);
+  H.act_w.assign(cap, 0.); H.act_w_new.assign(cap, 0.); H.act_norm.assign(cap, 0.); H.act_idx.assign(cap, -1);
+  H.events.resize((size_t)itrs * builds);
+  st.alg = alg; st.S = S; st.ld = ld; st.world = 1; st.rank = 0;
+  st.n_local = N; st.row_offset = 0; st.n_global = N; st.tol = tol; st.bnorm = bnorm; st.nsum = nsum;
+  st.An = H.An.data(); st.norms = H.norms.data(); st.b = H.b.data(); st.bn = H.bn.data();
+  st.xw = H.xw.data(); st.xw_new = H.xw_new.data(); st.xf = H.xf.data(); st.dir64 = H.dir64.data();
+  st.dir32 = H.dir32.data(); st.wrow = H.wrow.data(); st.err = bnorm;
+  st.cap = cap; st.act_idx = H.act_idx.data(); st.act_w = H.act_w.data(); st.act_w_new = H.act_w_new.data();
+  st.act_norm = H.act_norm.data(); st.act_rows = H.act_rows.data();
+  st.events = H.events.data();
+  const int nb = 37;
+  Blk B{0, 1, H.sred};
+  for (int bld = 0; bld < builds && !st.halted; ++bld) {
+    st.retried = 0;                       // snnls.py:40: local to each build() call
+    prepare_select(B, &st);
+    for (int i = 0; i < itrs; ++i) {
+      scan(H, nb);
+      st.cands = H.cands.data(); st.n_cands = nb;
+      if (st.halted) break;
+      finish_iteration(B, &st);
+      if (st.halted) break;
+      if (i + 1 < itrs) prepare_select(B, &st);
+    }
+  }
+  memcpy(events_out, H.events.data(), sizeof(bcg_iter_event) * st.n_events);
+  *n_events_out = st.n_events;
+  for (int k = 0; k < st.nact; ++k) { idx_out[k] = st.act_idx[k]; w_out[k] = st.act_w[k]; }
+  *k_out = st.nact;
+  *err_out = st.err;
+  *halted_out = st.halted;
+  return 0;
+}
+
+// OMP selection stand-in: returns the selected index sequence driven by host-provided weights
+extern "C" int hostcheck_omp_select(const float* An, const double* norms, const double* b, int S, int ld, int64_t N,
+                                    const int64_t* act_idx, const double* act_w, int nact, int64_t* f_out) {
+  Host H;
+  memset(&H.st, 0, sizeof(SolverState));
+  SolverState& st = H.st;
+  const int cap = nact + 2;
+  H.An.assign(An, An + (size_t)N * ld);
+  H.norms.assign(norms, norms + N);
+  H.b.assign(b, b + S);
+  H.bn.assign(S, 0.);
+  H.xw.assign(S, 0.); H.xw_new.assign(S, 0.); H.xf.assign(S, 0.); H.dir64.assign(2 * S, 0.);
+  H.dir32.assign(2 * ld, 0.f); H.wrow.assign(ld, 0.f);
+  H.act_rows.assign((size_t)cap * ld, 0.f);
+  H.act_w.assign(cap, 0.); H.act_w_new.assign(cap, 0.); H.act_norm.assign(cap, 0.); H.act_idx.assign(cap, -1);
+  st.alg = BCG_ALG_OMP; st.S = S; st.ld = ld; st.world = 1;
+  st.n_local = N; st.n_global = N; st.tol = 1e-12;
+  st.An = H.An.data(); st.norms = H.norms.data(); st.b = H.b.data(); st.bn = H.bn.data();
+  st.xw = H.xw.data(); st.xw_new = H.xw_new.data(); st.xf = H.xf.data(); st.dir64 = H.dir64.data();
+  st.dir32 = H.dir32.data(); st.wrow = H.wrow.data();
+  st.cap = cap; st.act_idx = H.act_idx.data(); st.act_w = H.act_w.data(); st.act_w_new = H.act_w_new.data();
+  st.act_norm = H.act_norm.data(); st.act_rows = H.act_rows.data();
+  for (int k = 0; k < nact; ++k) {
+    st.act_idx[k] = act_idx[k]; st.act_w[k] = act_w[k]; st.act_norm[k] = norms[act_idx[k]];
+    memcpy(&H.act_rows[(size_t)k * ld], &An[(size_t)act_idx[k] * ld], sizeof(float) * ld);
+  }
+  st.nact = nact;
+  Blk B{0, 1, H.sred};
+  refresh_iterate(B, &st);
+  prepare_select(B, &st);
+  scan(H, 37);
+  st.cands = H.cands.data(); st.n_cands = 37;
+  *f_out = omp_select(B, &st);
+  return 0;
+}

@@ -1,0 +1,251 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every call goes through the C-ABI
+(ctypes -> libbcg_b200.so); the checker is the oracle / the reference-generated golden fixtures.
+
+Tolerances (BASELINE north_star): selected indices bit-exact (ties absent), weights within 1e-5
+relative to the scale of the weight vector, error() within 1e-5 relative plus the a-priori bound
+of float32 storage of the unit rows (2^-24 sum_k w_k ||a_k||)."""
+import numpy as np
+import pytest
+from conftest import load_golden, lr_problem
+from oracle import greedy, models
+
+pytestmark = pytest.mark.gpu
+W_RTOL = 1e-5
+
+
+@pytest.fixture(scope='module')
+def bc():
+  import bayesiancoresets_b200 as bc
+  bc.Context.default()        # raises when there is no GPU: no silent fallback
+  return bc
+
+
+class IDProjector(object):
+  def update(self, wts, pts):
+    pass
+
+  def project(self, pts, grad=False):
+    return pts
+
+
+def assert_weights_close(w, w_ref):
+  np.testing.assert_allclose(w, w_ref, rtol=W_RTOL, atol=W_RTOL*np.abs(w_ref).max())
+
+
+def assert_errors_close(err, err_ref, vecs, w_ref):
+  norms = np.sqrt((vecs**2).sum(axis=1))
+  atol = 2.**-24*float(np.abs(w_ref).dot(norms)) + 1e-300
+  np.testing.assert_allclose(err, err_ref, rtol=W_RTOL, atol=atol)
+
+
+def algs(bc):
+  return {'giga': bc.snnls.GIGA, 'fw': bc.snnls.FrankWolfe, 'omp': bc.snnls.OrthoPursuit}
+
+
+# ---------------------------------------------------------------- matrix construction
+@pytest.mark.parametrize('shape', [(1000, 50), (257, 3), (64, 512), (33, 1000), (1, 7)])
+def test_from_host_roundtrip(bc, shape):
+  rng = np.random.RandomState(0)
+  X = rng.randn(*shape)*rng.uniform(0.1, 30., size=(shape[0], 1))
+  v = bc.DeviceVecs.from_host(X)
+  assert v.shape == shape
+  np.testing.assert_allclose(v.norms(), np.sqrt((X**2).sum(axis=1)), rtol=1e-14)
+  np.testing.assert_allclose(v.sum(axis=0), X.sum(axis=0), rtol=1e-12, atol=1e-12*np.abs(X).sum(axis=0).max())
+  np.testing.assert_allclose(v.to_numpy(), X, rtol=0, atol=2.**-23*np.abs(X).max(axis=1, keepdims=True).max())
+  assert v.norm_sum() == pytest.approx(np.sqrt((X**2).sum(axis=1)).sum(), rel=1e-13)
+  assert v.zero_rows() == 0
+
+
+def test_from_host_strided_and_zero_rows(bc):
+  rng = np.random.RandomState(1)
+  big = rng.randn(100, 40)
+  X = big[:, :24]                      # row stride 40, S = 24
+  X[5] = 0.
+  v = bc.DeviceVecs.from_host(X)
+  assert v.zero_rows() == 1
+  np.testing.assert_allclose(v.sum(axis=0), X.sum(axis=0), rtol=1e-12, atol=1e-13)
+  with pytest.raises(ValueError):
+    bc.snnls.GIGA(X.T, X.sum(axis=0))
+  Y = rng.randn(10, 4)
+  with pytest.raises(bc.util.NumericalPrecisionError):
+    bc.snnls.GIGA(Y.T, np.zeros(4))
+
+
+def check_projection(v, ref):
+  got = v.to_numpy()
+  scale = np.sqrt((ref**2).sum(axis=1, keepdims=True))
+  # unit rows are float32: absolute error <= 2^-24 * row norm (+ float64 evaluation noise)
+  assert np.max(np.abs(got - ref)/scale) < 2.**-23
+  np.testing.assert_allclose(v.norms(), scale[:, 0], rtol=1e-9)
+  np.testing.assert_allclose(v.sum(axis=0), ref.sum(axis=0), rtol=1e-9, atol=1e-9*np.abs(ref).sum(axis=0).max())
+
+
+def test_project_lr_golden(bc):
+  g = load_golden('lr_project_small')
+  check_projection(bc.DeviceVecs.project_lr(g['Z'], g['theta']), g['vecs'])
+  g = load_golden('lr_project_saturated')
+  check_projection(bc.DeviceVecs.project_lr(g['Z'], g['theta']), g['vecs'])
+
+
+def test_project_gaussian_poisson_golden(bc):
+  g = load_golden('gaussian_project_small')
+  check_projection(bc.DeviceVecs.project_gaussian(g['x'], g['theta'], g['Siginv']), g['vecs'])
+  for name in ('poisson_project_small', 'poisson_project_extreme'):
+    g = load_golden(name)
+    check_projection(bc.DeviceVecs.project_poisson(g['Z'], g['theta']), g['vecs'])
+
+
+@pytest.mark.parametrize('d,S', [(40, 200), (130, 96), (7, 1000)])
+def test_project_shapes_vs_oracle(bc, d, S):
+  rng = np.random.RandomState(d)
+  Z = rng.randn(300, d)
+  th = rng.randn(S, d)/np.sqrt(d)
+  check_projection(bc.DeviceVecs.project_lr(Z, th), models.project(models.lr_loglik, Z, th))
+  Siginv = np.eye(d) + 0.1*np.ones((d, d))
+  f = lambda x, t: models.gaussian_loglik(x, t, Siginv, 0.)
+  check_projection(bc.DeviceVecs.project_gaussian(Z, th, Siginv), models.project(f, Z, th))
+
+
+# ---------------------------------------------------------------- greedy loop vs golden / oracle
+def run_gpu(bc, vecs, alg, itrs):
+  cs = bc.HilbertCoreset(vecs, IDProjector(), snnls=algs(bc)[alg])
+  cs.build(itrs)
+  ev = cs.snnls.last_events
+  return cs, ev
+
+
+@pytest.mark.parametrize('alg', ['giga', 'fw', 'omp'])
+def test_c1_normal_golden(bc, alg):
+  g = load_golden('c1_normal_' + alg)
+  np.random.seed(int(g['seed']))
+  X = np.random.randn(int(g['N']), int(g['S']))
+  cs, ev = run_gpu(bc, X, alg, int(g['itrs']))
+  itok = 100 if alg != 'omp' else 45       # OMP: after K ~ S the residual is rounding noise
+  assert [e.f for e in ev][:itok] == list(g['sel'][:itok])
+  assert all(e.code == 0 for e in ev)
+  if alg != 'omp':
+    assert_errors_close([e.error for e in ev], g['errs'], X, g['w'])
+    assert_weights_close(cs.snnls.weights(), g['w'])
+    assert cs.snnls.size() == int(g['size'])
+    wts, pts, idcs = cs.get()
+    assert np.array_equal(idcs, np.flatnonzero(g['w'] > 0))
+    assert np.array_equal(pts, X[idcs])
+  else:
+    assert cs.error() < 1e-6*np.sqrt((X.sum(axis=0)**2).sum())
+    assert cs.snnls.size() <= 50
+
+
+@pytest.mark.parametrize('alg', ['giga', 'fw', 'omp'])
+def test_axis_ties_lowest_index_and_latch(bc, alg):
+  g = load_golden('axis12_' + alg)
+  X = np.eye(12)
+  cs, ev = run_gpu(bc, X, alg, int(g['itrs']))
+  assert [e.f for e in ev][:12] == list(range(12))
+  assert_weights_close(cs.snnls.weights(), g['w'])
+  if alg == 'giga':
+    assert [e.code for e in ev[12:]] == [1, 1]          # cdirnrm < TOL twice -> latch
+    assert cs.snnls.reached_numeric_limit and cs.reached_numeric_limit is False
+    n_before = len(cs.snnls.last_events)
+    cs.snnls.build(5)                                    # latched: returns immediately
+    assert len(cs.snnls.last_events) == n_before
+
+
+@pytest.mark.parametrize('alg', ['giga', 'fw', 'omp'])
+def test_lr_small_golden(bc, alg):
+  g = load_golden('lr_small_' + alg)
+  p = load_golden('lr_project_small')
+  prj = bc.LogisticRegressionProjector(lambda n, w, pts: p['theta'], int(p['S']))
+  cs = bc.HilbertCoreset(p['Z'], prj, snnls=algs(bc)[alg])
+  cs.build(int(g['itrs']))
+  ev = cs.snnls.last_events
+  nsel = len(g['sel']) if alg != 'omp' else 60
+  assert [e.f for e in ev if e.code == 0][:nsel] == list(g['sel'][:nsel])
+  if alg != 'omp':
+    assert_weights_close(cs.snnls.weights(), g['w'])
+    assert_errors_close(cs.error(), float(g['final_error']), p['vecs'], g['w'])
+
+
+def test_incremental_build_and_retry_flag(bc):
+  """build(k) is incremental; `retried_already` is local to each build() call (snnls.py:40)."""
+  np.random.seed(1)
+  X = np.random.randn(1000, 50)
+  a, _ = run_gpu(bc, X, 'giga', 60)
+  b = bc.HilbertCoreset(X, IDProjector())
+  for k in (1, 9, 20, 30):
+    b.build(k)
+  assert_weights_close(b.snnls.weights(), a.snnls.weights())
+  e = bc.HilbertCoreset(np.eye(6), IDProjector())
+  for _ in range(10):
+    e.build(1)
+  assert not e.snnls.reached_numeric_limit
+  e.reset()
+  assert e.snnls.size() == 0 and e.error() == pytest.approx(np.sqrt(6.))
+
+
+def test_optimize_never_worse(bc):
+  np.random.seed(2)
+  X = np.random.randn(2000, 40)
+  cs = bc.HilbertCoreset(X, IDProjector(), snnls=bc.snnls.FrankWolfe)
+  cs.build(30)
+  e0 = cs.error()
+  o = greedy.FrankWolfeOracle(X.T, X.sum(axis=0))
+  o.build(30)
+  o.optimize()
+  cs.optimize()
+  assert cs.error() <= e0*(1 + 1e-12)
+  assert cs.error() == pytest.approx(o.error(), rel=1e-5)
+
+
+@pytest.mark.parametrize('alg,N,S,itrs', [('giga', 200000, 256, 40), ('fw', 100000, 512, 40), ('giga', 50001, 100, 60)])
+def test_medium_vs_oracle(bc, alg, N, S, itrs):
+  Z, theta = lr_problem(11, N, 8, S)
+  vecs = models.project(models.lr_loglik, Z, theta)
+  o = greedy.ORACLES[alg](vecs.T, vecs.sum(axis=0))
+  oev = o.build(itrs)
+  prj = bc.LogisticRegressionProjector(lambda n, w, p: theta, S)
+  cs = bc.HilbertCoreset(Z, prj, snnls=algs(bc)[alg])
+  cs.build(itrs)
+  ev = cs.snnls.last_events
+  assert [e.f for e in ev] == [e[1] for e in oev]
+  assert_weights_close(cs.snnls.weights(), o.w)
+  assert_errors_close([e.error for e in ev], [e[2] for e in oev], vecs, o.w)
+
+
+def test_full_size_properties(bc):
+  """BASELINE configs[1] size (N=1e6, S=256): size-independent properties instead of the oracle."""
+  N, S, itrs = 1000000, 256, 60
+  Z, theta = lr_problem(0, N, 10, S)
+  prj = bc.LogisticRegressionProjector(lambda n, w, p: theta, S)
+  cs = bc.HilbertCoreset(Z, prj)
+  bnorm = cs.error()
+  cs.build(itrs)
+  ev = cs.snnls.last_events
+  errs = np.array([e.error for e in ev])
+  assert len(ev) == itrs and all(e.code == 0 for e in ev)
+  assert errs[0] < bnorm and np.all(np.diff(errs) <= 0)            # monotone (snnls.py:56-61)
+  wts, pts, idcs = cs.get()
+  assert wts.shape[0] <= itrs and np.all(wts > 0)
+  assert np.all(np.diff(idcs) > 0) and idcs.min() >= 0 and idcs.max() < N
+  assert np.array_equal(pts, Z[idcs])
+  # error() must equal ||A w - b|| recomputed on the host in float64 from the selected points only
+  sub = models.project(models.lr_loglik, Z[idcs], theta)
+  b = cs.snnls.b
+  assert cs.error() == pytest.approx(np.sqrt(((wts.dot(sub) - b)**2).sum()), rel=1e-5)
+  # the first selection maximises cos(a_n, b): check against a float64 host scan over a slab
+  f0 = ev[0].f
+  slab = models.project(models.lr_loglik, Z[:50000], theta)
+  cosb = slab.dot(b)/np.sqrt((slab**2).sum(axis=1))/np.sqrt((b**2).sum())
+  row_f0 = models.project(models.lr_loglik, Z[f0:f0+1], theta)[0]
+  cos_f0 = row_f0.dot(b)/np.sqrt((row_f0**2).sum())/np.sqrt((b**2).sum())
+  assert cos_f0 >= cosb.max() - 1e-12
+
+
+def test_empty_and_tiny_inputs(bc):
+  s = bc.snnls.GIGA(np.zeros((5, 0)), np.ones(5))
+  s.build(3)
+  assert s.size() == 0 and s.weights().shape == (0,)
+  X = np.array([[3., 4.]])
+  cs = bc.HilbertCoreset(X, IDProjector())
+  cs.build(3)
+  wts, pts, idcs = cs.get()
+  assert list(idcs) == [0] and wts[0] == pytest.approx(1.) and cs.error() < 1e-12

@@ -1,0 +1,140 @@
+"""CPU logic check of the single-block step logic (csrc/step_logic.h compiled for the host by
+tests/hostcheck/hostcheck.cpp) against the oracle.  TEST-ONLY: validates the iteration state
+machine (winner resolution + float64 re-scoring, reweight, monotone check, retry / latch) on a
+box without a GPU; the product library never runs this code on the CPU."""
+import ctypes
+import os
+import subprocess
+import tempfile
+import numpy as np
+import pytest
+from conftest import ROOT, load_golden
+from oracle import greedy
+
+ALG = {'giga': 0, 'fw': 1, 'omp': 2}
+# tolerance of the float32-storage engine against the float64 reference (BASELINE north_star):
+# 1e-5 relative to the scale of the weight vector, 1e-5 relative on error()
+W_RTOL = 1e-5
+
+
+def assert_errors_close(err, err_ref, vecs, w_ref):
+  """error() = ||A w - b||: 1e-5 relative, plus the a-priori bound of storing A as float32 unit rows
+  (every element of A carries a relative rounding of 2^-24, so ||dA w|| <= 2^-24 sum_k w_k ||a_k||)."""
+  norms = np.sqrt((vecs**2).sum(axis=1))
+  atol = 2.**-24*float(np.abs(w_ref).dot(norms))
+  np.testing.assert_allclose(err, err_ref, rtol=W_RTOL, atol=atol)
+
+
+def assert_weights_close(w, w_ref):
+  np.testing.assert_allclose(w, w_ref, rtol=W_RTOL, atol=W_RTOL*np.abs(w_ref).max())
+
+
+class Event(ctypes.Structure):
+  _fields_ = [('code', ctypes.c_int32), ('nact', ctypes.c_int32), ('f', ctypes.c_int64), ('error', ctypes.c_double),
+              ('aux0', ctypes.c_double), ('aux1', ctypes.c_double)]
+
+
+@pytest.fixture(scope='module')
+def lib():
+  out = os.path.join(tempfile.gettempdir(), 'bcg_hostcheck_%d.so' % os.getuid())
+  src = os.path.join(ROOT, 'tests', 'hostcheck', 'hostcheck.cpp')
+  subprocess.check_call(['g++', '-O2', '-std=c++17', '-shared', '-fPIC', '-o', out, src])
+  return ctypes.CDLL(out)
+
+
+def device_layout(vecs):
+  """what bcg_vecs_from_host_f64 produces: unit float32 rows (ld multiple of 4) + float64 norms"""
+  N, S = vecs.shape
+  ld = (S + 3)//4*4
+  norms = np.sqrt((vecs**2).sum(axis=1))
+  An = np.zeros((N, ld), dtype=np.float32)
+  An[:, :S] = (vecs/norms[:, None]).astype(np.float32)
+  return An, norms, ld
+
+
+def run_host(lib, vecs, alg, itrs, builds=1, tol=1e-12):
+  N, S = vecs.shape
+  An, norms, ld = device_layout(vecs)
+  b = vecs.sum(axis=0)
+  ev = (Event*(itrs*builds))()
+  nev, k, halted = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+  err = ctypes.c_double(0)
+  idx = np.zeros(itrs*builds + 8, dtype=np.int64)
+  w = np.zeros(itrs*builds + 8)
+  P = ctypes.c_void_p
+  lib.hostcheck_run(ctypes.c_int(ALG[alg]), P(An.ctypes.data), P(norms.ctypes.data), P(b.ctypes.data), ctypes.c_int(S),
+                    ctypes.c_int(ld), ctypes.c_int64(N), ctypes.c_double(float(norms.sum())), ctypes.c_int(itrs),
+                    ctypes.c_int(builds), ctypes.c_double(tol), ev, ctypes.byref(nev), P(idx.ctypes.data),
+                    P(w.ctypes.data), ctypes.byref(k), ctypes.byref(err), ctypes.byref(halted))
+  events = [(e.code, e.f, e.error) for e in ev[:nev.value]]
+  wd = np.zeros(N)
+  wd[idx[:k.value]] = w[:k.value]
+  return events, wd, err.value, bool(halted.value)
+
+
+@pytest.mark.parametrize('alg', ['giga', 'fw'])
+def test_step_logic_matches_oracle_c1(lib, alg):
+  np.random.seed(1)
+  X = np.random.randn(1000, 50)
+  o = greedy.ORACLES[alg](X.T, X.sum(axis=0))
+  oev = o.build(100)
+  ev, w, err, halted = run_host(lib, X, alg, 100)
+  assert [e[1] for e in ev] == [e[1] for e in oev]
+  assert [e[0] for e in ev] == [e[0] for e in oev]
+  assert_errors_close([e[2] for e in ev], [e[2] for e in oev], X, o.w)
+  assert_weights_close(w, o.w)
+  assert_errors_close(err, o.error(), X, o.w)
+  assert not halted
+
+
+@pytest.mark.parametrize('alg', ['giga', 'fw'])
+def test_step_logic_lr_small(lib, alg):
+  g = load_golden('lr_small_' + alg)
+  vecs = load_golden('lr_project_small')['vecs']
+  ev, w, err, halted = run_host(lib, vecs, alg, int(g['itrs']))
+  assert [e[1] for e in ev if e[0] == 0] == list(g['sel'])
+  assert_weights_close(w, g['w'])
+  assert_errors_close(err, float(g['final_error']), vecs, g['w'])
+
+
+@pytest.mark.parametrize('alg', ['giga', 'fw'])
+def test_step_logic_axis_ties_and_latch(lib, alg):
+  """X = I_12: exact ties -> lowest index; GIGA then fails twice (cdirnrm < TOL) and latches."""
+  X = np.eye(12)
+  o = greedy.ORACLES[alg](X.T, X.sum(axis=0))
+  oev = o.build(20)
+  ev, w, err, halted = run_host(lib, X, alg, 20)
+  assert [e[1] for e in ev][:12] == list(range(12))
+  assert [(e[0], e[1]) for e in ev] == [(e[0], e[1]) for e in oev]
+  assert halted == o.reached_numeric_limit
+  np.testing.assert_allclose(w, o.w, rtol=1e-9, atol=1e-12)
+
+
+def test_step_logic_retry_flag_is_per_build_call(lib):
+  """snnls.py:40: `retried_already` is local to build(); build(1) repeated never latches."""
+  X = np.eye(6)
+  o = greedy.GigaOracle(X.T, X.sum(axis=0))
+  for _ in range(10):
+    o.build(1)
+  ev, w, err, halted = run_host(lib, X, 'giga', 1, builds=10)
+  assert not o.reached_numeric_limit and not halted
+  assert [(e[0], e[1]) for e in ev] == [(e[0], e[1]) for e in o.events]
+
+
+def test_omp_select_matches_oracle(lib):
+  np.random.seed(3)
+  X = np.random.randn(400, 24)
+  An, norms, ld = device_layout(X)
+  b = X.sum(axis=0)
+  o = greedy.OrthoPursuitOracle(X.T, b)
+  P = ctypes.c_void_p
+  for it in range(20):     # K reaches S = 24 afterwards: residual ~1e-13, scores are rounding noise
+    act = np.flatnonzero(o.w > 0).astype(np.int64)
+    wa = o.w[act].copy()
+    f = ctypes.c_int64(-2)
+    lib.hostcheck_omp_select(P(An.ctypes.data), P(norms.ctypes.data), P(b.ctypes.data), ctypes.c_int(24),
+                             ctypes.c_int(ld), ctypes.c_int64(400), P(act.ctypes.data), P(wa.ctypes.data),
+                             ctypes.c_int(len(act)), ctypes.byref(f))
+    fo = int(o.select())
+    assert f.value == fo, it
+    o.reweight(fo)
