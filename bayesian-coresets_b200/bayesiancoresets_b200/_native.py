@@ -165,7 +165,8 @@ class DeviceVecs(object):
     if rows.dtype != np.float64 or rows.strides[1] != 8 or rows.strides[0] % 8 != 0 or rows.strides[0] < 8*rows.shape[1]:
       rows = _f64(rows)
     h = ctypes.c_void_p()
-    check(lib().bcg_vecs_from_host_f64(ctx.handle, _ptr(rows), rows.shape[0], rows.shape[1], rows.strides[0]//8,
+    ld_host = rows.strides[0]//8 if rows.shape[0] > 1 else rows.shape[1]   # strides of <= 1 row are arbitrary
+    check(lib().bcg_vecs_from_host_f64(ctx.handle, _ptr(rows), rows.shape[0], rows.shape[1], ld_host,
                                        ctypes.byref(h)))
     return cls(ctx, h)
 

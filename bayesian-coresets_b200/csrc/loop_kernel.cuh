@@ -1,0 +1,694 @@
+// The whole greedy build(itrs) loop of GIGA / Frank-Wolfe as ONE persistent cooperative kernel.
+//
+// Why: at N = 1e6, S = 256 the HBM roofline of one iteration is ~157 us; two kernel launches per
+// iteration plus a block-wide step kernel whose ~20 dependent global round trips cost ~30 us
+// throw 15 % away.  Here nothing is launched inside the loop:
+//   * one CTA per SM; warps 0..WPB-1 of every CTA are the streaming scan engines of
+//     scan_kernel.cuh (private TMA ring per warp), and their TMA pipeline runs ACROSS iterations
+//     -- the first tiles of iteration t+1 are already landing in shared memory while iteration t
+//     is being resolved, because the matrix does not change, only the direction does;
+//   * the extra warp of CTA 0 is the control warp: it keeps A w (float64) in registers for the
+//     whole build, waits for the grid to arrive, reduces the 2 candidates per CTA, fetches the
+//     winning row, does the geodesic / line-search reweight with warp shuffles only (no block
+//     barrier), publishes the next direction with a release store, and does the O(K)
+//     bookkeeping (weights rescale, active-set append, event log) while the grid is already
+//     scanning again;
+//   * grid-wide ordering is two monotonic counters in global memory (arrive / go).
+// Semantics are those of step_logic.h (snnls.py:41-78, giga.py:20-64, frankwolfe.py:15-40);
+// A w is updated incrementally (A w' = alpha A w + (w_f' - alpha w_f) a_f) and re-summed exactly
+// from the active set every kRefreshEvery iterations, off the critical path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "bcg_state.h"
+#include "scan_kernel.cuh"
+#include "step_kernels.cuh"
+
+namespace bcg {
+
+constexpr int kRefreshEvery = 16;
+
+struct LoopCtl {
+  unsigned int arrive;   // number of CTA arrivals so far (monotonic within a launch)
+  unsigned int go;       // iterations published so far
+  unsigned int stop;     // set (before go) when the loop ends early
+  unsigned int pad;
+};
+
+struct LoopArgs {
+  SolverState* st;
+  LoopCtl* ctl;
+  ScanCand* cta_cands;   // 2 per CTA: best and runner-up of the CTA's warps
+  const float* An;
+  int64_t n_rows;
+  int32_t ld, lpr, rps, stages, evict_first;
+  int32_t itrs;
+  int32_t wpb;           // scan warps per CTA (blockDim.x = (wpb + 1) * 32)
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu_u32(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_release_gpu_add(unsigned int* p, unsigned int v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ bool cand_better(float s2, uint32_t r2, float s1, uint32_t r1) {
+  // (score descending, row ascending); kNoRow never beats a real row
+  if (r2 == kNoRow) return false;
+  if (r1 == kNoRow) return true;
+  return s2 > s1 || (s2 == s1 && r2 < r1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// control warp helpers (lane l owns columns l, l+32, ... of every S-vector)
+// ---------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void wsum(double (&v)[N]) {
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
+}
+
+template <int J>
+__device__ __forceinline__ double row_score_warp(const SolverState* st, const float* row, int lane) {
+  const int S = st->S;
+  double v[2] = {0., 0.};
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int s = lane + 32 * j;
+    if (s < S) {
+      const double x = (double)__ldcg(row + s);
+      v[0] += x * st->dir64[s];
+      if (st->alg == BCG_ALG_GIGA) v[1] += x * st->dir64[S + s];
+    }
+  }
+  wsum<2>(v);
+  return st->alg == BCG_ALG_GIGA ? giga_score64(v[0], v[1]) : v[0];
+}
+
+// warp-level arg-best over the per-CTA candidates, skipping rows listed in `skip`
+__device__ __forceinline__ void warp_pick(const ScanCand* c, int n, const uint32_t* skip, int nskip, int lane,
+                                          float* s_out, uint32_t* r_out) {
+  float bs = -INFINITY;
+  uint32_t br = kNoRow;
+  for (int i = lane; i < n; i += 32) {
+    const unsigned long long raw = __ldcg(reinterpret_cast<const unsigned long long*>(c + i));
+    const float sc = __uint_as_float((unsigned int)(raw & 0xffffffffull));
+    const uint32_t rw = (uint32_t)(raw >> 32);
+    bool skipped = false;
+    for (int q = 0; q < nskip; ++q) skipped |= (skip[q] == rw);
+    if (!skipped && cand_better(sc, rw, bs, br)) { bs = sc; br = rw; }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const float s2 = __shfl_xor_sync(0xffffffffu, bs, off);
+    const uint32_t r2 = __shfl_xor_sync(0xffffffffu, br, off);
+    if (cand_better(s2, r2, bs, br)) { bs = s2; br = r2; }
+  }
+  *s_out = bs;
+  *r_out = br;
+}
+
+// warp-level version of mail_exchange (step_kernels.cuh): same protocol, one warp
+template <int J>
+__device__ __forceinline__ bool mail_exchange_warp(SolverState* st, int lane, uint32_t lrow, double lscore, int64_t* f,
+                                                   double* norm, const float** row) {
+  const int W = st->world, me = st->rank, ld = st->ld;
+  const unsigned long long seq = st->seq + 1ull;
+  const int par = (int)(seq & 1ull);
+  const int64_t sb = st->mail_slot_bytes;
+  const bool have = lrow != kNoRow;
+  const float* src = have ? st->An + (size_t)lrow * ld : nullptr;
+  const int64_t gidx = have ? st->row_offset + (int64_t)lrow : -1;
+  const double nrm = have ? st->norms[lrow] : 0.;
+  for (int p = 0; p < W; ++p) {
+    unsigned char* slot = st->mail_peer[p] + (int64_t)(par * W + me) * sb;
+    float* dst = reinterpret_cast<float*>(slot + sizeof(MailHeader));
+    if (have)
+      for (int s = lane; s < ld; s += 32) dst[s] = src[s];
+    if (lane == 0) {
+      MailHeader* h = reinterpret_cast<MailHeader*>(slot);
+      h->score = lscore; h->gidx = gidx; h->norm = nrm;
+    }
+  }
+  __threadfence_system();
+  __syncwarp();
+  bool ok = true;
+  if (lane < W) {
+    MailHeader* h = reinterpret_cast<MailHeader*>(st->mail_peer[lane] + (int64_t)(par * W + me) * sb);
+    st_release_sys_u64(&h->seq, seq);
+    const MailHeader* mine = reinterpret_cast<const MailHeader*>(st->mail_local + (int64_t)(par * W + lane) * sb);
+    const unsigned long long t0 = globaltimer_ns();
+    while (ld_acquire_sys_u64(&mine->seq) != seq) {
+      if (globaltimer_ns() - t0 > 10000000000ull) { ok = false; break; }
+      __nanosleep(64);
+    }
+  }
+  ok = __all_sync(0xffffffffu, ok);
+  if (!ok) return false;
+  int win = -1; double best = -INFINITY; int64_t bidx = -1;
+  for (int p = 0; p < W; ++p) {
+    const MailHeader* h = reinterpret_cast<const MailHeader*>(st->mail_local + (int64_t)(par * W + p) * sb);
+    const double sc = __ldcg(&h->score);
+    const int64_t gi = __ldcg(reinterpret_cast<const long long*>(&h->gidx));
+    if (gi < 0) continue;
+    if (win < 0 || sc > best || (sc == best && gi < bidx)) { win = p; best = sc; bidx = gi; }
+  }
+  const unsigned char* wslot = st->mail_local + (int64_t)(par * W + win) * sb;
+  *f = bidx;
+  *norm = __ldcg(&reinterpret_cast<const MailHeader*>(wslot)->norm);
+  *row = reinterpret_cast<const float*>(wslot + sizeof(MailHeader));
+  if (lane == 0) st->seq = seq;
+  __syncwarp();
+  return true;
+}
+
+// direction(s) for the next scan from the iterate held in registers; returns false when GIGA's
+// cdirnrm < TOL (giga.py:28-29).  n2 = sum xw^2, bx = sum bn*xw, e2 = sum (xw-b)^2 precomputed.
+template <int J>
+__device__ __forceinline__ bool publish_direction(SolverState* st, const double (&xw)[J], const double* sb,
+                                                  const double* sbn, int lane, double n2, double bx, double e2,
+                                                  double* cdirnrm_out) {
+  const int S = st->S, ld = st->ld;
+  if (st->alg == BCG_ALG_GIGA) {
+    double nw = sqrt(n2);
+    if (nw == 0.) nw = 1.;
+    const double bxw = bx / nw;
+    double cd[J];
+    double c2[1] = {0.};
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int s = lane + 32 * j;
+      cd[j] = 0.;
+      if (s < S) { cd[j] = sbn[s] - bxw * (xw[j] / nw); c2[0] += cd[j] * cd[j]; }
+    }
+    wsum<1>(c2);
+    const double cn = sqrt(c2[0]);
+    *cdirnrm_out = cn;
+    if (cn < st->tol) return false;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int s = lane + 32 * j;
+      if (s < ld) {
+        const double c = (s < S) ? cd[j] / cn : 0.;
+        const double x = (s < S) ? xw[j] / nw : 0.;
+        st->dir32[s] = (float)c;
+        st->dir32[ld + s] = (float)x;
+        if (s < S) { st->dir64[s] = c; st->dir64[S + s] = x; }
+      }
+    }
+  } else {
+    const double rn = sqrt(e2);
+    const double inv = rn > 0. ? 1. / rn : 1.;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int s = lane + 32 * j;
+      if (s < ld) {
+        const double r = (s < S) ? (sb[s] - xw[j]) * inv : 0.;
+        st->dir32[s] = (float)r;
+        if (s < S) st->dir64[s] = r;
+      }
+    }
+  }
+  return true;
+}
+
+template <int J>
+__device__ void control_loop(const LoopArgs& a, double* sb, double* sbn) {
+  SolverState* st = a.st;
+  LoopCtl* ctl = a.ctl;
+  const int lane = threadIdx.x & 31;
+  const int S = st->S, ld = st->ld;
+  const unsigned int G = gridDim.x;
+  const bool giga = st->alg == BCG_ALG_GIGA;
+
+  double xw[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int s = lane + 32 * j;
+    xw[j] = 0.;
+    if (s < S) { xw[j] = st->xw[s]; sb[s] = st->b[s]; sbn[s] = st->bn[s]; }
+  }
+  __syncwarp();
+
+  int nact = st->nact;
+  int retried = 0;                       // snnls.py:40: local to the build() call
+  int halted = 0;
+  int n_events = 0;
+  double err = st->err;
+  double sel_aux = 0.;
+  int npos = 0;
+  for (int k = lane; k < nact; k += 32) npos += (st->act_w[k] > 0.) ? 1 : 0;
+  npos = __reduce_add_sync(0xffffffffu, npos);
+
+  auto iterate_sums = [&](double& n2, double& bx, double& e2) {
+    double v[3] = {0., 0., 0.};
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int s = lane + 32 * j;
+      if (s < S) { v[0] += xw[j] * xw[j]; v[1] += sbn[s] * xw[j]; const double r = xw[j] - sb[s]; v[2] += r * r; }
+    }
+    wsum<3>(v);
+    n2 = v[0]; bx = v[1]; e2 = v[2];
+  };
+  auto push = [&](int code, int64_t f, double e, double a0, double a1) {
+    if (lane == 0) {
+      bcg_iter_event* ev = st->events + n_events;
+      ev->code = code; ev->nact = nact; ev->f = f; ev->error = e; ev->aux0 = a0; ev->aux1 = a1;
+    }
+    n_events += 1;
+  };
+  auto publish = [&](unsigned int it_done, bool stop) {
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) {
+      if (stop) *reinterpret_cast<volatile unsigned int*>(&ctl->stop) = 1u;
+      __threadfence();
+      st_release_gpu_u32(&ctl->go, it_done);
+    }
+    __syncwarp();
+  };
+
+  double n2, bx, e2;
+  iterate_sums(n2, bx, e2);
+  bool sel_ok = publish_direction<J>(st, xw, sb, sbn, lane, n2, bx, e2, &sel_aux);
+  publish(1u, !sel_ok && false);         // scans run even when selection failed once: see below
+
+  int it = 0;
+  for (; it < a.itrs; ++it) {
+    // ---- a failed selection (cdirnrm < TOL) repeats identically: resolve it without scanning ----
+    // (the grid is still released every iteration so the barrier protocol stays uniform)
+    // wait for the grid
+    if (lane == 0) {
+      const unsigned int want = G * (unsigned int)(it + 1);
+      while (ld_acquire_gpu_u32(&ctl->arrive) < want) __nanosleep(40);
+    }
+    __syncwarp();
+
+    bool failed = false;
+    int fcode = 0; int64_t f = -1; double fa0 = 0., fa1 = 0.;
+    double alpha = 0., beta = 0., nf_stored = 0., lscore = 0.;
+    const float* frow = nullptr;
+    double xf[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) xf[j] = 0.;
+    const bool nonempty = npos > 0;
+
+    if (!sel_ok) {
+      failed = true; fcode = BCG_IT_FAIL_CDIR; fa0 = sel_aux;
+    } else {
+      // ---- winner: best fp32 candidate; near ties re-scored in float64 --------------------------
+      const int nc = 2 * (int)G;
+      uint32_t chosen[kRescoreMax];
+      float top; uint32_t lrow;
+      warp_pick(a.cta_cands, nc, chosen, 0, lane, &top, &lrow);
+      int nch = 0;
+      if (lrow != kNoRow) {
+        chosen[nch++] = lrow;
+        const float thr = top - (2e-5f + 1e-5f * fabsf(top));
+        while (nch < kRescoreMax) {
+          float s2; uint32_t r2;
+          warp_pick(a.cta_cands, nc, chosen, nch, lane, &s2, &r2);
+          if (r2 == kNoRow || !(s2 >= thr)) break;
+          chosen[nch++] = r2;
+        }
+      }
+      lscore = (double)top;
+      if (nch > 1 || (st->world > 1 && nch == 1)) {
+        uint32_t brow = kNoRow; double best = -INFINITY;
+        for (int r = 0; r < nch; ++r) {
+          const double sc = row_score_warp<J>(st, st->An + (size_t)chosen[r] * ld, lane);
+          if (brow == kNoRow || sc > best || (sc == best && chosen[r] < brow)) { best = sc; brow = chosen[r]; }
+        }
+        lrow = brow; lscore = best;
+      }
+      if (st->world > 1) {
+        if (!mail_exchange_warp<J>(st, lane, lrow, lscore, &f, &nf_stored, &frow)) {
+          if (lane == 0) { st->comm_error = 1; }
+          halted = 1;
+          break;
+        }
+      } else {
+        f = st->row_offset + (int64_t)lrow;
+        nf_stored = st->norms[lrow];
+        frow = st->An + (size_t)lrow * ld;
+      }
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const int s = lane + 32 * j;
+        if (s < S) xf[j] = nf_stored * (double)__ldcg(frow + s);
+      }
+
+      // ---- line search ---------------------------------------------------------------------------
+      if (giga) {
+        double v[3] = {0., 0., 0.};            // xf.xf, bn.xf, xw.xf   (xw.xw = n2, bn.xw = bx known)
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          const int s = lane + 32 * j;
+          if (s < S) { v[0] += xf[j] * xf[j]; v[1] += sbn[s] * xf[j]; v[2] += xw[j] * xf[j]; }
+        }
+        wsum<3>(v);
+        double nw = sqrt(n2);
+        if (nw == 0.) nw = 1.;
+        const double nf = sqrt(v[0]);
+        const double bxf = v[1] / nf, bxw = bx / nw, xwxf = v[2] / (nw * nf);
+        const double gA = bxf - bxw * xwxf;
+        const double gB = bxw - bxf * xwxf;
+        if (gA <= 0. || gB < 0.) {
+          failed = true; fcode = BCG_IT_FAIL_GEODESIC; fa0 = gA; fa1 = gB;
+        } else {
+          const double ca = gB / (gA + gB) / nw;
+          const double cb = gA / (gA + gB) / nf;
+          double u[2] = {0., 0.};
+#pragma unroll
+          for (int j = 0; j < J; ++j) {
+            const int s = lane + 32 * j;
+            if (s < S) { const double x = ca * xw[j] + cb * xf[j]; u[0] += x * x; u[1] += x * sbn[s]; }
+          }
+          wsum<2>(u);
+          const double nx = sqrt(u[0]);
+          const double scale = st->bnorm / nx * (u[1] / nx);
+          alpha = ca * scale;
+          beta = cb * scale;
+        }
+      } else {
+        if (!nonempty) {
+          alpha = 0.;
+          beta = st->nsum / nf_stored;
+        } else {
+          const double r = st->nsum / nf_stored;
+          double v[2] = {0., 0.};
+#pragma unroll
+          for (int j = 0; j < J; ++j) {
+            const int s = lane + 32 * j;
+            if (s < S) { const double t = r * xf[j] - xw[j]; v[0] += t * (sb[s] - xw[j]); v[1] += t * t; }
+          }
+          wsum<2>(v);
+          if (v[0] < 0. || v[1] == 0. || v[0] > v[1]) {
+            failed = true; fcode = BCG_IT_FAIL_GAMMA; fa0 = v[0]; fa1 = v[1];
+          } else {
+            alpha = 1. - v[0] / v[1];
+            beta = r * v[0] / v[1];
+          }
+        }
+      }
+    }
+
+    // ---- apply: w <- alpha w ; w[f] <- max(0, w[f] + beta) ; A w incrementally ---------------------
+    int slot = -1;
+    double wf_new = 0.;
+    double xn[J];
+    double n2n = 0., bxn = 0., e2n = 0.;
+    if (!failed) {
+      int sl = 0x7fffffff;
+      for (int k = lane; k < nact; k += 32)
+        if (st->act_idx[k] == f && k < sl) sl = k;
+      sl = __reduce_min_sync(0xffffffffu, sl);
+      slot = (sl == 0x7fffffff) ? -1 : sl;
+      const double wf_old = slot >= 0 ? st->act_w[slot] : 0.;
+      wf_new = fmax(0., alpha * wf_old + beta);
+      const double delta = wf_new - alpha * wf_old;
+      double v[3] = {0., 0., 0.};
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const int s = lane + 32 * j;
+        xn[j] = 0.;
+        if (s < S) {
+          xn[j] = alpha * xw[j] + delta * xf[j];
+          v[0] += xn[j] * xn[j]; v[1] += sbn[s] * xn[j];
+          const double r = xn[j] - sb[s]; v[2] += r * r;
+        }
+      }
+      wsum<3>(v);
+      n2n = v[0]; bxn = v[1]; e2n = v[2];
+      const double err_new = sqrt(e2n);
+      if (nonempty && err_new > err) {         // snnls.py:58-61
+        failed = true; fcode = BCG_IT_FAIL_MONOTONE; fa0 = err_new; fa1 = err;
+      }
+    }
+
+    if (failed) {
+      // snnls.py:63-72.  The state is unchanged, so the retry fails identically: when another
+      // iteration is available it is consumed here (second consecutive failure -> latch).
+      push(fcode, f, err, fa0, fa1);
+      if (retried || it + 1 < a.itrs) {
+        if (!retried) { push(fcode, f, err, fa0, fa1); }
+        halted = 1;
+      } else {
+        retried = 1;
+      }
+      if (halted) break;
+      continue;                                 // it was the last iteration of this call
+    }
+
+    // commit the iterate, publish the next direction, THEN do the O(K) bookkeeping
+#pragma unroll
+    for (int j = 0; j < J; ++j) xw[j] = xn[j];
+    err = sqrt(e2n);
+    n2 = n2n; bx = bxn; e2 = e2n;
+    if (nonempty) retried = 0;                  // snnls.py:62
+    const bool last = (it + 1 == a.itrs);
+    if (!last) {
+      sel_ok = publish_direction<J>(st, xw, sb, sbn, lane, n2, bx, e2, &sel_aux);
+      publish((unsigned int)(it + 2), false);
+    }
+
+    // ---- bookkeeping (overlaps the next scan) --------------------------------------------------
+    int np = 0;
+    for (int k = lane; k < nact; k += 32) {
+      double wk = alpha * st->act_w[k];
+      if (k == slot) wk = wf_new;
+      st->act_w[k] = wk;
+      np += (wk > 0.) ? 1 : 0;
+    }
+    if (slot < 0) {
+      slot = nact;
+      for (int s = lane; s < ld; s += 32) st->act_rows[(size_t)slot * ld + s] = __ldcg(frow + s);
+      if (lane == 0) { st->act_idx[slot] = f; st->act_norm[slot] = nf_stored; st->act_w[slot] = wf_new; }
+      np += (lane == 0 && wf_new > 0.) ? 1 : 0;
+      nact += 1;
+    }
+    npos = __reduce_add_sync(0xffffffffu, np);
+    __syncwarp();
+    push(BCG_IT_OK, f, err, lscore, 0.);
+
+    if (((it + 1) % kRefreshEvery) == 0 && !last) {
+      // exact re-summation of A w from the active set (bounds the drift of the incremental update)
+      double xr[J];
+#pragma unroll
+      for (int j = 0; j < J; ++j) xr[j] = 0.;
+      for (int k = 0; k < nact; ++k) {
+        const double c = st->act_w[k] * st->act_norm[k];
+        if (c == 0.) continue;
+        const float* row = st->act_rows + (size_t)k * ld;
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          const int s = lane + 32 * j;
+          if (s < S) xr[j] += c * (double)row[s];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < J; ++j) xw[j] = xr[j];
+      iterate_sums(n2, bx, e2);
+      err = sqrt(e2);
+    }
+  }
+
+  // ---- end of the build call: stop the grid, write the state back -------------------------------
+  publish((unsigned int)(a.itrs + 2), true);
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int s = lane + 32 * j;
+    if (s < S) st->xw[s] = xw[j];
+  }
+  if (lane == 0) {
+    st->nact = nact;
+    st->err = err;
+    st->retried = retried;
+    st->halted = halted ? 1 : st->halted;
+    st->n_events = n_events;
+    st->select_failed = sel_ok ? 0 : 1;
+    st->sel_aux = sel_aux;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+template <int CH, int NDIR, int J>
+__global__ void __launch_bounds__(544, 1) greedy_loop_kernel(const LoopArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int wpb = a.wpb;
+  const uint32_t stage_floats = (uint32_t)a.rps * (uint32_t)a.ld;
+  const size_t ring_bytes = (size_t)wpb * a.stages * stage_floats * sizeof(float);
+  uint64_t* bars_all = reinterpret_cast<uint64_t*>(smem_raw + ring_bytes);
+  ScanCand* cta_c = reinterpret_cast<ScanCand*>(bars_all + wpb * a.stages);
+  double* sb = reinterpret_cast<double*>(cta_c + 32);
+  double* sbn = sb + a.st->S;
+
+  if (warp == wpb) {                    // control warp (only CTA 0's does anything)
+    if (blockIdx.x == 0) control_loop<J>(a, sb, sbn);
+    return;
+  }
+
+  LoopCtl* ctl = a.ctl;
+  const int64_t gw = (int64_t)blockIdx.x * wpb + warp;
+  const int64_t GW = (int64_t)gridDim.x * wpb;
+  float* wbuf = reinterpret_cast<float*>(smem_raw) + (size_t)warp * a.stages * stage_floats;
+  uint64_t* bars = bars_all + warp * a.stages;
+  if (lane == 0) {
+    for (int s = 0; s < a.stages; ++s) mbar_init(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  uint64_t policy;
+  if (a.evict_first)
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  else
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(policy));
+
+  const int lpr = a.lpr;
+  const int g = lane & (lpr - 1);
+  const int grp = lane / lpr;
+  const int ngrp = 32 / lpr;
+  const int nchunk = a.ld >> 2;
+  const int64_t n_chunks = (a.n_rows + a.rps - 1) / a.rps;
+  const int64_t n_my = (gw < n_chunks) ? (n_chunks - gw + GW - 1) / GW : 0;
+  const int64_t total = n_my * (int64_t)a.itrs;     // chunk visits over the whole build call
+
+  auto issue = [&](int64_t kk) {                      // kk: running chunk-visit counter of this warp
+    const int st = (int)(kk % a.stages);
+    const int64_t k = kk % n_my;
+    const int64_t row0 = (gw + k * GW) * a.rps;
+    const int64_t left = a.n_rows - row0;
+    const uint32_t nr = (uint32_t)(left < a.rps ? left : a.rps);
+    tma_load_rows(&bars[st], wbuf + (size_t)st * stage_floats, a.An + (size_t)row0 * a.ld, nr * (uint32_t)a.ld * 4u,
+                  policy);
+  };
+  if (lane == 0) {
+    const int64_t pre = total < a.stages ? total : a.stages;
+    for (int64_t kk = 0; kk < pre; ++kk) issue(kk);   // tiles do not depend on the direction
+  }
+
+  int64_t consumed = 0;
+  for (int it = 0; it < a.itrs; ++it) {
+    if (lane == 0)
+      while (ld_acquire_gpu_u32(&ctl->go) < (unsigned int)(it + 1)) __nanosleep(32);
+    __syncwarp();
+    if (*reinterpret_cast<volatile unsigned int*>(&ctl->stop)) break;
+
+    float4 d0[CH];
+    float4 d1[CH];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      const int c = g + j * lpr;
+      d0[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      d1[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < nchunk) {
+        d0[j] = __ldcg(reinterpret_cast<const float4*>(a.st->dir32) + c);
+        if (NDIR == 2) d1[j] = __ldcg(reinterpret_cast<const float4*>(a.st->dir32 + a.ld) + c);
+      }
+    }
+
+    float best = -INFINITY;
+    uint32_t brow = kNoRow;
+    for (int64_t k = 0; k < n_my; ++k) {
+      const int64_t kk = consumed + k;
+      const int st = (int)(kk % a.stages);
+      mbar_wait(&bars[st], (uint32_t)((kk / a.stages) & 1));
+      const int64_t row0 = (gw + k * GW) * a.rps;
+      const int64_t left = a.n_rows - row0;
+      const int nr = (int)(left < a.rps ? left : a.rps);
+      const float* tile = wbuf + (size_t)st * stage_floats;
+#pragma unroll 2
+      for (int rb = 0; rb < nr; rb += ngrp) {
+        const int r = rb + grp;
+        const float4* rowp = reinterpret_cast<const float4*>(tile + (size_t)(r < a.rps ? r : 0) * a.ld);
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+          const int c = g + j * lpr;
+          if (c < nchunk) {
+            const float4 x = rowp[c];
+            a0 = fmaf(x.x, d0[j].x, a0); a0 = fmaf(x.y, d0[j].y, a0);
+            a0 = fmaf(x.z, d0[j].z, a0); a0 = fmaf(x.w, d0[j].w, a0);
+            if (NDIR == 2) {
+              a1 = fmaf(x.x, d1[j].x, a1); a1 = fmaf(x.y, d1[j].y, a1);
+              a1 = fmaf(x.z, d1[j].z, a1); a1 = fmaf(x.w, d1[j].w, a1);
+            }
+          }
+        }
+        for (int off = lpr >> 1; off > 0; off >>= 1) {
+          a0 += __shfl_xor_sync(0xffffffffu, a0, off);
+          if (NDIR == 2) a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+        }
+        float score;
+        if (NDIR == 2) {
+          const float den = 1.f - a1 * a1;
+          score = (a1 > -1.f && den > 0.f) ? a0 * rsqrtf(den) : 0.f;
+        } else {
+          score = a0;
+        }
+        if (r < nr && score > best) { best = score; brow = (uint32_t)(row0 + r); }
+      }
+      __syncwarp();
+      if (lane == 0 && kk + a.stages < total) issue(kk + a.stages);   // may already belong to iteration it+1
+    }
+    consumed += n_my;
+
+    for (int off = lpr; off < 32; off <<= 1) {
+      const float s2 = __shfl_xor_sync(0xffffffffu, best, off);
+      const uint32_t r2 = __shfl_xor_sync(0xffffffffu, brow, off);
+      if (cand_better(s2, r2, best, brow)) { best = s2; brow = r2; }
+    }
+    if (lane == 0) { cta_c[warp].score = best; cta_c[warp].row = brow; }
+    named_bar_sync(1, wpb * 32);
+    if (warp == 0) {
+      // best and runner-up of the CTA's warps -> global, then arrive (release)
+      float s1 = -INFINITY; uint32_t r1 = kNoRow;
+      if (lane < wpb) { s1 = cta_c[lane].score; r1 = cta_c[lane].row; }
+      float bs = s1; uint32_t br = r1;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const float s2 = __shfl_xor_sync(0xffffffffu, bs, off);
+        const uint32_t r2 = __shfl_xor_sync(0xffffffffu, br, off);
+        if (cand_better(s2, r2, bs, br)) { bs = s2; br = r2; }
+      }
+      if (r1 == br) { s1 = -INFINITY; r1 = kNoRow; }     // exclude the winner, then second best
+      float ss = s1; uint32_t sr = r1;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const float s2 = __shfl_xor_sync(0xffffffffu, ss, off);
+        const uint32_t r2 = __shfl_xor_sync(0xffffffffu, sr, off);
+        if (cand_better(s2, r2, ss, sr)) { ss = s2; sr = r2; }
+      }
+      if (lane == 0) {
+        ScanCand c0; c0.score = bs; c0.row = br;
+        ScanCand c1; c1.score = ss; c1.row = sr;
+        a.cta_cands[2 * blockIdx.x] = c0;
+        a.cta_cands[2 * blockIdx.x + 1] = c1;
+        __threadfence();
+        red_release_gpu_add(&ctl->arrive, 1u);
+      }
+    }
+  }
+  // drain tiles that were prefetched for an iteration that will not run
+  {
+    const int64_t hi = (consumed + a.stages < total) ? consumed + a.stages : total;
+    for (int64_t kk = consumed; kk < hi; ++kk) mbar_wait(&bars[(int)(kk % a.stages)], (uint32_t)((kk / a.stages) & 1));
+  }
+}
+
+}  // namespace bcg

@@ -248,4 +248,4 @@ def test_empty_and_tiny_inputs(bc):
   cs = bc.HilbertCoreset(X, IDProjector())
   cs.build(3)
   wts, pts, idcs = cs.get()
-  assert list(idcs) == [0] and wts[0] == pytest.approx(1.) and cs.error() < 1e-12
+  assert list(idcs) == [0] and wts[0] == pytest.approx(1., rel=1e-6) and cs.error() < 1e-5
