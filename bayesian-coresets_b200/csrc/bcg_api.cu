@@ -14,8 +14,8 @@
 
 #include "../../include/bcg.h"
 #include "bcg_state.h"
+#include "kernel_args.h"
 #include "project_kernels.cuh"
-#include "scan_kernel.cuh"
 #include "step_kernels.cuh"
 
 using namespace bcg;
@@ -79,18 +79,15 @@ struct bcg_vecs {
   uint64_t zero_rows;
 };
 
-struct ScanConfig {
-  int ch, ndir, lpr, rps, stages, wpb, grid, evict_first;
-  size_t smem;
-};
-
 struct bcg_solver {
   bcg_ctx* ctx;
   bcg_vecs* v;
   SolverState h;      // host mirror (valid after every synchronising call)
   SolverState* d;
   ScanConfig sc;
-  bool scan_attr_set;
+  bool use_loop;            // persistent cooperative kernel available for this shape
+  LoopCtl* d_ctl;
+  ScanCand* d_cta_cands;
   int64_t* d_fout;
   unsigned char* mail;      // this rank's mailbox allocation
   int64_t mail_bytes;
@@ -101,7 +98,7 @@ struct bcg_solver {
   cudaEvent_t ev0, ev1;
   std::vector<cudaEvent_t> scan_ev;
   float build_ms, scan_ms;
-  int scan_launches, step_launches;
+  int scan_launches, step_launches, loop_launches;
 };
 
 static int use_device(bcg_ctx* ctx) {
@@ -489,65 +486,57 @@ static int choose_scan_config(bcg_solver* s) {
   ScanConfig& c = s->sc;
   const int nchunk = ld / 4;
   c.lpr = std::min(32, pow2ceil(nchunk));
-  const int need = (nchunk + c.lpr - 1) / c.lpr;
-  c.ch = pow2ceil(need);
-  if (c.ch > 8) return fail(BCG_ERR_UNSUPPORTED, "S=%d needs more than 8 float4 chunks per lane", s->v->S);
+  c.ch = pow2ceil((nchunk + c.lpr - 1) / c.lpr);
+  if (!scan_variant_exists(c.ch, c.lpr))
+    return fail(BCG_ERR_UNSUPPORTED, "no scan kernel for S=%d (ch=%d lpr=%d)", s->v->S, c.ch, c.lpr);
+  c.r = scan_variant_r(c.ch, c.lpr);
+  c.rb = c.r * (32 / c.lpr);
   c.ndir = (s->h.alg == BCG_ALG_GIGA) ? 2 : 1;
-  const int ngrp = 32 / c.lpr;
   const int row_bytes = ld * 4;
-  const int stage_bytes = env_int("BCG_SCAN_STAGE_BYTES", 4096);
-  c.rps = std::max(1, stage_bytes / row_bytes);
-  c.rps = std::max(ngrp, c.rps / ngrp * ngrp);
-  c.wpb = std::max(1, std::min(16, env_int("BCG_SCAN_WARPS", 16)));
+  const int batch_bytes = c.rb * row_bytes;
+  const int stage_bytes = env_int("BCG_SCAN_STAGE_BYTES", 8192);
+  const int nb = std::max(1, stage_bytes / batch_bytes);
+  c.rps = nb * c.rb;
+  c.wpb = std::max(1, std::min(11, env_int("BCG_SCAN_WARPS", 8)));   // loop kernel: <= 11 scan warps + 1 control warp
   c.stages = std::max(1, env_int("BCG_SCAN_STAGES", 3));
-  const int ctas = std::max(1, env_int("BCG_SCAN_CTAS_PER_SM", 1));
   c.evict_first = env_int("BCG_SCAN_EVICT_FIRST", 0);
-  const size_t budget = (size_t)(220 * 1024) / ctas;
-  auto smem_for = [&](int stages) { return (size_t)c.wpb * stages * c.rps * row_bytes + (size_t)c.wpb * stages * 8; };
-  while (c.stages > 1 && smem_for(c.stages) > budget) --c.stages;
-  while (c.rps > ngrp && smem_for(c.stages) > budget) c.rps -= ngrp;
-  c.smem = smem_for(c.stages);
-  if (c.smem > budget) return fail(BCG_ERR_UNSUPPORTED, "scan tile does not fit shared memory (ld=%d)", ld);
-  c.grid = s->ctx->sm_count * ctas;
-  return BCG_OK;
-}
-
-template <int CH, int NDIR>
-static int launch_scan_t(bcg_solver* s, const ScanArgs& a) {
-  if (!s->scan_attr_set) {
-    CK(cudaFuncSetAttribute(scan_kernel<CH, NDIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->sc.smem));
-    s->scan_attr_set = true;
+  const size_t budget = (size_t)(200 * 1024);
+  const size_t extra = 32 * sizeof(ScanCand) + 2 * (size_t)s->v->S * sizeof(double) + 128;   // loop kernel only
+  auto ring = [&](int stages, int rps) { return (size_t)c.wpb * stages * rps * row_bytes + (size_t)c.wpb * stages * 8; };
+  while (c.stages > 2 && ring(c.stages, c.rps) + extra > budget) --c.stages;
+  while (c.rps > c.rb && ring(c.stages, c.rps) + extra > budget) c.rps -= c.rb;
+  while (c.wpb > 1 && ring(c.stages, c.rps) + extra > budget) --c.wpb;
+  while (c.stages > 1 && ring(c.stages, c.rps) + extra > budget) --c.stages;
+  c.smem = ring(c.stages, c.rps);
+  c.loop_smem = c.smem + extra;
+  if (c.loop_smem > 227 * 1024) return fail(BCG_ERR_UNSUPPORTED, "scan tile does not fit shared memory (ld=%d)", ld);
+  c.grid = s->ctx->sm_count;
+  CK(scan_set_smem(c));
+  s->use_loop = false;
+  if (env_int("BCG_ENGINE", 2) >= 2 && s->h.alg != BCG_ALG_OMP && loop_variant_exists(c.ch, c.lpr)) {
+    int coop = 0, nbm = 0;
+    CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, s->ctx->device));
+    CK(loop_set_smem(c));
+    CK(loop_max_blocks_per_sm(c, &nbm));
+    s->use_loop = coop && nbm >= 1;
   }
-  scan_kernel<CH, NDIR><<<s->sc.grid, s->sc.wpb * 32, s->sc.smem, s->ctx->stream>>>(a);
-  CK(cudaGetLastError());
   return BCG_OK;
 }
 
 static int launch_scan(bcg_solver* s) {
   ScanArgs a;
-  a.An = s->v->An;
+  a.g.An = s->v->An;
+  a.g.n_rows = s->v->n;
+  a.g.ld = s->v->ld;
+  a.g.rps = s->sc.rps;
+  a.g.stages = s->sc.stages;
+  a.g.evict_first = s->sc.evict_first;
   a.dir = s->h.dir32;
   a.cands = s->h.cands;
   a.skip0 = &s->d->halted;
   a.skip1 = &s->d->select_failed;
-  a.n_rows = s->v->n;
-  a.ld = s->v->ld;
-  a.lpr = s->sc.lpr;
-  a.rps = s->sc.rps;
-  a.stages = s->sc.stages;
-  a.evict_first = s->sc.evict_first;
-  const int key = s->sc.ch * 10 + s->sc.ndir;
-  switch (key) {
-    case 11: return launch_scan_t<1, 1>(s, a);
-    case 12: return launch_scan_t<1, 2>(s, a);
-    case 21: return launch_scan_t<2, 1>(s, a);
-    case 22: return launch_scan_t<2, 2>(s, a);
-    case 41: return launch_scan_t<4, 1>(s, a);
-    case 42: return launch_scan_t<4, 2>(s, a);
-    case 81: return launch_scan_t<8, 1>(s, a);
-    case 82: return launch_scan_t<8, 2>(s, a);
-  }
-  return fail(BCG_ERR_UNSUPPORTED, "no scan kernel for ch=%d ndir=%d", s->sc.ch, s->sc.ndir);
+  CK(scan_launch(s->sc, a, s->ctx->stream));
+  return BCG_OK;
 }
 
 static int push_state(bcg_solver* s) {
@@ -606,10 +595,12 @@ extern "C" int bcg_solver_create(bcg_ctx* ctx, bcg_vecs* v, int32_t alg, const d
   s->mail = nullptr;
   s->mail_bytes = 0;
   s->peers_open = false;
-  s->scan_attr_set = false;
+  s->use_loop = false;
+  s->d_ctl = nullptr;
+  s->d_cta_cands = nullptr;
   s->profiling = 0;
   s->build_ms = s->scan_ms = 0.f;
-  s->scan_launches = s->step_launches = 0;
+  s->scan_launches = s->step_launches = s->loop_launches = 0;
   for (int i = 0; i < kMaxWorld; ++i) s->peer_ptrs[i] = nullptr;
   SolverState& h = s->h;
   h.alg = alg; h.S = S; h.ld = ld; h.world = 1; h.rank = 0;
@@ -633,6 +624,8 @@ extern "C" int bcg_solver_create(bcg_ctx* ctx, bcg_vecs* v, int32_t alg, const d
   CK(cudaMalloc(&h.cands, (size_t)h.n_cands * sizeof(ScanCand)));
   CK(cudaMalloc(&s->d_fout, sizeof(int64_t)));
   CK(cudaMalloc(&s->d, sizeof(SolverState)));
+  CK(cudaMalloc(&s->d_ctl, sizeof(LoopCtl)));
+  CK(cudaMalloc(&s->d_cta_cands, (size_t)2 * s->sc.grid * sizeof(ScanCand)));
   CK(cudaMemcpyAsync(h.b, b, S * sizeof(double), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(h.bn, bn.data(), S * sizeof(double), cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(h.xw, 0, S * sizeof(double), st));
@@ -658,7 +651,7 @@ extern "C" int bcg_solver_destroy(bcg_solver* s) {
     for (int p = 0; p < h.world; ++p)
       if (p != h.rank && s->peer_ptrs[p]) cudaIpcCloseMemHandle(s->peer_ptrs[p]);
   void* bufs[] = {h.b, h.bn, h.xw, h.xw_new, h.xf, h.dir64, h.dir32, h.wrow, h.cands, h.act_idx, h.act_w,
-                  h.act_w_new, h.act_norm, h.act_rows, h.events, s->d_fout, s->d, s->mail};
+                  h.act_w_new, h.act_norm, h.act_rows, h.events, s->d_fout, s->d, s->mail, s->d_ctl, s->d_cta_cands};
   for (void* p : bufs)
     if (p) cudaFree(p);
   for (cudaEvent_t e : s->scan_ev) cudaEventDestroy(e);
@@ -739,38 +732,67 @@ extern "C" int bcg_solver_build(bcg_solver* s, int32_t itrs, double tol, bcg_ite
   h.tol = tol;
   h.comm_error = 0;
   RET(push_state(s));
-  if (s->profiling) {
-    while ((int)s->scan_ev.size() < 2 * itrs) {
-      cudaEvent_t e;
-      CK(cudaEventCreate(&e));
-      s->scan_ev.push_back(e);
+  const bool loop = s->use_loop && !s->profiling;
+  if (loop) {
+    // the whole build call is ONE persistent cooperative kernel (loop_kernel.cuh)
+    LoopArgs la;
+    la.st = s->d;
+    la.ctl = s->d_ctl;
+    la.cta_cands = s->d_cta_cands;
+    la.g.An = s->v->An;
+    la.g.n_rows = s->v->n;
+    la.g.ld = s->v->ld;
+    la.g.rps = s->sc.rps;
+    la.g.stages = s->sc.stages;
+    la.g.evict_first = s->sc.evict_first;
+    la.itrs = itrs;
+    la.wpb = s->sc.wpb;
+    CK(cudaMemsetAsync(s->d_ctl, 0, sizeof(LoopCtl), st));
+    CK(cudaEventRecord(s->ev0, st));
+    CK(loop_launch(s->sc, la, st));
+    CK(cudaEventRecord(s->ev1, st));
+    RET(pull_state(s));
+    CK(cudaEventElapsedTime(&s->build_ms, s->ev0, s->ev1));
+    s->scan_launches = 0;
+    s->step_launches = 0;
+    s->loop_launches = 1;
+    s->scan_ms = 0.f;
+  } else {
+    if (s->profiling) {
+      while ((int)s->scan_ev.size() < 2 * itrs) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        s->scan_ev.push_back(e);
+      }
     }
-  }
-  CK(cudaEventRecord(s->ev0, st));
-  step_kernel<<<1, kStepThreads, 0, st>>>(s->d, 0, 1, 1);
-  for (int i = 0; i < itrs; ++i) {
-    if (s->profiling) CK(cudaEventRecord(s->scan_ev[2 * i], st));
-    RET(launch_scan(s));
-    if (s->profiling) CK(cudaEventRecord(s->scan_ev[2 * i + 1], st));
-    step_kernel<<<1, kStepThreads, 0, st>>>(s->d, 1, (i + 1 < itrs) ? 1 : 0, 0);
-  }
-  CK(cudaGetLastError());
-  CK(cudaEventRecord(s->ev1, st));
-  RET(pull_state(s));
-  CK(cudaEventElapsedTime(&s->build_ms, s->ev0, s->ev1));
-  s->scan_launches = itrs;
-  s->step_launches = itrs + 1;
-  s->scan_ms = 0.f;
-  if (s->profiling) {
+    CK(cudaEventRecord(s->ev0, st));
+    step_kernel<<<1, kStepThreads, 0, st>>>(s->d, 0, 1, 1);
     for (int i = 0; i < itrs; ++i) {
-      float ms = 0.f;
-      CK(cudaEventElapsedTime(&ms, s->scan_ev[2 * i], s->scan_ev[2 * i + 1]));
-      s->scan_ms += ms;
+      if (s->profiling) CK(cudaEventRecord(s->scan_ev[2 * i], st));
+      RET(launch_scan(s));
+      if (s->profiling) CK(cudaEventRecord(s->scan_ev[2 * i + 1], st));
+      step_kernel<<<1, kStepThreads, 0, st>>>(s->d, 1, (i + 1 < itrs) ? 1 : 0, 0);
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(s->ev1, st));
+    RET(pull_state(s));
+    CK(cudaEventElapsedTime(&s->build_ms, s->ev0, s->ev1));
+    s->scan_launches = itrs;
+    s->step_launches = itrs + 1;
+    s->loop_launches = 0;
+    s->scan_ms = 0.f;
+    if (s->profiling) {
+      for (int i = 0; i < itrs; ++i) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, s->scan_ev[2 * i], s->scan_ev[2 * i + 1]));
+        s->scan_ms += ms;
+      }
     }
   }
   const int ne = h.n_events;
   if (events && ne > 0) CK(cudaMemcpy(events, h.events, (size_t)ne * sizeof(bcg_iter_event), cudaMemcpyDeviceToHost));
   if (n_events) *n_events = ne;
+  if (h.comm_error == 2) return fail(BCG_ERR_STATE, "no comparable score in the scan (non-finite matrix entries?)");
   if (h.comm_error) return fail(BCG_ERR_COMM, "peer-memory candidate exchange timed out (a rank is missing)");
   return BCG_OK;
 }
@@ -885,7 +907,7 @@ extern "C" int bcg_solver_timing(bcg_solver* s, float* build_ms, float* scan_ms,
   if (build_ms) *build_ms = s->build_ms;
   if (scan_ms) *scan_ms = s->scan_ms;
   if (scan_launches) *scan_launches = s->scan_launches;
-  if (step_launches) *step_launches = s->step_launches;
+  if (step_launches) *step_launches = s->step_launches + s->loop_launches;
   return BCG_OK;
 }
 

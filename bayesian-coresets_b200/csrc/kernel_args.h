@@ -1,0 +1,65 @@
+// Launch-argument structs and the internal launcher interface between the translation units of
+// libbcg_b200.so (bcg_api.cu, kernels_scan.cu, kernels_loop.cu).  Host-compilable.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+#include "bcg_state.h"
+
+namespace bcg {
+
+// geometry of the streamed matrix and of the per-warp TMA ring
+struct ScanGeom {
+  const float* An;      // n_rows x ld, unit rows
+  int64_t n_rows;
+  int32_t ld;           // floats per row (multiple of 4)
+  int32_t rps;          // rows per stage (multiple of the batch size R * 32/LPR)
+  int32_t stages;
+  int32_t evict_first;  // L2 policy of the streaming loads
+};
+
+struct ScanArgs {
+  ScanGeom g;
+  const float* dir;       // NDIR x ld
+  ScanCand* cands;        // gridDim.x * warps_per_block
+  const int32_t* skip0;   // scan is skipped when *skip0 or *skip1 is non-zero (halted / select failed)
+  const int32_t* skip1;
+};
+
+struct LoopCtl {
+  unsigned int arrive;   // number of CTA arrivals so far (monotonic within a launch)
+  unsigned int go;       // iterations published so far
+  unsigned int stop;     // set (before go) when the loop ends early
+  unsigned int pad;
+};
+
+struct LoopArgs {
+  SolverState* st;
+  LoopCtl* ctl;
+  ScanCand* cta_cands;   // 2 per CTA: best and runner-up of the CTA's warps
+  ScanGeom g;
+  int32_t itrs;
+  int32_t wpb;           // scan warps per CTA (blockDim.x = (wpb + 1) * 32)
+};
+
+// template selection + launch geometry, chosen on the host from the row length
+struct ScanConfig {
+  int ch, ndir, lpr, r;      // template parameters of the scan core
+  int rb;                    // rows per batch = r * 32 / lpr
+  int rps, stages, wpb, grid, evict_first;
+  size_t smem;               // dynamic shared memory of scan_kernel
+  size_t loop_smem;          // dynamic shared memory of greedy_loop_kernel
+};
+
+// kernels_scan.cu
+bool scan_variant_exists(int ch, int lpr);
+int scan_variant_r(int ch, int lpr);
+cudaError_t scan_set_smem(const ScanConfig& c);
+cudaError_t scan_launch(const ScanConfig& c, const ScanArgs& a, cudaStream_t st);
+// kernels_loop.cu
+bool loop_variant_exists(int ch, int lpr);
+cudaError_t loop_set_smem(const ScanConfig& c);
+cudaError_t loop_max_blocks_per_sm(const ScanConfig& c, int* nb);
+cudaError_t loop_launch(const ScanConfig& c, const LoopArgs& a, cudaStream_t st);
+
+}  // namespace bcg

@@ -21,52 +21,13 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "bcg_state.h"
-#include "scan_kernel.cuh"
-#include "step_kernels.cuh"
+#include "scan_core.cuh"
+#include "step_logic.h"
+#include "sync_ptx.cuh"
 
 namespace bcg {
 
 constexpr int kRefreshEvery = 16;
-
-struct LoopCtl {
-  unsigned int arrive;   // number of CTA arrivals so far (monotonic within a launch)
-  unsigned int go;       // iterations published so far
-  unsigned int stop;     // set (before go) when the loop ends early
-  unsigned int pad;
-};
-
-struct LoopArgs {
-  SolverState* st;
-  LoopCtl* ctl;
-  ScanCand* cta_cands;   // 2 per CTA: best and runner-up of the CTA's warps
-  const float* An;
-  int64_t n_rows;
-  int32_t ld, lpr, rps, stages, evict_first;
-  int32_t itrs;
-  int32_t wpb;           // scan warps per CTA (blockDim.x = (wpb + 1) * 32)
-};
-
-__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_gpu_u32(unsigned int* p, unsigned int v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ void red_release_gpu_add(unsigned int* p, unsigned int v) {
-  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-__device__ __forceinline__ bool cand_better(float s2, uint32_t r2, float s1, uint32_t r1) {
-  // (score descending, row ascending); kNoRow never beats a real row
-  if (r2 == kNoRow) return false;
-  if (r1 == kNoRow) return true;
-  return s2 > s1 || (s2 == s1 && r2 < r1);
-}
 
 // ---------------------------------------------------------------------------------------------
 // control warp helpers (lane l owns columns l, l+32, ... of every S-vector)
@@ -184,13 +145,11 @@ __device__ __forceinline__ bool publish_direction(SolverState* st, const double 
     double nw = sqrt(n2);
     if (nw == 0.) nw = 1.;
     const double bxw = bx / nw;
-    double cd[J];
     double c2[1] = {0.};
 #pragma unroll
     for (int j = 0; j < J; ++j) {
       const int s = lane + 32 * j;
-      cd[j] = 0.;
-      if (s < S) { cd[j] = sbn[s] - bxw * (xw[j] / nw); c2[0] += cd[j] * cd[j]; }
+      if (s < S) { const double cd = sbn[s] - bxw * (xw[j] / nw); c2[0] += cd * cd; }
     }
     wsum<1>(c2);
     const double cn = sqrt(c2[0]);
@@ -200,8 +159,8 @@ __device__ __forceinline__ bool publish_direction(SolverState* st, const double 
     for (int j = 0; j < J; ++j) {
       const int s = lane + 32 * j;
       if (s < ld) {
-        const double c = (s < S) ? cd[j] / cn : 0.;
         const double x = (s < S) ? xw[j] / nw : 0.;
+        const double c = (s < S) ? (sbn[s] - bxw * x) / cn : 0.;
         st->dir32[s] = (float)c;
         st->dir32[ld + s] = (float)x;
         if (s < S) { st->dir64[s] = c; st->dir64[S + s] = x; }
@@ -282,7 +241,7 @@ __device__ void control_loop(const LoopArgs& a, double* sb, double* sbn) {
   double n2, bx, e2;
   iterate_sums(n2, bx, e2);
   bool sel_ok = publish_direction<J>(st, xw, sb, sbn, lane, n2, bx, e2, &sel_aux);
-  publish(1u, !sel_ok && false);         // scans run even when selection failed once: see below
+  publish(1u, false);
 
   int it = 0;
   for (; it < a.itrs; ++it) {
@@ -338,6 +297,10 @@ __device__ void control_loop(const LoopArgs& a, double* sb, double* sbn) {
           halted = 1;
           break;
         }
+      } else if (lrow == kNoRow) {               // no comparable score at all (non-finite matrix)
+        if (lane == 0) { st->comm_error = 2; }
+        halted = 1;
+        break;
       } else {
         f = st->row_offset + (int64_t)lrow;
         nf_stored = st->norms[lrow];
@@ -406,8 +369,7 @@ __device__ void control_loop(const LoopArgs& a, double* sb, double* sbn) {
 
     // ---- apply: w <- alpha w ; w[f] <- max(0, w[f] + beta) ; A w incrementally ---------------------
     int slot = -1;
-    double wf_new = 0.;
-    double xn[J];
+    double wf_new = 0., delta = 0.;
     double n2n = 0., bxn = 0., e2n = 0.;
     if (!failed) {
       int sl = 0x7fffffff;
@@ -417,16 +379,15 @@ __device__ void control_loop(const LoopArgs& a, double* sb, double* sbn) {
       slot = (sl == 0x7fffffff) ? -1 : sl;
       const double wf_old = slot >= 0 ? st->act_w[slot] : 0.;
       wf_new = fmax(0., alpha * wf_old + beta);
-      const double delta = wf_new - alpha * wf_old;
+      delta = wf_new - alpha * wf_old;
       double v[3] = {0., 0., 0.};
 #pragma unroll
       for (int j = 0; j < J; ++j) {
         const int s = lane + 32 * j;
-        xn[j] = 0.;
         if (s < S) {
-          xn[j] = alpha * xw[j] + delta * xf[j];
-          v[0] += xn[j] * xn[j]; v[1] += sbn[s] * xn[j];
-          const double r = xn[j] - sb[s]; v[2] += r * r;
+          const double x = alpha * xw[j] + delta * xf[j];
+          v[0] += x * x; v[1] += sbn[s] * x;
+          const double r = x - sb[s]; v[2] += r * r;
         }
       }
       wsum<3>(v);
@@ -453,7 +414,7 @@ __device__ void control_loop(const LoopArgs& a, double* sb, double* sbn) {
 
     // commit the iterate, publish the next direction, THEN do the O(K) bookkeeping
 #pragma unroll
-    for (int j = 0; j < J; ++j) xw[j] = xn[j];
+    for (int j = 0; j < J; ++j) xw[j] = alpha * xw[j] + delta * xf[j];
     err = sqrt(e2n);
     n2 = n2n; bx = bxn; e2 = e2n;
     if (nonempty) retried = 0;                  // snnls.py:62
@@ -525,16 +486,18 @@ __device__ void control_loop(const LoopArgs& a, double* sb, double* sbn) {
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <int CH, int NDIR, int J>
-__global__ void __launch_bounds__(544, 1) greedy_loop_kernel(const LoopArgs a) {
+template <int CH, int NDIR, int LPR, int R, int J>
+__global__ void __launch_bounds__(384, 1) greedy_loop_kernel(const LoopArgs a) {
+  using Core = ScanCore<CH, NDIR, LPR, R>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int wpb = a.wpb;
-  const uint32_t stage_floats = (uint32_t)a.rps * (uint32_t)a.ld;
-  const size_t ring_bytes = (size_t)wpb * a.stages * stage_floats * sizeof(float);
+  const ScanGeom& q = a.g;
+  const uint32_t stage_floats = (uint32_t)q.rps * (uint32_t)q.ld;
+  const size_t ring_bytes = (size_t)wpb * q.stages * stage_floats * sizeof(float);
   uint64_t* bars_all = reinterpret_cast<uint64_t*>(smem_raw + ring_bytes);
-  ScanCand* cta_c = reinterpret_cast<ScanCand*>(bars_all + wpb * a.stages);
+  ScanCand* cta_c = reinterpret_cast<ScanCand*>(bars_all + wpb * q.stages);
   double* sb = reinterpret_cast<double*>(cta_c + 32);
   double* sbn = sb + a.st->S;
 
@@ -546,43 +509,45 @@ __global__ void __launch_bounds__(544, 1) greedy_loop_kernel(const LoopArgs a) {
   LoopCtl* ctl = a.ctl;
   const int64_t gw = (int64_t)blockIdx.x * wpb + warp;
   const int64_t GW = (int64_t)gridDim.x * wpb;
-  float* wbuf = reinterpret_cast<float*>(smem_raw) + (size_t)warp * a.stages * stage_floats;
-  uint64_t* bars = bars_all + warp * a.stages;
+  float* wbuf = reinterpret_cast<float*>(smem_raw) + (size_t)warp * q.stages * stage_floats;
+  uint64_t* bars = bars_all + warp * q.stages;
   if (lane == 0) {
-    for (int s = 0; s < a.stages; ++s) mbar_init(&bars[s], 1);
+    for (int s = 0; s < q.stages; ++s) mbar_init(&bars[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  uint64_t policy;
-  if (a.evict_first)
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-  else
-    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(policy));
+  const uint64_t policy = l2_policy(q.evict_first);
 
-  const int lpr = a.lpr;
-  const int g = lane & (lpr - 1);
-  const int grp = lane / lpr;
-  const int ngrp = 32 / lpr;
-  const int nchunk = a.ld >> 2;
-  const int64_t n_chunks = (a.n_rows + a.rps - 1) / a.rps;
+  const int g = lane & (LPR - 1);
+  const int grp = lane / LPR;
+  const int nchunk = q.ld >> 2;
+  const int64_t n_chunks = (q.n_rows + q.rps - 1) / q.rps;
   const int64_t n_my = (gw < n_chunks) ? (n_chunks - gw + GW - 1) / GW : 0;
-  const int64_t total = n_my * (int64_t)a.itrs;     // chunk visits over the whole build call
+  const int64_t row_step = GW * q.rps;
 
-  auto issue = [&](int64_t kk) {                      // kk: running chunk-visit counter of this warp
-    const int st = (int)(kk % a.stages);
-    const int64_t k = kk % n_my;
-    const int64_t row0 = (gw + k * GW) * a.rps;
-    const int64_t left = a.n_rows - row0;
-    const uint32_t nr = (uint32_t)(left < a.rps ? left : a.rps);
-    tma_load_rows(&bars[st], wbuf + (size_t)st * stage_floats, a.An + (size_t)row0 * a.ld, nr * (uint32_t)a.ld * 4u,
-                  policy);
+  // Ring bookkeeping (all incremental).  Chunks are issued in consumption order, iteration after
+  // iteration, so the tile stream runs ahead ACROSS iterations: the slot freed by a consumed chunk
+  // is refilled with the chunk `stages` visits later, which may belong to the next iteration.
+  int issue_slot = 0;
+  int64_t issue_k = 0;         // chunk (within the iteration) of the next issue
+  int issue_it = 0;            // iteration it belongs to
+  int64_t outstanding = 0;     // issued, not yet consumed
+  auto issue_next = [&]() {    // lane 0 only
+    if (issue_it >= a.itrs || n_my == 0) return;
+    const int64_t row0 = (gw + issue_k * GW) * q.rps;
+    const int64_t left = q.n_rows - row0;
+    const uint32_t nr = (uint32_t)(left < q.rps ? left : q.rps);
+    tma_load_rows(&bars[issue_slot], wbuf + (size_t)issue_slot * stage_floats, q.An + (size_t)row0 * q.ld,
+                  nr * (uint32_t)q.ld * 4u, policy);
+    if (++issue_slot == q.stages) issue_slot = 0;
+    if (++issue_k == n_my) { issue_k = 0; ++issue_it; }
+    ++outstanding;
   };
-  if (lane == 0) {
-    const int64_t pre = total < a.stages ? total : a.stages;
-    for (int64_t kk = 0; kk < pre; ++kk) issue(kk);   // tiles do not depend on the direction
-  }
+  if (lane == 0)
+    for (int s = 0; s < q.stages; ++s) issue_next();   // tiles do not depend on the direction
 
-  int64_t consumed = 0;
+  int slot = 0;
+  uint32_t parity = 0;
   for (int it = 0; it < a.itrs; ++it) {
     if (lane == 0)
       while (ld_acquire_gpu_u32(&ctl->go) < (unsigned int)(it + 1)) __nanosleep(32);
@@ -591,89 +556,36 @@ __global__ void __launch_bounds__(544, 1) greedy_loop_kernel(const LoopArgs a) {
 
     float4 d0[CH];
     float4 d1[CH];
-#pragma unroll
-    for (int j = 0; j < CH; ++j) {
-      const int c = g + j * lpr;
-      d0[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      d1[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (c < nchunk) {
-        d0[j] = __ldcg(reinterpret_cast<const float4*>(a.st->dir32) + c);
-        if (NDIR == 2) d1[j] = __ldcg(reinterpret_cast<const float4*>(a.st->dir32 + a.ld) + c);
-      }
-    }
+    Core::load_dirs(a.st->dir32, q.ld, nchunk, g, d0, d1);
 
     float best = -INFINITY;
-    uint32_t brow = kNoRow;
+    uint32_t brow = kNoRowU;
+    int64_t row0 = gw * q.rps;
     for (int64_t k = 0; k < n_my; ++k) {
-      const int64_t kk = consumed + k;
-      const int st = (int)(kk % a.stages);
-      mbar_wait(&bars[st], (uint32_t)((kk / a.stages) & 1));
-      const int64_t row0 = (gw + k * GW) * a.rps;
-      const int64_t left = a.n_rows - row0;
-      const int nr = (int)(left < a.rps ? left : a.rps);
-      const float* tile = wbuf + (size_t)st * stage_floats;
-#pragma unroll 2
-      for (int rb = 0; rb < nr; rb += ngrp) {
-        const int r = rb + grp;
-        const float4* rowp = reinterpret_cast<const float4*>(tile + (size_t)(r < a.rps ? r : 0) * a.ld);
-        float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-        for (int j = 0; j < CH; ++j) {
-          const int c = g + j * lpr;
-          if (c < nchunk) {
-            const float4 x = rowp[c];
-            a0 = fmaf(x.x, d0[j].x, a0); a0 = fmaf(x.y, d0[j].y, a0);
-            a0 = fmaf(x.z, d0[j].z, a0); a0 = fmaf(x.w, d0[j].w, a0);
-            if (NDIR == 2) {
-              a1 = fmaf(x.x, d1[j].x, a1); a1 = fmaf(x.y, d1[j].y, a1);
-              a1 = fmaf(x.z, d1[j].z, a1); a1 = fmaf(x.w, d1[j].w, a1);
-            }
-          }
-        }
-        for (int off = lpr >> 1; off > 0; off >>= 1) {
-          a0 += __shfl_xor_sync(0xffffffffu, a0, off);
-          if (NDIR == 2) a1 += __shfl_xor_sync(0xffffffffu, a1, off);
-        }
-        float score;
-        if (NDIR == 2) {
-          const float den = 1.f - a1 * a1;
-          score = (a1 > -1.f && den > 0.f) ? a0 * rsqrtf(den) : 0.f;
-        } else {
-          score = a0;
-        }
-        if (r < nr && score > best) { best = score; brow = (uint32_t)(row0 + r); }
-      }
+      mbar_wait(&bars[slot], parity);
+      const int64_t left = q.n_rows - row0;
+      const int nr = (int)(left < q.rps ? left : q.rps);
+      const float* tile = wbuf + (size_t)slot * stage_floats;
+      for (int b0 = 0; b0 < nr; b0 += Core::RB)
+        Core::batch(tile + (size_t)b0 * q.ld, q.ld, nchunk, g, grp, nr - b0, (uint32_t)(row0 + b0), d0, d1, best, brow);
       __syncwarp();
-      if (lane == 0 && kk + a.stages < total) issue(kk + a.stages);   // may already belong to iteration it+1
+      if (lane == 0) { --outstanding; issue_next(); }
+      row0 += row_step;
+      if (++slot == q.stages) { slot = 0; parity ^= 1u; }
     }
-    consumed += n_my;
 
-    for (int off = lpr; off < 32; off <<= 1) {
-      const float s2 = __shfl_xor_sync(0xffffffffu, best, off);
-      const uint32_t r2 = __shfl_xor_sync(0xffffffffu, brow, off);
-      if (cand_better(s2, r2, best, brow)) { best = s2; brow = r2; }
-    }
+    Core::warp_merge(best, brow);
     if (lane == 0) { cta_c[warp].score = best; cta_c[warp].row = brow; }
     named_bar_sync(1, wpb * 32);
     if (warp == 0) {
       // best and runner-up of the CTA's warps -> global, then arrive (release)
-      float s1 = -INFINITY; uint32_t r1 = kNoRow;
+      float s1 = -INFINITY; uint32_t r1 = kNoRowU;
       if (lane < wpb) { s1 = cta_c[lane].score; r1 = cta_c[lane].row; }
       float bs = s1; uint32_t br = r1;
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        const float s2 = __shfl_xor_sync(0xffffffffu, bs, off);
-        const uint32_t r2 = __shfl_xor_sync(0xffffffffu, br, off);
-        if (cand_better(s2, r2, bs, br)) { bs = s2; br = r2; }
-      }
-      if (r1 == br) { s1 = -INFINITY; r1 = kNoRow; }     // exclude the winner, then second best
+      Core::warp_merge(bs, br);
+      if (r1 == br) { s1 = -INFINITY; r1 = kNoRowU; }     // exclude the winner, then second best
       float ss = s1; uint32_t sr = r1;
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        const float s2 = __shfl_xor_sync(0xffffffffu, ss, off);
-        const uint32_t r2 = __shfl_xor_sync(0xffffffffu, sr, off);
-        if (cand_better(s2, r2, ss, sr)) { ss = s2; sr = r2; }
-      }
+      Core::warp_merge(ss, sr);
       if (lane == 0) {
         ScanCand c0; c0.score = bs; c0.row = br;
         ScanCand c1; c1.score = ss; c1.row = sr;
@@ -684,10 +596,13 @@ __global__ void __launch_bounds__(544, 1) greedy_loop_kernel(const LoopArgs a) {
       }
     }
   }
-  // drain tiles that were prefetched for an iteration that will not run
+  // drain tiles that were prefetched for an iteration that will not run (early stop)
   {
-    const int64_t hi = (consumed + a.stages < total) ? consumed + a.stages : total;
-    for (int64_t kk = consumed; kk < hi; ++kk) mbar_wait(&bars[(int)(kk % a.stages)], (uint32_t)((kk / a.stages) & 1));
+    long long left = __shfl_sync(0xffffffffu, (long long)outstanding, 0);
+    for (; left > 0; --left) {
+      mbar_wait(&bars[slot], parity);
+      if (++slot == q.stages) { slot = 0; parity ^= 1u; }
+    }
   }
 }
 

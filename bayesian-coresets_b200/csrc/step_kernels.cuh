@@ -3,24 +3,11 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "step_logic.h"
+#include "sync_ptx.cuh"
 
 namespace bcg {
 
 constexpr int kStepThreads = 512;
-
-__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
 
 // Every rank posts (float64 score, global index, norm, unit row) of its best local row into slot
 // [parity][rank] of EVERY rank's mailbox with plain peer stores over NVLink, publishes it with a
