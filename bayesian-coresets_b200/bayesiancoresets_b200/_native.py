@@ -71,6 +71,8 @@ _PROTOTYPES = {
   'bcg_solver_timing': (_c.c_int, [_P, _c.POINTER(_c.c_float), _c.POINTER(_c.c_float), _c.POINTER(_c.c_int32),
                                    _c.POINTER(_c.c_int32)]),
   'bcg_solver_set_profiling': (_c.c_int, [_P, _c.c_int32]),
+  'bcg_solver_set_trace': (_c.c_int, [_P, _c.c_int32]),
+  'bcg_solver_get_trace': (_c.c_int, [_P, _c.c_int32, _P, _c.POINTER(_c.c_int32)]),
 }
 EXPORTED_SYMBOLS = sorted(_PROTOTYPES)
 
@@ -328,6 +330,19 @@ class NativeSolver(object):
 
   def set_profiling(self, on):
     check(lib().bcg_solver_set_profiling(self.handle, 1 if on else 0))
+
+  def set_trace(self, on):
+    check(lib().bcg_solver_set_trace(self.handle, 1 if on else 0))
+
+  def trace(self):
+    """(iters, 8) uint64 device timestamps (globaltimer ns) of the last build: grid arrived, direction
+    published, scan start, scan end (CTA 0 warp 0), then 4 control-warp milestones"""
+    n = ctypes.c_int32()
+    check(lib().bcg_solver_get_trace(self.handle, 0, None, ctypes.byref(n)))
+    out = np.zeros((n.value, 8), dtype=np.uint64)
+    if n.value:
+      check(lib().bcg_solver_get_trace(self.handle, n.value, _ptr(out), ctypes.byref(n)))
+    return out
 
   def timing(self):
     b, s = ctypes.c_float(), ctypes.c_float()

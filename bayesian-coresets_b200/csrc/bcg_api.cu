@@ -88,6 +88,9 @@ struct bcg_solver {
   bool use_loop;            // persistent cooperative kernel available for this shape
   LoopCtl* d_ctl;
   ScanCand* d_cta_cands;
+  int trace_on;
+  unsigned long long* d_trace;
+  int trace_cap, trace_n;
   int64_t* d_fout;
   unsigned char* mail;      // this rank's mailbox allocation
   int64_t mail_bytes;
@@ -498,7 +501,7 @@ static int choose_scan_config(bcg_solver* s) {
   const int nb = std::max(1, stage_bytes / batch_bytes);
   c.rps = nb * c.rb;
   c.wpb = std::max(1, std::min(11, env_int("BCG_SCAN_WARPS", 8)));   // loop kernel: <= 11 scan warps + 1 control warp
-  c.stages = std::max(1, env_int("BCG_SCAN_STAGES", 3));
+  c.stages = std::max(1, env_int("BCG_SCAN_STAGES", 2));
   c.evict_first = env_int("BCG_SCAN_EVICT_FIRST", 0);
   const size_t budget = (size_t)(200 * 1024);
   const size_t extra = 32 * sizeof(ScanCand) + 2 * (size_t)s->v->S * sizeof(double) + 128;   // loop kernel only
@@ -598,6 +601,9 @@ extern "C" int bcg_solver_create(bcg_ctx* ctx, bcg_vecs* v, int32_t alg, const d
   s->use_loop = false;
   s->d_ctl = nullptr;
   s->d_cta_cands = nullptr;
+  s->trace_on = 0;
+  s->d_trace = nullptr;
+  s->trace_cap = s->trace_n = 0;
   s->profiling = 0;
   s->build_ms = s->scan_ms = 0.f;
   s->scan_launches = s->step_launches = s->loop_launches = 0;
@@ -651,7 +657,7 @@ extern "C" int bcg_solver_destroy(bcg_solver* s) {
     for (int p = 0; p < h.world; ++p)
       if (p != h.rank && s->peer_ptrs[p]) cudaIpcCloseMemHandle(s->peer_ptrs[p]);
   void* bufs[] = {h.b, h.bn, h.xw, h.xw_new, h.xf, h.dir64, h.dir32, h.wrow, h.cands, h.act_idx, h.act_w,
-                  h.act_w_new, h.act_norm, h.act_rows, h.events, s->d_fout, s->d, s->mail, s->d_ctl, s->d_cta_cands};
+                  h.act_w_new, h.act_norm, h.act_rows, h.events, s->d_fout, s->d, s->mail, s->d_ctl, s->d_cta_cands, s->d_trace};
   for (void* p : bufs)
     if (p) cudaFree(p);
   for (cudaEvent_t e : s->scan_ev) cudaEventDestroy(e);
@@ -747,6 +753,19 @@ extern "C" int bcg_solver_build(bcg_solver* s, int32_t itrs, double tol, bcg_ite
     la.g.evict_first = s->sc.evict_first;
     la.itrs = itrs;
     la.wpb = s->sc.wpb;
+    la.trace = nullptr;
+    s->trace_n = 0;
+    if (s->trace_on) {
+      if (s->trace_cap < itrs) {
+        if (s->d_trace) CK(cudaFree(s->d_trace));
+        s->d_trace = nullptr;
+        CK(cudaMalloc(&s->d_trace, (size_t)itrs * 8 * sizeof(unsigned long long)));
+        s->trace_cap = itrs;
+      }
+      CK(cudaMemsetAsync(s->d_trace, 0, (size_t)itrs * 8 * sizeof(unsigned long long), st));
+      la.trace = s->d_trace;
+      s->trace_n = itrs;
+    }
     CK(cudaMemsetAsync(s->d_ctl, 0, sizeof(LoopCtl), st));
     CK(cudaEventRecord(s->ev0, st));
     CK(loop_launch(s->sc, la, st));
@@ -914,5 +933,21 @@ extern "C" int bcg_solver_timing(bcg_solver* s, float* build_ms, float* scan_ms,
 extern "C" int bcg_solver_set_profiling(bcg_solver* s, int32_t per_kernel_events) {
   if (!s) return fail(BCG_ERR_ARG, "null solver");
   s->profiling = per_kernel_events ? 1 : 0;
+  return BCG_OK;
+}
+
+extern "C" int bcg_solver_set_trace(bcg_solver* s, int32_t enable) {
+  if (!s) return fail(BCG_ERR_ARG, "null solver");
+  s->trace_on = enable ? 1 : 0;
+  return BCG_OK;
+}
+
+extern "C" int bcg_solver_get_trace(bcg_solver* s, int32_t cap_iters, uint64_t* out, int32_t* n_iters) {
+  if (!s || !n_iters) return fail(BCG_ERR_ARG, "null argument");
+  RET(use_device(s->ctx));
+  *n_iters = s->trace_n;
+  if (!out || s->trace_n == 0) return BCG_OK;
+  if (cap_iters < s->trace_n) return fail(BCG_ERR_ARG, "trace capacity too small");
+  CK(cudaMemcpy(out, s->d_trace, (size_t)s->trace_n * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   return BCG_OK;
 }

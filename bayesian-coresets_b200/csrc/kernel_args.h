@@ -40,6 +40,11 @@ struct LoopArgs {
   ScanGeom g;
   int32_t itrs;
   int32_t wpb;           // scan warps per CTA (blockDim.x = (wpb + 1) * 32)
+  // optional device timestamps (globaltimer ns), null when tracing is off:
+  //   trace[it*8 + 0] control: grid arrived      trace[it*8 + 1] control: next direction published
+  //   trace[it*8 + 2] CTA 0 warp 0: go observed   trace[it*8 + 3] CTA 0 warp 0: its scan finished
+  //   trace[it*8 + 4..7] control: candidates reduced / winning row fetched / line search done / committed
+  unsigned long long* trace;
 };
 
 // template selection + launch geometry, chosen on the host from the row length

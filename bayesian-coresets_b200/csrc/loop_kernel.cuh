@@ -104,18 +104,22 @@ __device__ __forceinline__ bool mail_exchange_warp(SolverState* st, int lane, ui
   }
   __threadfence_system();
   __syncwarp();
-  bool ok = true;
   if (lane < W) {
     MailHeader* h = reinterpret_cast<MailHeader*>(st->mail_peer[lane] + (int64_t)(par * W + me) * sb);
     st_release_sys_u64(&h->seq, seq);
-    const MailHeader* mine = reinterpret_cast<const MailHeader*>(st->mail_local + (int64_t)(par * W + lane) * sb);
-    const unsigned long long t0 = globaltimer_ns();
-    while (ld_acquire_sys_u64(&mine->seq) != seq) {
-      if (globaltimer_ns() - t0 > 10000000000ull) { ok = false; break; }
-      __nanosleep(64);
-    }
   }
-  ok = __all_sync(0xffffffffu, ok);
+  __syncwarp();
+  // warp-uniform wait: lane p watches peer p's slot in MY mailbox; bounded, a dead peer must not hang the GPU
+  const MailHeader* mine =
+      reinterpret_cast<const MailHeader*>(st->mail_local + (int64_t)(par * W + (lane < W ? lane : 0)) * sb);
+  const unsigned long long t0 = globaltimer_ns();
+  bool ok = true;
+  for (;;) {
+    const bool done = ld_acquire_sys_u64(&mine->seq) == seq;
+    if (__all_sync(0xffffffffu, done)) break;
+    if (__any_sync(0xffffffffu, globaltimer_ns() - t0 > 10000000000ull)) { ok = false; break; }
+    __nanosleep(64);
+  }
   if (!ok) return false;
   int win = -1; double best = -INFINITY; int64_t bidx = -1;
   for (int p = 0; p < W; ++p) {
@@ -141,29 +145,33 @@ __device__ __forceinline__ bool publish_direction(SolverState* st, const double 
                                                   const double* sbn, int lane, double n2, double bx, double e2,
                                                   double* cdirnrm_out) {
   const int S = st->S, ld = st->ld;
+  float* dir32 = st->dir32;
+  double* dir64 = st->dir64;
   if (st->alg == BCG_ALG_GIGA) {
     double nw = sqrt(n2);
     if (nw == 0.) nw = 1.;
-    const double bxw = bx / nw;
+    const double inw = 1. / nw;
+    const double bxw = bx * inw;
     double c2[1] = {0.};
 #pragma unroll
     for (int j = 0; j < J; ++j) {
       const int s = lane + 32 * j;
-      if (s < S) { const double cd = sbn[s] - bxw * (xw[j] / nw); c2[0] += cd * cd; }
+      if (s < S) { const double cd = sbn[s] - bxw * (xw[j] * inw); c2[0] += cd * cd; }
     }
     wsum<1>(c2);
     const double cn = sqrt(c2[0]);
     *cdirnrm_out = cn;
     if (cn < st->tol) return false;
+    const double icn = 1. / cn;
 #pragma unroll
     for (int j = 0; j < J; ++j) {
       const int s = lane + 32 * j;
       if (s < ld) {
-        const double x = (s < S) ? xw[j] / nw : 0.;
-        const double c = (s < S) ? (sbn[s] - bxw * x) / cn : 0.;
-        st->dir32[s] = (float)c;
-        st->dir32[ld + s] = (float)x;
-        if (s < S) { st->dir64[s] = c; st->dir64[S + s] = x; }
+        const double x = (s < S) ? xw[j] * inw : 0.;
+        const double c = (s < S) ? (sbn[s] - bxw * x) * icn : 0.;
+        dir32[s] = (float)c;
+        dir32[ld + s] = (float)x;
+        if (s < S) { dir64[s] = c; dir64[S + s] = x; }
       }
     }
   } else {
@@ -174,12 +182,50 @@ __device__ __forceinline__ bool publish_direction(SolverState* st, const double 
       const int s = lane + 32 * j;
       if (s < ld) {
         const double r = (s < S) ? (sb[s] - xw[j]) * inv : 0.;
-        st->dir32[s] = (float)r;
-        if (s < S) st->dir64[s] = r;
+        dir32[s] = (float)r;
+        if (s < S) dir64[s] = r;
       }
     }
   }
   return true;
+}
+
+// one pass over the per-CTA candidates: best and runner-up (score descending, row ascending)
+__device__ __forceinline__ void warp_top2(const ScanCand* c, int n, int lane, float* s1o, uint32_t* r1o, float* s2o,
+                                          uint32_t* r2o) {
+  float s1 = -INFINITY, s2 = -INFINITY;
+  uint32_t r1 = kNoRow, r2 = kNoRow;
+  constexpr int kPerLane = 12;                       // 2 * 148 CTAs / 32 lanes, rounded up; looped beyond that
+  for (int base = 0; base < n; base += 32 * kPerLane) {
+    unsigned long long raw[kPerLane];
+#pragma unroll
+    for (int q = 0; q < kPerLane; ++q) {             // all loads in flight together: one L2 round trip
+      const int i = base + lane + 32 * q;
+      raw[q] = (i < n) ? __ldcg(reinterpret_cast<const unsigned long long*>(c + i)) : 0xffffffff00000000ull;
+    }
+#pragma unroll
+    for (int q = 0; q < kPerLane; ++q) {
+      const float sc = __uint_as_float((unsigned int)(raw[q] & 0xffffffffull));
+      const uint32_t rw = (uint32_t)(raw[q] >> 32);
+      if (cand_better(sc, rw, s1, r1)) { s2 = s1; r2 = r1; s1 = sc; r1 = rw; }
+      else if (cand_better(sc, rw, s2, r2)) { s2 = sc; r2 = rw; }
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const float a1 = __shfl_xor_sync(0xffffffffu, s1, off);
+    const uint32_t b1 = __shfl_xor_sync(0xffffffffu, r1, off);
+    const float a2 = __shfl_xor_sync(0xffffffffu, s2, off);
+    const uint32_t b2 = __shfl_xor_sync(0xffffffffu, r2, off);
+    // merge two (best, runner-up) pairs; the same row never appears in both (rows are unique)
+    if (cand_better(a1, b1, s1, r1)) {
+      if (cand_better(s1, r1, a2, b2)) { s2 = s1; r2 = r1; } else { s2 = a2; r2 = b2; }
+      s1 = a1; r1 = b1;
+    } else if (cand_better(a1, b1, s2, r2)) {
+      s2 = a1; r2 = b1;
+    }
+  }
+  *s1o = s1; *r1o = r1; *s2o = s2; *r2o = r2;
 }
 
 template <int J>
@@ -190,6 +236,16 @@ __device__ void control_loop(const LoopArgs& a, double* sb, double* sbn) {
   const int S = st->S, ld = st->ld;
   const unsigned int G = gridDim.x;
   const bool giga = st->alg == BCG_ALG_GIGA;
+  const int world = st->world;
+  const int64_t row_offset = st->row_offset;
+  const double bnorm = st->bnorm, nsum = st->nsum;
+  const float* An = st->An;
+  const double* norms = st->norms;
+  int64_t* act_idx = st->act_idx;
+  double* act_w = st->act_w;
+  double* act_norm = st->act_norm;
+  float* act_rows = st->act_rows;
+  bcg_iter_event* events = st->events;
 
   double xw[J];
 #pragma unroll
@@ -207,7 +263,7 @@ __device__ void control_loop(const LoopArgs& a, double* sb, double* sbn) {
   double err = st->err;
   double sel_aux = 0.;
   int npos = 0;
-  for (int k = lane; k < nact; k += 32) npos += (st->act_w[k] > 0.) ? 1 : 0;
+  for (int k = lane; k < nact; k += 32) npos += (act_w[k] > 0.) ? 1 : 0;
   npos = __reduce_add_sync(0xffffffffu, npos);
 
   auto iterate_sums = [&](double& n2, double& bx, double& e2) {
@@ -222,17 +278,17 @@ __device__ void control_loop(const LoopArgs& a, double* sb, double* sbn) {
   };
   auto push = [&](int code, int64_t f, double e, double a0, double a1) {
     if (lane == 0) {
-      bcg_iter_event* ev = st->events + n_events;
+      bcg_iter_event* ev = events + n_events;
       ev->code = code; ev->nact = nact; ev->f = f; ev->error = e; ev->aux0 = a0; ev->aux1 = a1;
     }
+    __syncwarp();
     n_events += 1;
   };
+  // direction stores of all lanes -> __syncwarp -> release by lane 0 (cumulative over the warp's stores)
   auto publish = [&](unsigned int it_done, bool stop) {
-    __threadfence();
     __syncwarp();
     if (lane == 0) {
       if (stop) *reinterpret_cast<volatile unsigned int*>(&ctl->stop) = 1u;
-      __threadfence();
       st_release_gpu_u32(&ctl->go, it_done);
     }
     __syncwarp();
@@ -245,13 +301,8 @@ __device__ void control_loop(const LoopArgs& a, double* sb, double* sbn) {
 
   int it = 0;
   for (; it < a.itrs; ++it) {
-    // ---- a failed selection (cdirnrm < TOL) repeats identically: resolve it without scanning ----
-    // (the grid is still released every iteration so the barrier protocol stays uniform)
-    // wait for the grid
-    if (lane == 0) {
-      const unsigned int want = G * (unsigned int)(it + 1);
-      while (ld_acquire_gpu_u32(&ctl->arrive) < want) __nanosleep(40);
-    }
+    spin_until_ge_gpu_u32(&ctl->arrive, G * (unsigned int)(it + 1), 20);
+    if (a.trace && lane == 0) a.trace[(size_t)it * 8 + 0] = globaltimer_ns();
     __syncwarp();
 
     bool failed = false;
@@ -264,53 +315,62 @@ __device__ void control_loop(const LoopArgs& a, double* sb, double* sbn) {
     const bool nonempty = npos > 0;
 
     if (!sel_ok) {
+      // giga.py:28-29: the selection itself failed (the grid scanned a stale direction; ignored)
       failed = true; fcode = BCG_IT_FAIL_CDIR; fa0 = sel_aux;
     } else {
       // ---- winner: best fp32 candidate; near ties re-scored in float64 --------------------------
       const int nc = 2 * (int)G;
-      uint32_t chosen[kRescoreMax];
-      float top; uint32_t lrow;
-      warp_pick(a.cta_cands, nc, chosen, 0, lane, &top, &lrow);
-      int nch = 0;
-      if (lrow != kNoRow) {
+      float top, second; uint32_t lrow, row2;
+      warp_top2(a.cta_cands, nc, lane, &top, &lrow, &second, &row2);
+      lscore = (double)top;
+      if (a.trace && lane == 0) a.trace[(size_t)it * 8 + 4] = globaltimer_ns();
+      __syncwarp();
+      const float thr = top - (2e-5f + 1e-5f * fabsf(top));
+      const bool near_tie = (lrow != kNoRow) && (row2 != kNoRow) && (second >= thr);
+      if (near_tie || (world > 1 && lrow != kNoRow)) {
+        // rare path: gather up to kRescoreMax candidates within the threshold, re-score in float64
+        uint32_t chosen[kRescoreMax];
+        int nch = 0;
         chosen[nch++] = lrow;
-        const float thr = top - (2e-5f + 1e-5f * fabsf(top));
-        while (nch < kRescoreMax) {
+        while (near_tie && nch < kRescoreMax) {
           float s2; uint32_t r2;
           warp_pick(a.cta_cands, nc, chosen, nch, lane, &s2, &r2);
           if (r2 == kNoRow || !(s2 >= thr)) break;
           chosen[nch++] = r2;
         }
-      }
-      lscore = (double)top;
-      if (nch > 1 || (st->world > 1 && nch == 1)) {
         uint32_t brow = kNoRow; double best = -INFINITY;
         for (int r = 0; r < nch; ++r) {
-          const double sc = row_score_warp<J>(st, st->An + (size_t)chosen[r] * ld, lane);
+          const double sc = row_score_warp<J>(st, An + (size_t)chosen[r] * ld, lane);
           if (brow == kNoRow || sc > best || (sc == best && chosen[r] < brow)) { best = sc; brow = chosen[r]; }
         }
         lrow = brow; lscore = best;
       }
-      if (st->world > 1) {
+      if (world > 1) {
         if (!mail_exchange_warp<J>(st, lane, lrow, lscore, &f, &nf_stored, &frow)) {
           if (lane == 0) { st->comm_error = 1; }
+          __syncwarp();
           halted = 1;
           break;
         }
       } else if (lrow == kNoRow) {               // no comparable score at all (non-finite matrix)
         if (lane == 0) { st->comm_error = 2; }
+        __syncwarp();
         halted = 1;
         break;
       } else {
-        f = st->row_offset + (int64_t)lrow;
-        nf_stored = st->norms[lrow];
-        frow = st->An + (size_t)lrow * ld;
+        f = row_offset + (int64_t)lrow;
+        nf_stored = norms[lrow];
+        frow = An + (size_t)lrow * ld;
       }
 #pragma unroll
       for (int j = 0; j < J; ++j) {
         const int s = lane + 32 * j;
-        if (s < S) xf[j] = nf_stored * (double)__ldcg(frow + s);
+        if (s < S) xf[j] = (double)__ldcg(frow + s);
       }
+#pragma unroll
+      for (int j = 0; j < J; ++j) xf[j] *= nf_stored;
+      if (a.trace && lane == 0) a.trace[(size_t)it * 8 + 5] = globaltimer_ns() + (unsigned long long)(xf[0] == 12345.678);
+      __syncwarp();
 
       // ---- line search ---------------------------------------------------------------------------
       if (giga) {
@@ -340,16 +400,16 @@ __device__ void control_loop(const LoopArgs& a, double* sb, double* sbn) {
           }
           wsum<2>(u);
           const double nx = sqrt(u[0]);
-          const double scale = st->bnorm / nx * (u[1] / nx);
+          const double scale = bnorm / nx * (u[1] / nx);
           alpha = ca * scale;
           beta = cb * scale;
         }
       } else {
         if (!nonempty) {
           alpha = 0.;
-          beta = st->nsum / nf_stored;
+          beta = nsum / nf_stored;
         } else {
-          const double r = st->nsum / nf_stored;
+          const double r = nsum / nf_stored;
           double v[2] = {0., 0.};
 #pragma unroll
           for (int j = 0; j < J; ++j) {
@@ -368,18 +428,25 @@ __device__ void control_loop(const LoopArgs& a, double* sb, double* sbn) {
     }
 
     // ---- apply: w <- alpha w ; w[f] <- max(0, w[f] + beta) ; A w incrementally ---------------------
-    int slot = -1;
-    double wf_new = 0., delta = 0.;
+    // A w' = alpha A w + delta a_f with delta = w_f' - alpha w_f.  When alpha, beta >= 0 the clamp
+    // cannot engage and delta = beta, so the slot search stays off the critical path.
+    if (a.trace && lane == 0) a.trace[(size_t)it * 8 + 6] = globaltimer_ns() + (unsigned long long)(alpha == 12345.678);
+    __syncwarp();
+    int slot = -2;                               // -2: not searched yet
+    double wf_new = 0., delta = beta;
     double n2n = 0., bxn = 0., e2n = 0.;
-    if (!failed) {
+    auto find_slot = [&]() {
       int sl = 0x7fffffff;
       for (int k = lane; k < nact; k += 32)
-        if (st->act_idx[k] == f && k < sl) sl = k;
+        if (act_idx[k] == f && k < sl) sl = k;
       sl = __reduce_min_sync(0xffffffffu, sl);
       slot = (sl == 0x7fffffff) ? -1 : sl;
-      const double wf_old = slot >= 0 ? st->act_w[slot] : 0.;
+      const double wf_old = slot >= 0 ? act_w[slot] : 0.;
       wf_new = fmax(0., alpha * wf_old + beta);
-      delta = wf_new - alpha * wf_old;
+      return wf_new - alpha * wf_old;
+    };
+    if (!failed) {
+      if (!(alpha >= 0. && beta >= 0.)) delta = find_slot();
       double v[3] = {0., 0., 0.};
 #pragma unroll
       for (int j = 0; j < J; ++j) {
@@ -419,23 +486,29 @@ __device__ void control_loop(const LoopArgs& a, double* sb, double* sbn) {
     n2 = n2n; bx = bxn; e2 = e2n;
     if (nonempty) retried = 0;                  // snnls.py:62
     const bool last = (it + 1 == a.itrs);
+    if (a.trace && lane == 0) a.trace[(size_t)it * 8 + 7] = globaltimer_ns() + (unsigned long long)(err == 12345.678);
+    __syncwarp();
     if (!last) {
       sel_ok = publish_direction<J>(st, xw, sb, sbn, lane, n2, bx, e2, &sel_aux);
       publish((unsigned int)(it + 2), false);
     }
+    if (a.trace && lane == 0) a.trace[(size_t)it * 8 + 1] = globaltimer_ns();
+    __syncwarp();
 
     // ---- bookkeeping (overlaps the next scan) --------------------------------------------------
+    if (slot == -2) (void)find_slot();
     int np = 0;
     for (int k = lane; k < nact; k += 32) {
-      double wk = alpha * st->act_w[k];
+      double wk = alpha * act_w[k];
       if (k == slot) wk = wf_new;
-      st->act_w[k] = wk;
+      act_w[k] = wk;
       np += (wk > 0.) ? 1 : 0;
     }
     if (slot < 0) {
       slot = nact;
-      for (int s = lane; s < ld; s += 32) st->act_rows[(size_t)slot * ld + s] = __ldcg(frow + s);
-      if (lane == 0) { st->act_idx[slot] = f; st->act_norm[slot] = nf_stored; st->act_w[slot] = wf_new; }
+      for (int s = lane; s < ld; s += 32) act_rows[(size_t)slot * ld + s] = __ldcg(frow + s);
+      if (lane == 0) { act_idx[slot] = f; act_norm[slot] = nf_stored; act_w[slot] = wf_new; }
+      __syncwarp();
       np += (lane == 0 && wf_new > 0.) ? 1 : 0;
       nact += 1;
     }
@@ -449,9 +522,9 @@ __device__ void control_loop(const LoopArgs& a, double* sb, double* sbn) {
 #pragma unroll
       for (int j = 0; j < J; ++j) xr[j] = 0.;
       for (int k = 0; k < nact; ++k) {
-        const double c = st->act_w[k] * st->act_norm[k];
+        const double c = act_w[k] * act_norm[k];
         if (c == 0.) continue;
-        const float* row = st->act_rows + (size_t)k * ld;
+        const float* row = act_rows + (size_t)k * ld;
 #pragma unroll
         for (int j = 0; j < J; ++j) {
           const int s = lane + 32 * j;
@@ -528,31 +601,34 @@ __global__ void __launch_bounds__(384, 1) greedy_loop_kernel(const LoopArgs a) {
   // Ring bookkeeping (all incremental).  Chunks are issued in consumption order, iteration after
   // iteration, so the tile stream runs ahead ACROSS iterations: the slot freed by a consumed chunk
   // is refilled with the chunk `stages` visits later, which may belong to the next iteration.
+  // (all of it is warp-uniform: every lane tracks the same counters, the leader lane issues through
+  // PTX predicates -- no divergent branch anywhere in the scan warps)
+  const bool leader = lane == 0;
   int issue_slot = 0;
   int64_t issue_k = 0;         // chunk (within the iteration) of the next issue
   int issue_it = 0;            // iteration it belongs to
-  int64_t outstanding = 0;     // issued, not yet consumed
-  auto issue_next = [&]() {    // lane 0 only
-    if (issue_it >= a.itrs || n_my == 0) return;
-    const int64_t row0 = (gw + issue_k * GW) * q.rps;
-    const int64_t left = q.n_rows - row0;
-    const uint32_t nr = (uint32_t)(left < q.rps ? left : q.rps);
-    tma_load_rows(&bars[issue_slot], wbuf + (size_t)issue_slot * stage_floats, q.An + (size_t)row0 * q.ld,
-                  nr * (uint32_t)q.ld * 4u, policy);
-    if (++issue_slot == q.stages) issue_slot = 0;
-    if (++issue_k == n_my) { issue_k = 0; ++issue_it; }
-    ++outstanding;
+  int outstanding = 0;         // issued, not yet consumed
+  auto issue_next = [&]() {
+    if (issue_it < a.itrs && n_my > 0) {
+      const int64_t row0 = (gw + issue_k * GW) * q.rps;
+      const int64_t left = q.n_rows - row0;
+      const uint32_t nr = (uint32_t)(left < q.rps ? left : q.rps);
+      tma_load_rows(&bars[issue_slot], wbuf + (size_t)issue_slot * stage_floats, q.An + (size_t)row0 * q.ld,
+                    nr * (uint32_t)q.ld * 4u, policy, leader);
+      if (++issue_slot == q.stages) issue_slot = 0;
+      if (++issue_k == n_my) { issue_k = 0; ++issue_it; }
+      ++outstanding;
+    }
   };
-  if (lane == 0)
-    for (int s = 0; s < q.stages; ++s) issue_next();   // tiles do not depend on the direction
+  for (int s = 0; s < q.stages; ++s) issue_next();   // tiles do not depend on the direction
 
   int slot = 0;
   uint32_t parity = 0;
   for (int it = 0; it < a.itrs; ++it) {
-    if (lane == 0)
-      while (ld_acquire_gpu_u32(&ctl->go) < (unsigned int)(it + 1)) __nanosleep(32);
+    spin_until_ge_gpu_u32(&ctl->go, (unsigned int)(it + 1), 32);
+    if (__shfl_sync(0xffffffffu, *reinterpret_cast<volatile unsigned int*>(&ctl->stop), 0)) break;
+    if (a.trace && gw == 0 && lane == 0) a.trace[(size_t)it * 8 + 2] = globaltimer_ns();
     __syncwarp();
-    if (*reinterpret_cast<volatile unsigned int*>(&ctl->stop)) break;
 
     float4 d0[CH];
     float4 d1[CH];
@@ -568,12 +644,15 @@ __global__ void __launch_bounds__(384, 1) greedy_loop_kernel(const LoopArgs a) {
       const float* tile = wbuf + (size_t)slot * stage_floats;
       for (int b0 = 0; b0 < nr; b0 += Core::RB)
         Core::batch(tile + (size_t)b0 * q.ld, q.ld, nchunk, g, grp, nr - b0, (uint32_t)(row0 + b0), d0, d1, best, brow);
-      __syncwarp();
-      if (lane == 0) { --outstanding; issue_next(); }
+      __syncwarp();   // every lane's shared-memory reads of this stage are complete
+      --outstanding;
+      issue_next();
       row0 += row_step;
       if (++slot == q.stages) { slot = 0; parity ^= 1u; }
     }
 
+    if (a.trace && gw == 0 && lane == 0) a.trace[(size_t)it * 8 + 3] = globaltimer_ns();
+    __syncwarp();
     Core::warp_merge(best, brow);
     if (lane == 0) { cta_c[warp].score = best; cta_c[warp].row = brow; }
     named_bar_sync(1, wpb * 32);
@@ -598,8 +677,7 @@ __global__ void __launch_bounds__(384, 1) greedy_loop_kernel(const LoopArgs a) {
   }
   // drain tiles that were prefetched for an iteration that will not run (early stop)
   {
-    long long left = __shfl_sync(0xffffffffu, (long long)outstanding, 0);
-    for (; left > 0; --left) {
+    for (int left = outstanding; left > 0; --left) {
       mbar_wait(&bars[slot], parity);
       if (++slot == q.stages) { slot = 0; parity ^= 1u; }
     }

@@ -50,15 +50,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   } while (!done);
 }
 
-// arm the stage barrier with the byte count, then start the bulk copy global -> shared (UBLKCP)
+// Arm the stage barrier with the byte count, then start the bulk copy global -> shared (UBLKCP).
+// Called by ALL lanes with identical arguments; only the lane with `leader` set issues, through
+// PTX predicates rather than a branch.  (A lane-0 `if` around this, with loop-carried lane-0
+// state, left lane 0 permanently split from lanes 1-31 in the persistent kernel: every
+// instruction of the scan executed twice and the shuffles took the divergent slow path --
+// profiles/r01_v2_loop_divergence.md.)
 __device__ __forceinline__ void tma_load_rows(uint64_t* bar, float* dst, const float* src, uint32_t bytes,
-                                              uint64_t policy) {
+                                              uint64_t policy, bool leader) {
   const uint32_t b = smem_u32(bar);
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
   asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-          smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(b), "l"(policy)
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.u32 p, %5, 0;\n\t"
+      "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %2;\n\t"
+      "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n\t"
+      "}"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(b), "l"(policy), "r"((uint32_t)leader)
       : "memory");
 }
 

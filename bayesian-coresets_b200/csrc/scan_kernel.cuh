@@ -42,13 +42,14 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const ScanArgs a) {
   const int64_t row_step = GW * q.rps;
   // slot s of the ring always holds chunk k with k % stages == s, so a refill goes into the slot
   // that was just consumed; all ring bookkeeping is incremental (no 64-bit div/mod in the loop)
-  auto issue = [&](int slot, int64_t row0) {
+  const bool leader = lane == 0;
+  auto issue = [&](int slot, int64_t row0) {        // executed by all lanes, issued by the leader only
     const int64_t left = q.n_rows - row0;
     const uint32_t nr = (uint32_t)(left < q.rps ? left : q.rps);
     tma_load_rows(&bars[slot], wbuf + (size_t)slot * stage_floats, q.An + (size_t)row0 * q.ld, nr * (uint32_t)q.ld * 4u,
-                  policy);
+                  policy, leader);
   };
-  if (lane == 0) {
+  {
     const int pre = (int)(n_my < q.stages ? n_my : q.stages);
     for (int k = 0; k < pre; ++k) issue(k, (gw + k * GW) * q.rps);
   }
@@ -67,7 +68,7 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const ScanArgs a) {
     for (int b0 = 0; b0 < nr; b0 += Core::RB)
       Core::batch(tile + (size_t)b0 * q.ld, q.ld, nchunk, g, grp, nr - b0, (uint32_t)(row0 + b0), d0, d1, best, brow);
     __syncwarp();   // every lane's shared-memory reads of this stage are complete
-    if (lane == 0 && k + q.stages < n_my) issue(slot, row0 + ahead);
+    if (k + q.stages < n_my) issue(slot, row0 + ahead);
     row0 += row_step;
     if (++slot == q.stages) { slot = 0; parity ^= 1u; }
   }

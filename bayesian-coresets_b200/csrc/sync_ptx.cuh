@@ -22,6 +22,16 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// warp-uniform spin: every lane loads (one coalesced request), lane 0's value decides for all, so the
+// warp never splits while waiting
+__device__ __forceinline__ unsigned int spin_until_ge_gpu_u32(const unsigned int* p, unsigned int want, unsigned ns) {
+  unsigned int v = __shfl_sync(0xffffffffu, ld_acquire_gpu_u32(p), 0);
+  while (v < want) {
+    __nanosleep(ns);
+    v = __shfl_sync(0xffffffffu, ld_acquire_gpu_u32(p), 0);
+  }
+  return v;
+}
 __device__ __forceinline__ void st_release_gpu_u32(unsigned int* p, unsigned int v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }

@@ -138,6 +138,11 @@ int  bcg_solver_reset(bcg_solver* s);
 int  bcg_solver_timing(bcg_solver* s, float* build_ms, float* scan_ms, int32_t* scan_launches,
                        int32_t* step_launches);
 int  bcg_solver_set_profiling(bcg_solver* s, int32_t per_kernel_events);
+/* diagnostics of the persistent loop kernel: 8 device timestamps (globaltimer ns) per iteration of the
+ * last bcg_solver_build -- grid arrived, next direction published, scan started, scan finished (CTA 0),
+ * then 4 control-warp milestones (candidates reduced, row fetched, line search done, committed) */
+int  bcg_solver_set_trace(bcg_solver* s, int32_t enable);
+int  bcg_solver_get_trace(bcg_solver* s, int32_t cap_iters, uint64_t* out, int32_t* n_iters);
 
 #ifdef __cplusplus
 }
