@@ -1,0 +1,72 @@
+"""Multi-GPU parity check, launched under torchrun (one rank per GPU):
+   python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_check.py
+Every rank holds a contiguous shard of the rows; the result (selection sequence, weights, error, points)
+must equal the single-process oracle on the full data, on every rank."""
+import os
+import sys
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'bayesian-coresets_b200'))
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+
+def main():
+  import torch
+  import torch.distributed as dist
+  local_rank = int(os.environ['LOCAL_RANK'])
+  torch.cuda.set_device(local_rank)
+  dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+  import bayesiancoresets_b200 as bc
+  from oracle import greedy, models
+  from conftest import lr_problem
+  comm = bc.comm.TorchComm()
+  rank, world = comm.rank, comm.world
+  algs = {'giga': bc.snnls.GIGA, 'fw': bc.snnls.FrankWolfe, 'omp': bc.snnls.OrthoPursuit}
+
+  def check(N, d, S, itrs, alg, shard=None):
+    Z, theta = lr_problem(21, N, d, S)
+    vecs = models.project(models.lr_loglik, Z, theta)
+    o = greedy.ORACLES[alg](vecs.T, vecs.sum(axis=0))
+    oev = o.build(itrs)
+    lo, hi = shard(rank, world) if shard else bc.comm.even_shard(N, rank, world)
+    prj = bc.LogisticRegressionProjector(lambda n, w, p: theta, S)
+    cs = bc.HilbertCoreset(Z[lo:hi], prj, snnls=algs[alg], comm=comm)
+    cs.build(itrs)
+    ev = cs.snnls.last_events
+    nsel = len(oev) if alg != 'omp' else min(len(oev), int(0.6*S))
+    got, ref = [e.f for e in ev][:nsel], [e[1] for e in oev][:nsel]
+    assert got == ref, (alg, rank, got[:10], ref[:10])
+    if alg != 'omp':
+      w = cs.snnls.weights()
+      assert np.max(np.abs(w - o.w)) <= 1e-5*np.abs(o.w).max(), (alg, rank)
+      norms = np.sqrt((vecs**2).sum(axis=1))
+      assert abs(cs.error() - o.error()) <= 1e-5*o.error() + 2.**-24*np.abs(o.w).dot(norms)
+      wts, pts, idcs = cs.get()
+      assert np.array_equal(idcs, np.flatnonzero(o.w > 0)) and np.array_equal(pts, Z[idcs])
+    comm.barrier()
+    if rank == 0:
+      print('mgpu %s N=%d S=%d world=%d: %d iterations identical to the oracle' % (alg, N, S, world, nsel), flush=True)
+
+  check(20000, 6, 128, 40, 'giga')
+  check(20000, 6, 128, 40, 'fw')
+  check(5000, 5, 64, 25, 'omp')
+  check(30011, 8, 512, 30, 'giga')
+  check(4099, 4, 50, 30, 'giga')
+  # very uneven shards: rank 0 owns 3 rows, the last rank the rest
+  def lopsided(r, w):
+    N = 9000
+    cuts = [0] + [3 + i for i in range(w - 1)] + [N]
+    return cuts[r], cuts[r + 1]
+  check(9000, 6, 256, 30, 'giga', shard=lopsided)
+  os.environ['BCG_ENGINE'] = '1'          # launch-per-iteration engine with the block-wide exchange
+  check(20000, 6, 128, 30, 'giga')
+  if rank == 0:
+    print('MGPU OK', flush=True)
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+  main()
