@@ -13,6 +13,6 @@ from . import util
 from . import snnls
 from .projector import (Projector, BlackBoxProjector, LogisticRegressionProjector, GaussianProjector,
                         PoissonProjector)
-from .coreset import Coreset, HilbertCoreset
-from ._native import DeviceVecs, Context, BcgError
+from .coreset import Coreset, HilbertCoreset, SparseVICoreset, BatchPSVICoreset
+from ._native import DeviceVecs, Dataset, Context, BcgError
 from . import comm

@@ -16,6 +16,7 @@ ERR_NAMES = {1: 'BCG_ERR_CUDA', 2: 'BCG_ERR_ARG', 3: 'BCG_ERR_NO_DEVICE', 4: 'BC
              6: 'BCG_ERR_COMM', 7: 'BCG_ERR_UNSUPPORTED'}
 ERR_ZERO_B = 4
 ALG_GIGA, ALG_FW, ALG_OMP = 0, 1, 2
+MODEL_LR, MODEL_GAUSSIAN, MODEL_POISSON = 0, 1, 2
 IT_OK, IT_FAIL_CDIR, IT_FAIL_GEODESIC, IT_FAIL_GAMMA, IT_FAIL_MONOTONE = 0, 1, 2, 3, 4
 
 
@@ -48,6 +49,9 @@ _PROTOTYPES = {
   'bcg_vecs_project_lr': (_c.c_int, [_P, _P, _c.c_int64, _c.c_int32, _P, _c.c_int32, _PP]),
   'bcg_vecs_project_gaussian': (_c.c_int, [_P, _P, _c.c_int64, _c.c_int32, _P, _c.c_int32, _P, _PP]),
   'bcg_vecs_project_poisson': (_c.c_int, [_P, _P, _c.c_int64, _c.c_int32, _P, _c.c_int32, _PP]),
+  'bcg_dataset_create': (_c.c_int, [_P, _P, _c.c_int64, _c.c_int32, _PP]),
+  'bcg_dataset_destroy': (_c.c_int, [_P]),
+  'bcg_dataset_project': (_c.c_int, [_P, _c.c_int32, _c.c_int32, _P, _c.c_int32, _P, _PP, _P, _P]),
   'bcg_vecs_shape': (_c.c_int, [_P, _c.POINTER(_c.c_int64), _c.POINTER(_c.c_int32), _c.POINTER(_c.c_int32)]),
   'bcg_vecs_colsum': (_c.c_int, [_P, _P]),
   'bcg_vecs_norm_sum': (_c.c_int, [_P, _c.POINTER(_c.c_double)]),
@@ -61,6 +65,7 @@ _PROTOTYPES = {
   'bcg_solver_comm_connect': (_c.c_int, [_P, _c.c_int32, _c.c_int32, _P]),
   'bcg_solver_build': (_c.c_int, [_P, _c.c_int32, _c.c_double, _c.POINTER(IterEvent), _c.POINTER(_c.c_int32)]),
   'bcg_solver_omp_select': (_c.c_int, [_P, _c.POINTER(_c.c_int64)]),
+  'bcg_solver_probe_argmax': (_c.c_int, [_P, _P, _c.POINTER(_c.c_int64), _c.POINTER(_c.c_double)]),
   'bcg_solver_error': (_c.c_int, [_P, _c.POINTER(_c.c_double)]),
   'bcg_solver_size': (_c.c_int, [_P, _c.POINTER(_c.c_int64), _c.POINTER(_c.c_int64)]),
   'bcg_solver_halted': (_c.c_int, [_P, _c.POINTER(_c.c_int32)]),
@@ -141,6 +146,37 @@ class Context(object):
     check(lib().bcg_ctx_flush_l2(self.handle, int(nbytes)))
 
 
+class Dataset(object):
+  """bcg_dataset: the (n, d) data uploaded once and projected many times."""
+  def __init__(self, Z, ctx=None):
+    self.ctx = ctx or Context.default()
+    Z = _f64(np.atleast_2d(Z))
+    self.shape = Z.shape
+    self.handle = ctypes.c_void_p()
+    check(lib().bcg_dataset_create(self.ctx.handle, _ptr(Z), Z.shape[0], Z.shape[1], ctypes.byref(self.handle)))
+
+  def project(self, model, theta, Siginv=None, vecs=False, rows=False, colsum=False):
+    """evaluate + row-centre on the device; returns (DeviceVecs | None, ndarray rows | None, ndarray colsum | None)"""
+    theta = _f64(np.atleast_2d(theta))
+    S, d = theta.shape
+    si = None if Siginv is None else _f64(Siginv)
+    hv = ctypes.c_void_p()
+    out_rows = np.empty((self.shape[0], S)) if rows else None
+    out_cs = np.empty(S) if colsum else None
+    check(lib().bcg_dataset_project(self.handle, model, d, _ptr(theta), S, None if si is None else _ptr(si),
+                                    ctypes.byref(hv) if vecs else None, None if out_rows is None else _ptr(out_rows),
+                                    None if out_cs is None else _ptr(out_cs)))
+    return (DeviceVecs(self.ctx, hv) if vecs else None), out_rows, out_cs
+
+  def __del__(self):
+    try:
+      if self.handle:
+        lib().bcg_dataset_destroy(self.handle)
+        self.handle = None
+    except Exception:
+      pass
+
+
 class DeviceVecs(object):
   """bcg_vecs: device-resident (n, S) projection -- unit float32 rows + float64 norms.
 
@@ -174,34 +210,15 @@ class DeviceVecs(object):
 
   @classmethod
   def project_lr(cls, Z, theta, ctx=None):
-    ctx = ctx or Context.default()
-    Z, theta = _f64(np.atleast_2d(Z)), _f64(np.atleast_2d(theta))
-    if Z.shape[1] != theta.shape[1]:
-      raise ValueError('Z and theta disagree on the feature dimension')
-    h = ctypes.c_void_p()
-    check(lib().bcg_vecs_project_lr(ctx.handle, _ptr(Z), Z.shape[0], Z.shape[1], _ptr(theta), theta.shape[0],
-                                    ctypes.byref(h)))
-    return cls(ctx, h)
+    return Dataset(Z, ctx).project(MODEL_LR, theta, vecs=True)[0]
 
   @classmethod
   def project_gaussian(cls, x, theta, Siginv, ctx=None):
-    ctx = ctx or Context.default()
-    x, theta, Siginv = _f64(np.atleast_2d(x)), _f64(np.atleast_2d(theta)), _f64(Siginv)
-    h = ctypes.c_void_p()
-    check(lib().bcg_vecs_project_gaussian(ctx.handle, _ptr(x), x.shape[0], x.shape[1], _ptr(theta), theta.shape[0],
-                                          _ptr(Siginv), ctypes.byref(h)))
-    return cls(ctx, h)
+    return Dataset(x, ctx).project(MODEL_GAUSSIAN, theta, Siginv, vecs=True)[0]
 
   @classmethod
   def project_poisson(cls, Z, theta, ctx=None):
-    ctx = ctx or Context.default()
-    Z, theta = _f64(np.atleast_2d(Z)), _f64(np.atleast_2d(theta))
-    if Z.shape[1] != theta.shape[1] + 1:
-      raise ValueError('Z must be [x, y] with one more column than theta')
-    h = ctypes.c_void_p()
-    check(lib().bcg_vecs_project_poisson(ctx.handle, _ptr(Z), Z.shape[0], theta.shape[1], _ptr(theta), theta.shape[0],
-                                         ctypes.byref(h)))
-    return cls(ctx, h)
+    return Dataset(Z, ctx).project(MODEL_POISSON, theta, vecs=True)[0]
 
   # ---- ndarray-like surface -----------------------------------------------------------------
   @property
@@ -238,12 +255,19 @@ class DeviceVecs(object):
     check(lib().bcg_vecs_rows_f64(self.handle, row0, nrows, _ptr(out)))
     return out
 
+  def argmax_dot(self, direction):
+    """(row, value) of max_n <a_n/||a_n||, direction> over the rows (float64 re-scored, ties -> lowest row)"""
+    if getattr(self, '_probe', None) is None:
+      self._probe = NativeSolver(self, ALG_FW, np.ones(self.shape[1]), 0., hold=False)
+    return self._probe.probe_argmax(direction)
+
   def __array__(self, dtype=None, copy=None):
     a = self.to_numpy()
     return a if dtype is None else a.astype(dtype)
 
   def __del__(self):
     try:
+      self._probe = None
       if self.handle:
         lib().bcg_vecs_destroy(self.handle)
         self.handle = None
@@ -265,8 +289,9 @@ class DeviceVecsT(object):
 
 class NativeSolver(object):
   """bcg_solver"""
-  def __init__(self, vecs, alg, b, norm_sum, row_offset=0, n_global=None):
-    self.vecs = vecs           # keep the matrix alive
+  def __init__(self, vecs, alg, b, norm_sum, row_offset=0, n_global=None, hold=True):
+    self.vecs = vecs if hold else None     # keep the matrix alive (not for a probe owned BY the matrix: no cycle)
+    self._S = vecs.shape[1]
     b = _f64(b)
     if b.shape != (vecs.shape[1],):
       raise ValueError('b must have shape (S,)')
@@ -296,6 +321,12 @@ class NativeSolver(object):
     check(lib().bcg_solver_omp_select(self.handle, ctypes.byref(f)))
     return f.value
 
+  def probe_argmax(self, direction):
+    d = _f64(direction)
+    f, sc = ctypes.c_int64(), ctypes.c_double()
+    check(lib().bcg_solver_probe_argmax(self.handle, _ptr(d), ctypes.byref(f), ctypes.byref(sc)))
+    return f.value, sc.value
+
   def error(self):
     v = ctypes.c_double()
     check(lib().bcg_solver_error(self.handle, ctypes.byref(v)))
@@ -316,7 +347,7 @@ class NativeSolver(object):
     return idx, w
 
   def active_rows(self, first, count):
-    out = np.empty((count, self.vecs.shape[1]))
+    out = np.empty((count, self._S))
     if count:
       check(lib().bcg_solver_active_rows(self.handle, first, count, _ptr(out)))
     return out

@@ -1,0 +1,61 @@
+"""BatchPSVICoreset on the device (reference: coreset/bpsvi.py:6-63).
+
+One gradient evaluation needs project(data).sum(axis=0) over all N data points -- computed by the
+column-sum-only projection on the device, the N x S matrix is never written -- plus the
+projection and (K, S, d) gradients of the K pseudo-points, which are K-sized host algebra."""
+import numpy as np
+from ..util import nn_opt
+from .coreset import Coreset
+
+
+class BatchPSVICoreset(Coreset):
+  def __init__(self, data, ll_projector, opt_itrs, n_subsample_opt=None, step_sched=lambda i: 1./(1.+i), **kw):
+    self.data = data
+    self.ll_projector = ll_projector
+    self.opt_itrs = opt_itrs
+    self.n_subsample_opt = None if n_subsample_opt is None else min(data.shape[0], n_subsample_opt)
+    self.step_sched = step_sched
+    super().__init__(**kw)
+
+  def _build(self, sz):
+    init_idcs = np.random.choice(self.data.shape[0], size=sz, replace=False)     # bpsvi.py:17
+    self.pts = np.array(self.data[init_idcs], dtype=np.float64)
+    self.wts = self.data.shape[0]/sz*np.ones(sz)
+    self.idcs = -1*np.ones(sz)
+    self._optimize()
+
+  def _data_sum(self, w, p):
+    """bpsvi.py:24-35: refresh the samples, column sums of the (sub)sampled tangent space"""
+    prj = self.ll_projector
+    prj.update(w, p)
+    if self.n_subsample_opt is None:
+      rows, scaling, cache = self.data, 1., True
+    else:
+      sub = np.random.randint(self.data.shape[0], size=self.n_subsample_opt)
+      rows, scaling, cache = self.data[sub], self.data.shape[0]/self.n_subsample_opt, False
+    if hasattr(prj, 'project_sum'):
+      return scaling*prj.project_sum(rows, cache=cache)
+    return scaling*prj.project(rows).sum(axis=0)
+
+  def gradient(self, x, sz, d):
+    """bpsvi.py:46-55 -- one gradient evaluation (the "grad step" of BASELINE config 5)"""
+    w = x[:sz]
+    p = x[sz:].reshape((sz, d))
+    total = self._data_sum(w, p)
+    corevecs, pgrads = self.ll_projector.project(p, grad=True)
+    resid = total - w.dot(corevecs)
+    wgrad = -corevecs.dot(resid)/corevecs.shape[1]
+    ugrad = -(w[:, np.newaxis, np.newaxis]*pgrads*resid[np.newaxis, :, np.newaxis]).sum(axis=1)/corevecs.shape[1]
+    return np.hstack((wgrad, ugrad.reshape(sz*d)))
+
+  def _optimize(self):
+    sz = self.wts.shape[0]
+    d = self.pts.shape[1]
+    x0 = np.hstack((self.wts, self.pts.reshape(sz*d)))
+    xf = nn_opt(x0, lambda x: self.gradient(x, sz, d), nn_idcs=np.arange(sz), opt_itrs=self.opt_itrs,
+                step_sched=self.step_sched)
+    self.wts = xf[:sz]
+    self.pts = xf[sz:].reshape((sz, d))
+
+  def error(self):
+    return 0.   # as the reference (bpsvi.py:62-63)

@@ -1,0 +1,89 @@
+"""SparseVICoreset on the device (reference: coreset/sparsevi.py:7-79).
+
+Every build iteration re-samples the projector at the current coreset and re-projects ALL data
+(1 + opt_itrs) times.  Here the data are uploaded once; the selection pass materialises the
+N x S matrix on the device and takes the correlation arg-max with the scan kernel
+(sparsevi.py:51,56-57), and the opt_itrs gradient passes only need project(data).sum(axis=0)
+(sparsevi.py:71-72), which the column-sum-only projection computes without ever writing the
+N x S matrix.  The K core points are projected in float64 and read back (K x S, tiny).
+Host-side pieces (sampler, nn_opt, the K-sized algebra) stay NumPy, in the reference's call
+order, so seeded runs consume the global RNG identically."""
+import numpy as np
+from ..util import nn_opt
+from .. import _native as nat
+from .coreset import Coreset
+
+
+class SparseVICoreset(Coreset):
+  def __init__(self, data, ll_projector, n_subsample_select=None, n_subsample_opt=None, opt_itrs=100,
+               step_sched=lambda i: 1./(1.+i), **kw):
+    self.data = data
+    self.ll_projector = ll_projector
+    self.n_subsample_select = None if n_subsample_select is None else min(data.shape[0], n_subsample_select)
+    self.n_subsample_opt = None if n_subsample_opt is None else min(data.shape[0], n_subsample_opt)
+    self.step_sched = step_sched
+    self.opt_itrs = opt_itrs
+    super().__init__(**kw)
+
+  def _build(self, itrs):
+    for _ in range(itrs):
+      self._select()
+      self._optimize()
+
+  # ---- projections -----------------------------------------------------------------------------
+  def _draw(self, n_subsample, w, p):
+    """sparsevi.py:25-35: refresh the samples, then choose the rows of the tangent space"""
+    self.ll_projector.update(w, p)
+    if n_subsample is None:
+      return self.data, 1., None, True
+    sub = np.random.randint(self.data.shape[0], size=n_subsample)
+    return self.data[sub], self.data.shape[0]/n_subsample, sub, False
+
+  def _corevecs(self, S):
+    if self.pts.size > 0:
+      return self.ll_projector.project(self.pts)          # sparsevi.py:38
+    return np.zeros((0, S))
+
+  def _device_vecs(self, rows, cache):
+    prj = self.ll_projector
+    if hasattr(prj, 'project_device'):
+      return prj.project_device(rows, cache=cache)
+    return nat.DeviceVecs.from_host(prj.project(rows))    # user-callback projector: host evaluation
+
+  def _sum(self, rows, cache):
+    prj = self.ll_projector
+    if hasattr(prj, 'project_sum'):
+      return prj.project_sum(rows, cache=cache)
+    return prj.project(rows).sum(axis=0)
+
+  # ---- sparsevi.py:44-67 -------------------------------------------------------------------------
+  def _select(self):
+    rows, scaling, sub, cache = self._draw(self.n_subsample_select, self.wts, self.pts)
+    vecs = self._device_vecs(rows, cache)
+    S = vecs.shape[1]
+    corevecs = self._corevecs(S)
+    resid = scaling*vecs.sum(axis=0) - self.wts.dot(corevecs)
+    # corrs = vecs.dot(resid)/||vecs_n||/S : arg-max and maximum on the device
+    best, dot = vecs.argmax_dot(resid)
+    corr_max = dot/S
+    corecorrs = np.fabs(corevecs.dot(resid)/np.sqrt((corevecs**2).sum(axis=1)))/S
+    if corecorrs.size == 0 or corr_max > corecorrs.max():
+      f = sub[best] if sub is not None else best
+      if f not in self.idcs:
+        self.wts = np.append(self.wts, 0.)
+        self.idcs = np.append(self.idcs, np.int64(f))
+        row = np.asarray(self.data[f], dtype=np.float64)[np.newaxis, :]
+        self.pts = row if self.pts.size == 0 else np.vstack((self.pts, row))
+
+  # ---- sparsevi.py:69-76 -------------------------------------------------------------------------
+  def _optimize(self):
+    def grd(w):
+      rows, scaling, sub, cache = self._draw(self.n_subsample_opt, w, self.pts)
+      colsum = self._sum(rows, cache)
+      corevecs = self._corevecs(colsum.shape[0])
+      resid = scaling*colsum - w.dot(corevecs)
+      return -corevecs.dot(resid)/corevecs.shape[1]
+    self.wts = nn_opt(self.wts, grd, opt_itrs=self.opt_itrs, step_sched=self.step_sched)
+
+  def error(self):
+    return 0.   # as the reference (sparsevi.py:78-79): no KL estimate

@@ -44,53 +44,80 @@ class BlackBoxProjector(Projector):
 
 
 class _DeviceModelProjector(Projector):
-  """sampler(n, wts, pts) -> (n, D) stays on the host (RNG parity, projector.py:31-32); the
-  samples are uploaded with every projection (<= S*d float64)."""
+  """sampler(n, wts, pts) -> (n, D) stays on the host (RNG parity, projector.py:31-32); the samples are
+  uploaded with every projection (<= S*d float64).  The data are uploaded once per array object
+  (SparseVI / BatchPSVI project the same `data` at every optimisation step) and projected on the device:
+
+    project_device(pts) -> DeviceVecs          the resident unit-row matrix (Hilbert / SparseVI selection)
+    project_sum(pts)    -> (S,) ndarray        column sums only; the N x S matrix is never written
+    project(pts)        -> (n, S) ndarray      float64 rows read back (drop-in Projector.project)"""
+  _model = None
+
   def __init__(self, sampler, projection_dimension, ctx=None):
     self.projection_dimension = projection_dimension
     self.sampler = sampler
     self.ctx = ctx
+    self._cache = (None, None)
     self.update(np.array([]), np.array([]))
 
   def update(self, wts, pts):
     self.samples = np.asarray(self.sampler(self.projection_dimension, wts, pts), dtype=np.float64)
 
-  def project_device(self, pts):
-    raise NotImplementedError
+  def _siginv(self):
+    return None
+
+  def _dataset(self, pts, cache):
+    if cache and self._cache[0] is pts:
+      return self._cache[1]
+    ds = nat.Dataset(pts, ctx=self.ctx)
+    if cache:
+      self._cache = (pts, ds)
+    return ds
+
+  def project_device(self, pts, cache=False):
+    return self._dataset(pts, cache).project(self._model, self.samples, self._siginv(), vecs=True)[0]
+
+  def project_sum(self, pts, cache=True):
+    return self._dataset(pts, cache).project(self._model, self.samples, self._siginv(), colsum=True)[2]
 
   def _grad(self, pts):
     raise ValueError('grad_loglikelihood was requested but is not available for this projector')
 
   def project(self, pts, grad=False):
-    lls = self.project_device(pts).to_numpy()
+    pts2 = np.atleast_2d(pts)
+    lls = self._dataset(pts2, False).project(self._model, self.samples, self._siginv(), rows=True)[1]
     if not grad:
       return lls
     # (n, S, d) gradients are only ever requested for the K pseudo-points of BatchPSVI
     # (bpsvi.py:37); K*S*d host arithmetic, centred over the LAST axis as projector.py:26 does
-    glls = self._grad(np.atleast_2d(pts))
+    glls = self._grad(pts2)
     glls -= glls.mean(axis=2)[:, :, np.newaxis]
     return lls, glls
 
 
 class LogisticRegressionProjector(_DeviceModelProjector):
   """log-likelihood of examples/common/model_lr.py:25-32 with z_n = y_n x_n."""
-  def project_device(self, pts):
-    return nat.DeviceVecs.project_lr(pts, self.samples, ctx=self.ctx)
+  _model = nat.MODEL_LR
 
   def _grad(self, z):
     m = -z.dot(self.samples.T)                           # model_lr.py:50-57
-    sig = np.where(m < 100, np.exp(np.minimum(m, 100.))/(1. + np.exp(np.minimum(m, 100.))), 1.)
+    small = m < 100
+    sig = np.ones_like(m)
+    em = np.exp(m[small])
+    sig[small] = em/(1. + em)
     return sig[:, :, np.newaxis]*self.samples[np.newaxis, :, :]
 
 
 class GaussianProjector(_DeviceModelProjector):
   """log-likelihood of examples/common/model_gaussian.py:4-10 (known covariance)."""
+  _model = nat.MODEL_GAUSSIAN
+
   def __init__(self, sampler, projection_dimension, Siginv, ctx=None):
     self.Siginv = np.asarray(Siginv, dtype=np.float64)
     super().__init__(sampler, projection_dimension, ctx=ctx)
 
-  def project_device(self, pts):
-    return nat.DeviceVecs.project_gaussian(pts, self.samples, self.Siginv, ctx=self.ctx)
+  def _siginv(self):
+    return self.Siginv
 
   def _grad(self, x):
     return self.samples.dot(self.Siginv)[np.newaxis, :, :] - x.dot(self.Siginv)[:, np.newaxis, :]
@@ -98,5 +125,18 @@ class GaussianProjector(_DeviceModelProjector):
 
 class PoissonProjector(_DeviceModelProjector):
   """log-likelihood of examples/common/model_poiss.py:25-38, z_n = [x_n, y_n]."""
-  def project_device(self, pts):
-    return nat.DeviceVecs.project_poisson(pts, self.samples, ctx=self.ctx)
+  _model = nat.MODEL_POISSON
+
+  def _grad(self, z):
+    # model_poiss.py:58-67 with the reference's broadcast defect repaired (th[np.newaxis,:,:]) and a zero
+    # d/dy column, as documented in SURVEY.md section 8c
+    x, y = z[:, :-1], z[:, -1][:, np.newaxis]
+    s = x.dot(self.samples.T)
+    big = s > -100
+    s[big] = np.log(np.maximum(s[big], 0) + np.log1p(np.exp(-np.fabs(s[big]))))
+    g = y - np.exp(s)
+    nz = np.exp(s) > 1e-15
+    yy = np.broadcast_to(y, s.shape)
+    g[nz] = (yy[nz]*np.exp(-s[nz]) - 1.)*(1. - np.exp(-np.exp(s[nz])))
+    gx = g[:, :, np.newaxis]*self.samples[np.newaxis, :, :]
+    return np.concatenate((gx, np.zeros(gx.shape[:2] + (1,))), axis=2)

@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <thread>
 #include <vector>
 
 #include "../../include/bcg.h"
@@ -67,6 +68,8 @@ struct bcg_ctx {
   cudaStream_t stream;
   float* flush_buf;
   int64_t flush_bytes;
+  unsigned char* pin[2];      // pinned staging for host -> device uploads
+  cudaEvent_t pin_done[2];
 };
 
 struct bcg_vecs {
@@ -139,6 +142,7 @@ extern "C" int bcg_ctx_create(int device, bcg_ctx** out) {
   c->device = device;
   c->flush_buf = nullptr;
   c->flush_bytes = 0;
+  c->pin[0] = c->pin[1] = nullptr;
   CK(cudaSetDevice(device));
   CK(cudaGetDeviceProperties(&c->prop, device));
   if (c->prop.major < 10)
@@ -154,6 +158,8 @@ extern "C" int bcg_ctx_destroy(bcg_ctx* ctx) {
   if (!ctx) return BCG_OK;
   cudaSetDevice(ctx->device);
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+  for (int i = 0; i < 2; ++i)
+    if (ctx->pin[i]) { cudaFreeHost(ctx->pin[i]); cudaEventDestroy(ctx->pin_done[i]); }
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return BCG_OK;
@@ -190,6 +196,55 @@ extern "C" int bcg_ctx_flush_l2(bcg_ctx* ctx, int64_t bytes) {
   }
   fill_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(ctx->flush_buf, bytes / 4, 0.f);
   CK(cudaGetLastError());
+  return BCG_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// host -> device upload of pageable memory: multi-threaded memcpy into two pinned staging
+// buffers, overlapped with the asynchronous copies (a plain cudaMemcpy from pageable memory
+// runs at a fraction of the PCIe rate)
+// ------------------------------------------------------------------------------------------
+static const size_t kPinChunk = (size_t)32 << 20;
+
+static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+  unsigned hw = std::thread::hardware_concurrency();
+  int nt = (int)std::max(1u, std::min(8u, hw ? hw / 2 : 1u));
+  if (bytes < ((size_t)4 << 20)) nt = 1;
+  if (nt == 1) { memcpy(dst, src, bytes); return; }
+  std::vector<std::thread> th;
+  const size_t per = (bytes / nt + 4095) / 4096 * 4096;
+  for (int t = 0; t < nt; ++t) {
+    const size_t off = (size_t)t * per;
+    if (off >= bytes) break;
+    const size_t len = std::min(per, bytes - off);
+    th.emplace_back([=]() { memcpy((char*)dst + off, (const char*)src + off, len); });
+  }
+  for (auto& x : th) x.join();
+}
+
+static int h2d(bcg_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (bytes == 0) return BCG_OK;
+  if (bytes < ((size_t)1 << 20)) {
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));   // the source may be a temporary of the caller
+    return BCG_OK;
+  }
+  for (int i = 0; i < 2; ++i)
+    if (!ctx->pin[i]) {
+      CK(cudaMallocHost(&ctx->pin[i], kPinChunk));
+      CK(cudaEventCreateWithFlags(&ctx->pin_done[i], cudaEventDisableTiming));
+    }
+  int c = 0;
+  for (size_t off = 0; off < bytes; off += kPinChunk, ++c) {
+    const int i = c & 1;
+    const size_t len = std::min(kPinChunk, bytes - off);
+    if (c >= 2) CK(cudaEventSynchronize(ctx->pin_done[i]));
+    parallel_memcpy(ctx->pin[i], (const char*)src + off, len);
+    CK(cudaMemcpyAsync((char*)dst + off, ctx->pin[i], len, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->pin_done[i], ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
   return BCG_OK;
 }
 
@@ -316,61 +371,111 @@ extern "C" int bcg_vecs_from_host_f64(bcg_ctx* ctx, const double* rows, int64_t 
   return BCG_OK;
 }
 
+struct bcg_dataset {
+  bcg_ctx* ctx;
+  int64_t n;
+  int32_t zld;
+  double* Z;      // device, n x zld float64
+};
+
+extern "C" int bcg_dataset_create(bcg_ctx* ctx, const double* Z, int64_t n, int32_t zld, bcg_dataset** out) {
+  RET(use_device(ctx));
+  if (!out || n < 0 || zld <= 0 || (n > 0 && !Z)) return fail(BCG_ERR_ARG, "bad arguments");
+  bcg_dataset* ds = new bcg_dataset();
+  ds->ctx = ctx; ds->n = n; ds->zld = zld; ds->Z = nullptr;
+  if (n > 0) {
+    CK(cudaMalloc(&ds->Z, (size_t)n * zld * sizeof(double)));
+    RET(h2d(ctx, ds->Z, Z, (size_t)n * zld * sizeof(double)));
+  }
+  *out = ds;
+  return BCG_OK;
+}
+
+extern "C" int bcg_dataset_destroy(bcg_dataset* ds) {
+  if (!ds) return BCG_OK;
+  cudaSetDevice(ds->ctx->device);
+  if (ds->Z) cudaFree(ds->Z);
+  delete ds;
+  return BCG_OK;
+}
+
 template <int J>
-static int launch_project(bcg_ctx* ctx, const ProjectArgs& a, int grid, size_t smem, int ktile) {
-  (void)ktile;
+static int launch_project(bcg_ctx* ctx, const ProjectArgs& a, int grid, size_t smem) {
   CK(cudaFuncSetAttribute(project_kernel<J>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   project_kernel<J><<<grid, kProjWarps * 32, smem, ctx->stream>>>(a);
   CK(cudaGetLastError());
   return BCG_OK;
 }
 
-// common driver: Z (n x zld) host, thetaT (d x S) host (already transposed), coff (S) host or null
-static int project_common(bcg_ctx* ctx, const double* Z, int64_t n, int32_t zld, int32_t d, const double* thetaT,
-                          const double* coff, int32_t S, int model, bcg_vecs** out) {
-  *out = nullptr;
-  if (d <= 0) return fail(BCG_ERR_ARG, "d must be positive");
+// common driver.  thetaT (d x S, already transposed) and coff (S or null) are host arrays.
+// out_vecs: materialise the unit-row matrix; rows64: host n x S float64 centred rows; colsum: host S.
+static int project_common(bcg_dataset* ds, int32_t d, const double* thetaT, const double* coff, int32_t S, int model,
+                          bcg_vecs** out_vecs, double* rows64, double* colsum) {
+  bcg_ctx* ctx = ds->ctx;
+  const int64_t n = ds->n;
+  if (out_vecs) *out_vecs = nullptr;
+  if (d <= 0 || S <= 0) return fail(BCG_ERR_ARG, "d and S must be positive");
+  if (S > 1024) return fail(BCG_ERR_UNSUPPORTED, "S=%d > 1024 is not supported", S);
+  if ((model == MODEL_POISSON ? d + 1 : d) > ds->zld) return fail(BCG_ERR_ARG, "dataset has too few columns");
   bcg_vecs* v = nullptr;
-  RET(vecs_alloc(ctx, n, S, &v));
-  if (n == 0) { *out = v; return BCG_OK; }
+  if (out_vecs) RET(vecs_alloc(ctx, n, S, &v));
+  if (n == 0) {
+    if (out_vecs) *out_vecs = v;
+    if (colsum) memset(colsum, 0, (size_t)S * sizeof(double));
+    return BCG_OK;
+  }
+  const int ld = (S + 3) / 4 * 4;
   const size_t cs_bytes = (size_t)kProjWarps * (S + 1) * sizeof(double);
   const size_t budget = 200 * 1024;
   if (cs_bytes + (size_t)S * sizeof(double) > budget)
     return fail(BCG_ERR_UNSUPPORTED, "projection tile does not fit shared memory for S=%d", S);
   const int ktile = (int)std::min<size_t>(std::min<size_t>(kProjKTile, (size_t)d), (budget - cs_bytes) / ((size_t)S * sizeof(double)));
   const size_t smem = (size_t)ktile * S * sizeof(double) + cs_bytes;
-  double *dZ = nullptr, *dT = nullptr, *dC = nullptr, *d_partial = nullptr;
+  double *dT = nullptr, *dC = nullptr, *d_partial = nullptr, *d_rows = nullptr, *d_out = nullptr;
   unsigned long long* d_zero = nullptr;
   const int64_t nbatch = (n + kProjWarps - 1) / kProjWarps;
   const int grid = (int)std::min<int64_t>(nbatch, (int64_t)ctx->sm_count);
-  CK(cudaMalloc(&dZ, (size_t)n * zld * sizeof(double)));
   CK(cudaMalloc(&dT, (size_t)d * S * sizeof(double)));
   CK(cudaMalloc(&d_partial, (size_t)grid * (S + 1) * sizeof(double)));
   CK(cudaMalloc(&d_zero, sizeof(unsigned long long)));
   CK(cudaMemsetAsync(d_zero, 0, sizeof(unsigned long long), ctx->stream));
-  CK(cudaMemcpyAsync(dZ, Z, (size_t)n * zld * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(dT, thetaT, (size_t)d * S * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   if (coff) {
     CK(cudaMalloc(&dC, (size_t)S * sizeof(double)));
     CK(cudaMemcpyAsync(dC, coff, (size_t)S * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   }
+  if (rows64) CK(cudaMalloc(&d_rows, (size_t)n * S * sizeof(double)));
   ProjectArgs a;
-  a.Z = dZ; a.theta = dT; a.coff = dC; a.An = v->An; a.norms = v->norms; a.partial = d_partial;
-  a.zero_rows = d_zero; a.n = n; a.zld = zld; a.d = d; a.S = S; a.ld = v->ld; a.model = model; a.ktile = ktile;
+  a.Z = ds->Z; a.theta = dT; a.coff = dC; a.An = v ? v->An : nullptr; a.norms = v ? v->norms : nullptr;
+  a.out64 = d_rows; a.partial = d_partial; a.zero_rows = d_zero; a.n = n; a.zld = ds->zld; a.d = d; a.S = S;
+  a.ld = ld; a.model = model; a.ktile = ktile;
   int rc;
-  switch (j_for_ld(v->ld)) {
-    case 1: rc = launch_project<1>(ctx, a, grid, smem, ktile); break;
-    case 2: rc = launch_project<2>(ctx, a, grid, smem, ktile); break;
-    case 4: rc = launch_project<4>(ctx, a, grid, smem, ktile); break;
-    case 8: rc = launch_project<8>(ctx, a, grid, smem, ktile); break;
-    case 16: rc = launch_project<16>(ctx, a, grid, smem, ktile); break;
-    default: rc = launch_project<32>(ctx, a, grid, smem, ktile); break;
+  switch (j_for_ld(ld)) {
+    case 1: rc = launch_project<1>(ctx, a, grid, smem); break;
+    case 2: rc = launch_project<2>(ctx, a, grid, smem); break;
+    case 4: rc = launch_project<4>(ctx, a, grid, smem); break;
+    case 8: rc = launch_project<8>(ctx, a, grid, smem); break;
+    case 16: rc = launch_project<16>(ctx, a, grid, smem); break;
+    default: rc = launch_project<32>(ctx, a, grid, smem); break;
   }
   RET(rc);
-  RET(finish_colsum(v, d_partial, grid, d_zero));
-  cudaFree(dZ); cudaFree(dT); cudaFree(d_partial); cudaFree(d_zero);
+  if (v) {
+    RET(finish_colsum(v, d_partial, grid, d_zero));
+    if (colsum) memcpy(colsum, v->colsum.data(), (size_t)S * sizeof(double));
+  } else {
+    const int S1 = S + 1;
+    CK(cudaMalloc(&d_out, S1 * sizeof(double)));
+    colsum_reduce_kernel<<<(S1 + 127) / 128, 128, 0, ctx->stream>>>(d_partial, grid, S1, d_out);
+    CK(cudaGetLastError());
+    if (colsum) CK(cudaMemcpyAsync(colsum, d_out, (size_t)S * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (rows64) CK(cudaMemcpyAsync(rows64, d_rows, (size_t)n * S * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(dT); cudaFree(d_partial); cudaFree(d_zero);
   if (dC) cudaFree(dC);
-  *out = v;
+  if (d_rows) cudaFree(d_rows);
+  if (d_out) cudaFree(d_out);
+  if (out_vecs) *out_vecs = v;
   return BCG_OK;
 }
 
@@ -381,39 +486,63 @@ static std::vector<double> transpose_sd(const double* theta, int S, int d) {
   return t;
 }
 
-extern "C" int bcg_vecs_project_lr(bcg_ctx* ctx, const double* Z, int64_t n, int32_t d, const double* theta,
-                                   int32_t S, bcg_vecs** out) {
+// model: BCG_MODEL_*; theta: host S x d; Siginv: host d x d (Gaussian only).  Any of out_vecs / rows64 /
+// colsum may be null; with only colsum the N x S matrix is never written (K3b).
+extern "C" int bcg_dataset_project(bcg_dataset* ds, int32_t model, int32_t d, const double* theta, int32_t S,
+                                   const double* Siginv, bcg_vecs** out_vecs, double* rows64, double* colsum) {
+  if (!ds || !theta) return fail(BCG_ERR_ARG, "null argument");
+  RET(use_device(ds->ctx));
+  if (model == BCG_MODEL_LR) {
+    std::vector<double> tT = transpose_sd(theta, S, d);
+    return project_common(ds, d, tT.data(), nullptr, S, MODEL_LR, out_vecs, rows64, colsum);
+  }
+  if (model == BCG_MODEL_POISSON) {
+    std::vector<double> tT = transpose_sd(theta, S, d);
+    return project_common(ds, d, tT.data(), nullptr, S, MODEL_POISSON, out_vecs, rows64, colsum);
+  }
+  if (model == BCG_MODEL_GAUSSIAN) {
+    if (!Siginv) return fail(BCG_ERR_ARG, "Siginv is required for the Gaussian model");
+    // after row-centring only  x . (Siginv theta_s) - 0.5 theta_s . Siginv theta_s  survives (model_gaussian.py:4-10)
+    std::vector<double> tT((size_t)S * d), coff(S);
+    for (int s = 0; s < S; ++s) {
+      double q = 0.;
+      for (int i = 0; i < d; ++i) {
+        double m = 0.;
+        for (int j = 0; j < d; ++j) m += Siginv[(size_t)i * d + j] * theta[(size_t)s * d + j];
+        tT[(size_t)i * S + s] = m;
+        q += theta[(size_t)s * d + i] * m;
+      }
+      coff[s] = -0.5 * q;
+    }
+    return project_common(ds, d, tT.data(), coff.data(), S, MODEL_LINEAR, out_vecs, rows64, colsum);
+  }
+  return fail(BCG_ERR_ARG, "unknown model %d", model);
+}
+
+static int project_host(bcg_ctx* ctx, int model, const double* Z, int64_t n, int32_t zld, int32_t d, const double* theta,
+                        int32_t S, const double* Siginv, bcg_vecs** out) {
   RET(use_device(ctx));
   if (!out || !theta || (n > 0 && !Z)) return fail(BCG_ERR_ARG, "null argument");
-  std::vector<double> tT = transpose_sd(theta, S, d);
-  return project_common(ctx, Z, n, d, d, tT.data(), nullptr, S, MODEL_LR, out);
+  bcg_dataset* ds = nullptr;
+  RET(bcg_dataset_create(ctx, Z, n, zld, &ds));
+  const int rc = bcg_dataset_project(ds, model, d, theta, S, Siginv, out, nullptr, nullptr);
+  bcg_dataset_destroy(ds);
+  return rc;
+}
+
+extern "C" int bcg_vecs_project_lr(bcg_ctx* ctx, const double* Z, int64_t n, int32_t d, const double* theta,
+                                   int32_t S, bcg_vecs** out) {
+  return project_host(ctx, BCG_MODEL_LR, Z, n, d, d, theta, S, nullptr, out);
 }
 
 extern "C" int bcg_vecs_project_gaussian(bcg_ctx* ctx, const double* x, int64_t n, int32_t d, const double* theta,
                                          int32_t S, const double* Siginv, bcg_vecs** out) {
-  RET(use_device(ctx));
-  if (!out || !theta || !Siginv || (n > 0 && !x)) return fail(BCG_ERR_ARG, "null argument");
-  // after row-centring only  x . (Siginv theta_s) - 0.5 theta_s . Siginv theta_s  survives (model_gaussian.py:4-10)
-  std::vector<double> tT((size_t)S * d), coff(S);
-  for (int s = 0; s < S; ++s) {
-    double q = 0.;
-    for (int i = 0; i < d; ++i) {
-      double m = 0.;
-      for (int j = 0; j < d; ++j) m += Siginv[(size_t)i * d + j] * theta[(size_t)s * d + j];
-      tT[(size_t)i * S + s] = m;
-      q += theta[(size_t)s * d + i] * m;
-    }
-    coff[s] = -0.5 * q;
-  }
-  return project_common(ctx, x, n, d, d, tT.data(), coff.data(), S, MODEL_LINEAR, out);
+  return project_host(ctx, BCG_MODEL_GAUSSIAN, x, n, d, d, theta, S, Siginv, out);
 }
 
 extern "C" int bcg_vecs_project_poisson(bcg_ctx* ctx, const double* Z, int64_t n, int32_t d, const double* theta,
                                         int32_t S, bcg_vecs** out) {
-  RET(use_device(ctx));
-  if (!out || !theta || (n > 0 && !Z)) return fail(BCG_ERR_ARG, "null argument");
-  std::vector<double> tT = transpose_sd(theta, S, d);
-  return project_common(ctx, Z, n, d + 1, d, tT.data(), nullptr, S, MODEL_POISSON, out);
+  return project_host(ctx, BCG_MODEL_POISSON, Z, n, d + 1, d, theta, S, nullptr, out);
 }
 
 extern "C" int bcg_vecs_shape(bcg_vecs* v, int64_t* n, int32_t* S, int32_t* ld) {
@@ -628,7 +757,7 @@ extern "C" int bcg_solver_create(bcg_ctx* ctx, bcg_vecs* v, int32_t alg, const d
   CK(cudaMalloc(&h.dir32, 2 * ld * sizeof(float)));
   CK(cudaMalloc(&h.wrow, ld * sizeof(float)));
   CK(cudaMalloc(&h.cands, (size_t)h.n_cands * sizeof(ScanCand)));
-  CK(cudaMalloc(&s->d_fout, sizeof(int64_t)));
+  CK(cudaMalloc(&s->d_fout, 2 * sizeof(int64_t)));
   CK(cudaMalloc(&s->d, sizeof(SolverState)));
   CK(cudaMalloc(&s->d_ctl, sizeof(LoopCtl)));
   CK(cudaMalloc(&s->d_cta_cands, (size_t)2 * s->sc.grid * sizeof(ScanCand)));
@@ -831,6 +960,46 @@ extern "C" int bcg_solver_omp_select(bcg_solver* s, int64_t* f) {
   CK(cudaMemcpyAsync(f, s->d_fout, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   RET(pull_state(s));
   if (s->h.comm_error) return fail(BCG_ERR_COMM, "peer-memory candidate exchange timed out (a rank is missing)");
+  return BCG_OK;
+}
+
+// argmax over the local rows of <a_n / ||a_n||, dir> (sparsevi.py:51,56-57: corrs = vecs.dot(resid)/norms);
+// no solver state is changed.  *score = the float64 inner product of the winning unit row with dir.
+extern "C" int bcg_solver_probe_argmax(bcg_solver* s, const double* dir, int64_t* f, double* score) {
+  if (!s || !dir || !f || !score) return fail(BCG_ERR_ARG, "null argument");
+  RET(use_device(s->ctx));
+  if (s->h.alg == BCG_ALG_GIGA) return fail(BCG_ERR_STATE, "probe needs a one-direction solver (FW / OMP)");
+  if (s->v->n == 0) { *f = -1; *score = 0.; return BCG_OK; }
+  const int S = s->h.S, ld = s->h.ld;
+  double nrm = 0.;
+  for (int i = 0; i < S; ++i) nrm += dir[i] * dir[i];
+  nrm = sqrt(nrm);
+  const double inv = nrm > 0. ? 1. / nrm : 1.;
+  std::vector<double> d64(S);
+  std::vector<float> d32(ld, 0.f);
+  for (int i = 0; i < S; ++i) { d64[i] = dir[i] * inv; d32[i] = (float)d64[i]; }
+  cudaStream_t st = s->ctx->stream;
+  const int keep_sel = s->h.select_failed, keep_halt = s->h.halted;
+  s->h.select_failed = 0;
+  s->h.halted = 0;
+  RET(push_state(s));
+  CK(cudaMemcpyAsync(s->h.dir64, d64.data(), S * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(s->h.dir32, d32.data(), ld * sizeof(float), cudaMemcpyHostToDevice, st));
+  RET(launch_scan(s));
+  double* d_score = reinterpret_cast<double*>(s->d_fout + 1);
+  probe_kernel<<<1, kStepThreads, 0, st>>>(s->d, s->d_fout, d_score);
+  CK(cudaGetLastError());
+  int64_t hf = -1;
+  double hs = 0.;
+  CK(cudaMemcpyAsync(&hf, s->d_fout, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&hs, d_score, sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  s->h.select_failed = keep_sel;
+  s->h.halted = keep_halt;
+  RET(push_state(s));
+  CK(cudaStreamSynchronize(st));
+  *f = hf;
+  *score = hs * nrm;
   return BCG_OK;
 }
 

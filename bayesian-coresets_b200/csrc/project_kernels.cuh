@@ -30,28 +30,39 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// v[j] holds the centred, unnormalised value of column lane + 32 j of one row
+// v[j] holds the centred, unnormalised value of column lane + 32 j of one row.  Outputs are optional:
+// out_row (unit float32 row) + norm_out for the resident matrix, out64 (float64 row, unnormalised) for
+// small host read-backs, neither for the column-sum-only pass (K3b).
 template <int J>
 __device__ __forceinline__ void finalize_row(const double (&v)[J], int S, int ld, int lane, float* out_row,
-                                             double* norm_out, double (&colsum)[J], double& normsum,
+                                             double* norm_out, double* out64, double (&colsum)[J], double& normsum,
                                              unsigned long long* zero_rows) {
   double ss = 0.;
 #pragma unroll
   for (int j = 0; j < J; ++j) {
     const int s = lane + 32 * j;
-    if (s < S) ss += v[j] * v[j];
+    if (s < S) { ss += v[j] * v[j]; colsum[j] += v[j]; }
   }
+  if (out64) {
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int s = lane + 32 * j;
+      if (s < S) out64[s] = v[j];
+    }
+  }
+  if (!out_row && !norm_out) return;
   ss = warp_sum(ss);
   const double norm = sqrt(ss);
   const double inv = norm > 0. ? 1. / norm : 0.;
+  if (out_row) {
 #pragma unroll
-  for (int j = 0; j < J; ++j) {
-    const int s = lane + 32 * j;
-    if (s < ld) out_row[s] = (s < S) ? (float)(v[j] * inv) : 0.f;
-    if (s < S) colsum[j] += v[j];
+    for (int j = 0; j < J; ++j) {
+      const int s = lane + 32 * j;
+      if (s < ld) out_row[s] = (s < S) ? (float)(v[j] * inv) : 0.f;
+    }
   }
   if (lane == 0) {
-    *norm_out = norm;
+    if (norm_out) *norm_out = norm;
     normsum += norm;
     if (norm == 0.) atomicAdd(zero_rows, 1ull);
   }
@@ -104,7 +115,7 @@ __global__ void __launch_bounds__(kProjWarps * 32) ingest_kernel(const double* s
       const int s = lane + 32 * j;
       v[j] = (s < S) ? src[row * src_ld + s] : 0.;
     }
-    finalize_row<J>(v, S, ld, lane, An + (size_t)row * ld, norms + row, colsum, normsum, zero_rows);
+    finalize_row<J>(v, S, ld, lane, An + (size_t)row * ld, norms + row, nullptr, colsum, normsum, zero_rows);
   }
   flush_colsum<J>(colsum, normsum, S, smem_cs, partial);
 }
@@ -114,8 +125,9 @@ struct ProjectArgs {
   const double* Z;       // n x zld  (LR: z = y x; LINEAR: x; POISSON: [x, y])
   const double* theta;   // d x S, TRANSPOSED samples (LINEAR: Siginv theta^T)
   const double* coff;    // S        per-column offset (LINEAR: -0.5 theta Siginv theta) or null
-  float* An;
-  double* norms;
+  float* An;             // unit float32 rows (null: not materialised)
+  double* norms;         // row norms (null with An)
+  double* out64;         // n x S float64 centred rows (null unless requested)
   double* partial;
   unsigned long long* zero_rows;
   int64_t n;
@@ -197,7 +209,8 @@ __global__ void __launch_bounds__(kProjWarps * 32) project_kernel(const ProjectA
       const double mean = warp_sum(sum) / (double)S;     // projector.py:21
 #pragma unroll
       for (int j = 0; j < J; ++j) acc[j] -= mean;
-      finalize_row<J>(acc, S, a.ld, lane, a.An + (size_t)row * a.ld, a.norms + row, colsum, normsum, a.zero_rows);
+      finalize_row<J>(acc, S, a.ld, lane, a.An ? a.An + (size_t)row * a.ld : nullptr, a.An ? a.norms + row : nullptr,
+                      a.out64 ? a.out64 + (size_t)row * S : nullptr, colsum, normsum, a.zero_rows);
     }
   }
   flush_colsum<J>(colsum, normsum, S, smem_cs, a.partial);

@@ -98,6 +98,18 @@ __global__ void __launch_bounds__(kStepThreads, 1) omp_select_kernel(SolverState
   if (threadIdx.x == 0) *f_out = f;
 }
 
+// local argmax of <unit row, dir> with float64 re-scoring; no state change (SparseVI selection)
+__global__ void __launch_bounds__(kStepThreads, 1) probe_kernel(SolverState* st, int64_t* f_out, double* score_out) {
+  __shared__ double sred[256];
+  Blk B{(int)threadIdx.x, (int)blockDim.x, sred};
+  uint32_t lrow; double sc;
+  pick_local(B, st, true, &lrow, &sc);
+  if (threadIdx.x == 0) {
+    *f_out = (lrow == kNoRow) ? -1 : st->row_offset + (int64_t)lrow;
+    *score_out = sc;
+  }
+}
+
 __global__ void __launch_bounds__(kStepThreads, 1) refresh_kernel(SolverState* st) {
   __shared__ double sred[256];
   Blk B{(int)threadIdx.x, (int)blockDim.x, sred};

@@ -50,6 +50,11 @@ extern "C" {
 #define BCG_ERR_COMM       6   /* peer-memory exchange failed or timed out */
 #define BCG_ERR_UNSUPPORTED 7  /* shape outside the supported range (e.g. S > 1024) */
 
+/* models (bcg_dataset_project) */
+#define BCG_MODEL_LR       0   /* examples/common/model_lr.py:25-32        z_n = y_n x_n */
+#define BCG_MODEL_GAUSSIAN 1   /* examples/common/model_gaussian.py:4-10   known covariance */
+#define BCG_MODEL_POISSON  2   /* examples/common/model_poiss.py:25-38     z_n = [x_n, y_n] */
+
 /* algorithms (bcg_solver_create) */
 #define BCG_ALG_GIGA 0
 #define BCG_ALG_FW   1
@@ -72,6 +77,7 @@ typedef struct bcg_iter_event {
 } bcg_iter_event;
 
 typedef struct bcg_ctx    bcg_ctx;     /* one CUDA device + stream */
+typedef struct bcg_dataset bcg_dataset; /* device-resident N_local x d data (float64) */
 typedef struct bcg_vecs   bcg_vecs;    /* device-resident N_local x S projection */
 typedef struct bcg_solver bcg_solver;  /* greedy sparse-NNLS state over a bcg_vecs */
 
@@ -100,6 +106,17 @@ int  bcg_vecs_project_gaussian(bcg_ctx* ctx, const double* x, int64_t n, int32_t
 /* Z: host n x (d+1) = [x, y]; theta: host S x d */
 int  bcg_vecs_project_poisson(bcg_ctx* ctx, const double* Z, int64_t n, int32_t d, const double* theta,
                               int32_t S, bcg_vecs** out);
+/* Device-resident dataset: upload Z (n x zld float64) once, project it many times (SparseVI / BatchPSVI
+ * re-project with new samples at every optimisation step: sparsevi.py:23-42, bpsvi.py:24-40).
+ * bcg_dataset_project evaluates model `model` for the S samples theta (host S x d) and row-centres it
+ * (projector.py:19-21).  Optional outputs: out_vecs = the resident unit-row matrix; rows64 = host n x S
+ * float64 centred rows (what Projector.project returns; for small n); colsum = host S column sums.  With
+ * only colsum requested the N x S matrix is never written (the project(data).sum(axis=0) of
+ * sparsevi.py:71-72 / bpsvi.py:49-51). */
+int  bcg_dataset_create(bcg_ctx* ctx, const double* Z, int64_t n, int32_t zld, bcg_dataset** out);
+int  bcg_dataset_destroy(bcg_dataset* ds);
+int  bcg_dataset_project(bcg_dataset* ds, int32_t model, int32_t d, const double* theta, int32_t S,
+                         const double* Siginv, bcg_vecs** out_vecs, double* rows64, double* colsum);
 int  bcg_vecs_shape(bcg_vecs* v, int64_t* n, int32_t* S, int32_t* ld);
 int  bcg_vecs_colsum(bcg_vecs* v, double* out_S);          /* sum over local rows of the centred vectors */
 int  bcg_vecs_norm_sum(bcg_vecs* v, double* out);          /* sum of local row norms */
@@ -124,6 +141,9 @@ int  bcg_solver_build(bcg_solver* s, int32_t itrs, double tol, bcg_iter_event* e
 /* OMP selection step: residual scan + negative direction over the active set; the selected row
  * joins the active set with weight 1 (orthopursuit.py:17-38).  *f = selected global index. */
 int  bcg_solver_omp_select(bcg_solver* s, int64_t* f);
+/* argmax over the local rows of <a_n/||a_n||, dir> and its float64 value; no state change.  Needs a
+ * one-direction solver (BCG_ALG_FW / BCG_ALG_OMP).  Replaces sparsevi.py:51,56-57. */
+int  bcg_solver_probe_argmax(bcg_solver* s, const double* dir, int64_t* f, double* score);
 int  bcg_solver_error(bcg_solver* s, double* err);
 int  bcg_solver_size(bcg_solver* s, int64_t* n_positive, int64_t* n_stored);
 int  bcg_solver_halted(bcg_solver* s, int32_t* reached_numeric_limit);

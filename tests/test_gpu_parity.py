@@ -249,3 +249,92 @@ def test_empty_and_tiny_inputs(bc):
   cs.build(3)
   wts, pts, idcs = cs.get()
   assert list(idcs) == [0] and wts[0] == pytest.approx(1., rel=1e-6) and cs.error() < 1e-5
+
+
+# ---------------------------------------------------------------- projector API, SparseVI, BatchPSVI
+def test_projector_project_rows_sum_and_argmax(bc):
+  g = load_golden('lr_project_small')
+  prj = bc.LogisticRegressionProjector(lambda n, w, p: g['theta'], int(g['S']))
+  rows = prj.project(g['Z'][:100])                      # float64 read-back: what Projector.project returns
+  np.testing.assert_allclose(rows, g['vecs'][:100], rtol=1e-11, atol=1e-12)
+  np.testing.assert_allclose(prj.project_sum(g['Z']), g['vecs'].sum(axis=0), rtol=1e-11, atol=1e-9)
+  lls, glls = prj.project(g['Z'][:7], grad=True)
+  g2 = load_golden('lr_project_grad')
+  np.testing.assert_allclose(lls, g2['lls'], rtol=1e-11, atol=1e-12)
+  np.testing.assert_allclose(glls, g2['glls'], rtol=1e-12, atol=1e-14)
+  vecs = prj.project_device(g['Z'])
+  rng = np.random.RandomState(3)
+  for _ in range(3):
+    r = rng.randn(int(g['S']))
+    corr = g['vecs'].dot(r)/np.sqrt((g['vecs']**2).sum(axis=1))
+    f, val = vecs.argmax_dot(r)
+    assert f == int(corr.argmax())
+    assert val == pytest.approx(corr.max(), rel=1e-6)
+
+
+def test_sparsevi_golden(bc):
+  import scipy.linalg as sl
+  g = load_golden('sparsevi_gaussian')
+  d = int(g['d'])
+  np.random.seed(int(g['seed']))
+  xs = np.random.multivariate_normal(np.ones(d), np.eye(d), int(g['N']))
+
+  def sampler_w(n, wts, pts):
+    if wts is None or pts is None or pts.shape[0] == 0:
+      wts, pts = np.zeros(1), np.zeros((1, d))
+    L = np.linalg.cholesky(np.eye(d) + wts.sum()*np.eye(d))
+    U = sl.solve_triangular(L, np.eye(d), lower=True, overwrite_b=True, check_finite=False).T
+    mu = np.dot(U.dot(U.T), np.dot(np.eye(d), np.zeros(d)) + np.dot(np.eye(d), (wts[:, np.newaxis]*pts).sum(axis=0)))
+    return mu + np.random.randn(n, d).dot(U.T)
+  prj = bc.GaussianProjector(sampler_w, int(g['S']), np.eye(d))
+  svi = bc.SparseVICoreset(xs, prj, opt_itrs=int(g['opt_itrs']))
+  svi.build(int(g['itrs']))
+  assert np.array_equal(svi.idcs, g['raw_idcs'])
+  np.testing.assert_allclose(svi.wts, g['raw_wts'], rtol=1e-6, atol=1e-9)
+  wts, pts, idcs = svi.get()
+  assert np.array_equal(pts, g['pts']) and svi.error() == 0.
+
+
+def test_sparsevi_subsampled_vs_oracle(bc):
+  from oracle import coresets
+  rng = np.random.RandomState(5)
+  x = rng.randn(2000, 4) + 1.
+  th = rng.randn(24, 4)
+
+  def make(prj_cls, **kw):
+    return prj_cls(lambda n, w, p: th + 0.01*np.random.randn(*th.shape), 24, **kw)
+  np.random.seed(3)
+  a = bc.SparseVICoreset(x, make(bc.GaussianProjector, Siginv=np.eye(4)), n_subsample_select=500, n_subsample_opt=300, opt_itrs=8)
+  a.build(5)
+  np.random.seed(3)
+  f = lambda xx, tt: models.gaussian_loglik(xx, tt, np.eye(4), 0.)
+  o = coresets.SparseVIOracle(x, models.OracleProjector(lambda n, w, p: th + 0.01*np.random.randn(*th.shape), 24, f),
+                              n_subsample_select=500, n_subsample_opt=300, opt_itrs=8)
+  o.build(5)
+  assert np.array_equal(a.idcs, o.idcs)
+  np.testing.assert_allclose(a.wts, o.wts, rtol=1e-6, atol=1e-9)
+
+
+def test_bpsvi_golden(bc):
+  g = load_golden('bpsvi_lr')
+  Z, theta = lr_problem(int(g['seed']), int(g['N']), int(g['d']), int(g['S']))
+  np.random.seed(int(g['build_seed']))
+  prj = bc.LogisticRegressionProjector(lambda n, w, p: theta, int(g['S']))
+  bp = bc.BatchPSVICoreset(Z, prj, opt_itrs=int(g['opt_itrs']))
+  bp.build(int(g['sz']))
+  np.testing.assert_allclose(bp.wts, g['wts'], rtol=1e-9, atol=1e-12)
+  np.testing.assert_allclose(bp.pts, g['pts'], rtol=1e-9, atol=1e-12)
+
+
+def test_bpsvi_poisson_gradient_vs_oracle(bc):
+  """config 5 shape in miniature: Poisson BatchPSVI gradient (with the documented repaired grad_z)"""
+  from oracle import coresets
+  g = load_golden('poisson_project_small')
+  Z, th = g['Z'], g['theta']
+  prj = bc.PoissonProjector(lambda n, w, p: th, th.shape[0])
+  bp = bc.BatchPSVICoreset(Z, prj, opt_itrs=1)
+  o = coresets.BatchPSVIOracle(Z, models.OracleProjector(lambda n, w, p: th, th.shape[0], models.poisson_loglik,
+                                                         models.poisson_grad_z_loglik_fixed), opt_itrs=1)
+  sz, d = 6, Z.shape[1]
+  x = np.hstack((np.full(sz, Z.shape[0]/sz), Z[:sz].reshape(-1)))
+  np.testing.assert_allclose(bp.gradient(x.copy(), sz, d), o.gradient(x.copy(), sz, d), rtol=1e-9, atol=1e-9)
