@@ -117,6 +117,14 @@ def cpu_reference_run(workload, steps, warmup, sample_rows=None):
   from oracle import greedy, models
   N, d, S = WORKLOADS[workload]
   cores = os.cpu_count()
+  try:
+    # torchrun exports OMP_NUM_THREADS=1: give the CPU reference every host core it can use
+    import threadpoolctl
+    threadpoolctl.threadpool_limits(limits=cores)
+    used = [p.get('num_threads') for p in threadpoolctl.threadpool_info() if p.get('user_api') == 'blas']
+    cores = max(used) if used else cores
+  except Exception:
+    pass
   if sample_rows is None:
     sample_rows = min(N, max(20_000, int(1.28e8 / S)))      # ~1 GB float64 matrix (+1 GB copy)
   Z, th_true = lr_shard(0, 0, sample_rows, d)
