@@ -52,6 +52,7 @@ _PROTOTYPES = {
   'bcg_dataset_create': (_c.c_int, [_P, _P, _c.c_int64, _c.c_int32, _PP]),
   'bcg_dataset_destroy': (_c.c_int, [_P]),
   'bcg_dataset_project': (_c.c_int, [_P, _c.c_int32, _c.c_int32, _P, _c.c_int32, _P, _PP, _P, _P]),
+  'bcg_dataset_project_linear': (_c.c_int, [_P, _c.c_int32, _P, _P, _c.c_int32, _PP, _P, _P]),
   'bcg_vecs_shape': (_c.c_int, [_P, _c.POINTER(_c.c_int64), _c.POINTER(_c.c_int32), _c.POINTER(_c.c_int32)]),
   'bcg_vecs_colsum': (_c.c_int, [_P, _P]),
   'bcg_vecs_norm_sum': (_c.c_int, [_P, _c.POINTER(_c.c_double)]),
@@ -163,9 +164,15 @@ class Dataset(object):
     hv = ctypes.c_void_p()
     out_rows = np.empty((self.shape[0], S)) if rows else None
     out_cs = np.empty(S) if colsum else None
-    check(lib().bcg_dataset_project(self.handle, model, d, _ptr(theta), S, None if si is None else _ptr(si),
-                                    ctypes.byref(hv) if vecs else None, None if out_rows is None else _ptr(out_rows),
-                                    None if out_cs is None else _ptr(out_cs)))
+    outs = (ctypes.byref(hv) if vecs else None, None if out_rows is None else _ptr(out_rows),
+            None if out_cs is None else _ptr(out_cs))
+    if model == MODEL_GAUSSIAN:
+      # after row-centring only x.(Siginv theta_s) - 0.5 theta_s.Siginv.theta_s survives (model_gaussian.py:4-10)
+      A = _f64(theta.dot(si))
+      coff = _f64(-0.5*(A*theta).sum(axis=1))
+      check(lib().bcg_dataset_project_linear(self.handle, d, _ptr(A), _ptr(coff), S, *outs))
+    else:
+      check(lib().bcg_dataset_project(self.handle, model, d, _ptr(theta), S, None, *outs))
     return (DeviceVecs(self.ctx, hv) if vecs else None), out_rows, out_cs
 
   def __del__(self):

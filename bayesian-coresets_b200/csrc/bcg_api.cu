@@ -17,6 +17,7 @@
 #include "bcg_state.h"
 #include "kernel_args.h"
 #include "project_kernels.cuh"
+#include "project_sum_kernel.cuh"
 #include "step_kernels.cuh"
 
 using namespace bcg;
@@ -424,6 +425,33 @@ static int project_common(bcg_dataset* ds, int32_t d, const double* thetaT, cons
     if (colsum) memset(colsum, 0, (size_t)S * sizeof(double));
     return BCG_OK;
   }
+  if (!out_vecs && !rows64 && colsum && d >= env_int("BCG_PROJSUM_MIN_D", 24) && n >= 4096) {
+    // K3b, GEMM-shaped: register-tiled float64 kernel (project_sum_kernel.cuh)
+    double *dT = nullptr, *dC = nullptr, *d_partial = nullptr, *d_out = nullptr;
+    const int64_t nrb = (n + kPsBM - 1) / kPsBM;
+    const int grid = (int)std::min<int64_t>(nrb, (int64_t)ctx->sm_count);
+    CK(cudaMalloc(&dT, (size_t)d * S * sizeof(double)));
+    CK(cudaMalloc(&d_partial, (size_t)grid * S * sizeof(double)));
+    CK(cudaMalloc(&d_out, (size_t)S * sizeof(double)));
+    CK(cudaMemsetAsync(d_partial, 0, (size_t)grid * S * sizeof(double), ctx->stream));
+    CK(cudaMemcpyAsync(dT, thetaT, (size_t)d * S * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (coff) {
+      CK(cudaMalloc(&dC, (size_t)S * sizeof(double)));
+      CK(cudaMemcpyAsync(dC, coff, (size_t)S * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    ProjectSumArgs pa;
+    pa.Z = ds->Z; pa.thetaT = dT; pa.coff = dC; pa.partial = d_partial; pa.n = n; pa.zld = ds->zld; pa.d = d; pa.S = S;
+    pa.model = model;
+    project_sum_kernel<<<grid, kPsThreads, 0, ctx->stream>>>(pa);
+    CK(cudaGetLastError());
+    project_sum_finish_kernel<<<1, 256, 0, ctx->stream>>>(d_partial, grid, S, d_out);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(colsum, d_out, (size_t)S * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(dT); cudaFree(d_partial); cudaFree(d_out);
+    if (dC) cudaFree(dC);
+    return BCG_OK;
+  }
   const int ld = (S + 3) / 4 * 4;
   const size_t cs_bytes = (size_t)kProjWarps * (S + 1) * sizeof(double);
   const size_t budget = 200 * 1024;
@@ -517,6 +545,16 @@ extern "C" int bcg_dataset_project(bcg_dataset* ds, int32_t model, int32_t d, co
     return project_common(ds, d, tT.data(), coff.data(), S, MODEL_LINEAR, out_vecs, rows64, colsum);
   }
   return fail(BCG_ERR_ARG, "unknown model %d", model);
+}
+
+// Gaussian model with the S x d matrix A = theta Siginv and the offsets c_s = -0.5 theta_s Siginv theta_s
+// precomputed by the caller (BLAS on the host instead of the O(S d^2) loop above)
+extern "C" int bcg_dataset_project_linear(bcg_dataset* ds, int32_t d, const double* A, const double* coff, int32_t S,
+                                          bcg_vecs** out_vecs, double* rows64, double* colsum) {
+  if (!ds || !A) return fail(BCG_ERR_ARG, "null argument");
+  RET(use_device(ds->ctx));
+  std::vector<double> tT = transpose_sd(A, S, d);
+  return project_common(ds, d, tT.data(), coff, S, MODEL_LINEAR, out_vecs, rows64, colsum);
 }
 
 static int project_host(bcg_ctx* ctx, int model, const double* Z, int64_t n, int32_t zld, int32_t d, const double* theta,

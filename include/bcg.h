@@ -117,6 +117,10 @@ int  bcg_dataset_create(bcg_ctx* ctx, const double* Z, int64_t n, int32_t zld, b
 int  bcg_dataset_destroy(bcg_dataset* ds);
 int  bcg_dataset_project(bcg_dataset* ds, int32_t model, int32_t d, const double* theta, int32_t S,
                          const double* Siginv, bcg_vecs** out_vecs, double* rows64, double* colsum);
+/* ll_ns = x_n . A_s + coff_s : the Gaussian model with A = theta Siginv (host S x d) and
+ * coff_s = -0.5 theta_s Siginv theta_s precomputed by the caller */
+int  bcg_dataset_project_linear(bcg_dataset* ds, int32_t d, const double* A, const double* coff, int32_t S,
+                                bcg_vecs** out_vecs, double* rows64, double* colsum);
 int  bcg_vecs_shape(bcg_vecs* v, int64_t* n, int32_t* S, int32_t* ld);
 int  bcg_vecs_colsum(bcg_vecs* v, double* out_S);          /* sum over local rows of the centred vectors */
 int  bcg_vecs_norm_sum(bcg_vecs* v, double* out);          /* sum of local row norms */

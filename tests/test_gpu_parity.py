@@ -338,3 +338,24 @@ def test_bpsvi_poisson_gradient_vs_oracle(bc):
   sz, d = 6, Z.shape[1]
   x = np.hstack((np.full(sz, Z.shape[0]/sz), Z[:sz].reshape(-1)))
   np.testing.assert_allclose(bp.gradient(x.copy(), sz, d), o.gradient(x.copy(), sz, d), rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize('n,d,S', [(5000, 40, 200), (4500, 130, 512), (4200, 25, 600)])
+def test_project_sum_tiled_kernel_vs_oracle(bc, n, d, S):
+  """K3b register-tiled float64 kernel (n >= 4096, d >= 24): column sums without the N x S matrix"""
+  rng = np.random.RandomState(n + d)
+  X = rng.randn(n, d)
+  th = rng.randn(S, d)/np.sqrt(d)
+  ref = models.project(models.lr_loglik, X, th).sum(axis=0)
+  got = bc.LogisticRegressionProjector(lambda k, w, p: th, S).project_sum(X)
+  np.testing.assert_allclose(got, ref, rtol=1e-9, atol=1e-9*np.abs(ref).max())
+  Siginv = np.eye(d) + 0.05*np.ones((d, d))
+  f = lambda x, t: models.gaussian_loglik(x, t, Siginv, 0.)
+  ref = models.project(f, X, th).sum(axis=0)
+  got = bc.GaussianProjector(lambda k, w, p: th, S, Siginv).project_sum(X)
+  np.testing.assert_allclose(got, ref, rtol=1e-9, atol=1e-9*np.abs(ref).max())
+  y = rng.poisson(np.log1p(np.exp(X.dot(th[0])))).astype(np.float64)
+  Zp = np.hstack((X, y[:, None]))
+  ref = models.project(models.poisson_loglik, Zp, th).sum(axis=0)
+  got = bc.PoissonProjector(lambda k, w, p: th, S).project_sum(Zp)
+  np.testing.assert_allclose(got, ref, rtol=1e-9, atol=1e-9*np.abs(ref).max())
