@@ -136,8 +136,12 @@ struct ProjectArgs {
 
 __device__ __forceinline__ double link_value(int model, double lin, double y) {
   if (model == MODEL_LR) {
-    const double m = -lin;                               // model_lr.py:28-31
-    return (m < 100.) ? -log1p(exp(m)) : -m;
+    // model_lr.py:28-31: -log1p(exp(m)) for m < 100, else -m, with m = -z.theta.  Evaluated as
+    // -(max(m,0) + log1p(exp(-|m|))): the same function (for m >= 100 the log1p term is < 4e-44 and
+    // vanishes in float64, which is the reference's linear branch), but exp/log1p always take the
+    // same code path for every lane -- the direct form diverges inside log1p and ran 9x slower.
+    const double m = -lin;
+    return -(fmax(m, 0.) + log1p(exp(-fabs(m))));
   }
   if (model == MODEL_POISSON) {
     double s = lin;                                      // model_poiss.py:26-29
