@@ -442,7 +442,9 @@ static int project_common(bcg_dataset* ds, int32_t d, const double* thetaT, cons
     ProjectSumArgs pa;
     pa.Z = ds->Z; pa.thetaT = dT; pa.coff = dC; pa.partial = d_partial; pa.n = n; pa.zld = ds->zld; pa.d = d; pa.S = S;
     pa.model = model;
-    project_sum_kernel<<<grid, kPsThreads, 0, ctx->stream>>>(pa);
+    if (model == MODEL_LR) project_sum_kernel<MODEL_LR><<<grid, kPsThreads, 0, ctx->stream>>>(pa);
+    else if (model == MODEL_POISSON) project_sum_kernel<MODEL_POISSON><<<grid, kPsThreads, 0, ctx->stream>>>(pa);
+    else project_sum_kernel<MODEL_LINEAR><<<grid, kPsThreads, 0, ctx->stream>>>(pa);
     CK(cudaGetLastError());
     project_sum_finish_kernel<<<1, 256, 0, ctx->stream>>>(d_partial, grid, S, d_out);
     CK(cudaGetLastError());

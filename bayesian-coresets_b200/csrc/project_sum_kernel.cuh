@@ -32,6 +32,14 @@ struct ProjectSumArgs {
   int32_t zld, d, S, model;
 };
 
+// out-of-line link: the epilogue applies it to 64 accumulators per thread; inlining 64 copies of the
+// float64 exp/log1p bodies made the kernel ~600 KB of SASS and instruction-fetch bound
+template <int MODEL>
+__device__ __noinline__ double link_call(double lin, double y) { return link_value(MODEL, lin, y); }
+template <>
+__device__ __forceinline__ double link_call<MODEL_LINEAR>(double lin, double) { return lin; }
+
+template <int MODEL>
 __global__ void __launch_bounds__(kPsThreads, 1) project_sum_kernel(const ProjectSumArgs a) {
   __shared__ __align__(16) double zs[kPsKT][kPsZs];
   __shared__ __align__(16) double ts[kPsKT][kPsBN];
@@ -52,7 +60,7 @@ __global__ void __launch_bounds__(kPsThreads, 1) project_sum_kernel(const Projec
 
   for (int64_t rb = blockIdx.x; rb < nrowblocks; rb += gridDim.x) {
     const int64_t row0 = rb * kPsBM;
-    if (a.model == MODEL_POISSON) {
+    if (MODEL == MODEL_POISSON) {
       __syncthreads();
       if (t < kPsBM) ys[t] = (row0 + t < a.n) ? a.Z[(row0 + t) * a.zld + d] : 0.;
     }
@@ -115,13 +123,13 @@ __global__ void __launch_bounds__(kPsThreads, 1) project_sum_kernel(const Projec
       for (int i = 0; i < 8; ++i) {
         const int rl = wr * 32 + lr * 8 + i;
         const bool live = row0 + rl < a.n;
-        const double y = (a.model == MODEL_POISSON) ? ys[rl] : 0.;
+        const double y = (MODEL == MODEL_POISSON) ? ys[rl] : 0.;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int c = col0 + wc * 64 + 16 * (j >> 1) + lc * 2 + (j & 1);
           double lin = acc[i][j];
           if (a.coff && c < S) lin += a.coff[c];
-          const double v = link_value(a.model, lin, y);
+          const double v = link_call<MODEL>(lin, y);
           cs[j] += (live && c < S) ? v : 0.;
         }
       }
