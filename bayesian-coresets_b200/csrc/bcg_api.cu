@@ -92,6 +92,8 @@ struct bcg_solver {
   bool use_loop;            // persistent cooperative kernel available for this shape
   LoopCtl* d_ctl;
   ScanCand* d_cta_cands;
+  unsigned int* d_claims;
+  int claims_cap;
   int trace_on;
   unsigned long long* d_trace;
   int trace_cap, trace_n;
@@ -673,7 +675,7 @@ static int choose_scan_config(bcg_solver* s) {
   c.stages = std::max(1, env_int("BCG_SCAN_STAGES", 2));
   c.evict_first = env_int("BCG_SCAN_EVICT_FIRST", 0);
   const size_t budget = (size_t)(200 * 1024);
-  const size_t extra = 32 * sizeof(ScanCand) + 2 * (size_t)s->v->S * sizeof(double) + 128;   // loop kernel only
+  const size_t extra = 32 * sizeof(ScanCand) + 2 * (size_t)s->v->S * sizeof(double) + 16 * 8 * 12 + 128;   // loop kernel only
   auto ring = [&](int stages, int rps) { return (size_t)c.wpb * stages * rps * row_bytes + (size_t)c.wpb * stages * 8; };
   while (c.stages > 2 && ring(c.stages, c.rps) + extra > budget) --c.stages;
   while (c.rps > c.rb && ring(c.stages, c.rps) + extra > budget) c.rps -= c.rb;
@@ -770,6 +772,8 @@ extern "C" int bcg_solver_create(bcg_ctx* ctx, bcg_vecs* v, int32_t alg, const d
   s->use_loop = false;
   s->d_ctl = nullptr;
   s->d_cta_cands = nullptr;
+  s->d_claims = nullptr;
+  s->claims_cap = 0;
   s->trace_on = 0;
   s->d_trace = nullptr;
   s->trace_cap = s->trace_n = 0;
@@ -826,7 +830,7 @@ extern "C" int bcg_solver_destroy(bcg_solver* s) {
     for (int p = 0; p < h.world; ++p)
       if (p != h.rank && s->peer_ptrs[p]) cudaIpcCloseMemHandle(s->peer_ptrs[p]);
   void* bufs[] = {h.b, h.bn, h.xw, h.xw_new, h.xf, h.dir64, h.dir32, h.wrow, h.cands, h.act_idx, h.act_w,
-                  h.act_w_new, h.act_norm, h.act_rows, h.events, s->d_fout, s->d, s->mail, s->d_ctl, s->d_cta_cands, s->d_trace};
+                  h.act_w_new, h.act_norm, h.act_rows, h.events, s->d_fout, s->d, s->mail, s->d_ctl, s->d_cta_cands, s->d_trace, s->d_claims};
   for (void* p : bufs)
     if (p) cudaFree(p);
   for (cudaEvent_t e : s->scan_ev) cudaEventDestroy(e);
@@ -922,6 +926,15 @@ extern "C" int bcg_solver_build(bcg_solver* s, int32_t itrs, double tol, bcg_ite
     la.g.evict_first = s->sc.evict_first;
     la.itrs = itrs;
     la.wpb = s->sc.wpb;
+    if (s->claims_cap < itrs) {
+      if (s->d_claims) CK(cudaFree(s->d_claims));
+      s->d_claims = nullptr;
+      CK(cudaMalloc(&s->d_claims, (size_t)itrs * sizeof(unsigned int)));
+      s->claims_cap = itrs;
+    }
+    CK(cudaMemsetAsync(s->d_claims, 0, (size_t)itrs * sizeof(unsigned int), st));
+    la.claims = s->d_claims;
+    la.static_frac = (float)env_int("BCG_STATIC_PCT", 80) / 100.f;
     la.trace = nullptr;
     s->trace_n = 0;
     if (s->trace_on) {

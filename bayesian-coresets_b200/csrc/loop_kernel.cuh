@@ -102,7 +102,8 @@ __device__ __forceinline__ bool mail_exchange_warp(SolverState* st, int lane, ui
       h->score = lscore; h->gidx = gidx; h->norm = nrm;
     }
   }
-  __threadfence_system();
+  // payload stores of all lanes -> __syncwarp -> system-scope release by the W flag-writing lanes (the
+  // release is cumulative over the warp's earlier stores; no per-lane __threadfence_system needed)
   __syncwarp();
   if (lane < W) {
     MailHeader* h = reinterpret_cast<MailHeader*>(st->mail_peer[lane] + (int64_t)(par * W + me) * sb);
@@ -595,32 +596,68 @@ __global__ void __launch_bounds__(384, 1) greedy_loop_kernel(const LoopArgs a) {
   const int grp = lane / LPR;
   const int nchunk = q.ld >> 2;
   const int64_t n_chunks = (q.n_rows + q.rps - 1) / q.rps;
-  const int64_t n_my = (gw < n_chunks) ? (n_chunks - gw + GW - 1) / GW : 0;
-  const int64_t row_step = GW * q.rps;
+  // Work split per iteration: the first n_s chunks of every warp are STATIC (chunk gw + k GW, interleaved so
+  // that neighbouring warps stream neighbouring rows); the remaining chunks [n_static, n_chunks) are claimed
+  // DYNAMICALLY with one atomic per chunk from a per-iteration counter, so SMs that the memory system serves
+  // faster take more of the tail and the whole grid arrives together (measured: with a purely static split
+  // the first CTA finished ~30 us before the last one at N = 1e6, S = 256).
+  const int64_t n_s = (int64_t)((double)(n_chunks / GW) * a.static_frac);
+  const int64_t n_static = n_s * GW;
 
-  // Ring bookkeeping (all incremental).  Chunks are issued in consumption order, iteration after
-  // iteration, so the tile stream runs ahead ACROSS iterations: the slot freed by a consumed chunk
-  // is refilled with the chunk `stages` visits later, which may belong to the next iteration.
-  // (all of it is warp-uniform: every lane tracks the same counters, the leader lane issues through
-  // PTX predicates -- no divergent branch anywhere in the scan warps)
+  // Ring bookkeeping, all warp-uniform (every lane tracks the same counters; the leader lane issues copies
+  // and claims through PTX predicates -- no divergent branch anywhere in the scan warps).  Chunks are
+  // issued in consumption order, iteration after iteration, so the tile stream runs ahead ACROSS
+  // iterations.  sm_row0 / sm_it describe what each ring slot holds.
   const bool leader = lane == 0;
+  int64_t* sm_row0 = reinterpret_cast<int64_t*>(sbn + a.st->S) + warp * q.stages;
+  int* sm_it = reinterpret_cast<int*>(reinterpret_cast<int64_t*>(sbn + a.st->S) + wpb * q.stages) + warp * q.stages;
   int issue_slot = 0;
-  int64_t issue_k = 0;         // chunk (within the iteration) of the next issue
-  int issue_it = 0;            // iteration it belongs to
+  int64_t issue_k = 0;         // static chunks of iteration issue_it issued so far
+  int issue_it = 0;            // iteration the next issue belongs to
   int outstanding = 0;         // issued, not yet consumed
+  unsigned int pending = 0;    // pre-claimed dynamic chunk (valid in lane 0 when have_pending)
+  bool have_pending = false;
+  auto claim = [&](int it_claim) {                  // asynchronous: the result is only read at the next issue
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.u32 p, %2, 0;\n\t"
+        "@p atom.global.add.u32 %0, [%1], 1;\n\t}"
+        : "=r"(pending)
+        : "l"(a.claims + it_claim), "r"((uint32_t)leader)
+        : "memory");
+    have_pending = true;
+  };
   auto issue_next = [&]() {
-    if (issue_it < a.itrs && n_my > 0) {
-      const int64_t row0 = (gw + issue_k * GW) * q.rps;
+    for (;;) {
+      if (issue_it >= a.itrs || n_chunks == 0) return;
+      int64_t c;
+      if (issue_k < n_s) {
+        c = gw + issue_k * GW;
+        ++issue_k;
+      } else {
+        if (!have_pending) claim(issue_it);
+        c = n_static + (int64_t)__shfl_sync(0xffffffffu, pending, 0);
+        have_pending = false;
+        if (c >= n_chunks) {                         // this iteration's chunks are all taken: next iteration
+          ++issue_it;
+          issue_k = 0;
+          continue;
+        }
+      }
+      const int64_t row0 = c * q.rps;
       const int64_t left = q.n_rows - row0;
       const uint32_t nr = (uint32_t)(left < q.rps ? left : q.rps);
       tma_load_rows(&bars[issue_slot], wbuf + (size_t)issue_slot * stage_floats, q.An + (size_t)row0 * q.ld,
                     nr * (uint32_t)q.ld * 4u, policy, leader);
+      if (leader) { sm_row0[issue_slot] = row0; sm_it[issue_slot] = issue_it; }
       if (++issue_slot == q.stages) issue_slot = 0;
-      if (++issue_k == n_my) { issue_k = 0; ++issue_it; }
       ++outstanding;
+      if (issue_k >= n_s) claim(issue_it);           // pre-claim: its latency hides behind the next tile's math
+      return;
     }
   };
   for (int s = 0; s < q.stages; ++s) issue_next();   // tiles do not depend on the direction
+  __syncwarp();
 
   int slot = 0;
   uint32_t parity = 0;
@@ -636,18 +673,18 @@ __global__ void __launch_bounds__(384, 1) greedy_loop_kernel(const LoopArgs a) {
 
     float best = -INFINITY;
     uint32_t brow = kNoRowU;
-    int64_t row0 = gw * q.rps;
-    for (int64_t k = 0; k < n_my; ++k) {
+    while (outstanding > 0 && sm_it[slot] == it) {   // uniform: shared-memory broadcast reads
       mbar_wait(&bars[slot], parity);
+      const int64_t row0 = sm_row0[slot];
       const int64_t left = q.n_rows - row0;
       const int nr = (int)(left < q.rps ? left : q.rps);
       const float* tile = wbuf + (size_t)slot * stage_floats;
       for (int b0 = 0; b0 < nr; b0 += Core::RB)
         Core::batch(tile + (size_t)b0 * q.ld, q.ld, nchunk, g, grp, nr - b0, (uint32_t)(row0 + b0), d0, d1, best, brow);
-      __syncwarp();   // every lane's shared-memory reads of this stage are complete
+      __syncwarp();   // every lane's shared-memory reads of this stage (and of its slot record) are complete
       --outstanding;
       issue_next();
-      row0 += row_step;
+      __syncwarp();   // the leader's slot record is visible to all lanes
       if (++slot == q.stages) { slot = 0; parity ^= 1u; }
     }
 
