@@ -675,7 +675,7 @@ static int choose_scan_config(bcg_solver* s) {
   c.stages = std::max(1, env_int("BCG_SCAN_STAGES", 2));
   c.evict_first = env_int("BCG_SCAN_EVICT_FIRST", 0);
   const size_t budget = (size_t)(200 * 1024);
-  const size_t extra = 32 * sizeof(ScanCand) + 2 * (size_t)s->v->S * sizeof(double) + 16 * 8 * 12 + 128;   // loop kernel only
+  const size_t extra = 32 * sizeof(ScanCand) + 4 * (size_t)s->v->S * sizeof(double) + 64 + 16 * 8 * 12 + 128;   // loop kernel only
   auto ring = [&](int stages, int rps) { return (size_t)c.wpb * stages * rps * row_bytes + (size_t)c.wpb * stages * 8; };
   while (c.stages > 2 && ring(c.stages, c.rps) + extra > budget) --c.stages;
   while (c.rps > c.rb && ring(c.stages, c.rps) + extra > budget) c.rps -= c.rb;

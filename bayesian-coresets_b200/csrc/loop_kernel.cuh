@@ -40,21 +40,29 @@ __device__ __forceinline__ void wsum(double (&v)[N]) {
     for (int off = 16; off > 0; off >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
 }
 
+// float64 score of one unit row against the current direction(s) held in shared memory (sdir: 2 x S)
 template <int J>
-__device__ __forceinline__ double row_score_warp(const SolverState* st, const float* row, int lane) {
-  const int S = st->S;
+__device__ __forceinline__ double row_score_regs(const double (&x)[J], const double* sdir, int S, bool giga, int lane) {
   double v[2] = {0., 0.};
 #pragma unroll
   for (int j = 0; j < J; ++j) {
     const int s = lane + 32 * j;
     if (s < S) {
-      const double x = (double)__ldcg(row + s);
-      v[0] += x * st->dir64[s];
-      if (st->alg == BCG_ALG_GIGA) v[1] += x * st->dir64[S + s];
+      v[0] += x[j] * sdir[s];
+      if (giga) v[1] += x[j] * sdir[S + s];
     }
   }
   wsum<2>(v);
-  return st->alg == BCG_ALG_GIGA ? giga_score64(v[0], v[1]) : v[0];
+  return giga ? giga_score64(v[0], v[1]) : v[0];
+}
+
+template <int J>
+__device__ __forceinline__ void load_row(const float* row, int S, int lane, double (&x)[J]) {
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int s = lane + 32 * j;
+    x[j] = (s < S) ? (double)__ldcg(row + s) : 0.;
+  }
 }
 
 // warp-level arg-best over the per-CTA candidates, skipping rows listed in `skip`
@@ -80,75 +88,90 @@ __device__ __forceinline__ void warp_pick(const ScanCand* c, int n, const uint32
   *r_out = br;
 }
 
-// warp-level version of mail_exchange (step_kernels.cuh): same protocol, one warp
+// N-sharding exchange, warp-level (protocol of mail_exchange in step_kernels.cuh).  Everything the
+// exchange needs is hoisted into MailCtx / shared memory once per build call; the candidate row is
+// already in registers.  Critical path: payload stores to all peers -> release of W flags -> acquire of
+// the W flags in my mailbox -> W headers read in parallel (one lane each) -> winner's row.
+struct MailCtx {
+  int W, me, ld;
+  int64_t sb;                 // slot bytes
+  unsigned char* local;       // my mailbox
+  unsigned char** peers;      // shared-memory array of the W mapped mailboxes
+  unsigned long long seq;     // running sequence number (kept in registers, stored back at the end)
+};
+
 template <int J>
-__device__ __forceinline__ bool mail_exchange_warp(SolverState* st, int lane, uint32_t lrow, double lscore, int64_t* f,
-                                                   double* norm, const float** row) {
-  const int W = st->world, me = st->rank, ld = st->ld;
-  const unsigned long long seq = st->seq + 1ull;
+__device__ __forceinline__ bool mail_exchange_warp(MailCtx& mc, int lane, int S, const double (&xrow)[J], bool have,
+                                                   double lscore, int64_t gidx, double nrm, int64_t* f, double* norm,
+                                                   const float** row) {
+  const int W = mc.W, me = mc.me;
+  const unsigned long long seq = ++mc.seq;
   const int par = (int)(seq & 1ull);
-  const int64_t sb = st->mail_slot_bytes;
-  const bool have = lrow != kNoRow;
-  const float* src = have ? st->An + (size_t)lrow * ld : nullptr;
-  const int64_t gidx = have ? st->row_offset + (int64_t)lrow : -1;
-  const double nrm = have ? st->norms[lrow] : 0.;
+  const int64_t my_off = (int64_t)(par * W + me) * mc.sb;
   for (int p = 0; p < W; ++p) {
-    unsigned char* slot = st->mail_peer[p] + (int64_t)(par * W + me) * sb;
+    unsigned char* slot = mc.peers[p] + my_off;
     float* dst = reinterpret_cast<float*>(slot + sizeof(MailHeader));
-    if (have)
-      for (int s = lane; s < ld; s += 32) dst[s] = src[s];
+    if (have) {
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const int s = lane + 32 * j;
+        if (s < S) dst[s] = (float)xrow[j];
+      }
+    }
     if (lane == 0) {
       MailHeader* h = reinterpret_cast<MailHeader*>(slot);
-      h->score = lscore; h->gidx = gidx; h->norm = nrm;
+      h->score = lscore; h->gidx = have ? gidx : -1; h->norm = nrm;
     }
   }
   // payload stores of all lanes -> __syncwarp -> system-scope release by the W flag-writing lanes (the
-  // release is cumulative over the warp's earlier stores; no per-lane __threadfence_system needed)
+  // release is cumulative over the warp's earlier stores)
   __syncwarp();
-  if (lane < W) {
-    MailHeader* h = reinterpret_cast<MailHeader*>(st->mail_peer[lane] + (int64_t)(par * W + me) * sb);
-    st_release_sys_u64(&h->seq, seq);
-  }
+  if (lane < W) st_release_sys_u64(&reinterpret_cast<MailHeader*>(mc.peers[lane] + my_off)->seq, seq);
   __syncwarp();
-  // warp-uniform wait: lane p watches peer p's slot in MY mailbox; bounded, a dead peer must not hang the GPU
+  // warp-uniform wait: lane p watches peer p's slot in MY mailbox; bounded (a dead peer must not hang the GPU)
   const MailHeader* mine =
-      reinterpret_cast<const MailHeader*>(st->mail_local + (int64_t)(par * W + (lane < W ? lane : 0)) * sb);
-  const unsigned long long t0 = globaltimer_ns();
-  bool ok = true;
-  for (;;) {
+      reinterpret_cast<const MailHeader*>(mc.local + (int64_t)(par * W + (lane < W ? lane : 0)) * mc.sb);
+  unsigned long long t0 = 0;
+  for (unsigned int spins = 0;; ++spins) {
     const bool done = ld_acquire_sys_u64(&mine->seq) == seq;
     if (__all_sync(0xffffffffu, done)) break;
-    if (__any_sync(0xffffffffu, globaltimer_ns() - t0 > 10000000000ull)) { ok = false; break; }
-    __nanosleep(64);
+    if ((spins & 1023u) == 1023u) {
+      const unsigned long long now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      if (__any_sync(0xffffffffu, now - t0 > 10000000000ull)) return false;
+    }
   }
-  if (!ok) return false;
-  int win = -1; double best = -INFINITY; int64_t bidx = -1;
-  for (int p = 0; p < W; ++p) {
-    const MailHeader* h = reinterpret_cast<const MailHeader*>(st->mail_local + (int64_t)(par * W + p) * sb);
-    const double sc = __ldcg(&h->score);
-    const int64_t gi = __ldcg(reinterpret_cast<const long long*>(&h->gidx));
-    if (gi < 0) continue;
-    if (win < 0 || sc > best || (sc == best && gi < bidx)) { win = p; best = sc; bidx = gi; }
+  // lane p reads header p; warp arg-max: max score, ties -> lowest global index
+  double sc = -INFINITY; long long gi = -1; double nm = 0.;
+  if (lane < W) {
+    sc = __ldcg(&mine->score);
+    gi = __ldcg(reinterpret_cast<const long long*>(&mine->gidx));
+    nm = __ldcg(&mine->norm);
   }
-  const unsigned char* wslot = st->mail_local + (int64_t)(par * W + win) * sb;
-  *f = bidx;
-  *norm = __ldcg(&reinterpret_cast<const MailHeader*>(wslot)->norm);
-  *row = reinterpret_cast<const float*>(wslot + sizeof(MailHeader));
-  if (lane == 0) st->seq = seq;
-  __syncwarp();
+  int win = (gi >= 0) ? lane : -1;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const double s2 = __shfl_xor_sync(0xffffffffu, sc, off);
+    const long long g2 = __shfl_xor_sync(0xffffffffu, gi, off);
+    const double n2 = __shfl_xor_sync(0xffffffffu, nm, off);
+    const int w2 = __shfl_xor_sync(0xffffffffu, win, off);
+    const bool take = (w2 >= 0) && (win < 0 || s2 > sc || (s2 == sc && g2 < gi));
+    if (take) { sc = s2; gi = g2; nm = n2; win = w2; }
+  }
+  if (win < 0) return false;
+  *f = gi;
+  *norm = nm;
+  *row = reinterpret_cast<const float*>(mc.local + (int64_t)(par * W + win) * mc.sb + sizeof(MailHeader));
   return true;
 }
 
 // direction(s) for the next scan from the iterate held in registers; returns false when GIGA's
 // cdirnrm < TOL (giga.py:28-29).  n2 = sum xw^2, bx = sum bn*xw, e2 = sum (xw-b)^2 precomputed.
 template <int J>
-__device__ __forceinline__ bool publish_direction(SolverState* st, const double (&xw)[J], const double* sb,
-                                                  const double* sbn, int lane, double n2, double bx, double e2,
-                                                  double* cdirnrm_out) {
-  const int S = st->S, ld = st->ld;
-  float* dir32 = st->dir32;
-  double* dir64 = st->dir64;
-  if (st->alg == BCG_ALG_GIGA) {
+__device__ __forceinline__ bool publish_direction(float* dir32, double* dir64, int S, int ld, bool giga, double tol,
+                                                  const double (&xw)[J], const double* sb, const double* sbn, int lane,
+                                                  double n2, double bx, double e2, double* cdirnrm_out) {
+  if (giga) {
     double nw = sqrt(n2);
     if (nw == 0.) nw = 1.;
     const double inw = 1. / nw;
@@ -162,7 +185,7 @@ __device__ __forceinline__ bool publish_direction(SolverState* st, const double 
     wsum<1>(c2);
     const double cn = sqrt(c2[0]);
     *cdirnrm_out = cn;
-    if (cn < st->tol) return false;
+    if (cn < tol) return false;
     const double icn = 1. / cn;
 #pragma unroll
     for (int j = 0; j < J; ++j) {
@@ -230,7 +253,7 @@ __device__ __forceinline__ void warp_top2(const ScanCand* c, int n, int lane, fl
 }
 
 template <int J>
-__device__ void control_loop(const LoopArgs& a, double* sb, double* sbn) {
+__device__ void control_loop(const LoopArgs& a, double* sb, double* sbn, double* sdir, unsigned char** speers) {
   SolverState* st = a.st;
   LoopCtl* ctl = a.ctl;
   const int lane = threadIdx.x & 31;
@@ -239,7 +262,12 @@ __device__ void control_loop(const LoopArgs& a, double* sb, double* sbn) {
   const bool giga = st->alg == BCG_ALG_GIGA;
   const int world = st->world;
   const int64_t row_offset = st->row_offset;
-  const double bnorm = st->bnorm, nsum = st->nsum;
+  const double bnorm = st->bnorm, nsum = st->nsum, tol = st->tol;
+  float* dir32 = st->dir32;
+  MailCtx mc;
+  mc.W = world; mc.me = st->rank; mc.ld = ld; mc.sb = st->mail_slot_bytes; mc.local = st->mail_local;
+  mc.peers = speers; mc.seq = st->seq;
+  if (lane < world && world > 1) speers[lane] = st->mail_peer[lane];
   const float* An = st->An;
   const double* norms = st->norms;
   int64_t* act_idx = st->act_idx;
@@ -297,7 +325,7 @@ __device__ void control_loop(const LoopArgs& a, double* sb, double* sbn) {
 
   double n2, bx, e2;
   iterate_sums(n2, bx, e2);
-  bool sel_ok = publish_direction<J>(st, xw, sb, sbn, lane, n2, bx, e2, &sel_aux);
+  bool sel_ok = publish_direction<J>(dir32, sdir, S, ld, giga, tol, xw, sb, sbn, lane, n2, bx, e2, &sel_aux);
   publish(1u, false);
 
   int it = 0;
@@ -328,12 +356,12 @@ __device__ void control_loop(const LoopArgs& a, double* sb, double* sbn) {
       __syncwarp();
       const float thr = top - (2e-5f + 1e-5f * fabsf(top));
       const bool near_tie = (lrow != kNoRow) && (row2 != kNoRow) && (second >= thr);
-      if (near_tie || (world > 1 && lrow != kNoRow)) {
+      if (near_tie) {
         // rare path: gather up to kRescoreMax candidates within the threshold, re-score in float64
         uint32_t chosen[kRescoreMax];
         int nch = 0;
         chosen[nch++] = lrow;
-        while (near_tie && nch < kRescoreMax) {
+        while (nch < kRescoreMax) {
           float s2; uint32_t r2;
           warp_pick(a.cta_cands, nc, chosen, nch, lane, &s2, &r2);
           if (r2 == kNoRow || !(s2 >= thr)) break;
@@ -341,32 +369,36 @@ __device__ void control_loop(const LoopArgs& a, double* sb, double* sbn) {
         }
         uint32_t brow = kNoRow; double best = -INFINITY;
         for (int r = 0; r < nch; ++r) {
-          const double sc = row_score_warp<J>(st, An + (size_t)chosen[r] * ld, lane);
+          double xr[J];
+          load_row<J>(An + (size_t)chosen[r] * ld, S, lane, xr);
+          const double sc = row_score_regs<J>(xr, sdir, S, giga, lane);
           if (brow == kNoRow || sc > best || (sc == best && chosen[r] < brow)) { best = sc; brow = chosen[r]; }
         }
         lrow = brow; lscore = best;
       }
+      const bool have = lrow != kNoRow;
+      if (world == 1 && !have) {                 // no comparable score at all (non-finite matrix)
+        if (lane == 0) { st->comm_error = 2; }
+        __syncwarp();
+        halted = 1;
+        break;
+      }
+      if (have) {
+        nf_stored = norms[lrow];
+        load_row<J>(An + (size_t)lrow * ld, S, lane, xf);        // unit row; scaled by the norm below
+        f = row_offset + (int64_t)lrow;
+        frow = An + (size_t)lrow * ld;
+      }
       if (world > 1) {
-        if (!mail_exchange_warp<J>(st, lane, lrow, lscore, &f, &nf_stored, &frow)) {
+        // cross-rank comparison needs the float64 score of the local best
+        if (have) lscore = row_score_regs<J>(xf, sdir, S, giga, lane);
+        if (!mail_exchange_warp<J>(mc, lane, S, xf, have, lscore, f, nf_stored, &f, &nf_stored, &frow)) {
           if (lane == 0) { st->comm_error = 1; }
           __syncwarp();
           halted = 1;
           break;
         }
-      } else if (lrow == kNoRow) {               // no comparable score at all (non-finite matrix)
-        if (lane == 0) { st->comm_error = 2; }
-        __syncwarp();
-        halted = 1;
-        break;
-      } else {
-        f = row_offset + (int64_t)lrow;
-        nf_stored = norms[lrow];
-        frow = An + (size_t)lrow * ld;
-      }
-#pragma unroll
-      for (int j = 0; j < J; ++j) {
-        const int s = lane + 32 * j;
-        if (s < S) xf[j] = (double)__ldcg(frow + s);
+        load_row<J>(frow, S, lane, xf);                          // the winner's unit row from my mailbox
       }
 #pragma unroll
       for (int j = 0; j < J; ++j) xf[j] *= nf_stored;
@@ -490,7 +522,7 @@ __device__ void control_loop(const LoopArgs& a, double* sb, double* sbn) {
     if (a.trace && lane == 0) a.trace[(size_t)it * 8 + 7] = globaltimer_ns() + (unsigned long long)(err == 12345.678);
     __syncwarp();
     if (!last) {
-      sel_ok = publish_direction<J>(st, xw, sb, sbn, lane, n2, bx, e2, &sel_aux);
+      sel_ok = publish_direction<J>(dir32, sdir, S, ld, giga, tol, xw, sb, sbn, lane, n2, bx, e2, &sel_aux);
       publish((unsigned int)(it + 2), false);
     }
     if (a.trace && lane == 0) a.trace[(size_t)it * 8 + 1] = globaltimer_ns();
@@ -554,6 +586,7 @@ __device__ void control_loop(const LoopArgs& a, double* sb, double* sbn) {
     st->n_events = n_events;
     st->select_failed = sel_ok ? 0 : 1;
     st->sel_aux = sel_aux;
+    st->seq = mc.seq;
   }
 }
 
@@ -575,8 +608,12 @@ __global__ void __launch_bounds__(384, 1) greedy_loop_kernel(const LoopArgs a) {
   double* sb = reinterpret_cast<double*>(cta_c + 32);
   double* sbn = sb + a.st->S;
 
+  // shared memory after the rings: barriers | per-warp candidates | b, bn (2 S) | float64 directions (2 S) |
+  // peer mailbox pointers (8) | ring slot records
+  double* sdir = sbn + a.st->S;
+  unsigned char** speers = reinterpret_cast<unsigned char**>(sdir + 2 * a.st->S);
   if (warp == wpb) {                    // control warp (only CTA 0's does anything)
-    if (blockIdx.x == 0) control_loop<J>(a, sb, sbn);
+    if (blockIdx.x == 0) control_loop<J>(a, sb, sbn, sdir, speers);
     return;
   }
 
@@ -609,8 +646,8 @@ __global__ void __launch_bounds__(384, 1) greedy_loop_kernel(const LoopArgs a) {
   // issued in consumption order, iteration after iteration, so the tile stream runs ahead ACROSS
   // iterations.  sm_row0 / sm_it describe what each ring slot holds.
   const bool leader = lane == 0;
-  int64_t* sm_row0 = reinterpret_cast<int64_t*>(sbn + a.st->S) + warp * q.stages;
-  int* sm_it = reinterpret_cast<int*>(reinterpret_cast<int64_t*>(sbn + a.st->S) + wpb * q.stages) + warp * q.stages;
+  int64_t* sm_row0 = reinterpret_cast<int64_t*>(speers + kMaxWorld) + warp * q.stages;
+  int* sm_it = reinterpret_cast<int*>(reinterpret_cast<int64_t*>(speers + kMaxWorld) + wpb * q.stages) + warp * q.stages;
   int issue_slot = 0;
   int64_t issue_k = 0;         // static chunks of iteration issue_it issued so far
   int issue_it = 0;            // iteration the next issue belongs to
