@@ -5,11 +5,19 @@ column-sum-only projection on the device, the N x S matrix is never written -- p
 projection and (K, S, d) gradients of the K pseudo-points, which are K-sized host algebra."""
 import numpy as np
 from ..util import nn_opt
+from ..comm import SerialComm, shard_layout
 from .coreset import Coreset
 
 
 class BatchPSVICoreset(Coreset):
-  def __init__(self, data, ll_projector, opt_itrs, n_subsample_opt=None, step_sched=lambda i: 1./(1.+i), **kw):
+  def __init__(self, data, ll_projector, opt_itrs, n_subsample_opt=None, step_sched=lambda i: 1./(1.+i), comm=None,
+               **kw):
+    # with a communicator `data` is this rank's shard of the rows: the data column sums are all-reduced
+    # (one S-vector per gradient step); the K pseudo-points and their optimiser state are replicated
+    self.comm = comm or SerialComm()
+    self.row_offset, self.n_global, _ = shard_layout(self.comm, data.shape[0])
+    if self.comm.world > 1 and n_subsample_opt is not None:
+      raise NotImplementedError('subsampling with N-sharding is not supported')
     self.data = data
     self.ll_projector = ll_projector
     self.opt_itrs = opt_itrs
@@ -18,9 +26,13 @@ class BatchPSVICoreset(Coreset):
     super().__init__(**kw)
 
   def _build(self, sz):
-    init_idcs = np.random.choice(self.data.shape[0], size=sz, replace=False)     # bpsvi.py:17
-    self.pts = np.array(self.data[init_idcs], dtype=np.float64)
-    self.wts = self.data.shape[0]/sz*np.ones(sz)
+    init_idcs = np.random.choice(self.n_global, size=sz, replace=False)          # bpsvi.py:17 (same draw on every rank)
+    if self.comm.world == 1:
+      self.pts = np.array(self.data[init_idcs], dtype=np.float64)
+    else:
+      from ..comm import gather_rows
+      self.pts = np.array(gather_rows(self.comm, self.data, self.row_offset, init_idcs), dtype=np.float64)
+    self.wts = self.n_global/sz*np.ones(sz)
     self.idcs = -1*np.ones(sz)
     self._optimize()
 
@@ -33,9 +45,10 @@ class BatchPSVICoreset(Coreset):
     else:
       sub = np.random.randint(self.data.shape[0], size=self.n_subsample_opt)
       rows, scaling, cache = self.data[sub], self.data.shape[0]/self.n_subsample_opt, False
-    if hasattr(prj, 'project_sum'):
-      return scaling*prj.project_sum(rows, cache=cache)
-    return scaling*prj.project(rows).sum(axis=0)
+    local = prj.project_sum(rows, cache=cache) if hasattr(prj, 'project_sum') else prj.project(rows).sum(axis=0)
+    if self.comm.world > 1:
+      local = self.comm.allreduce_sum(local)
+    return scaling*local
 
   def gradient(self, x, sz, d):
     """bpsvi.py:46-55 -- one gradient evaluation (the "grad step" of BASELINE config 5)"""

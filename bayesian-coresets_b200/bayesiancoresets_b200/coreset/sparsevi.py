@@ -10,13 +10,20 @@ Host-side pieces (sampler, nn_opt, the K-sized algebra) stay NumPy, in the refer
 order, so seeded runs consume the global RNG identically."""
 import numpy as np
 from ..util import nn_opt
+from ..comm import SerialComm, shard_layout
 from .. import _native as nat
 from .coreset import Coreset
 
 
 class SparseVICoreset(Coreset):
   def __init__(self, data, ll_projector, n_subsample_select=None, n_subsample_opt=None, opt_itrs=100,
-               step_sched=lambda i: 1./(1.+i), **kw):
+               step_sched=lambda i: 1./(1.+i), comm=None, **kw):
+    # with a communicator `data` is this rank's contiguous shard of the rows; column sums are all-reduced,
+    # the selection arg-max is resolved over the ranks (lowest global index wins ties), indices are global
+    self.comm = comm or SerialComm()
+    self.row_offset, self.n_global, _ = shard_layout(self.comm, data.shape[0])
+    if self.comm.world > 1 and (n_subsample_select is not None or n_subsample_opt is not None):
+      raise NotImplementedError('subsampling with N-sharding is not supported')
     self.data = data
     self.ll_projector = ll_projector
     self.n_subsample_select = None if n_subsample_select is None else min(data.shape[0], n_subsample_select)
@@ -52,9 +59,16 @@ class SparseVICoreset(Coreset):
 
   def _sum(self, rows, cache):
     prj = self.ll_projector
-    if hasattr(prj, 'project_sum'):
-      return prj.project_sum(rows, cache=cache)
-    return prj.project(rows).sum(axis=0)
+    local = prj.project_sum(rows, cache=cache) if hasattr(prj, 'project_sum') else prj.project(rows).sum(axis=0)
+    return self.comm.allreduce_sum(local) if self.comm.world > 1 else local
+
+  def _row(self, f):
+    """data row with global index f (owned by exactly one rank)"""
+    if self.comm.world == 1:
+      return np.asarray(self.data[f], dtype=np.float64)
+    mine = self.row_offset <= f < self.row_offset + self.data.shape[0]
+    piece = np.asarray(self.data[f - self.row_offset], dtype=np.float64) if mine else None
+    return [p for p in self.comm.allgather_object(piece) if p is not None][0]
 
   # ---- sparsevi.py:44-67 -------------------------------------------------------------------------
   def _select(self):
@@ -62,9 +76,15 @@ class SparseVICoreset(Coreset):
     vecs = self._device_vecs(rows, cache)
     S = vecs.shape[1]
     corevecs = self._corevecs(S)
-    resid = scaling*vecs.sum(axis=0) - self.wts.dot(corevecs)
+    total = vecs.sum(axis=0)
+    if self.comm.world > 1:
+      total = self.comm.allreduce_sum(total)
+    resid = scaling*total - self.wts.dot(corevecs)
     # corrs = vecs.dot(resid)/||vecs_n||/S : arg-max and maximum on the device
     best, dot = vecs.argmax_dot(resid)
+    if self.comm.world > 1:
+      cands = [c for c in self.comm.allgather_object((dot, self.row_offset + best if best >= 0 else -1)) if c[1] >= 0]
+      dot, best = max(cands, key=lambda c: (c[0], -c[1]))
     corr_max = dot/S
     corecorrs = np.fabs(corevecs.dot(resid)/np.sqrt((corevecs**2).sum(axis=1)))/S
     if corecorrs.size == 0 or corr_max > corecorrs.max():
@@ -72,7 +92,7 @@ class SparseVICoreset(Coreset):
       if f not in self.idcs:
         self.wts = np.append(self.wts, 0.)
         self.idcs = np.append(self.idcs, np.int64(f))
-        row = np.asarray(self.data[f], dtype=np.float64)[np.newaxis, :]
+        row = self._row(f)[np.newaxis, :]
         self.pts = row if self.pts.size == 0 else np.vstack((self.pts, row))
 
   # ---- sparsevi.py:69-76 -------------------------------------------------------------------------

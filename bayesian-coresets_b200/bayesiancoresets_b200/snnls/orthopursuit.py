@@ -14,13 +14,29 @@ class OrthoPursuit(SparseNNLS):
   K active columns (K x S, gathered from the device's replicated active set)."""
   _alg = nat.ALG_OMP
 
+  def _active_problem(self):
+    """as the base class, but the float64 active rows are mirrored on the host incrementally: one new
+    row (S float64) crosses PCIe per iteration instead of the whole K x S active set"""
+    idx, w = self._native.active()
+    have = 0 if getattr(self, '_rows', None) is None else self._rows.shape[0]
+    if idx.shape[0] > have:
+      new = self._native.active_rows(have, idx.shape[0] - have)
+      self._rows = new if have == 0 else np.vstack((self._rows, new))
+    pos = np.flatnonzero(w > 0)
+    pos = pos[np.argsort(idx[pos], kind='stable')]
+    return idx, w, pos, np.ascontiguousarray(self._rows[pos].T)
+
+  def reset(self):
+    super().reset()
+    self._rows = None
+
   def _run(self, itrs):
     events = []
     retried = False
     for _ in range(itrs):
-      nonempty = self.size() > 0
+      idx0, prev_w = self._native.active()
+      nonempty = bool((prev_w > 0).any())
       prev_error = self.error()
-      _, prev_w = self._native.active()
       f = self._native.omp_select()                       # orthopursuit.py:17-38 (w[f] = 1 on device)
       idx, w, pos, Aact = self._active_problem()
       res = nnls(Aact, self.b, maxiter=100*self.n_global)  # orthopursuit.py:40

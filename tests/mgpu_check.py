@@ -60,6 +60,33 @@ def main():
     cuts = [0] + [3 + i for i in range(w - 1)] + [N]
     return cuts[r], cuts[r + 1]
   check(9000, 6, 256, 30, 'giga', shard=lopsided)
+  # SparseVI / BatchPSVI N-sharded: same result as the single-process oracle
+  from oracle import coresets
+  rng = np.random.RandomState(5)
+  x = rng.randn(3000, 4) + 1.
+  th = rng.randn(24, 4)
+  lo, hi = bc.comm.even_shard(3000, rank, world)
+  np.random.seed(3)
+  a = bc.SparseVICoreset(x[lo:hi], bc.GaussianProjector(lambda n, w, p: th + 0.01*np.random.randn(*th.shape), 24, np.eye(4)),
+                         opt_itrs=6, comm=comm)
+  a.build(4)
+  np.random.seed(3)
+  fg = lambda xx, tt: models.gaussian_loglik(xx, tt, np.eye(4), 0.)
+  o = coresets.SparseVIOracle(x, models.OracleProjector(lambda n, w, p: th + 0.01*np.random.randn(*th.shape), 24, fg), opt_itrs=6)
+  o.build(4)
+  assert np.array_equal(a.idcs, o.idcs), (a.idcs, o.idcs)
+  assert np.allclose(a.wts, o.wts, rtol=1e-6, atol=1e-9) and np.array_equal(a.pts, o.pts)
+  Zb, thb = lr_problem(8, 2000, 4, 32)
+  np.random.seed(9)
+  bp = bc.BatchPSVICoreset(Zb[slice(*bc.comm.even_shard(2000, rank, world))], bc.LogisticRegressionProjector(lambda n, w, p: thb, 32),
+                           opt_itrs=5, comm=comm)
+  bp.build(6)
+  np.random.seed(9)
+  ob = coresets.BatchPSVIOracle(Zb, models.OracleProjector(lambda n, w, p: thb, 32, models.lr_loglik, models.lr_grad_z_loglik), opt_itrs=5)
+  ob.build(6)
+  assert np.allclose(bp.wts, ob.wts, rtol=1e-8) and np.allclose(bp.pts, ob.pts, rtol=1e-8, atol=1e-10)
+  if rank == 0:
+    print('mgpu sparsevi / bpsvi world=%d: identical to the oracle' % world, flush=True)
   os.environ['BCG_ENGINE'] = '1'          # launch-per-iteration engine with the block-wide exchange
   check(20000, 6, 128, 30, 'giga')
   if rank == 0:
