@@ -110,6 +110,19 @@ def measured_peak():
     return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
 
 
+def measured_traffic_ratio(kernel, S):
+  """DRAM bytes / algorithmic bytes of the dominant kernel from the committed `ncu --set full` capture
+  (profiles/r01_loop_traffic.json, written by profiles/extract_traffic.py); None when there is no capture"""
+  try:
+    with open(os.path.join(ROOT, 'profiles', 'r01_loop_traffic.json')) as f:
+      t = json.load(f)
+    if t.get('kernel') == kernel and int(t.get('S', -1)) == int(S):
+      return float(t['dram_bytes']) / float(t['algorithmic_bytes'])
+  except Exception:
+    pass
+  return None
+
+
 def cpu_reference_run(workload, steps, warmup, sample_rows=None):
   """The reference's CPU path for this workload: float64 NumPy/OpenBLAS port of
   HilbertCoreset(...GIGA).build (oracle/, bit-identical to the reference) on all host cores, on a
@@ -266,6 +279,7 @@ def main():
   r = measure(args.workload, args.steps, args.warmup, not args.no_e2e)
   peak, peak_src = measured_peak()
   achieved = r['bytes_per_launch'] / (r['kernel_ms'] * 1e-3) / 1e9
+  ratio = measured_traffic_ratio(r['kernel'], r['S'])
   value = args.steps / (r['build_ms'] * 1e-3)
   line = {
     'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
@@ -278,7 +292,10 @@ def main():
     'gpu_launches': r['launches'],
     'clocks': r['clocks'],
     'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                 'traffic': None, 'kernel': r['kernel'], 'bytes_per_launch': r['bytes_per_launch'],
+                 'traffic': None if ratio is None else ratio * r['bytes_per_launch'],
+                 'traffic_source': None if ratio is None else
+                 'ncu dram__bytes_read+write per algorithmic byte (profiles/r01_loop_traffic.json) x bytes_per_launch',
+                 'kernel': r['kernel'], 'bytes_per_launch': r['bytes_per_launch'],
                  'avg_launch_ms': r['kernel_ms'], 'peak_source': peak_src,
                  'kernel_share_of_step': r['kernel_ms'] * r['launches_per_step'] * args.steps / r['build_ms']},
   }

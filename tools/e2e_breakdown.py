@@ -1,6 +1,7 @@
 """diagnostic: where the end-to-end construction time goes (upload / projection / solver setup / build / read-back)"""
-import sys, time
-sys.path.insert(0, 'bayesian-coresets_b200'); sys.path.insert(0, '.')
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'bayesian-coresets_b200')); sys.path.insert(0, ROOT)
 import numpy as np
 import bayesiancoresets_b200 as bc
 from bayesiancoresets_b200 import _native as nat

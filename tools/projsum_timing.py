@@ -1,6 +1,7 @@
 """diagnostic: time the column-sum-only projection kernel alone (Gaussian = pure GEMM, Poisson = GEMM + link)"""
-import sys, time
-sys.path.insert(0, 'bayesian-coresets_b200'); sys.path.insert(0, '.')
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'bayesian-coresets_b200')); sys.path.insert(0, ROOT)
 import numpy as np
 import bayesiancoresets_b200 as bc
 N, d, S = int(float(sys.argv[1])), int(sys.argv[2]), int(sys.argv[3])

@@ -1,6 +1,7 @@
 """diagnostic: per-iteration device timeline of the persistent loop kernel"""
 import sys, os
-sys.path.insert(0, 'bayesian-coresets_b200'); sys.path.insert(0, '.')
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'bayesian-coresets_b200')); sys.path.insert(0, ROOT)
 import numpy as np
 import bayesiancoresets_b200 as bc
 from bench import lr_shard, lr_samples, WORKLOADS
