@@ -359,3 +359,65 @@ def test_project_sum_tiled_kernel_vs_oracle(bc, n, d, S):
   ref = models.project(models.poisson_loglik, Zp, th).sum(axis=0)
   got = bc.PoissonProjector(lambda k, w, p: th, S).project_sum(Zp)
   np.testing.assert_allclose(got, ref, rtol=1e-9, atol=1e-9*np.abs(ref).max())
+
+
+# ---------------------------------------------------------------- remaining API paths
+def test_hilbert_subsample_golden(bc):
+  """hilbert.py:13-22: sorted de-duplicated subsample from the global RNG"""
+  g = load_golden('lr_subsample_giga')
+  Z, theta = lr_problem(int(g['seed']), int(g['N']), int(g['d']), int(g['S']))
+  prj = bc.LogisticRegressionProjector(lambda n, w, p: theta, int(g['S']))
+  np.random.seed(int(g['sub_seed']))
+  cs = bc.HilbertCoreset(Z, prj, n_subsample=int(g['n_subsample']))
+  cs.build(int(g['itrs']))
+  assert np.array_equal(cs.sub_idcs, g['sub_idcs'])
+  assert [e.f for e in cs.snnls.last_events] == list(g['sel'])
+  wts, pts, idcs = cs.get()
+  assert np.array_equal(idcs, g['sub_idcs'][g['w'] > 0]) and np.array_equal(pts, Z[idcs])
+  assert_weights_close(cs.snnls.weights(), g['w'])
+
+
+@pytest.mark.parametrize('alg', ['giga', 'fw'])
+def test_wide_rows_use_launch_per_iteration_engine(bc, alg):
+  """S > 512 is outside the persistent kernel's control warp: the scan + step kernels take over"""
+  rng = np.random.RandomState(12)
+  X = rng.randn(3000, 640)*rng.uniform(0.5, 2., size=(3000, 1))
+  o = greedy.ORACLES[alg](X.T, X.sum(axis=0))
+  oev = o.build(25)
+  cs, ev = run_gpu(bc, X, alg, 25)
+  assert [e.f for e in ev] == [e[1] for e in oev]
+  assert_weights_close(cs.snnls.weights(), o.w)
+
+
+def test_coreset_optimize_and_blackbox_projector(bc):
+  """Coreset.optimize (coreset.py:47-64) through HilbertCoreset._optimize; BlackBoxProjector host callbacks"""
+  g = load_golden('lr_project_small')
+  prj = bc.BlackBoxProjector(lambda n, w, p: g['theta'], int(g['S']), models.lr_loglik)
+  cs = bc.HilbertCoreset(g['Z'], prj, snnls=bc.snnls.GIGA)
+  cs.build(30)
+  e0 = cs.error()
+  cs.optimize()
+  assert cs.error() <= e0*(1 + 1e-12) and not cs.reached_numeric_limit
+  o = greedy.GigaOracle(g['vecs'].T, g['vecs'].sum(axis=0))
+  o.build(30)
+  o.optimize()
+  assert cs.error() == pytest.approx(o.error(), rel=1e-5)
+  wts, pts, idcs = cs.get()
+  assert np.array_equal(idcs, np.flatnonzero(o.w > 0))
+
+
+def test_sparsevi_with_blackbox_projector(bc):
+  """a user-callback projector still works with SparseVI: host evaluation, device arg-max"""
+  from oracle import coresets
+  rng = np.random.RandomState(7)
+  x = rng.randn(800, 3) + 1.
+  th = rng.randn(16, 3)
+  f = lambda xx, tt: models.gaussian_loglik(xx, tt, np.eye(3), 0.)
+  np.random.seed(1)
+  a = bc.SparseVICoreset(x, bc.BlackBoxProjector(lambda n, w, p: th, 16, f), opt_itrs=5)
+  a.build(3)
+  np.random.seed(1)
+  o = coresets.SparseVIOracle(x, models.OracleProjector(lambda n, w, p: th, 16, f), opt_itrs=5)
+  o.build(3)
+  assert np.array_equal(a.idcs, o.idcs)
+  np.testing.assert_allclose(a.wts, o.wts, rtol=1e-6, atol=1e-9)
