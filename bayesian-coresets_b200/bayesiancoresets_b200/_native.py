@@ -67,6 +67,7 @@ _PROTOTYPES = {
   'bcg_solver_build': (_c.c_int, [_P, _c.c_int32, _c.c_double, _c.POINTER(IterEvent), _c.POINTER(_c.c_int32)]),
   'bcg_solver_omp_select': (_c.c_int, [_P, _c.POINTER(_c.c_int64)]),
   'bcg_solver_probe_argmax': (_c.c_int, [_P, _P, _c.POINTER(_c.c_int64), _c.POINTER(_c.c_double)]),
+  'bcg_solver_nnls': (_c.c_int, [_P, _c.c_int32]),
   'bcg_solver_error': (_c.c_int, [_P, _c.POINTER(_c.c_double)]),
   'bcg_solver_size': (_c.c_int, [_P, _c.POINTER(_c.c_int64), _c.POINTER(_c.c_int64)]),
   'bcg_solver_halted': (_c.c_int, [_P, _c.POINTER(_c.c_int32)]),
@@ -333,6 +334,9 @@ class NativeSolver(object):
     f, sc = ctypes.c_int64(), ctypes.c_double()
     check(lib().bcg_solver_probe_argmax(self.handle, _ptr(d), ctypes.byref(f), ctypes.byref(sc)))
     return f.value, sc.value
+
+  def nnls(self, from_scratch=False):
+    check(lib().bcg_solver_nnls(self.handle, 1 if from_scratch else 0))
 
   def error(self):
     v = ctypes.c_double()

@@ -3,6 +3,7 @@
 optimize / reset, attributes w / A / b / reached_numeric_limit -- with the greedy loop running
 on the device through the C-ABI (bcg_solver_build)."""
 import logging
+import os
 import secrets
 import numpy as np
 from scipy.optimize import nnls
@@ -132,13 +133,17 @@ class SparseNNLS(object):
 
   def optimize(self):
     prev_cost = self.error()
-    idx, w, pos, Aact = self._active_problem()
-    if pos.shape[0] == 0:
+    idx, w = self._native.active()
+    if not (w > 0).any():
       return
-    res = nnls(Aact, self.b, maxiter=100*self.n_global)
-    w_new = w.copy()
-    w_new[pos] = res[0]
-    self._native.set_weights(w_new)
+    if os.environ.get('BCG_NNLS', 'device') == 'scipy':
+      idx, w, pos, Aact = self._active_problem()
+      res = nnls(Aact, self.b, maxiter=100*self.n_global)
+      w_new = w.copy()
+      w_new[pos] = res[0]
+      self._native.set_weights(w_new)
+    else:
+      self._native.nnls(from_scratch=True)          # float64 Lawson-Hanson on the device (csrc/nnls_logic.h)
     new_cost = self.error()
     if new_cost > prev_cost*(1. + util.TOL):
       self.log.warning('self.optimize() returned a solution with increasing error. Numeric limit possibly '

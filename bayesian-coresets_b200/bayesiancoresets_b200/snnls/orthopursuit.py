@@ -1,3 +1,4 @@
+import os
 import numpy as np
 from scipy.optimize import nnls
 
@@ -9,10 +10,18 @@ from .. import _native as nat
 class OrthoPursuit(SparseNNLS):
   """Orthogonal matching pursuit (reference: snnls/orthopursuit.py:7-42).
 
-  Selection (the N x S residual-correlation scan, plus the negative direction over the active
-  set) runs on the device; the reweight is the reference's own `scipy.optimize.nnls` call on the
-  K active columns (K x S, gathered from the device's replicated active set)."""
+  Everything runs on the device, `build(itrs)` without a host round trip per iteration: the
+  N x S residual-correlation scan, the negative direction over the active set, and the NNLS
+  re-solve on the K active columns (float64 Lawson-Hanson, warm-started from the previous passive
+  set -- csrc/nnls_logic.h; the NNLS minimiser is unique, so it equals `scipy.optimize.nnls`).
+  With BCG_NNLS=scipy in the environment the reweight is the reference's own SciPy call on the
+  host instead (kept for cross-checking)."""
   _alg = nat.ALG_OMP
+
+  def _run(self, itrs):
+    if os.environ.get('BCG_NNLS', 'device') == 'scipy':
+      return self._run_scipy(itrs)
+    return super()._run(itrs)
 
   def _active_problem(self):
     """as the base class, but the float64 active rows are mirrored on the host incrementally: one new
@@ -30,7 +39,7 @@ class OrthoPursuit(SparseNNLS):
     super().reset()
     self._rows = None
 
-  def _run(self, itrs):
+  def _run_scipy(self, itrs):
     events = []
     retried = False
     for _ in range(itrs):

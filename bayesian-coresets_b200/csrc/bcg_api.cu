@@ -94,6 +94,9 @@ struct bcg_solver {
   ScanCand* d_cta_cands;
   unsigned int* d_claims;
   int claims_cap;
+  NnlsWork nw;              // device buffers of the NNLS factorisation (host copy of the struct)
+  NnlsWork* d_nw;
+  int nw_cap;
   int trace_on;
   unsigned long long* d_trace;
   int trace_cap, trace_n;
@@ -774,6 +777,9 @@ extern "C" int bcg_solver_create(bcg_ctx* ctx, bcg_vecs* v, int32_t alg, const d
   s->d_cta_cands = nullptr;
   s->d_claims = nullptr;
   s->claims_cap = 0;
+  memset(&s->nw, 0, sizeof(NnlsWork));
+  s->d_nw = nullptr;
+  s->nw_cap = 0;
   s->trace_on = 0;
   s->d_trace = nullptr;
   s->trace_cap = s->trace_n = 0;
@@ -832,6 +838,9 @@ extern "C" int bcg_solver_destroy(bcg_solver* s) {
   void* bufs[] = {h.b, h.bn, h.xw, h.xw_new, h.xf, h.dir64, h.dir32, h.wrow, h.cands, h.act_idx, h.act_w,
                   h.act_w_new, h.act_norm, h.act_rows, h.events, s->d_fout, s->d, s->mail, s->d_ctl, s->d_cta_cands, s->d_trace, s->d_claims};
   for (void* p : bufs)
+    if (p) cudaFree(p);
+  void* nb[] = {s->nw.Q, s->nw.R, s->nw.c, s->nw.z, s->nw.wP, s->nw.h, s->nw.v, s->nw.P, s->nw.Z, s->nw.inP, s->d_nw};
+  for (void* p : nb)
     if (p) cudaFree(p);
   for (cudaEvent_t e : s->scan_ev) cudaEventDestroy(e);
   cudaEventDestroy(s->ev0);
@@ -894,11 +903,59 @@ extern "C" int bcg_solver_comm_connect(bcg_solver* s, int32_t world, int32_t ran
   return BCG_OK;
 }
 
+// (re)allocate the NNLS work space for the current active-set capacity; a fresh work space is invalid
+static int ensure_nnls(bcg_solver* s) {
+  const int cap = s->h.cap, S = s->h.S;
+  if (s->d_nw && s->nw_cap == cap) return BCG_OK;
+  NnlsWork& w = s->nw;
+  void* old[] = {w.Q, w.R, w.c, w.z, w.wP, w.h, w.v, w.P, w.Z, w.inP};
+  for (void* p : old)
+    if (p) CK(cudaFree(p));
+  memset(&w, 0, sizeof(NnlsWork));
+  CK(cudaMalloc(&w.Q, (size_t)cap * S * sizeof(double)));
+  CK(cudaMalloc(&w.R, (size_t)cap * cap * sizeof(double)));
+  CK(cudaMalloc(&w.c, (size_t)cap * sizeof(double)));
+  CK(cudaMalloc(&w.z, (size_t)2 * cap * sizeof(double)));
+  CK(cudaMalloc(&w.wP, (size_t)cap * sizeof(double)));
+  CK(cudaMalloc(&w.h, (size_t)cap * sizeof(double)));
+  CK(cudaMalloc(&w.v, (size_t)S * sizeof(double)));
+  CK(cudaMalloc(&w.P, (size_t)cap * sizeof(int32_t)));
+  CK(cudaMalloc(&w.Z, (size_t)cap * sizeof(int32_t)));
+  CK(cudaMalloc(&w.inP, (size_t)cap * sizeof(int32_t)));
+  CK(cudaMemsetAsync(w.inP, 0, (size_t)cap * sizeof(int32_t), s->ctx->stream));
+  w.cap = cap;
+  w.valid = 0;
+  if (!s->d_nw) CK(cudaMalloc(&s->d_nw, sizeof(NnlsWork)));
+  CK(cudaMemcpyAsync(s->d_nw, &w, sizeof(NnlsWork), cudaMemcpyHostToDevice, s->ctx->stream));
+  CK(cudaStreamSynchronize(s->ctx->stream));
+  s->nw_cap = cap;
+  return BCG_OK;
+}
+
+static int invalidate_nnls(bcg_solver* s) {
+  if (!s->d_nw) return BCG_OK;
+  const int32_t zero = 0;
+  CK(cudaMemcpyAsync(&s->d_nw->valid, &zero, sizeof(int32_t), cudaMemcpyHostToDevice, s->ctx->stream));
+  return BCG_OK;
+}
+
+// NNLS re-solve over the stored rows with positive weight, on the device (snnls.py:82-97 with from_scratch = 1;
+// orthopursuit.py:39-41 warm-started with from_scratch = 0).  Refreshes A w and error().
+extern "C" int bcg_solver_nnls(bcg_solver* s, int32_t from_scratch) {
+  if (!s) return fail(BCG_ERR_ARG, "null solver");
+  RET(use_device(s->ctx));
+  RET(ensure_nnls(s));
+  RET(push_state(s));
+  nnls_kernel<<<1, kStepThreads, 0, s->ctx->stream>>>(s->d, s->d_nw, from_scratch ? 1 : 0);
+  CK(cudaGetLastError());
+  RET(pull_state(s));
+  return BCG_OK;
+}
+
 extern "C" int bcg_solver_build(bcg_solver* s, int32_t itrs, double tol, bcg_iter_event* events, int32_t* n_events) {
   if (!s) return fail(BCG_ERR_ARG, "null solver");
   RET(use_device(s->ctx));
   if (n_events) *n_events = 0;
-  if (s->h.alg == BCG_ALG_OMP) return fail(BCG_ERR_STATE, "OMP iterations are driven with bcg_solver_omp_select");
   if (itrs <= 0 || s->h.halted || (s->v->n == 0 && s->h.world == 1)) return BCG_OK;
   cudaStream_t st = s->ctx->stream;
   SolverState& h = s->h;
@@ -912,7 +969,25 @@ extern "C" int bcg_solver_build(bcg_solver* s, int32_t itrs, double tol, bcg_ite
   h.comm_error = 0;
   RET(push_state(s));
   const bool loop = s->use_loop && !s->profiling;
-  if (loop) {
+  if (h.alg == BCG_ALG_OMP) {
+    // OrthoPursuit: selection scan + on-device NNLS per iteration, no host round trip inside the loop
+    RET(ensure_nnls(s));
+    CK(cudaEventRecord(s->ev0, st));
+    step_kernel<<<1, kStepThreads, 0, st>>>(s->d, 0, 0, 1);           // reset the per-call retry flag
+    for (int i = 0; i < itrs; ++i) {
+      step_kernel<<<1, kStepThreads, 0, st>>>(s->d, 0, 1, 0);         // residual direction
+      RET(launch_scan(s));
+      omp_iteration_kernel<<<1, kStepThreads, 0, st>>>(s->d, s->d_nw);
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(s->ev1, st));
+    RET(pull_state(s));
+    CK(cudaEventElapsedTime(&s->build_ms, s->ev0, s->ev1));
+    s->scan_launches = itrs;
+    s->step_launches = 2 * itrs + 1;
+    s->loop_launches = 0;
+    s->scan_ms = 0.f;
+  } else if (loop) {
     // the whole build call is ONE persistent cooperative kernel (loop_kernel.cuh)
     LoopArgs la;
     la.st = s->d;
@@ -1121,6 +1196,7 @@ extern "C" int bcg_solver_set_weights(bcg_solver* s, const double* w, int64_t k)
   RET(use_device(s->ctx));
   cudaStream_t st = s->ctx->stream;
   if (k > 0) CK(cudaMemcpyAsync(s->h.act_w, w, (size_t)k * sizeof(double), cudaMemcpyHostToDevice, st));
+  RET(invalidate_nnls(s));
   refresh_kernel<<<1, kStepThreads, 0, st>>>(s->d);
   CK(cudaGetLastError());
   RET(pull_state(s));
@@ -1136,6 +1212,7 @@ extern "C" int bcg_solver_reset(bcg_solver* s) {
   h.retried = 0;
   h.select_failed = 0;
   h.err = h.bnorm;
+  RET(invalidate_nnls(s));
   CK(cudaMemsetAsync(h.xw, 0, h.S * sizeof(double), s->ctx->stream));
   RET(push_state(s));
   CK(cudaStreamSynchronize(s->ctx->stream));

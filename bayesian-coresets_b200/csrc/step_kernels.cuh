@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "step_logic.h"
+#include "nnls_logic.h"
 #include "sync_ptx.cuh"
 
 namespace bcg {
@@ -108,6 +109,43 @@ __global__ void __launch_bounds__(kStepThreads, 1) probe_kernel(SolverState* st,
     *f_out = (lrow == kNoRow) ? -1 : st->row_offset + (int64_t)lrow;
     *score_out = sc;
   }
+}
+
+// OMP iteration on the device (orthopursuit.py:17-42 inside snnls.py:41-78): selection (+ w[f] = 1), NNLS
+// re-solve on the active set, monotone-error check with revert, event log, retry / latch.
+// act_w_new keeps the weights from before the iteration for the revert.
+__global__ void __launch_bounds__(kStepThreads, 1) omp_iteration_kernel(SolverState* st, NnlsWork* W) {
+  __shared__ double sred[256];
+  Blk B{(int)threadIdx.x, (int)blockDim.x, sred};
+  if (st->halted) return;
+  bool nonempty;
+  count_positive(B, st, &nonempty);
+  const double prev_err = st->err;
+  const int nact0 = st->nact;
+  for (int k = B.tid; k < nact0; k += B.nthr) st->act_w_new[k] = st->act_w[k];
+  B.sync();
+  const int64_t f = omp_select(B, st);
+  if (st->comm_error) return;
+  nnls_solve(B, st, W, 0);
+  const double err = st->err;
+  if (nonempty && err > prev_err) {                      // snnls.py:58-61: revert
+    for (int k = B.tid; k < st->nact; k += B.nthr) st->act_w[k] = (k < nact0) ? st->act_w_new[k] : 0.;
+    B.sync();
+    if (B.tid == 0) W->valid = 0;
+    B.sync();
+    refresh_iterate(B, st);
+    if (B.tid == 0) fail_event(st, BCG_IT_FAIL_MONOTONE, f, err, prev_err);
+  } else if (B.tid == 0) {
+    if (nonempty) st->retried = 0;
+    push_event(st, BCG_IT_OK, f, st->nact, err, 0., 0.);
+  }
+  B.sync();
+}
+
+__global__ void __launch_bounds__(kStepThreads, 1) nnls_kernel(SolverState* st, NnlsWork* W, int from_scratch) {
+  __shared__ double sred[256];
+  Blk B{(int)threadIdx.x, (int)blockDim.x, sred};
+  nnls_solve(B, st, W, from_scratch);
 }
 
 __global__ void __launch_bounds__(kStepThreads, 1) refresh_kernel(SolverState* st) {

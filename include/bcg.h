@@ -20,6 +20,7 @@
  *                              orthopursuit.py:9-15
  *   bcg_solver_build           snnls/snnls.py:31-79 driving giga.py:20-64 / frankwolfe.py:15-40
  *   bcg_solver_omp_select      orthopursuit.py:17-35 (+ the w[f] = 1 of :38)
+ *   bcg_solver_nnls            orthopursuit.py:39-41, snnls/snnls.py:82-97 (scipy.optimize.nnls)
  *   bcg_solver_error           snnls/snnls.py:28-29
  *   bcg_solver_active / size   snnls/snnls.py:22-26 (sparse form of w)
  *   bcg_solver_set_weights     the write-back of snnls.py:88 / orthopursuit.py:41
@@ -148,6 +149,10 @@ int  bcg_solver_omp_select(bcg_solver* s, int64_t* f);
 /* argmax over the local rows of <a_n/||a_n||, dir> and its float64 value; no state change.  Needs a
  * one-direction solver (BCG_ALG_FW / BCG_ALG_OMP).  Replaces sparsevi.py:51,56-57. */
 int  bcg_solver_probe_argmax(bcg_solver* s, const double* dir, int64_t* f, double* score);
+/* NNLS re-solve over the stored rows with positive weight, on the device, float64 Lawson-Hanson
+ * (snnls.py:82-97 optimize() with from_scratch = 1; orthopursuit.py:39-41 with a warm start otherwise).
+ * For BCG_ALG_OMP bcg_solver_build runs selection + this solve per iteration without host round trips. */
+int  bcg_solver_nnls(bcg_solver* s, int32_t from_scratch);
 int  bcg_solver_error(bcg_solver* s, double* err);
 int  bcg_solver_size(bcg_solver* s, int64_t* n_positive, int64_t* n_stored);
 int  bcg_solver_halted(bcg_solver* s, int32_t* reached_numeric_limit);

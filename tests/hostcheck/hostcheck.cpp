@@ -134,3 +134,61 @@ extern "C" int hostcheck_omp_select(const float* An, const double* norms, const 
   *f_out = omp_select(B, &st);
   return 0;
 }
+
+// ---- NNLS logic check ------------------------------------------------------------------------
+#include "../../bayesian-coresets_b200/csrc/nnls_logic.h"
+
+namespace {
+struct NnlsHost {
+  Host H;
+  NnlsWork W;
+  std::vector<double> Q, R, c, z, wP, h, v;
+  std::vector<int32_t> P, Z, inP;
+};
+}  // namespace
+
+// sequence of warm-started solves: at step t the columns cols[0..counts[t]) are in the problem; columns whose
+// weight is positive after step t-1 keep it, new columns enter with weight 1 (what omp_select does).
+// w_out: steps x ncols solutions.
+extern "C" int hostcheck_nnls_sequence(const float* An, const double* norms, const double* b, int S, int ld, int64_t N,
+                                       const int64_t* cols, int ncols, const int* counts, int steps, int from_scratch,
+                                       double* w_out, int* rebuilds_out) {
+  NnlsHost X;
+  Host& H = X.H;
+  memset(&H.st, 0, sizeof(SolverState));
+  SolverState& st = H.st;
+  const int cap = ncols + 2;
+  H.An.assign(An, An + (size_t)N * ld);
+  H.norms.assign(norms, norms + N);
+  H.b.assign(b, b + S);
+  H.bn.assign(S, 0.); H.xw.assign(S, 0.); H.xw_new.assign(S, 0.); H.xf.assign(S, 0.); H.dir64.assign(2 * S, 0.);
+  H.dir32.assign(2 * ld, 0.f); H.wrow.assign(ld, 0.f);
+  H.act_rows.assign((size_t)cap * ld, 0.f);
+  H.act_w.assign(cap, 0.); H.act_w_new.assign(cap, 0.); H.act_norm.assign(cap, 0.); H.act_idx.assign(cap, -1);
+  st.alg = BCG_ALG_OMP; st.S = S; st.ld = ld; st.world = 1; st.n_local = N; st.n_global = N;
+  st.An = H.An.data(); st.norms = H.norms.data(); st.b = H.b.data(); st.bn = H.bn.data();
+  st.xw = H.xw.data(); st.xw_new = H.xw_new.data(); st.xf = H.xf.data(); st.dir64 = H.dir64.data();
+  st.dir32 = H.dir32.data(); st.wrow = H.wrow.data();
+  st.cap = cap; st.act_idx = H.act_idx.data(); st.act_w = H.act_w.data(); st.act_w_new = H.act_w_new.data();
+  st.act_norm = H.act_norm.data(); st.act_rows = H.act_rows.data();
+  X.Q.assign((size_t)cap * S, 0.); X.R.assign((size_t)cap * cap, 0.); X.c.assign(cap, 0.); X.z.assign(2 * cap, 0.);
+  X.wP.assign(cap, 0.); X.h.assign(cap, 0.); X.v.assign(S, 0.); X.P.assign(cap, 0); X.Z.assign(cap, 0); X.inP.assign(cap, 0);
+  NnlsWork& W = X.W;
+  memset(&W, 0, sizeof(W));
+  W.Q = X.Q.data(); W.R = X.R.data(); W.c = X.c.data(); W.z = X.z.data(); W.wP = X.wP.data(); W.h = X.h.data();
+  W.v = X.v.data(); W.P = X.P.data(); W.Z = X.Z.data(); W.inP = X.inP.data(); W.cap = cap;
+  Blk B{0, 1, H.sred};
+  int have = 0, reb = 0;
+  for (int t = 0; t < steps; ++t) {
+    for (; have < counts[t]; ++have) {
+      st.act_idx[have] = cols[have]; st.act_norm[have] = norms[cols[have]]; st.act_w[have] = 1.;
+      memcpy(&H.act_rows[(size_t)have * ld], &An[(size_t)cols[have] * ld], sizeof(float) * ld);
+    }
+    st.nact = have;
+    nnls_solve(B, &st, &W, from_scratch);
+    reb += W.rebuilds;
+    for (int k = 0; k < ncols; ++k) w_out[(size_t)t * ncols + k] = k < have ? st.act_w[k] : 0.;
+  }
+  *rebuilds_out = reb;
+  return 0;
+}

@@ -421,3 +421,23 @@ def test_sparsevi_with_blackbox_projector(bc):
   o.build(3)
   assert np.array_equal(a.idcs, o.idcs)
   np.testing.assert_allclose(a.wts, o.wts, rtol=1e-6, atol=1e-9)
+
+
+def test_device_nnls_equals_scipy_path(bc, monkeypatch):
+  """OMP with the on-device NNLS (default) and with the reference's SciPy call give the same coreset"""
+  g = load_golden('lr_project_small')
+  prj = bc.LogisticRegressionProjector(lambda n, w, p: g['theta'], int(g['S']))
+  a = bc.HilbertCoreset(g['Z'], prj, snnls=bc.snnls.OrthoPursuit)
+  a.build(50)
+  monkeypatch.setenv('BCG_NNLS', 'scipy')
+  b = bc.HilbertCoreset(g['Z'], prj, snnls=bc.snnls.OrthoPursuit)
+  b.build(50)
+  monkeypatch.delenv('BCG_NNLS')
+  assert [e.f for e in a.snnls.last_events] == [e.f for e in b.snnls.last_events]
+  np.testing.assert_allclose(a.snnls.weights(), b.snnls.weights(), rtol=1e-6, atol=1e-9*b.snnls.weights().max())
+  assert a.error() == pytest.approx(b.error(), rel=1e-6)
+  # incremental builds continue from the kept factorisation
+  c = bc.HilbertCoreset(g['Z'], prj, snnls=bc.snnls.OrthoPursuit)
+  for k in (1, 4, 20, 25):
+    c.build(k)
+  np.testing.assert_allclose(c.snnls.weights(), a.snnls.weights(), rtol=1e-6, atol=1e-9*a.snnls.weights().max())

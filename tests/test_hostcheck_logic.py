@@ -138,3 +138,44 @@ def test_omp_select_matches_oracle(lib):
     fo = int(o.select())
     assert f.value == fo, it
     o.reweight(fo)
+
+
+# ---------------------------------------------------------------- device NNLS logic vs scipy.optimize.nnls
+def run_nnls_sequence(lib, vecs, b, cols, counts, from_scratch=0):
+  An, norms, ld = device_layout(vecs)
+  N, S = vecs.shape
+  cols = np.asarray(cols, dtype=np.int64)
+  counts = np.asarray(counts, dtype=np.int32)
+  out = np.zeros((len(counts), len(cols)))
+  reb = ctypes.c_int(0)
+  P = ctypes.c_void_p
+  lib.hostcheck_nnls_sequence(P(An.ctypes.data), P(norms.ctypes.data), P(b.ctypes.data), ctypes.c_int(S), ctypes.c_int(ld),
+                              ctypes.c_int64(N), P(cols.ctypes.data), ctypes.c_int(len(cols)), P(counts.ctypes.data),
+                              ctypes.c_int(len(counts)), ctypes.c_int(from_scratch), P(out.ctypes.data), ctypes.byref(reb))
+  A32 = (An[:, :S].astype(np.float64)*norms[:, None])           # the columns exactly as the device holds them
+  return out, A32, reb.value
+
+
+@pytest.mark.parametrize('seed,shift', [(0, 0.0), (1, 0.5), (2, 2.0)])
+def test_nnls_logic_matches_scipy(lib, seed, shift):
+  """growing column sets, warm-started (OMP pattern) and from scratch (optimize()); shift > 0 makes the
+  columns strongly correlated so that weights hit zero and the step-back / removal path runs"""
+  from scipy.optimize import nnls
+  rng = np.random.RandomState(seed)
+  S, N, K = 40, 300, 28
+  vecs = rng.randn(N, S) + shift
+  b = vecs[rng.choice(N, 60)].sum(axis=0) + 0.3*rng.randn(S)
+  cols = rng.choice(N, K, replace=False)
+  counts = list(range(1, K + 1))
+  for scratch in (0, 1):
+    out, A32, reb = run_nnls_sequence(lib, vecs, b, cols, counts, from_scratch=scratch)
+    active = np.zeros(K, dtype=bool)
+    for t, cnt in enumerate(counts):
+      # the problem at step t: columns that were positive after step t-1 plus the new one (orthopursuit.py:38-41)
+      active[cnt - 1] = True
+      ref = np.zeros(K)
+      ref[active] = nnls(A32[cols[active]].T, b, maxiter=100000)[0]
+      np.testing.assert_allclose(out[t], ref, rtol=1e-7, atol=1e-9*max(1., np.abs(ref).max()))
+      active = ref > 0
+    if shift >= 2.0:
+      assert (out[-1] == 0).any()          # some weights were driven to zero along the way
