@@ -749,6 +749,7 @@ static int ensure_capacity(bcg_solver* s, int extra) {
   RET(grow(&h.act_w, (size_t)h.cap, (size_t)ncap, st));
   RET(grow(&h.act_w_new, (size_t)h.cap, (size_t)ncap, st));
   RET(grow(&h.act_norm, (size_t)h.cap, (size_t)ncap, st));
+  RET(grow(&h.act_tmp, (size_t)h.cap, (size_t)ncap, st));
   RET(grow(&h.act_rows, (size_t)h.cap * h.ld, (size_t)ncap * h.ld, st));
   h.cap = ncap;
   return BCG_OK;
@@ -836,7 +837,7 @@ extern "C" int bcg_solver_destroy(bcg_solver* s) {
     for (int p = 0; p < h.world; ++p)
       if (p != h.rank && s->peer_ptrs[p]) cudaIpcCloseMemHandle(s->peer_ptrs[p]);
   void* bufs[] = {h.b, h.bn, h.xw, h.xw_new, h.xf, h.dir64, h.dir32, h.wrow, h.cands, h.act_idx, h.act_w,
-                  h.act_w_new, h.act_norm, h.act_rows, h.events, s->d_fout, s->d, s->mail, s->d_ctl, s->d_cta_cands, s->d_trace, s->d_claims};
+                  h.act_w_new, h.act_norm, h.act_tmp, h.act_rows, h.events, s->d_fout, s->d, s->mail, s->d_ctl, s->d_cta_cands, s->d_trace, s->d_claims};
   for (void* p : bufs)
     if (p) cudaFree(p);
   void* nb[] = {s->nw.Q, s->nw.R, s->nw.c, s->nw.z, s->nw.wP, s->nw.h, s->nw.v, s->nw.P, s->nw.Z, s->nw.inP, s->d_nw};

@@ -48,6 +48,7 @@ struct SolverState {
   double* act_w;                    // cap
   double* act_w_new;                // cap
   double* act_norm;                 // cap
+  double* act_tmp;                  // cap       scratch (per-row values of the active set)
   float* act_rows;                  // cap x ld  copies of the unit rows
   // ---- loop control ----------------------------------------------------------------------
   int32_t retried, halted, select_failed, n_events;

@@ -392,13 +392,31 @@ BCG_HD int64_t omp_select(const Blk& B, SolverState* st) {
   }
   if (nonempty) {
     // negative direction over the active set (w > 0), lowest global index wins ties
+    // -dots over the active rows, one warp per row (coalesced), then the block arg-max
+    {
+#ifdef __CUDA_ARCH__
+      const int lane = B.tid & 31, warp = B.tid >> 5, nwp = B.nthr >> 5, lanes = 32;
+#else
+      const int lane = 0, warp = 0, nwp = 1, lanes = 1;
+#endif
+      for (int k = warp; k < st->nact; k += nwp) {
+        double d = 0.;
+        if (st->act_w[k] > 0.) {
+          const float* row = st->act_rows + (size_t)k * ld;
+          for (int s = lane; s < S; s += lanes) d += (double)row[s] * st->dir64[s];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+#endif
+        }
+        if (lane == 0) st->act_tmp[k] = -d;
+      }
+      B.sync();
+    }
     double key = -INFINITY; int64_t id = -1; int pl = -1;
     for (int k = B.tid; k < st->nact; k += B.nthr) {
       if (!(st->act_w[k] > 0.)) continue;
-      double d = 0.;
-      const float* row = st->act_rows + (size_t)k * ld;
-      for (int s = 0; s < S; ++s) d += (double)row[s] * st->dir64[s];
-      const double ng = -d;
+      const double ng = st->act_tmp[k];
       const int64_t gi = st->act_idx[k];
       if (id < 0 || ng > key || (ng == key && gi < id)) { key = ng; id = gi; pl = k; }
     }

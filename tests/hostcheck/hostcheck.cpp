@@ -16,7 +16,7 @@ namespace {
 struct Host {
   SolverState st;
   std::vector<float> An, dir32, wrow, act_rows;
-  std::vector<double> norms, b, bn, xw, xw_new, xf, dir64, act_w, act_w_new, act_norm;
+  std::vector<double> norms, b, bn, xw, xw_new, xf, dir64, act_w, act_w_new, act_norm, act_tmp;
   std::vector<int64_t> act_idx;
   std::vector<ScanCand> cands;
   std::vector<bcg_iter_event> events;
@@ -66,7 +66,7 @@ extern "C" int hostcheck_run(int alg, const float* An, const double* norms, cons
   H.xw.assign(S, 0.); H.xw_new.assign(S, 0.); H.xf.assign(S, 0.); H.dir64.assign(2 * S, 0.);
   H.dir32.assign(2 * ld, 0.f); H.wrow.assign(ld, 0.f);
   H.act_rows.assign((size_t)cap * ld, 0.f);
-  H.act_w.assign(cap, 0.); H.act_w_new.assign(cap, 0.); H.act_norm.assign(cap, 0.); H.act_idx.assign(cap, -1);
+  H.act_w.assign(cap, 0.); H.act_w_new.assign(cap, 0.); H.act_norm.assign(cap, 0.); H.act_tmp.assign(cap, 0.); H.act_idx.assign(cap, -1);
   H.events.resize((size_t)itrs * builds);
   st.alg = alg; st.S = S; st.ld = ld; st.world = 1; st.rank = 0;
   st.n_local = N; st.row_offset = 0; st.n_global = N; st.tol = tol; st.bnorm = bnorm; st.nsum = nsum;
@@ -74,7 +74,7 @@ extern "C" int hostcheck_run(int alg, const float* An, const double* norms, cons
   st.xw = H.xw.data(); st.xw_new = H.xw_new.data(); st.xf = H.xf.data(); st.dir64 = H.dir64.data();
   st.dir32 = H.dir32.data(); st.wrow = H.wrow.data(); st.err = bnorm;
   st.cap = cap; st.act_idx = H.act_idx.data(); st.act_w = H.act_w.data(); st.act_w_new = H.act_w_new.data();
-  st.act_norm = H.act_norm.data(); st.act_rows = H.act_rows.data();
+  st.act_norm = H.act_norm.data(); st.act_tmp = H.act_tmp.data(); st.act_rows = H.act_rows.data();
   st.events = H.events.data();
   const int nb = 37;
   Blk B{0, 1, H.sred};
@@ -113,14 +113,14 @@ extern "C" int hostcheck_omp_select(const float* An, const double* norms, const 
   H.xw.assign(S, 0.); H.xw_new.assign(S, 0.); H.xf.assign(S, 0.); H.dir64.assign(2 * S, 0.);
   H.dir32.assign(2 * ld, 0.f); H.wrow.assign(ld, 0.f);
   H.act_rows.assign((size_t)cap * ld, 0.f);
-  H.act_w.assign(cap, 0.); H.act_w_new.assign(cap, 0.); H.act_norm.assign(cap, 0.); H.act_idx.assign(cap, -1);
+  H.act_w.assign(cap, 0.); H.act_w_new.assign(cap, 0.); H.act_norm.assign(cap, 0.); H.act_tmp.assign(cap, 0.); H.act_idx.assign(cap, -1);
   st.alg = BCG_ALG_OMP; st.S = S; st.ld = ld; st.world = 1;
   st.n_local = N; st.n_global = N; st.tol = 1e-12;
   st.An = H.An.data(); st.norms = H.norms.data(); st.b = H.b.data(); st.bn = H.bn.data();
   st.xw = H.xw.data(); st.xw_new = H.xw_new.data(); st.xf = H.xf.data(); st.dir64 = H.dir64.data();
   st.dir32 = H.dir32.data(); st.wrow = H.wrow.data();
   st.cap = cap; st.act_idx = H.act_idx.data(); st.act_w = H.act_w.data(); st.act_w_new = H.act_w_new.data();
-  st.act_norm = H.act_norm.data(); st.act_rows = H.act_rows.data();
+  st.act_norm = H.act_norm.data(); st.act_tmp = H.act_tmp.data(); st.act_rows = H.act_rows.data();
   for (int k = 0; k < nact; ++k) {
     st.act_idx[k] = act_idx[k]; st.act_w[k] = act_w[k]; st.act_norm[k] = norms[act_idx[k]];
     memcpy(&H.act_rows[(size_t)k * ld], &An[(size_t)act_idx[k] * ld], sizeof(float) * ld);
@@ -164,13 +164,13 @@ extern "C" int hostcheck_nnls_sequence(const float* An, const double* norms, con
   H.bn.assign(S, 0.); H.xw.assign(S, 0.); H.xw_new.assign(S, 0.); H.xf.assign(S, 0.); H.dir64.assign(2 * S, 0.);
   H.dir32.assign(2 * ld, 0.f); H.wrow.assign(ld, 0.f);
   H.act_rows.assign((size_t)cap * ld, 0.f);
-  H.act_w.assign(cap, 0.); H.act_w_new.assign(cap, 0.); H.act_norm.assign(cap, 0.); H.act_idx.assign(cap, -1);
+  H.act_w.assign(cap, 0.); H.act_w_new.assign(cap, 0.); H.act_norm.assign(cap, 0.); H.act_tmp.assign(cap, 0.); H.act_idx.assign(cap, -1);
   st.alg = BCG_ALG_OMP; st.S = S; st.ld = ld; st.world = 1; st.n_local = N; st.n_global = N;
   st.An = H.An.data(); st.norms = H.norms.data(); st.b = H.b.data(); st.bn = H.bn.data();
   st.xw = H.xw.data(); st.xw_new = H.xw_new.data(); st.xf = H.xf.data(); st.dir64 = H.dir64.data();
   st.dir32 = H.dir32.data(); st.wrow = H.wrow.data();
   st.cap = cap; st.act_idx = H.act_idx.data(); st.act_w = H.act_w.data(); st.act_w_new = H.act_w_new.data();
-  st.act_norm = H.act_norm.data(); st.act_rows = H.act_rows.data();
+  st.act_norm = H.act_norm.data(); st.act_tmp = H.act_tmp.data(); st.act_rows = H.act_rows.data();
   X.Q.assign((size_t)cap * S, 0.); X.R.assign((size_t)cap * cap, 0.); X.c.assign(cap, 0.); X.z.assign(2 * cap, 0.);
   X.wP.assign(cap, 0.); X.h.assign(cap, 0.); X.v.assign(S, 0.); X.P.assign(cap, 0); X.Z.assign(cap, 0); X.inP.assign(cap, 0);
   NnlsWork& W = X.W;
