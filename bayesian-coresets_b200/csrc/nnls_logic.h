@@ -40,6 +40,7 @@ struct NnlsWork {
   int32_t* inP;   // cap   slot -> 1 when the slot is in P
   int32_t nP, nZ, cap, valid;
   int32_t outer_iters, rebuilds;   // diagnostics of the last solve
+  int32_t first_removed;           // first P position dropped by the last step-back (block-uniform hand-over)
 };
 
 BCG_HD int blk_lane(const Blk& B) {
@@ -264,15 +265,17 @@ BCG_HD void nnls_solve(const Blk& B, SolverState* st, NnlsWork* W, int from_scra
       B.sync();
       // drop the columns that reached zero (to the zero set), compact P, rebuild the factorisation
       if (B.tid == 0) {
-        int keep = 0;
+        int keep = 0, first = -1;
         for (int p = 0; p < W->nP; ++p) {
           if (W->wP[p] > 1e-15 * wmax) { W->P[keep] = W->P[p]; W->wP[keep] = W->wP[p]; ++keep; }
-          else { W->inP[W->P[p]] = 0; W->Z[W->nZ++] = W->P[p]; }
+          else { if (first < 0) first = p; W->inP[W->P[p]] = 0; W->Z[W->nZ++] = W->P[p]; }
         }
         W->nP = keep;
+        W->first_removed = (first < 0) ? keep : first;
       }
       B.sync();
-      nnls_rebuild(B, st, W);
+      const int first_removed = W->first_removed;
+      nnls_rebuild(B, st, W, first_removed < W->nP ? first_removed : W->nP);
       if (W->nP == 0) break;
     }
   }
