@@ -146,15 +146,17 @@ BCG_HD void nnls_solve_R(const Blk& B, NnlsWork* W) {
   B.sync();
 }
 
-// rebuild the QR for the slots currently listed in P (after removals), keeping their weights
-BCG_HD void nnls_rebuild(const Blk& B, SolverState* st, NnlsWork* W) {
+// Rebuild the factorisation for the slots currently listed in P (after removals), keeping their weights.
+// Positions < from were not touched by the removal: their q vectors, T columns and c entries stay valid;
+// only the columns behind the first removed position are re-appended.
+BCG_HD void nnls_rebuild(const Blk& B, SolverState* st, NnlsWork* W, int from) {
   const int n = W->nP;
-  // stash slots and weights in z / h (scratch), then re-append
-  // the append only writes positions < i of P / wP while re-inserting entry i, so both can be read in place
-  if (B.tid == 0) W->nP = 0;
   B.sync();
-  int kept = 0;
-  for (int i = 0; i < n; ++i) {
+  if (B.tid == 0) W->nP = from;
+  B.sync();
+  int kept = from;
+  for (int i = from; i < n; ++i) {
+    // the append only writes positions <= i of P / wP while re-inserting entry i: read in place first
     const int slot = W->P[i];
     const double w = W->wP[i];
     B.sync();
