@@ -48,6 +48,32 @@ static int fail(int code, const char* fmt, ...) {
     if (r__ != BCG_OK) return r__; \
   } while (0)
 
+// temporary device / pinned-host buffers that are released on every exit path
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t n) { return cudaMalloc(&p, (n ? n : 1) * sizeof(T)); }
+  operator T*() const { return p; }
+};
+template <typename T>
+struct PinBuf {
+  T* p = nullptr;
+  PinBuf() {}
+  PinBuf(const PinBuf&) = delete;
+  PinBuf& operator=(const PinBuf&) = delete;
+  ~PinBuf() { if (p) cudaFreeHost(p); }
+  cudaError_t alloc(size_t n) { return cudaMallocHost(&p, (n ? n : 1) * sizeof(T)); }
+  operator T*() const { return p; }
+};
+struct EventPair {
+  cudaEvent_t e[2] = {nullptr, nullptr};
+  ~EventPair() { for (auto x : e) if (x) cudaEventDestroy(x); }
+};
+
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return (v && *v) ? atoi(v) : dflt;
@@ -287,8 +313,8 @@ static int vecs_alloc(bcg_ctx* ctx, int64_t n, int32_t S, bcg_vecs** out) {
 static int finish_colsum(bcg_vecs* v, const double* d_partial, int nparts, unsigned long long* d_zero) {
   bcg_ctx* ctx = v->ctx;
   const int S1 = v->S + 1;
-  double* d_out = nullptr;
-  CK(cudaMalloc(&d_out, S1 * sizeof(double)));
+  DevBuf<double> d_out;
+  CK(d_out.alloc(S1));
   colsum_reduce_kernel<<<(S1 + 127) / 128, 128, 0, ctx->stream>>>(d_partial, nparts, S1, d_out);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(v->colsum.data(), d_out, S1 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -296,7 +322,6 @@ static int finish_colsum(bcg_vecs* v, const double* d_partial, int nparts, unsig
   CK(cudaMemcpyAsync(&z, d_zero, sizeof(z), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   v->zero_rows = z;
-  CK(cudaFree(d_out));
   return BCG_OK;
 }
 
@@ -324,6 +349,43 @@ static int dispatch_ingest(bcg_ctx* ctx, const double* src, int64_t src_ld, int6
   }
 }
 
+// double-buffered pinned staging: host memcpy of chunk c+1 overlaps H2D + ingest of chunk c
+static int ingest_host_rows(bcg_ctx* ctx, const double* rows, int64_t n, int32_t S, int64_t ld_host, bcg_vecs* v) {
+  const int64_t chunk_rows = std::max<int64_t>(1, std::min<int64_t>(n, (32ll << 20) / ((int64_t)S * 8)));
+  const int nchunks = (int)((n + chunk_rows - 1) / chunk_rows);
+  const int grid = (int)std::min<int64_t>((chunk_rows + kProjWarps - 1) / kProjWarps, (int64_t)ctx->sm_count * 2);
+  PinBuf<double> pin[2];
+  DevBuf<double> dev[2];
+  EventPair done;
+  DevBuf<double> d_partial;
+  DevBuf<unsigned long long> d_zero;
+  const size_t celems = (size_t)chunk_rows * S;
+  for (int i = 0; i < 2; ++i) {
+    CK(pin[i].alloc(celems));
+    CK(dev[i].alloc(celems));
+    CK(cudaEventCreateWithFlags(&done.e[i], cudaEventDisableTiming));
+  }
+  CK(d_partial.alloc((size_t)nchunks * grid * (S + 1)));
+  CK(d_zero.alloc(1));
+  CK(cudaMemsetAsync(d_zero, 0, sizeof(unsigned long long), ctx->stream));
+  for (int c = 0; c < nchunks; ++c) {
+    const int i = c & 1;
+    const int64_t r0 = (int64_t)c * chunk_rows;
+    const int64_t nr = std::min<int64_t>(chunk_rows, n - r0);
+    if (c >= 2) CK(cudaEventSynchronize(done.e[i]));
+    if (ld_host == S) {
+      parallel_memcpy(pin[i], rows + r0 * ld_host, (size_t)nr * S * sizeof(double));
+    } else {
+      for (int64_t r = 0; r < nr; ++r) memcpy(pin[i].p + r * S, rows + (r0 + r) * ld_host, (size_t)S * sizeof(double));
+    }
+    CK(cudaMemcpyAsync(dev[i], pin[i], (size_t)nr * S * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    RET(dispatch_ingest(ctx, dev[i], S, nr, v, r0, d_partial.p + (size_t)c * grid * (S + 1), grid, d_zero));
+    CK(cudaEventRecord(done.e[i], ctx->stream));
+  }
+  RET(finish_colsum(v, d_partial, nchunks * grid, d_zero));
+  return BCG_OK;
+}
+
 extern "C" int bcg_vecs_from_host_f64(bcg_ctx* ctx, const double* rows, int64_t n, int32_t S, int64_t ld_host,
                                       bcg_vecs** out) {
   RET(use_device(ctx));
@@ -332,47 +394,8 @@ extern "C" int bcg_vecs_from_host_f64(bcg_ctx* ctx, const double* rows, int64_t 
   bcg_vecs* v = nullptr;
   RET(vecs_alloc(ctx, n, S, &v));
   if (n == 0) { *out = v; return BCG_OK; }
-
-  // double-buffered pinned staging: host memcpy of chunk c+1 overlaps H2D + ingest of chunk c
-  const int64_t chunk_rows = std::max<int64_t>(1, std::min<int64_t>(n, (32ll << 20) / ((int64_t)S * 8)));
-  const int nchunks = (int)((n + chunk_rows - 1) / chunk_rows);
-  const int grid = (int)std::min<int64_t>((chunk_rows + kProjWarps - 1) / kProjWarps, (int64_t)ctx->sm_count * 2);
-  double* pin[2] = {nullptr, nullptr};
-  double* dev[2] = {nullptr, nullptr};
-  cudaEvent_t done[2];
-  double* d_partial = nullptr;
-  unsigned long long* d_zero = nullptr;
-  const size_t cbytes = (size_t)chunk_rows * S * sizeof(double);
-  for (int i = 0; i < 2; ++i) {
-    CK(cudaMallocHost(&pin[i], cbytes));
-    CK(cudaMalloc(&dev[i], cbytes));
-    CK(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
-  }
-  CK(cudaMalloc(&d_partial, (size_t)nchunks * grid * (S + 1) * sizeof(double)));
-  CK(cudaMalloc(&d_zero, sizeof(unsigned long long)));
-  CK(cudaMemsetAsync(d_zero, 0, sizeof(unsigned long long), ctx->stream));
-  for (int c = 0; c < nchunks; ++c) {
-    const int i = c & 1;
-    const int64_t r0 = (int64_t)c * chunk_rows;
-    const int64_t nr = std::min<int64_t>(chunk_rows, n - r0);
-    if (c >= 2) CK(cudaEventSynchronize(done[i]));
-    if (ld_host == S) {
-      memcpy(pin[i], rows + r0 * ld_host, (size_t)nr * S * sizeof(double));
-    } else {
-      for (int64_t r = 0; r < nr; ++r) memcpy(pin[i] + r * S, rows + (r0 + r) * ld_host, (size_t)S * sizeof(double));
-    }
-    CK(cudaMemcpyAsync(dev[i], pin[i], (size_t)nr * S * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    RET(dispatch_ingest(ctx, dev[i], S, nr, v, r0, d_partial + (size_t)c * grid * (S + 1), grid, d_zero));
-    CK(cudaEventRecord(done[i], ctx->stream));
-  }
-  RET(finish_colsum(v, d_partial, nchunks * grid, d_zero));
-  for (int i = 0; i < 2; ++i) {
-    cudaFreeHost(pin[i]);
-    cudaFree(dev[i]);
-    cudaEventDestroy(done[i]);
-  }
-  cudaFree(d_partial);
-  cudaFree(d_zero);
+  const int rc = ingest_host_rows(ctx, rows, n, S, ld_host, v);
+  if (rc != BCG_OK) { bcg_vecs_destroy(v); return rc; }
   *out = v;
   return BCG_OK;
 }
@@ -423,42 +446,43 @@ static int project_common(bcg_dataset* ds, int32_t d, const double* thetaT, cons
   if (d <= 0 || S <= 0) return fail(BCG_ERR_ARG, "d and S must be positive");
   if (S > 1024) return fail(BCG_ERR_UNSUPPORTED, "S=%d > 1024 is not supported", S);
   if ((model == MODEL_POISSON ? d + 1 : d) > ds->zld) return fail(BCG_ERR_ARG, "dataset has too few columns");
-  bcg_vecs* v = nullptr;
-  if (out_vecs) RET(vecs_alloc(ctx, n, S, &v));
   if (n == 0) {
-    if (out_vecs) *out_vecs = v;
+    if (out_vecs) RET(vecs_alloc(ctx, 0, S, out_vecs));
     if (colsum) memset(colsum, 0, (size_t)S * sizeof(double));
     return BCG_OK;
   }
+  cudaStream_t st = ctx->stream;
+  DevBuf<double> dT, dC, d_partial, d_out, d_rows;
+  DevBuf<unsigned long long> d_zero;
+  CK(dT.alloc((size_t)d * S));
+  CK(cudaMemcpyAsync(dT, thetaT, (size_t)d * S * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (coff) {
+    CK(dC.alloc(S));
+    CK(cudaMemcpyAsync(dC, coff, (size_t)S * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+
   if (!out_vecs && !rows64 && colsum && d >= env_int("BCG_PROJSUM_MIN_D", 24) && n >= 4096) {
     // K3b, GEMM-shaped: register-tiled float64 kernel (project_sum_kernel.cuh)
-    double *dT = nullptr, *dC = nullptr, *d_partial = nullptr, *d_out = nullptr;
     const int64_t nrb = (n + kPsBM - 1) / kPsBM;
     const int grid = (int)std::min<int64_t>(nrb, (int64_t)ctx->sm_count);
-    CK(cudaMalloc(&dT, (size_t)d * S * sizeof(double)));
-    CK(cudaMalloc(&d_partial, (size_t)grid * S * sizeof(double)));
-    CK(cudaMalloc(&d_out, (size_t)S * sizeof(double)));
-    CK(cudaMemsetAsync(d_partial, 0, (size_t)grid * S * sizeof(double), ctx->stream));
-    CK(cudaMemcpyAsync(dT, thetaT, (size_t)d * S * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    if (coff) {
-      CK(cudaMalloc(&dC, (size_t)S * sizeof(double)));
-      CK(cudaMemcpyAsync(dC, coff, (size_t)S * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    }
+    CK(d_partial.alloc((size_t)grid * S));
+    CK(d_out.alloc(S));
+    CK(cudaMemsetAsync(d_partial, 0, (size_t)grid * S * sizeof(double), st));
     ProjectSumArgs pa;
     pa.Z = ds->Z; pa.thetaT = dT; pa.coff = dC; pa.partial = d_partial; pa.n = n; pa.zld = ds->zld; pa.d = d; pa.S = S;
     pa.model = model;
-    if (model == MODEL_LR) project_sum_kernel<MODEL_LR><<<grid, kPsThreads, 0, ctx->stream>>>(pa);
-    else if (model == MODEL_POISSON) project_sum_kernel<MODEL_POISSON><<<grid, kPsThreads, 0, ctx->stream>>>(pa);
-    else project_sum_kernel<MODEL_LINEAR><<<grid, kPsThreads, 0, ctx->stream>>>(pa);
+    if (model == MODEL_LR) project_sum_kernel<MODEL_LR><<<grid, kPsThreads, 0, st>>>(pa);
+    else if (model == MODEL_POISSON) project_sum_kernel<MODEL_POISSON><<<grid, kPsThreads, 0, st>>>(pa);
+    else project_sum_kernel<MODEL_LINEAR><<<grid, kPsThreads, 0, st>>>(pa);
     CK(cudaGetLastError());
-    project_sum_finish_kernel<<<1, 256, 0, ctx->stream>>>(d_partial, grid, S, d_out);
+    project_sum_finish_kernel<<<1, 256, 0, st>>>(d_partial, grid, S, d_out);
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(colsum, d_out, (size_t)S * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(dT); cudaFree(d_partial); cudaFree(d_out);
-    if (dC) cudaFree(dC);
+    CK(cudaMemcpyAsync(colsum, d_out, (size_t)S * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     return BCG_OK;
   }
+
+  // K3 (and K3b for small d): one warp per row, theta tile in shared memory (project_kernels.cuh)
   const int ld = (S + 3) / 4 * 4;
   const size_t cs_bytes = (size_t)kProjWarps * (S + 1) * sizeof(double);
   const size_t budget = 200 * 1024;
@@ -466,50 +490,43 @@ static int project_common(bcg_dataset* ds, int32_t d, const double* thetaT, cons
     return fail(BCG_ERR_UNSUPPORTED, "projection tile does not fit shared memory for S=%d", S);
   const int ktile = (int)std::min<size_t>(std::min<size_t>(kProjKTile, (size_t)d), (budget - cs_bytes) / ((size_t)S * sizeof(double)));
   const size_t smem = (size_t)ktile * S * sizeof(double) + cs_bytes;
-  double *dT = nullptr, *dC = nullptr, *d_partial = nullptr, *d_rows = nullptr, *d_out = nullptr;
-  unsigned long long* d_zero = nullptr;
   const int64_t nbatch = (n + kProjWarps - 1) / kProjWarps;
   const int grid = (int)std::min<int64_t>(nbatch, (int64_t)ctx->sm_count);
-  CK(cudaMalloc(&dT, (size_t)d * S * sizeof(double)));
-  CK(cudaMalloc(&d_partial, (size_t)grid * (S + 1) * sizeof(double)));
-  CK(cudaMalloc(&d_zero, sizeof(unsigned long long)));
-  CK(cudaMemsetAsync(d_zero, 0, sizeof(unsigned long long), ctx->stream));
-  CK(cudaMemcpyAsync(dT, thetaT, (size_t)d * S * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  if (coff) {
-    CK(cudaMalloc(&dC, (size_t)S * sizeof(double)));
-    CK(cudaMemcpyAsync(dC, coff, (size_t)S * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  }
-  if (rows64) CK(cudaMalloc(&d_rows, (size_t)n * S * sizeof(double)));
-  ProjectArgs a;
-  a.Z = ds->Z; a.theta = dT; a.coff = dC; a.An = v ? v->An : nullptr; a.norms = v ? v->norms : nullptr;
-  a.out64 = d_rows; a.partial = d_partial; a.zero_rows = d_zero; a.n = n; a.zld = ds->zld; a.d = d; a.S = S;
-  a.ld = ld; a.model = model; a.ktile = ktile;
-  int rc;
-  switch (j_for_ld(ld)) {
-    case 1: rc = launch_project<1>(ctx, a, grid, smem); break;
-    case 2: rc = launch_project<2>(ctx, a, grid, smem); break;
-    case 4: rc = launch_project<4>(ctx, a, grid, smem); break;
-    case 8: rc = launch_project<8>(ctx, a, grid, smem); break;
-    case 16: rc = launch_project<16>(ctx, a, grid, smem); break;
-    default: rc = launch_project<32>(ctx, a, grid, smem); break;
-  }
-  RET(rc);
-  if (v) {
-    RET(finish_colsum(v, d_partial, grid, d_zero));
-    if (colsum) memcpy(colsum, v->colsum.data(), (size_t)S * sizeof(double));
-  } else {
-    const int S1 = S + 1;
-    CK(cudaMalloc(&d_out, S1 * sizeof(double)));
-    colsum_reduce_kernel<<<(S1 + 127) / 128, 128, 0, ctx->stream>>>(d_partial, grid, S1, d_out);
-    CK(cudaGetLastError());
-    if (colsum) CK(cudaMemcpyAsync(colsum, d_out, (size_t)S * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  }
-  if (rows64) CK(cudaMemcpyAsync(rows64, d_rows, (size_t)n * S * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  cudaFree(dT); cudaFree(d_partial); cudaFree(d_zero);
-  if (dC) cudaFree(dC);
-  if (d_rows) cudaFree(d_rows);
-  if (d_out) cudaFree(d_out);
+  bcg_vecs* v = nullptr;
+  if (out_vecs) RET(vecs_alloc(ctx, n, S, &v));
+  auto body = [&]() -> int {
+    CK(d_partial.alloc((size_t)grid * (S + 1)));
+    CK(d_zero.alloc(1));
+    CK(cudaMemsetAsync(d_zero, 0, sizeof(unsigned long long), st));
+    if (rows64) CK(d_rows.alloc((size_t)n * S));
+    ProjectArgs a;
+    a.Z = ds->Z; a.theta = dT; a.coff = dC; a.An = v ? v->An : nullptr; a.norms = v ? v->norms : nullptr;
+    a.out64 = d_rows; a.partial = d_partial; a.zero_rows = d_zero; a.n = n; a.zld = ds->zld; a.d = d; a.S = S;
+    a.ld = ld; a.model = model; a.ktile = ktile;
+    switch (j_for_ld(ld)) {
+      case 1: RET(launch_project<1>(ctx, a, grid, smem)); break;
+      case 2: RET(launch_project<2>(ctx, a, grid, smem)); break;
+      case 4: RET(launch_project<4>(ctx, a, grid, smem)); break;
+      case 8: RET(launch_project<8>(ctx, a, grid, smem)); break;
+      case 16: RET(launch_project<16>(ctx, a, grid, smem)); break;
+      default: RET(launch_project<32>(ctx, a, grid, smem)); break;
+    }
+    if (v) {
+      RET(finish_colsum(v, d_partial, grid, d_zero));
+      if (colsum) memcpy(colsum, v->colsum.data(), (size_t)S * sizeof(double));
+    } else if (colsum) {
+      const int S1 = S + 1;
+      CK(d_out.alloc(S1));
+      colsum_reduce_kernel<<<(S1 + 127) / 128, 128, 0, st>>>(d_partial, grid, S1, d_out);
+      CK(cudaGetLastError());
+      CK(cudaMemcpyAsync(colsum, d_out, (size_t)S * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    if (rows64) CK(cudaMemcpyAsync(rows64, d_rows, (size_t)n * S * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return BCG_OK;
+  };
+  const int rc = body();
+  if (rc != BCG_OK) { if (v) bcg_vecs_destroy(v); return rc; }
   if (out_vecs) *out_vecs = v;
   return BCG_OK;
 }
@@ -631,8 +648,8 @@ extern "C" int bcg_vecs_rows_f64(bcg_vecs* v, int64_t row0, int64_t nrows, doubl
   if (row0 < 0 || nrows < 0 || row0 + nrows > v->n) return fail(BCG_ERR_ARG, "row range out of bounds");
   RET(use_device(v->ctx));
   const int64_t chunk = std::max<int64_t>(1, (64ll << 20) / ((int64_t)v->S * 8));
-  double* tmp = nullptr;
-  CK(cudaMalloc(&tmp, (size_t)std::min(chunk, std::max<int64_t>(nrows, 1)) * v->S * sizeof(double)));
+  DevBuf<double> tmp;
+  CK(tmp.alloc((size_t)std::min(chunk, std::max<int64_t>(nrows, 1)) * v->S));
   for (int64_t r = 0; r < nrows; r += chunk) {
     const int64_t nr = std::min(chunk, nrows - r);
     const int64_t tot = nr * v->S;
@@ -642,7 +659,6 @@ extern "C" int bcg_vecs_rows_f64(bcg_vecs* v, int64_t row0, int64_t nrows, doubl
     CK(cudaMemcpyAsync(out + r * v->S, tmp, (size_t)tot * sizeof(double), cudaMemcpyDeviceToHost, v->ctx->stream));
     CK(cudaStreamSynchronize(v->ctx->stream));
   }
-  CK(cudaFree(tmp));
   return BCG_OK;
 }
 
@@ -755,39 +771,9 @@ static int ensure_capacity(bcg_solver* s, int extra) {
   return BCG_OK;
 }
 
-extern "C" int bcg_solver_create(bcg_ctx* ctx, bcg_vecs* v, int32_t alg, const double* b, double norm_sum,
-                                 int64_t row_offset, int64_t n_global, bcg_solver** out) {
-  RET(use_device(ctx));
-  if (!out || !v || !b) return fail(BCG_ERR_ARG, "null argument");
-  if (alg != BCG_ALG_GIGA && alg != BCG_ALG_FW && alg != BCG_ALG_OMP) return fail(BCG_ERR_ARG, "unknown alg %d", alg);
-  *out = nullptr;
+static int solver_init(bcg_solver* s, bcg_ctx* ctx, bcg_vecs* v, int32_t alg, const double* b, double bnorm, double norm_sum,
+                       int64_t row_offset, int64_t n_global) {
   const int S = v->S, ld = v->ld;
-  double bnorm = 0.;
-  for (int i = 0; i < S; ++i) bnorm += b[i] * b[i];
-  bnorm = sqrt(bnorm);
-  if (alg == BCG_ALG_GIGA && bnorm == 0.) return fail(BCG_ERR_ZERO_B, "norm of b must be > 0");
-  bcg_solver* s = new bcg_solver();
-  memset(&s->h, 0, sizeof(SolverState));
-  s->ctx = ctx;
-  s->v = v;
-  s->mail = nullptr;
-  s->mail_bytes = 0;
-  s->peers_open = false;
-  s->use_loop = false;
-  s->d_ctl = nullptr;
-  s->d_cta_cands = nullptr;
-  s->d_claims = nullptr;
-  s->claims_cap = 0;
-  memset(&s->nw, 0, sizeof(NnlsWork));
-  s->d_nw = nullptr;
-  s->nw_cap = 0;
-  s->trace_on = 0;
-  s->d_trace = nullptr;
-  s->trace_cap = s->trace_n = 0;
-  s->profiling = 0;
-  s->build_ms = s->scan_ms = 0.f;
-  s->scan_launches = s->step_launches = s->loop_launches = 0;
-  for (int i = 0; i < kMaxWorld; ++i) s->peer_ptrs[i] = nullptr;
   SolverState& h = s->h;
   h.alg = alg; h.S = S; h.ld = ld; h.world = 1; h.rank = 0;
   h.n_local = v->n; h.row_offset = row_offset; h.n_global = n_global;
@@ -824,6 +810,48 @@ extern "C" int bcg_solver_create(bcg_ctx* ctx, bcg_vecs* v, int32_t alg, const d
   CK(cudaEventCreate(&s->ev0));
   CK(cudaEventCreate(&s->ev1));
   CK(cudaStreamSynchronize(st));
+  return BCG_OK;
+}
+
+
+extern "C" int bcg_solver_create(bcg_ctx* ctx, bcg_vecs* v, int32_t alg, const double* b, double norm_sum,
+                                 int64_t row_offset, int64_t n_global, bcg_solver** out) {
+  RET(use_device(ctx));
+  if (!out || !v || !b) return fail(BCG_ERR_ARG, "null argument");
+  if (alg != BCG_ALG_GIGA && alg != BCG_ALG_FW && alg != BCG_ALG_OMP) return fail(BCG_ERR_ARG, "unknown alg %d", alg);
+  *out = nullptr;
+  const int S = v->S;
+  double bnorm = 0.;
+  for (int i = 0; i < S; ++i) bnorm += b[i] * b[i];
+  bnorm = sqrt(bnorm);
+  if (alg == BCG_ALG_GIGA && bnorm == 0.) return fail(BCG_ERR_ZERO_B, "norm of b must be > 0");
+  bcg_solver* s = new bcg_solver();
+  memset(&s->h, 0, sizeof(SolverState));
+  s->d = nullptr;
+  s->d_fout = nullptr;
+  s->ev0 = s->ev1 = nullptr;
+  s->ctx = ctx;
+  s->v = v;
+  s->mail = nullptr;
+  s->mail_bytes = 0;
+  s->peers_open = false;
+  s->use_loop = false;
+  s->d_ctl = nullptr;
+  s->d_cta_cands = nullptr;
+  s->d_claims = nullptr;
+  s->claims_cap = 0;
+  memset(&s->nw, 0, sizeof(NnlsWork));
+  s->d_nw = nullptr;
+  s->nw_cap = 0;
+  s->trace_on = 0;
+  s->d_trace = nullptr;
+  s->trace_cap = s->trace_n = 0;
+  s->profiling = 0;
+  s->build_ms = s->scan_ms = 0.f;
+  s->scan_launches = s->step_launches = s->loop_launches = 0;
+  for (int i = 0; i < kMaxWorld; ++i) s->peer_ptrs[i] = nullptr;
+  const int rc = solver_init(s, ctx, v, alg, b, bnorm, norm_sum, row_offset, n_global);
+  if (rc != BCG_OK) { bcg_solver_destroy(s); return rc; }
   *out = s;
   return BCG_OK;
 }
@@ -844,8 +872,8 @@ extern "C" int bcg_solver_destroy(bcg_solver* s) {
   for (void* p : nb)
     if (p) cudaFree(p);
   for (cudaEvent_t e : s->scan_ev) cudaEventDestroy(e);
-  cudaEventDestroy(s->ev0);
-  cudaEventDestroy(s->ev1);
+  if (s->ev0) cudaEventDestroy(s->ev0);
+  if (s->ev1) cudaEventDestroy(s->ev1);
   delete s;
   return BCG_OK;
 }
@@ -1180,14 +1208,13 @@ extern "C" int bcg_solver_active_rows(bcg_solver* s, int64_t first, int64_t coun
   if (count == 0) return BCG_OK;
   cudaStream_t st = s->ctx->stream;
   const int64_t tot = count * s->h.S;
-  double* tmp = nullptr;
-  CK(cudaMalloc(&tmp, (size_t)tot * sizeof(double)));
+  DevBuf<double> tmp;
+  CK(tmp.alloc((size_t)tot));
   expand_active_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(s->h.act_rows, s->h.act_norm, first, count, s->h.S,
                                                                    s->h.ld, tmp);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, tmp, (size_t)tot * sizeof(double), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  CK(cudaFree(tmp));
   return BCG_OK;
 }
 
