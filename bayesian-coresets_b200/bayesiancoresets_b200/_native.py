@@ -44,6 +44,7 @@ _PROTOTYPES = {
   'bcg_ctx_info': (_c.c_int, [_P, _c.c_char_p, _c.c_int, _c.POINTER(_c.c_int), _c.POINTER(_c.c_int),
                               _c.POINTER(_c.c_int), _c.POINTER(_c.c_int64)]),
   'bcg_ctx_synchronize': (_c.c_int, [_P]),
+  'bcg_ctx_mem_info': (_c.c_int, [_P, _c.POINTER(_c.c_int64), _c.POINTER(_c.c_int64)]),
   'bcg_ctx_flush_l2': (_c.c_int, [_P, _c.c_int64]),
   'bcg_vecs_from_host_f64': (_c.c_int, [_P, _P, _c.c_int64, _c.c_int32, _c.c_int64, _PP]),
   'bcg_vecs_project_lr': (_c.c_int, [_P, _P, _c.c_int64, _c.c_int32, _P, _c.c_int32, _PP]),
@@ -143,6 +144,11 @@ class Context(object):
 
   def synchronize(self):
     check(lib().bcg_ctx_synchronize(self.handle))
+
+  def mem_info(self):
+    f, t = ctypes.c_int64(), ctypes.c_int64()
+    check(lib().bcg_ctx_mem_info(self.handle, ctypes.byref(f), ctypes.byref(t)))
+    return f.value, t.value
 
   def flush_l2(self, nbytes=256 << 20):
     check(lib().bcg_ctx_flush_l2(self.handle, int(nbytes)))

@@ -211,6 +211,15 @@ extern "C" int bcg_ctx_info(bcg_ctx* ctx, char* name, int name_cap, int* sm_coun
   return BCG_OK;
 }
 
+extern "C" int bcg_ctx_mem_info(bcg_ctx* ctx, int64_t* free_bytes, int64_t* total_bytes) {
+  RET(use_device(ctx));
+  size_t f = 0, t = 0;
+  CK(cudaMemGetInfo(&f, &t));
+  if (free_bytes) *free_bytes = (int64_t)f;
+  if (total_bytes) *total_bytes = (int64_t)t;
+  return BCG_OK;
+}
+
 extern "C" int bcg_ctx_synchronize(bcg_ctx* ctx) {
   RET(use_device(ctx));
   CK(cudaStreamSynchronize(ctx->stream));

@@ -91,6 +91,7 @@ int  bcg_ctx_destroy(bcg_ctx* ctx);
 int  bcg_ctx_info(bcg_ctx* ctx, char* name, int name_cap, int* sm_count, int* cc_major, int* cc_minor,
                   int64_t* total_mem_bytes);
 int  bcg_ctx_synchronize(bcg_ctx* ctx);
+int  bcg_ctx_mem_info(bcg_ctx* ctx, int64_t* free_bytes, int64_t* total_bytes);
 /* write `bytes` of device scratch (evicts L2 between timed iterations) */
 int  bcg_ctx_flush_l2(bcg_ctx* ctx, int64_t bytes);
 

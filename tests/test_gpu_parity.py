@@ -441,3 +441,32 @@ def test_device_nnls_equals_scipy_path(bc, monkeypatch):
   for k in (1, 4, 20, 25):
     c.build(k)
   np.testing.assert_allclose(c.snnls.weights(), a.snnls.weights(), rtol=1e-6, atol=1e-9*a.snnls.weights().max())
+
+
+def test_handles_release_device_memory(bc):
+  """every handle frees what it allocated (matrices, solver state, NNLS work space, datasets, probes)"""
+  import gc
+  ctx = bc.Context.default()
+  g = load_golden('lr_project_small')
+  prj = bc.LogisticRegressionProjector(lambda n, w, p: g['theta'], int(g['S']))
+
+  def cycle():
+    for cls in (bc.snnls.GIGA, bc.snnls.FrankWolfe, bc.snnls.OrthoPursuit):
+      cs = bc.HilbertCoreset(g['Z'], prj, snnls=cls)
+      cs.build(12)
+      cs.optimize()
+    v = prj.project_device(g['Z'])
+    v.argmax_dot(np.ones(int(g['S'])))
+    prj.project_sum(g['Z'], cache=False)
+    svi = bc.SparseVICoreset(g['Z'][:500], prj, opt_itrs=2)
+    svi.build(2)
+  cycle()
+  gc.collect()
+  ctx.synchronize()
+  free0, _ = ctx.mem_info()
+  for _ in range(5):
+    cycle()
+  gc.collect()
+  ctx.synchronize()
+  free1, _ = ctx.mem_info()
+  assert free0 - free1 < (8 << 20), (free0, free1)
