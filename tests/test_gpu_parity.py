@@ -470,3 +470,33 @@ def test_handles_release_device_memory(bc):
   ctx.synchronize()
   free1, _ = ctx.mem_info()
   assert free0 - free1 < (8 << 20), (free0, free1)
+
+
+def test_duplicate_rows_resolve_to_lowest_index(bc):
+  """exact duplicates score identically in float32 and float64: ndarray.argmax picks the first one"""
+  rng = np.random.RandomState(21)
+  base = rng.randn(6000, 96)
+  X = np.vstack((base, base[::-1].copy()))           # row i and row 11999 - i are identical
+  o = greedy.GigaOracle(X.T, X.sum(axis=0))
+  oev = o.build(40)
+  cs, ev = run_gpu(bc, X, 'giga', 40)
+  assert [e.f for e in ev] == [e[1] for e in oev]
+  assert all(e.f < 6000 for e in ev)
+
+
+@pytest.mark.parametrize('alg', ['giga', 'fw'])
+def test_tolerance_and_failure_latch_follow_the_reference(bc, alg):
+  """util.TOL is honoured (giga.py:28): with a huge tolerance GIGA's selection fails at once, is retried once
+  and latches the numeric limit; FW does not use TOL and keeps going"""
+  np.random.seed(4)
+  X = np.random.randn(500, 30)
+  bc.util.set_tolerance(10.)
+  try:
+    o = greedy.ORACLES[alg](X.T, X.sum(axis=0), tol=10.)
+    oev = o.build(6)
+    cs, ev = run_gpu(bc, X, alg, 6)
+  finally:
+    bc.util.set_tolerance(1e-12)
+  assert [(e.code, e.f) for e in ev] == [(e[0], e[1]) for e in oev]
+  assert cs.snnls.reached_numeric_limit == o.reached_numeric_limit
+  assert cs.snnls.size() == o.size()
