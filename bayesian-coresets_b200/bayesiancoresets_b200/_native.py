@@ -52,8 +52,8 @@ _PROTOTYPES = {
   'bcg_vecs_project_poisson': (_c.c_int, [_P, _P, _c.c_int64, _c.c_int32, _P, _c.c_int32, _PP]),
   'bcg_dataset_create': (_c.c_int, [_P, _P, _c.c_int64, _c.c_int32, _PP]),
   'bcg_dataset_destroy': (_c.c_int, [_P]),
-  'bcg_dataset_project': (_c.c_int, [_P, _c.c_int32, _c.c_int32, _P, _c.c_int32, _P, _PP, _P, _P]),
-  'bcg_dataset_project_linear': (_c.c_int, [_P, _c.c_int32, _P, _P, _c.c_int32, _PP, _P, _P]),
+  'bcg_dataset_project': (_c.c_int, [_P, _P, _c.c_int64, _c.c_int32, _c.c_int32, _P, _c.c_int32, _P, _PP, _P, _P]),
+  'bcg_dataset_project_linear': (_c.c_int, [_P, _P, _c.c_int64, _c.c_int32, _P, _P, _c.c_int32, _PP, _P, _P]),
   'bcg_vecs_shape': (_c.c_int, [_P, _c.POINTER(_c.c_int64), _c.POINTER(_c.c_int32), _c.POINTER(_c.c_int32)]),
   'bcg_vecs_colsum': (_c.c_int, [_P, _P]),
   'bcg_vecs_norm_sum': (_c.c_int, [_P, _c.POINTER(_c.c_double)]),
@@ -163,13 +163,17 @@ class Dataset(object):
     self.handle = ctypes.c_void_p()
     check(lib().bcg_dataset_create(self.ctx.handle, _ptr(Z), Z.shape[0], Z.shape[1], ctypes.byref(self.handle)))
 
-  def project(self, model, theta, Siginv=None, vecs=False, rows=False, colsum=False):
-    """evaluate + row-centre on the device; returns (DeviceVecs | None, ndarray rows | None, ndarray colsum | None)"""
+  def project(self, model, theta, Siginv=None, vecs=False, rows=False, colsum=False, sub=None):
+    """evaluate + row-centre on the device; returns (DeviceVecs | None, ndarray rows | None, ndarray colsum | None).
+    sub: optional int64 row indices -- only those rows are projected (gathered on the device)."""
     theta = _f64(np.atleast_2d(theta))
     S, d = theta.shape
     si = None if Siginv is None else _f64(Siginv)
     hv = ctypes.c_void_p()
-    out_rows = np.empty((self.shape[0], S)) if rows else None
+    idx = None if sub is None else np.ascontiguousarray(sub, dtype=np.int64)
+    nsel = 0 if idx is None else idx.shape[0]
+    sel = (None if idx is None else _ptr(idx), nsel)
+    out_rows = np.empty((self.shape[0] if idx is None else nsel, S)) if rows else None
     out_cs = np.empty(S) if colsum else None
     outs = (ctypes.byref(hv) if vecs else None, None if out_rows is None else _ptr(out_rows),
             None if out_cs is None else _ptr(out_cs))
@@ -177,9 +181,9 @@ class Dataset(object):
       # after row-centring only x.(Siginv theta_s) - 0.5 theta_s.Siginv.theta_s survives (model_gaussian.py:4-10)
       A = _f64(theta.dot(si))
       coff = _f64(-0.5*(A*theta).sum(axis=1))
-      check(lib().bcg_dataset_project_linear(self.handle, d, _ptr(A), _ptr(coff), S, *outs))
+      check(lib().bcg_dataset_project_linear(self.handle, sel[0], sel[1], d, _ptr(A), _ptr(coff), S, *outs))
     else:
-      check(lib().bcg_dataset_project(self.handle, model, d, _ptr(theta), S, None, *outs))
+      check(lib().bcg_dataset_project(self.handle, sel[0], sel[1], model, d, _ptr(theta), S, None, *outs))
     return (DeviceVecs(self.ctx, hv) if vecs else None), out_rows, out_cs
 
   def __del__(self):

@@ -40,12 +40,14 @@ class BatchPSVICoreset(Coreset):
     """bpsvi.py:24-35: refresh the samples, column sums of the (sub)sampled tangent space"""
     prj = self.ll_projector
     prj.update(w, p)
-    if self.n_subsample_opt is None:
-      rows, scaling, cache = self.data, 1., True
-    else:
+    sub, scaling = None, 1.
+    if self.n_subsample_opt is not None:
       sub = np.random.randint(self.data.shape[0], size=self.n_subsample_opt)
-      rows, scaling, cache = self.data[sub], self.data.shape[0]/self.n_subsample_opt, False
-    local = prj.project_sum(rows, cache=cache) if hasattr(prj, 'project_sum') else prj.project(rows).sum(axis=0)
+      scaling = self.data.shape[0]/self.n_subsample_opt
+    if hasattr(prj, 'project_sum'):
+      local = prj.project_sum(self.data, cache=True, sub=sub)      # rows gathered on the device
+    else:
+      local = prj.project(self.data if sub is None else self.data[sub]).sum(axis=0)
     if self.comm.world > 1:
       local = self.comm.allreduce_sum(local)
     return scaling*local
@@ -55,10 +57,16 @@ class BatchPSVICoreset(Coreset):
     w = x[:sz]
     p = x[sz:].reshape((sz, d))
     total = self._data_sum(w, p)
-    corevecs, pgrads = self.ll_projector.project(p, grad=True)
-    resid = total - w.dot(corevecs)
+    prj = self.ll_projector
+    if hasattr(prj, 'grad_contract'):
+      corevecs = prj.project(p)
+      resid = total - w.dot(corevecs)
+      ugrad = prj.grad_contract(p, w, resid)              # (K x S).(S x d) instead of the (K, S, d) array
+    else:
+      corevecs, pgrads = prj.project(p, grad=True)
+      resid = total - w.dot(corevecs)
+      ugrad = -(w[:, np.newaxis, np.newaxis]*pgrads*resid[np.newaxis, :, np.newaxis]).sum(axis=1)/corevecs.shape[1]
     wgrad = -corevecs.dot(resid)/corevecs.shape[1]
-    ugrad = -(w[:, np.newaxis, np.newaxis]*pgrads*resid[np.newaxis, :, np.newaxis]).sum(axis=1)/corevecs.shape[1]
     return np.hstack((wgrad, ugrad.reshape(sz*d)))
 
   def _optimize(self):

@@ -24,11 +24,13 @@ class HilbertCoreset(Coreset):
         raise NotImplementedError('n_subsample with N-sharding is not supported')
       # hilbert.py:13-22: sorted, de-duplicated subsample from the global RNG, zero rows removed
       sub_idcs = np.unique(np.random.randint(data.shape[0], size=n_subsample))
-      vecs = project(data[sub_idcs])
+      on_device = hasattr(ll_projector, 'project_device')
+      sub_project = (lambda idx: project(data, sub=idx)) if on_device else (lambda idx: project(data[idx]))
+      vecs = sub_project(sub_idcs)
       nonzero = (vecs.norms() > 0.) if isinstance(vecs, nat.DeviceVecs) else (np.sqrt((vecs**2).sum(axis=1)) > 0.)
       if not nonzero.all():
         sub_idcs = sub_idcs[nonzero]
-        vecs = project(data[sub_idcs])
+        vecs = sub_project(sub_idcs)
     b = vecs.sum(axis=0)
     extra = {}
     if self.comm.world > 1:

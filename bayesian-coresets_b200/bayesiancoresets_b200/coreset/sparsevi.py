@@ -42,24 +42,28 @@ class SparseVICoreset(Coreset):
     """sparsevi.py:25-35: refresh the samples, then choose the rows of the tangent space"""
     self.ll_projector.update(w, p)
     if n_subsample is None:
-      return self.data, 1., None, True
+      return 1., None
     sub = np.random.randint(self.data.shape[0], size=n_subsample)
-    return self.data[sub], self.data.shape[0]/n_subsample, sub, False
+    return self.data.shape[0]/n_subsample, sub
 
   def _corevecs(self, S):
     if self.pts.size > 0:
       return self.ll_projector.project(self.pts)          # sparsevi.py:38
     return np.zeros((0, S))
 
-  def _device_vecs(self, rows, cache):
+  def _device_vecs(self, sub):
     prj = self.ll_projector
     if hasattr(prj, 'project_device'):
-      return prj.project_device(rows, cache=cache)
-    return nat.DeviceVecs.from_host(prj.project(rows))    # user-callback projector: host evaluation
+      return prj.project_device(self.data, cache=True, sub=sub)     # subsample rows are gathered on the device
+    rows = self.data if sub is None else self.data[sub]
+    return nat.DeviceVecs.from_host(prj.project(rows))              # user-callback projector: host evaluation
 
-  def _sum(self, rows, cache):
+  def _sum(self, sub):
     prj = self.ll_projector
-    local = prj.project_sum(rows, cache=cache) if hasattr(prj, 'project_sum') else prj.project(rows).sum(axis=0)
+    if hasattr(prj, 'project_sum'):
+      local = prj.project_sum(self.data, cache=True, sub=sub)
+    else:
+      local = prj.project(self.data if sub is None else self.data[sub]).sum(axis=0)
     return self.comm.allreduce_sum(local) if self.comm.world > 1 else local
 
   def _row(self, f):
@@ -72,8 +76,8 @@ class SparseVICoreset(Coreset):
 
   # ---- sparsevi.py:44-67 -------------------------------------------------------------------------
   def _select(self):
-    rows, scaling, sub, cache = self._draw(self.n_subsample_select, self.wts, self.pts)
-    vecs = self._device_vecs(rows, cache)
+    scaling, sub = self._draw(self.n_subsample_select, self.wts, self.pts)
+    vecs = self._device_vecs(sub)
     S = vecs.shape[1]
     corevecs = self._corevecs(S)
     total = vecs.sum(axis=0)
@@ -98,8 +102,8 @@ class SparseVICoreset(Coreset):
   # ---- sparsevi.py:69-76 -------------------------------------------------------------------------
   def _optimize(self):
     def grd(w):
-      rows, scaling, sub, cache = self._draw(self.n_subsample_opt, w, self.pts)
-      colsum = self._sum(rows, cache)
+      scaling, sub = self._draw(self.n_subsample_opt, w, self.pts)
+      colsum = self._sum(sub)
       corevecs = self._corevecs(colsum.shape[0])
       resid = scaling*colsum - w.dot(corevecs)
       return -corevecs.dot(resid)/corevecs.shape[1]

@@ -447,10 +447,13 @@ static int launch_project(bcg_ctx* ctx, const ProjectArgs& a, int grid, size_t s
 
 // common driver.  thetaT (d x S, already transposed) and coff (S or null) are host arrays.
 // out_vecs: materialise the unit-row matrix; rows64: host n x S float64 centred rows; colsum: host S.
-static int project_common(bcg_dataset* ds, int32_t d, const double* thetaT, const double* coff, int32_t S, int model,
-                          bcg_vecs** out_vecs, double* rows64, double* colsum) {
+static int project_common(bcg_dataset* ds, const int64_t* rowidx, int64_t nsel, int32_t d, const double* thetaT,
+                          const double* coff, int32_t S, int model, bcg_vecs** out_vecs, double* rows64, double* colsum) {
   bcg_ctx* ctx = ds->ctx;
-  const int64_t n = ds->n;
+  const int64_t n = rowidx ? nsel : ds->n;
+  if (rowidx)
+    for (int64_t i = 0; i < nsel; ++i)
+      if (rowidx[i] < 0 || rowidx[i] >= ds->n) return fail(BCG_ERR_ARG, "row index %lld out of range", (long long)rowidx[i]);
   if (out_vecs) *out_vecs = nullptr;
   if (d <= 0 || S <= 0) return fail(BCG_ERR_ARG, "d and S must be positive");
   if (S > 1024) return fail(BCG_ERR_UNSUPPORTED, "S=%d > 1024 is not supported", S);
@@ -463,6 +466,11 @@ static int project_common(bcg_dataset* ds, int32_t d, const double* thetaT, cons
   cudaStream_t st = ctx->stream;
   DevBuf<double> dT, dC, d_partial, d_out, d_rows;
   DevBuf<unsigned long long> d_zero;
+  DevBuf<int64_t> d_idx;
+  if (rowidx) {
+    CK(d_idx.alloc((size_t)n));
+    CK(cudaMemcpyAsync(d_idx, rowidx, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  }
   CK(dT.alloc((size_t)d * S));
   CK(cudaMemcpyAsync(dT, thetaT, (size_t)d * S * sizeof(double), cudaMemcpyHostToDevice, st));
   if (coff) {
@@ -478,7 +486,7 @@ static int project_common(bcg_dataset* ds, int32_t d, const double* thetaT, cons
     CK(d_out.alloc(S));
     CK(cudaMemsetAsync(d_partial, 0, (size_t)grid * S * sizeof(double), st));
     ProjectSumArgs pa;
-    pa.Z = ds->Z; pa.thetaT = dT; pa.coff = dC; pa.partial = d_partial; pa.n = n; pa.zld = ds->zld; pa.d = d; pa.S = S;
+    pa.Z = ds->Z; pa.rowidx = rowidx ? d_idx.p : nullptr; pa.thetaT = dT; pa.coff = dC; pa.partial = d_partial; pa.n = n; pa.zld = ds->zld; pa.d = d; pa.S = S;
     pa.model = model;
     if (model == MODEL_LR) project_sum_kernel<MODEL_LR><<<grid, kPsThreads, 0, st>>>(pa);
     else if (model == MODEL_POISSON) project_sum_kernel<MODEL_POISSON><<<grid, kPsThreads, 0, st>>>(pa);
@@ -509,7 +517,7 @@ static int project_common(bcg_dataset* ds, int32_t d, const double* thetaT, cons
     CK(cudaMemsetAsync(d_zero, 0, sizeof(unsigned long long), st));
     if (rows64) CK(d_rows.alloc((size_t)n * S));
     ProjectArgs a;
-    a.Z = ds->Z; a.theta = dT; a.coff = dC; a.An = v ? v->An : nullptr; a.norms = v ? v->norms : nullptr;
+    a.Z = ds->Z; a.rowidx = rowidx ? d_idx.p : nullptr; a.theta = dT; a.coff = dC; a.An = v ? v->An : nullptr; a.norms = v ? v->norms : nullptr;
     a.out64 = d_rows; a.partial = d_partial; a.zero_rows = d_zero; a.n = n; a.zld = ds->zld; a.d = d; a.S = S;
     a.ld = ld; a.model = model; a.ktile = ktile;
     switch (j_for_ld(ld)) {
@@ -549,17 +557,18 @@ static std::vector<double> transpose_sd(const double* theta, int S, int d) {
 
 // model: BCG_MODEL_*; theta: host S x d; Siginv: host d x d (Gaussian only).  Any of out_vecs / rows64 /
 // colsum may be null; with only colsum the N x S matrix is never written (K3b).
-extern "C" int bcg_dataset_project(bcg_dataset* ds, int32_t model, int32_t d, const double* theta, int32_t S,
-                                   const double* Siginv, bcg_vecs** out_vecs, double* rows64, double* colsum) {
+extern "C" int bcg_dataset_project(bcg_dataset* ds, const int64_t* rowidx, int64_t nsel, int32_t model, int32_t d,
+                                   const double* theta, int32_t S, const double* Siginv, bcg_vecs** out_vecs,
+                                   double* rows64, double* colsum) {
   if (!ds || !theta) return fail(BCG_ERR_ARG, "null argument");
   RET(use_device(ds->ctx));
   if (model == BCG_MODEL_LR) {
     std::vector<double> tT = transpose_sd(theta, S, d);
-    return project_common(ds, d, tT.data(), nullptr, S, MODEL_LR, out_vecs, rows64, colsum);
+    return project_common(ds, rowidx, nsel, d, tT.data(), nullptr, S, MODEL_LR, out_vecs, rows64, colsum);
   }
   if (model == BCG_MODEL_POISSON) {
     std::vector<double> tT = transpose_sd(theta, S, d);
-    return project_common(ds, d, tT.data(), nullptr, S, MODEL_POISSON, out_vecs, rows64, colsum);
+    return project_common(ds, rowidx, nsel, d, tT.data(), nullptr, S, MODEL_POISSON, out_vecs, rows64, colsum);
   }
   if (model == BCG_MODEL_GAUSSIAN) {
     if (!Siginv) return fail(BCG_ERR_ARG, "Siginv is required for the Gaussian model");
@@ -575,19 +584,20 @@ extern "C" int bcg_dataset_project(bcg_dataset* ds, int32_t model, int32_t d, co
       }
       coff[s] = -0.5 * q;
     }
-    return project_common(ds, d, tT.data(), coff.data(), S, MODEL_LINEAR, out_vecs, rows64, colsum);
+    return project_common(ds, rowidx, nsel, d, tT.data(), coff.data(), S, MODEL_LINEAR, out_vecs, rows64, colsum);
   }
   return fail(BCG_ERR_ARG, "unknown model %d", model);
 }
 
 // Gaussian model with the S x d matrix A = theta Siginv and the offsets c_s = -0.5 theta_s Siginv theta_s
 // precomputed by the caller (BLAS on the host instead of the O(S d^2) loop above)
-extern "C" int bcg_dataset_project_linear(bcg_dataset* ds, int32_t d, const double* A, const double* coff, int32_t S,
-                                          bcg_vecs** out_vecs, double* rows64, double* colsum) {
+extern "C" int bcg_dataset_project_linear(bcg_dataset* ds, const int64_t* rowidx, int64_t nsel, int32_t d, const double* A,
+                                          const double* coff, int32_t S, bcg_vecs** out_vecs, double* rows64,
+                                          double* colsum) {
   if (!ds || !A) return fail(BCG_ERR_ARG, "null argument");
   RET(use_device(ds->ctx));
   std::vector<double> tT = transpose_sd(A, S, d);
-  return project_common(ds, d, tT.data(), coff, S, MODEL_LINEAR, out_vecs, rows64, colsum);
+  return project_common(ds, rowidx, nsel, d, tT.data(), coff, S, MODEL_LINEAR, out_vecs, rows64, colsum);
 }
 
 static int project_host(bcg_ctx* ctx, int model, const double* Z, int64_t n, int32_t zld, int32_t d, const double* theta,
@@ -596,7 +606,7 @@ static int project_host(bcg_ctx* ctx, int model, const double* Z, int64_t n, int
   if (!out || !theta || (n > 0 && !Z)) return fail(BCG_ERR_ARG, "null argument");
   bcg_dataset* ds = nullptr;
   RET(bcg_dataset_create(ctx, Z, n, zld, &ds));
-  const int rc = bcg_dataset_project(ds, model, d, theta, S, Siginv, out, nullptr, nullptr);
+  const int rc = bcg_dataset_project(ds, nullptr, 0, model, d, theta, S, Siginv, out, nullptr, nullptr);
   bcg_dataset_destroy(ds);
   return rc;
 }

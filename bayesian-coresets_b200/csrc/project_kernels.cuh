@@ -122,7 +122,8 @@ __global__ void __launch_bounds__(kProjWarps * 32) ingest_kernel(const double* s
 
 // ---- model projection ---------------------------------------------------------------------
 struct ProjectArgs {
-  const double* Z;       // n x zld  (LR: z = y x; LINEAR: x; POISSON: [x, y])
+  const double* Z;       // rows x zld  (LR: z = y x; LINEAR: x; POISSON: [x, y])
+  const int64_t* rowidx; // optional gather: output row r reads data row rowidx[r] (subsampled tangent spaces)
   const double* theta;   // d x S, TRANSPOSED samples (LINEAR: Siginv theta^T)
   const double* coff;    // S        per-column offset (LINEAR: -0.5 theta Siginv theta) or null
   float* An;             // unit float32 rows (null: not materialised)
@@ -186,7 +187,8 @@ __global__ void __launch_bounds__(kProjWarps * 32) project_kernel(const ProjectA
         tile_loaded = true;
       }
       if (live) {
-        const double zreg = (lane < kn) ? a.Z[row * a.zld + k0 + lane] : 0.;
+        const int64_t zr = a.rowidx ? a.rowidx[row] : row;
+        const double zreg = (lane < kn) ? a.Z[zr * a.zld + k0 + lane] : 0.;
         for (int k = 0; k < kn; ++k) {
           const double zk = __shfl_sync(0xffffffffu, zreg, k);
 #pragma unroll
@@ -198,7 +200,7 @@ __global__ void __launch_bounds__(kProjWarps * 32) project_kernel(const ProjectA
       }
     }
     if (live) {
-      const double y = (a.model == MODEL_POISSON) ? a.Z[row * a.zld + d] : 0.;
+      const double y = (a.model == MODEL_POISSON) ? a.Z[(a.rowidx ? a.rowidx[row] : row) * a.zld + d] : 0.;
       double sum = 0.;
 #pragma unroll
       for (int j = 0; j < J; ++j) {

@@ -24,7 +24,8 @@ constexpr int kPsBM = 128, kPsBN = 128, kPsKT = 8, kPsThreads = 256;
 constexpr int kPsZs = kPsBM + 2;     // padded row length of the transposed z tile (conflict-free stores)
 
 struct ProjectSumArgs {
-  const double* Z;       // n x zld
+  const double* Z;       // rows x zld
+  const int64_t* rowidx; // optional gather (n entries)
   const double* thetaT;  // d x S
   const double* coff;    // S or null
   double* partial;       // gridDim.x x S raw column sums
@@ -62,7 +63,7 @@ __global__ void __launch_bounds__(kPsThreads, 1) project_sum_kernel(const Projec
     const int64_t row0 = rb * kPsBM;
     if (MODEL == MODEL_POISSON) {
       __syncthreads();
-      if (t < kPsBM) ys[t] = (row0 + t < a.n) ? a.Z[(row0 + t) * a.zld + d] : 0.;
+      if (t < kPsBM) ys[t] = (row0 + t < a.n) ? a.Z[(a.rowidx ? a.rowidx[row0 + t] : row0 + t) * a.zld + d] : 0.;
     }
     for (int ct = 0; ct < ncoltiles; ++ct) {
       const int col0 = ct * kPsBN;
@@ -76,10 +77,11 @@ __global__ void __launch_bounds__(kPsThreads, 1) project_sum_kernel(const Projec
       double zreg[4], treg[4];
       auto gload = [&](int k0) {
         const int64_t r = row0 + zrow;
+        const int64_t zr = (r < a.n && a.rowidx) ? a.rowidx[r] : r;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int k = k0 + zhalf * 4 + q;
-          zreg[q] = (r < a.n && k < d) ? a.Z[r * a.zld + k] : 0.;
+          zreg[q] = (r < a.n && k < d) ? a.Z[zr * a.zld + k] : 0.;
         }
         const int k = k0 + tk;
 #pragma unroll

@@ -117,12 +117,16 @@ int  bcg_vecs_project_poisson(bcg_ctx* ctx, const double* Z, int64_t n, int32_t 
  * sparsevi.py:71-72 / bpsvi.py:49-51). */
 int  bcg_dataset_create(bcg_ctx* ctx, const double* Z, int64_t n, int32_t zld, bcg_dataset** out);
 int  bcg_dataset_destroy(bcg_dataset* ds);
-int  bcg_dataset_project(bcg_dataset* ds, int32_t model, int32_t d, const double* theta, int32_t S,
-                         const double* Siginv, bcg_vecs** out_vecs, double* rows64, double* colsum);
+/* rowidx (host, nsel entries) or NULL: project only the listed data rows, in that order, gathered on the
+ * device -- the `data[sub_idcs]` of the subsampled tangent spaces (sparsevi.py:33-35, bpsvi.py:33-35,
+ * hilbert.py:16-17) without re-uploading the rows */
+int  bcg_dataset_project(bcg_dataset* ds, const int64_t* rowidx, int64_t nsel, int32_t model, int32_t d,
+                         const double* theta, int32_t S, const double* Siginv, bcg_vecs** out_vecs,
+                         double* rows64, double* colsum);
 /* ll_ns = x_n . A_s + coff_s : the Gaussian model with A = theta Siginv (host S x d) and
  * coff_s = -0.5 theta_s Siginv theta_s precomputed by the caller */
-int  bcg_dataset_project_linear(bcg_dataset* ds, int32_t d, const double* A, const double* coff, int32_t S,
-                                bcg_vecs** out_vecs, double* rows64, double* colsum);
+int  bcg_dataset_project_linear(bcg_dataset* ds, const int64_t* rowidx, int64_t nsel, int32_t d, const double* A,
+                                const double* coff, int32_t S, bcg_vecs** out_vecs, double* rows64, double* colsum);
 int  bcg_vecs_shape(bcg_vecs* v, int64_t* n, int32_t* S, int32_t* ld);
 int  bcg_vecs_colsum(bcg_vecs* v, double* out_S);          /* sum over local rows of the centred vectors */
 int  bcg_vecs_norm_sum(bcg_vecs* v, double* out);          /* sum of local row norms */

@@ -500,3 +500,36 @@ def test_tolerance_and_failure_latch_follow_the_reference(bc, alg):
   assert [(e.code, e.f) for e in ev] == [(e[0], e[1]) for e in oev]
   assert cs.snnls.reached_numeric_limit == o.reached_numeric_limit
   assert cs.snnls.size() == o.size()
+
+
+def test_device_row_gather_and_grad_contract(bc):
+  """subsampled projections gather rows on the device; the pseudo-point gradient contraction equals the
+  reference's (K, S, d) formulation (bpsvi.py:53) for all three models"""
+  g = load_golden('lr_project_small')
+  Z, th = g['Z'], g['theta']
+  prj = bc.LogisticRegressionProjector(lambda n, w, p: th, th.shape[0])
+  sub = np.array([5, 17, 5, 2999, 0, 1024, 77], dtype=np.int64)
+  np.testing.assert_allclose(prj.project_sum(Z, sub=sub), g['vecs'][sub].sum(axis=0), rtol=1e-11, atol=1e-11)
+  np.testing.assert_allclose(prj.project_device(Z, sub=sub).norms(), np.sqrt((g['vecs'][sub]**2).sum(axis=1)), rtol=1e-9)
+  big = np.random.RandomState(0).randint(3000, size=5000)
+  Zw = np.hstack((Z, np.random.RandomState(1).randn(3000, 30)))       # d = 36 -> tiled column-sum kernel
+  thw = np.random.RandomState(2).randn(64, 36)/6.
+  prjw = bc.LogisticRegressionProjector(lambda n, w, p: thw, 64)
+  np.testing.assert_allclose(prjw.project_sum(Zw, sub=big), models.project(models.lr_loglik, Zw[big], thw).sum(axis=0),
+                             rtol=1e-9, atol=1e-9)
+  rng = np.random.RandomState(3)
+  w, resid = rng.rand(7) + 0.1, rng.randn(th.shape[0])
+  pts = Z[:7]
+
+  def reference(glls):
+    glls = glls - glls.mean(axis=2)[:, :, None]
+    return -(w[:, None, None]*glls*resid[None, :, None]).sum(axis=1)/th.shape[0]
+  np.testing.assert_allclose(prj.grad_contract(pts, w, resid), reference(models.lr_grad_z_loglik(pts, th)), rtol=1e-10, atol=1e-12)
+  Siginv = np.eye(6) + 0.1
+  gp = bc.GaussianProjector(lambda n, w_, p: th, th.shape[0], Siginv)
+  np.testing.assert_allclose(gp.grad_contract(pts, w, resid), reference(models.gaussian_grad_x_loglik(pts, th, Siginv)),
+                             rtol=1e-10, atol=1e-12)
+  zp = np.hstack((pts, rng.poisson(2., (7, 1)).astype(float)))
+  pp = bc.PoissonProjector(lambda n, w_, p: th, th.shape[0])
+  np.testing.assert_allclose(pp.grad_contract(zp, w, resid), reference(models.poisson_grad_z_loglik_fixed(zp, th)),
+                             rtol=1e-10, atol=1e-12)
