@@ -50,6 +50,7 @@ _PROTOTYPES = {
   'bcg_vecs_project_lr': (_c.c_int, [_P, _P, _c.c_int64, _c.c_int32, _P, _c.c_int32, _PP]),
   'bcg_vecs_project_gaussian': (_c.c_int, [_P, _P, _c.c_int64, _c.c_int32, _P, _c.c_int32, _P, _PP]),
   'bcg_vecs_project_poisson': (_c.c_int, [_P, _P, _c.c_int64, _c.c_int32, _P, _c.c_int32, _PP]),
+  'bcg_vecs_project_linear': (_c.c_int, [_P, _P, _c.c_int64, _c.c_int32, _P, _P, _c.c_int32, _PP]),
   'bcg_dataset_create': (_c.c_int, [_P, _P, _c.c_int64, _c.c_int32, _PP]),
   'bcg_dataset_destroy': (_c.c_int, [_P]),
   'bcg_dataset_project': (_c.c_int, [_P, _P, _c.c_int64, _c.c_int32, _c.c_int32, _P, _c.c_int32, _P, _PP, _P, _P]),
@@ -227,16 +228,39 @@ class DeviceVecs(object):
     return cls(ctx, h)
 
   @classmethod
+  def project_host(cls, model, Z, theta, Siginv=None, ctx=None):
+    """project a HOST array once (upload pipelined with the kernels; the data are not kept on the device)"""
+    ctx = ctx or Context.default()
+    Z, theta = _f64(np.atleast_2d(Z)), _f64(np.atleast_2d(theta))
+    S, d = theta.shape
+    h = ctypes.c_void_p()
+    if model == MODEL_GAUSSIAN:
+      A = _f64(theta.dot(_f64(Siginv)))
+      coff = _f64(-0.5*(A*theta).sum(axis=1))
+      if Z.shape[1] != d:
+        raise ValueError('x and theta disagree on the feature dimension')
+      check(lib().bcg_vecs_project_linear(ctx.handle, _ptr(Z), Z.shape[0], d, _ptr(A), _ptr(coff), S, ctypes.byref(h)))
+    elif model == MODEL_LR:
+      if Z.shape[1] != d:
+        raise ValueError('Z and theta disagree on the feature dimension')
+      check(lib().bcg_vecs_project_lr(ctx.handle, _ptr(Z), Z.shape[0], d, _ptr(theta), S, ctypes.byref(h)))
+    else:
+      if Z.shape[1] != d + 1:
+        raise ValueError('Z must be [x, y] with one more column than theta')
+      check(lib().bcg_vecs_project_poisson(ctx.handle, _ptr(Z), Z.shape[0], d, _ptr(theta), S, ctypes.byref(h)))
+    return cls(ctx, h)
+
+  @classmethod
   def project_lr(cls, Z, theta, ctx=None):
-    return Dataset(Z, ctx).project(MODEL_LR, theta, vecs=True)[0]
+    return cls.project_host(MODEL_LR, Z, theta, ctx=ctx)
 
   @classmethod
   def project_gaussian(cls, x, theta, Siginv, ctx=None):
-    return Dataset(x, ctx).project(MODEL_GAUSSIAN, theta, Siginv, vecs=True)[0]
+    return cls.project_host(MODEL_GAUSSIAN, x, theta, Siginv, ctx=ctx)
 
   @classmethod
   def project_poisson(cls, Z, theta, ctx=None):
-    return Dataset(Z, ctx).project(MODEL_POISSON, theta, vecs=True)[0]
+    return cls.project_host(MODEL_POISSON, Z, theta, ctx=ctx)
 
   # ---- ndarray-like surface -----------------------------------------------------------------
   @property

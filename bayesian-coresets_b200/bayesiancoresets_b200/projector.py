@@ -76,6 +76,9 @@ class _DeviceModelProjector(Projector):
 
   def project_device(self, pts, cache=False, sub=None):
     """sub: optional row indices into pts -- only those rows are projected, gathered on the device"""
+    if not cache and sub is None and self._cache[0] is not pts:
+      # one-off projection of a host array (HilbertCoreset): upload pipelined with the projection kernels
+      return nat.DeviceVecs.project_host(self._model, pts, self.samples, self._siginv(), ctx=self.ctx)
     return self._dataset(pts, cache or sub is not None).project(self._model, self.samples, self._siginv(), vecs=True,
                                                                 sub=sub)[0]
 

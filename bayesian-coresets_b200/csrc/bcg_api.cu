@@ -97,6 +97,7 @@ struct bcg_ctx {
   int64_t flush_bytes;
   unsigned char* pin[2];      // pinned staging for host -> device uploads
   cudaEvent_t pin_done[2];
+  cudaStream_t copy_stream;   // second stream: uploads that overlap kernels on `stream`
 };
 
 struct bcg_vecs {
@@ -182,6 +183,7 @@ extern "C" int bcg_ctx_create(int device, bcg_ctx** out) {
                 c->prop.major, c->prop.minor);
   c->sm_count = c->prop.multiProcessorCount;
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   *out = c;
   return BCG_OK;
 }
@@ -193,6 +195,7 @@ extern "C" int bcg_ctx_destroy(bcg_ctx* ctx) {
   for (int i = 0; i < 2; ++i)
     if (ctx->pin[i]) { cudaFreeHost(ctx->pin[i]); cudaEventDestroy(ctx->pin_done[i]); }
   cudaStreamDestroy(ctx->stream);
+  cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
   return BCG_OK;
 }
@@ -555,6 +558,9 @@ static std::vector<double> transpose_sd(const double* theta, int S, int d) {
   return t;
 }
 
+static int prepare_model(int model, int d, const double* theta, int S, const double* Siginv, std::vector<double>& tT,
+                         std::vector<double>& coff, int* kmodel);
+
 // model: BCG_MODEL_*; theta: host S x d; Siginv: host d x d (Gaussian only).  Any of out_vecs / rows64 /
 // colsum may be null; with only colsum the N x S matrix is never written (K3b).
 extern "C" int bcg_dataset_project(bcg_dataset* ds, const int64_t* rowidx, int64_t nsel, int32_t model, int32_t d,
@@ -562,31 +568,11 @@ extern "C" int bcg_dataset_project(bcg_dataset* ds, const int64_t* rowidx, int64
                                    double* rows64, double* colsum) {
   if (!ds || !theta) return fail(BCG_ERR_ARG, "null argument");
   RET(use_device(ds->ctx));
-  if (model == BCG_MODEL_LR) {
-    std::vector<double> tT = transpose_sd(theta, S, d);
-    return project_common(ds, rowidx, nsel, d, tT.data(), nullptr, S, MODEL_LR, out_vecs, rows64, colsum);
-  }
-  if (model == BCG_MODEL_POISSON) {
-    std::vector<double> tT = transpose_sd(theta, S, d);
-    return project_common(ds, rowidx, nsel, d, tT.data(), nullptr, S, MODEL_POISSON, out_vecs, rows64, colsum);
-  }
-  if (model == BCG_MODEL_GAUSSIAN) {
-    if (!Siginv) return fail(BCG_ERR_ARG, "Siginv is required for the Gaussian model");
-    // after row-centring only  x . (Siginv theta_s) - 0.5 theta_s . Siginv theta_s  survives (model_gaussian.py:4-10)
-    std::vector<double> tT((size_t)S * d), coff(S);
-    for (int s = 0; s < S; ++s) {
-      double q = 0.;
-      for (int i = 0; i < d; ++i) {
-        double m = 0.;
-        for (int j = 0; j < d; ++j) m += Siginv[(size_t)i * d + j] * theta[(size_t)s * d + j];
-        tT[(size_t)i * S + s] = m;
-        q += theta[(size_t)s * d + i] * m;
-      }
-      coff[s] = -0.5 * q;
-    }
-    return project_common(ds, rowidx, nsel, d, tT.data(), coff.data(), S, MODEL_LINEAR, out_vecs, rows64, colsum);
-  }
-  return fail(BCG_ERR_ARG, "unknown model %d", model);
+  std::vector<double> tT, coff;
+  int kmodel = 0;
+  RET(prepare_model(model, d, theta, S, Siginv, tT, coff, &kmodel));
+  return project_common(ds, rowidx, nsel, d, tT.data(), coff.empty() ? nullptr : coff.data(), S, kmodel, out_vecs, rows64,
+                        colsum);
 }
 
 // Gaussian model with the S x d matrix A = theta Siginv and the offsets c_s = -0.5 theta_s Siginv theta_s
@@ -600,15 +586,128 @@ extern "C" int bcg_dataset_project_linear(bcg_dataset* ds, const int64_t* rowidx
   return project_common(ds, rowidx, nsel, d, tT.data(), coff, S, MODEL_LINEAR, out_vecs, rows64, colsum);
 }
 
+// thetaT (d x S) / coff (S) / kernel model for a C-ABI model id; Gaussian: A = theta Siginv, c = -0.5 theta.A
+static int prepare_model(int model, int d, const double* theta, int S, const double* Siginv, std::vector<double>& tT,
+                         std::vector<double>& coff, int* kmodel) {
+  coff.clear();
+  if (model == BCG_MODEL_LR || model == BCG_MODEL_POISSON) {
+    tT = transpose_sd(theta, S, d);
+    *kmodel = model == BCG_MODEL_LR ? MODEL_LR : MODEL_POISSON;
+    return BCG_OK;
+  }
+  if (model == BCG_MODEL_GAUSSIAN) {
+    if (!Siginv) return fail(BCG_ERR_ARG, "Siginv is required for the Gaussian model");
+    tT.assign((size_t)S * d, 0.);
+    coff.assign(S, 0.);
+    for (int s = 0; s < S; ++s) {
+      double q = 0.;
+      for (int i = 0; i < d; ++i) {
+        double m = 0.;
+        for (int j = 0; j < d; ++j) m += Siginv[(size_t)i * d + j] * theta[(size_t)s * d + j];
+        tT[(size_t)i * S + s] = m;
+        q += theta[(size_t)s * d + i] * m;
+      }
+      coff[s] = -0.5 * q;
+    }
+    *kmodel = MODEL_LINEAR;
+    return BCG_OK;
+  }
+  return fail(BCG_ERR_ARG, "unknown model %d", model);
+}
+
+// Projection straight from a HOST array, chunked and software-pipelined: while chunk c is being projected on
+// `stream`, chunk c+1 is staged (multi-threaded memcpy into pinned memory) and copied on `copy_stream`.  The
+// data are not kept on the device (HilbertCoreset projects once).  thetaT: d x S, coff: S or null (host).
+static int project_host_pipelined(bcg_ctx* ctx, int kmodel, const double* Z, int64_t n, int32_t zld, int32_t d,
+                                  const double* thetaT, const double* coff, int32_t S, bcg_vecs** out) {
+  *out = nullptr;
+  if (d <= 0 || S <= 0) return fail(BCG_ERR_ARG, "d and S must be positive");
+  if ((kmodel == MODEL_POISSON ? d + 1 : d) > zld) return fail(BCG_ERR_ARG, "data has too few columns");
+  bcg_vecs* v = nullptr;
+  RET(vecs_alloc(ctx, n, S, &v));
+  if (n == 0) { *out = v; return BCG_OK; }
+  auto body = [&]() -> int {
+    cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
+    const int ld = v->ld;
+    const size_t cs_bytes = (size_t)kProjWarps * (S + 1) * sizeof(double);
+    const size_t budget = 200 * 1024;
+    if (cs_bytes + (size_t)S * sizeof(double) > budget)
+      return fail(BCG_ERR_UNSUPPORTED, "projection tile does not fit shared memory for S=%d", S);
+    const int ktile = (int)std::min<size_t>(std::min<size_t>(kProjKTile, (size_t)d), (budget - cs_bytes) / ((size_t)S * sizeof(double)));
+    const size_t smem = (size_t)ktile * S * sizeof(double) + cs_bytes;
+    const int64_t chunk_rows = std::max<int64_t>(4096, std::min<int64_t>(n, ((int64_t)16 << 20) / ((int64_t)zld * 8)));
+    const int nchunks = (int)((n + chunk_rows - 1) / chunk_rows);
+    const int grid = (int)std::min<int64_t>((chunk_rows + kProjWarps - 1) / kProjWarps, (int64_t)ctx->sm_count);
+    PinBuf<double> pin[2];
+    DevBuf<double> dev[2], dT, dC, d_partial;
+    DevBuf<unsigned long long> d_zero;
+    EventPair copied, kdone;
+    const size_t celems = (size_t)chunk_rows * zld;
+    for (int i = 0; i < 2; ++i) {
+      CK(pin[i].alloc(celems));
+      CK(dev[i].alloc(celems));
+      CK(cudaEventCreateWithFlags(&copied.e[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&kdone.e[i], cudaEventDisableTiming));
+    }
+    CK(dT.alloc((size_t)d * S));
+    CK(d_partial.alloc((size_t)nchunks * grid * (S + 1)));
+    CK(d_zero.alloc(1));
+    CK(cudaMemsetAsync(d_zero, 0, sizeof(unsigned long long), st));
+    CK(cudaMemcpyAsync(dT, thetaT, (size_t)d * S * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (coff) {
+      CK(dC.alloc(S));
+      CK(cudaMemcpyAsync(dC, coff, (size_t)S * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    for (int c = 0; c < nchunks; ++c) {
+      const int i = c & 1;
+      const int64_t r0 = (int64_t)c * chunk_rows;
+      const int64_t nr = std::min<int64_t>(chunk_rows, n - r0);
+      if (c >= 2) CK(cudaEventSynchronize(kdone.e[i]));            // staging + device buffer i are free again
+      parallel_memcpy(pin[i], Z + r0 * zld, (size_t)nr * zld * sizeof(double));
+      CK(cudaMemcpyAsync(dev[i], pin[i], (size_t)nr * zld * sizeof(double), cudaMemcpyHostToDevice, cs));
+      CK(cudaEventRecord(copied.e[i], cs));
+      CK(cudaStreamWaitEvent(st, copied.e[i], 0));
+      ProjectArgs a;
+      a.Z = dev[i]; a.rowidx = nullptr; a.theta = dT; a.coff = dC; a.An = v->An + (size_t)r0 * ld; a.norms = v->norms + r0;
+      a.out64 = nullptr; a.partial = d_partial.p + (size_t)c * grid * (S + 1); a.zero_rows = d_zero; a.n = nr; a.zld = zld;
+      a.d = d; a.S = S; a.ld = ld; a.model = kmodel; a.ktile = ktile;
+      switch (j_for_ld(ld)) {
+        case 1: RET(launch_project<1>(ctx, a, grid, smem)); break;
+        case 2: RET(launch_project<2>(ctx, a, grid, smem)); break;
+        case 4: RET(launch_project<4>(ctx, a, grid, smem)); break;
+        case 8: RET(launch_project<8>(ctx, a, grid, smem)); break;
+        case 16: RET(launch_project<16>(ctx, a, grid, smem)); break;
+        default: RET(launch_project<32>(ctx, a, grid, smem)); break;
+      }
+      CK(cudaEventRecord(kdone.e[i], st));
+    }
+    RET(finish_colsum(v, d_partial, nchunks * grid, d_zero));
+    CK(cudaStreamSynchronize(cs));
+    return BCG_OK;
+  };
+  const int rc = body();
+  if (rc != BCG_OK) { bcg_vecs_destroy(v); return rc; }
+  *out = v;
+  return BCG_OK;
+}
+
 static int project_host(bcg_ctx* ctx, int model, const double* Z, int64_t n, int32_t zld, int32_t d, const double* theta,
                         int32_t S, const double* Siginv, bcg_vecs** out) {
   RET(use_device(ctx));
   if (!out || !theta || (n > 0 && !Z)) return fail(BCG_ERR_ARG, "null argument");
-  bcg_dataset* ds = nullptr;
-  RET(bcg_dataset_create(ctx, Z, n, zld, &ds));
-  const int rc = bcg_dataset_project(ds, nullptr, 0, model, d, theta, S, Siginv, out, nullptr, nullptr);
-  bcg_dataset_destroy(ds);
-  return rc;
+  std::vector<double> tT, coff;
+  int kmodel = 0;
+  RET(prepare_model(model, d, theta, S, Siginv, tT, coff, &kmodel));
+  return project_host_pipelined(ctx, kmodel, Z, n, zld, d, tT.data(), coff.empty() ? nullptr : coff.data(), S, out);
+}
+
+// Gaussian model with A = theta Siginv (host S x d) and coff_s = -0.5 theta_s Siginv theta_s precomputed by the caller
+extern "C" int bcg_vecs_project_linear(bcg_ctx* ctx, const double* x, int64_t n, int32_t d, const double* A,
+                                       const double* coff, int32_t S, bcg_vecs** out) {
+  RET(use_device(ctx));
+  if (!out || !A || (n > 0 && !x)) return fail(BCG_ERR_ARG, "null argument");
+  std::vector<double> tT = transpose_sd(A, S, d);
+  return project_host_pipelined(ctx, MODEL_LINEAR, x, n, d, d, tT.data(), coff, S, out);
 }
 
 extern "C" int bcg_vecs_project_lr(bcg_ctx* ctx, const double* Z, int64_t n, int32_t d, const double* theta,

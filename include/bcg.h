@@ -99,7 +99,9 @@ int  bcg_ctx_flush_l2(bcg_ctx* ctx, int64_t bytes);
 /* rows: host, row-major, n x S float64 with row stride ld_host (elements) */
 int  bcg_vecs_from_host_f64(bcg_ctx* ctx, const double* rows, int64_t n, int32_t S, int64_t ld_host,
                             bcg_vecs** out);
-/* Z: host n x d float64 (z_n = y_n x_n); theta: host S x d float64 */
+/* The three bcg_vecs_project_* calls take HOST arrays and pipeline the upload with the projection (chunks are
+ * staged and copied while the previous chunk is being projected); the data are not kept on the device.
+ * Z: host n x d float64 (z_n = y_n x_n); theta: host S x d float64 */
 int  bcg_vecs_project_lr(bcg_ctx* ctx, const double* Z, int64_t n, int32_t d, const double* theta, int32_t S,
                          bcg_vecs** out);
 /* x: host n x d; theta: host S x d; Siginv: host d x d (symmetric) */
@@ -127,6 +129,9 @@ int  bcg_dataset_project(bcg_dataset* ds, const int64_t* rowidx, int64_t nsel, i
  * coff_s = -0.5 theta_s Siginv theta_s precomputed by the caller */
 int  bcg_dataset_project_linear(bcg_dataset* ds, const int64_t* rowidx, int64_t nsel, int32_t d, const double* A,
                                 const double* coff, int32_t S, bcg_vecs** out_vecs, double* rows64, double* colsum);
+/* host-array Gaussian projection with A = theta Siginv and coff precomputed (see bcg_dataset_project_linear) */
+int  bcg_vecs_project_linear(bcg_ctx* ctx, const double* x, int64_t n, int32_t d, const double* A, const double* coff,
+                             int32_t S, bcg_vecs** out);
 int  bcg_vecs_shape(bcg_vecs* v, int64_t* n, int32_t* S, int32_t* ld);
 int  bcg_vecs_colsum(bcg_vecs* v, double* out_S);          /* sum over local rows of the centred vectors */
 int  bcg_vecs_norm_sum(bcg_vecs* v, double* out);          /* sum of local row norms */
