@@ -1157,6 +1157,7 @@ extern "C" int bcg_solver_build(bcg_solver* s, int32_t itrs, double tol, bcg_ite
     CK(cudaMemsetAsync(s->d_claims, 0, (size_t)itrs * sizeof(unsigned int), st));
     la.claims = s->d_claims;
     la.static_frac = (float)env_int("BCG_STATIC_PCT", 100) / 100.f;   // measured: a larger dynamic share only costs (atomics); the grid is HBM-bound either way
+    la.l2_prefetch = env_int("BCG_L2_PREFETCH", 0);
     la.trace = nullptr;
     s->trace_n = 0;
     if (s->trace_on) {

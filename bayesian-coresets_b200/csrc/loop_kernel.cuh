@@ -727,6 +727,16 @@ __global__ void __launch_bounds__(384, 1) greedy_loop_kernel(const LoopArgs a) {
 
     if (a.trace && gw == 0 && lane == 0) a.trace[(size_t)it * 8 + 3] = globaltimer_ns();
     __syncwarp();
+    // While the control warp resolves this iteration (~6 us + the grid skew) the shared-memory rings are full
+    // and HBM would idle: pull this warp's next static chunks (beyond the ring) into L2 in the meantime.
+    if (issue_it < a.itrs) {
+      for (int p = 0; p < a.l2_prefetch; ++p) {
+        const int64_t kpf = issue_k + p;
+        if (kpf >= n_s) break;
+        const int64_t row0 = (gw + kpf * GW) * q.rps;
+        tma_prefetch_l2(q.An + (size_t)row0 * q.ld, (uint32_t)q.rps * (uint32_t)q.ld * 4u, leader);
+      }
+    }
     Core::warp_merge(best, brow);
     if (lane == 0) { cta_c[warp].score = best; cta_c[warp].row = brow; }
     named_bar_sync(1, wpb * 32);
