@@ -727,8 +727,10 @@ __global__ void __launch_bounds__(384, 1) greedy_loop_kernel(const LoopArgs a) {
 
     if (a.trace && gw == 0 && lane == 0) a.trace[(size_t)it * 8 + 3] = globaltimer_ns();
     __syncwarp();
-    // While the control warp resolves this iteration (~6 us + the grid skew) the shared-memory rings are full
-    // and HBM would idle: pull this warp's next static chunks (beyond the ring) into L2 in the meantime.
+    // Experiment (BCG_L2_PREFETCH, default 0 = off): while the control warp resolves this iteration the
+    // shared-memory rings are full and HBM idles for ~5 us; pulling the next chunks into L2 meanwhile was
+    // measured to be slightly SLOWER (N=1e6, S=256: 154.4 us/iter off, 155.5 / 156.7 / 157.7 with 2 / 4 / 8
+    // chunks per warp), so it stays off.
     if (issue_it < a.itrs) {
       for (int p = 0; p < a.l2_prefetch; ++p) {
         const int64_t kpf = issue_k + p;

@@ -55,7 +55,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // PTX predicates rather than a branch.  (A lane-0 `if` around this, with loop-carried lane-0
 // state, left lane 0 permanently split from lanes 1-31 in the persistent kernel: every
 // instruction of the scan executed twice and the shuffles took the divergent slow path --
-// profiles/r01_v2_loop_divergence.md.)
+// profiles/r01_analysis.md.)
 __device__ __forceinline__ void tma_load_rows(uint64_t* bar, float* dst, const float* src, uint32_t bytes,
                                               uint64_t policy, bool leader) {
   const uint32_t b = smem_u32(bar);
