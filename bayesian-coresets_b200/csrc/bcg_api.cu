@@ -18,6 +18,7 @@
 #include "kernel_args.h"
 #include "project_kernels.cuh"
 #include "project_sum_kernel.cuh"
+#include "project_sum_mma_kernel.cuh"
 #include "step_kernels.cuh"
 
 using namespace bcg;
@@ -491,9 +492,15 @@ static int project_common(bcg_dataset* ds, const int64_t* rowidx, int64_t nsel, 
     ProjectSumArgs pa;
     pa.Z = ds->Z; pa.rowidx = rowidx ? d_idx.p : nullptr; pa.thetaT = dT; pa.coff = dC; pa.partial = d_partial; pa.n = n; pa.zld = ds->zld; pa.d = d; pa.S = S;
     pa.model = model;
-    if (model == MODEL_LR) project_sum_kernel<MODEL_LR><<<grid, kPsThreads, 0, st>>>(pa);
-    else if (model == MODEL_POISSON) project_sum_kernel<MODEL_POISSON><<<grid, kPsThreads, 0, st>>>(pa);
-    else project_sum_kernel<MODEL_LINEAR><<<grid, kPsThreads, 0, st>>>(pa);
+    if (env_int("BCG_PROJSUM_MMA", 1)) {                 // float64 tensor cores (DMMA)
+      if (model == MODEL_LR) project_sum_mma_kernel<MODEL_LR><<<grid, kPsThreads, 0, st>>>(pa);
+      else if (model == MODEL_POISSON) project_sum_mma_kernel<MODEL_POISSON><<<grid, kPsThreads, 0, st>>>(pa);
+      else project_sum_mma_kernel<MODEL_LINEAR><<<grid, kPsThreads, 0, st>>>(pa);
+    } else {                                             // float64 FMA pipe
+      if (model == MODEL_LR) project_sum_kernel<MODEL_LR><<<grid, kPsThreads, 0, st>>>(pa);
+      else if (model == MODEL_POISSON) project_sum_kernel<MODEL_POISSON><<<grid, kPsThreads, 0, st>>>(pa);
+      else project_sum_kernel<MODEL_LINEAR><<<grid, kPsThreads, 0, st>>>(pa);
+    }
     CK(cudaGetLastError());
     project_sum_finish_kernel<<<1, 256, 0, st>>>(d_partial, grid, S, d_out);
     CK(cudaGetLastError());
