@@ -492,7 +492,10 @@ static int project_common(bcg_dataset* ds, const int64_t* rowidx, int64_t nsel, 
     ProjectSumArgs pa;
     pa.Z = ds->Z; pa.rowidx = rowidx ? d_idx.p : nullptr; pa.thetaT = dT; pa.coff = dC; pa.partial = d_partial; pa.n = n; pa.zld = ds->zld; pa.d = d; pa.S = S;
     pa.model = model;
-    if (env_int("BCG_PROJSUM_MMA", 1)) {                 // float64 tensor cores (DMMA)
+    // float64 tensor cores (DMMA) for the pure contraction (Gaussian: 1.8x the FMA-pipe kernel); for LR / Poisson
+    // the link evaluations dominate and the DMMA variant measured slower and erratic (BCG_PROJSUM_MMA=2 forces it)
+    const int mma = env_int("BCG_PROJSUM_MMA", 1);
+    if (mma >= 2 || (mma == 1 && model == MODEL_LINEAR)) {
       if (model == MODEL_LR) project_sum_mma_kernel<MODEL_LR><<<grid, kPsThreads, 0, st>>>(pa);
       else if (model == MODEL_POISSON) project_sum_mma_kernel<MODEL_POISSON><<<grid, kPsThreads, 0, st>>>(pa);
       else project_sum_mma_kernel<MODEL_LINEAR><<<grid, kPsThreads, 0, st>>>(pa);
