@@ -2,6 +2,7 @@
 // Host side: handle management, uploads, kernel launches on a private stream.  There is no CPU
 // compute path: without a CUDA device every entry point fails with BCG_ERR_NO_DEVICE.
 #include <cuda_runtime.h>
+#include <chrono>
 #include <math.h>
 #include <stdarg.h>
 #include <stdint.h>
@@ -99,6 +100,8 @@ struct bcg_ctx {
   unsigned char* pin[2];      // pinned staging for host -> device uploads
   cudaEvent_t pin_done[2];
   cudaStream_t copy_stream;   // second stream: uploads that overlap kernels on `stream`
+  void* scratch[8];           // per-context device scratch, grown on demand (no malloc/free per projection pass)
+  size_t scratch_bytes[8];
 };
 
 struct bcg_vecs {
@@ -141,6 +144,21 @@ struct bcg_solver {
   int scan_launches, step_launches, loop_launches;
 };
 
+// context-owned scratch slot `i` of at least `bytes` (contents undefined); calls on one context are serialised
+// and every user synchronises the stream before returning, so slots are free again at the next call
+static int ctx_scratch(bcg_ctx* ctx, int i, size_t bytes, void** out) {
+  if (ctx->scratch_bytes[i] < bytes) {
+    if (ctx->scratch[i]) CK(cudaFree(ctx->scratch[i]));
+    ctx->scratch[i] = nullptr;
+    ctx->scratch_bytes[i] = 0;
+    const size_t want = std::max(bytes, (size_t)1 << 20);
+    CK(cudaMalloc(&ctx->scratch[i], want));
+    ctx->scratch_bytes[i] = want;
+  }
+  *out = ctx->scratch[i];
+  return BCG_OK;
+}
+
 static int use_device(bcg_ctx* ctx) {
   if (!ctx) return fail(BCG_ERR_ARG, "null context");
   CK(cudaSetDevice(ctx->device));
@@ -177,6 +195,7 @@ extern "C" int bcg_ctx_create(int device, bcg_ctx** out) {
   c->flush_buf = nullptr;
   c->flush_bytes = 0;
   c->pin[0] = c->pin[1] = nullptr;
+  for (int i = 0; i < 8; ++i) { c->scratch[i] = nullptr; c->scratch_bytes[i] = 0; }
   CK(cudaSetDevice(device));
   CK(cudaGetDeviceProperties(&c->prop, device));
   if (c->prop.major < 10)
@@ -193,6 +212,8 @@ extern "C" int bcg_ctx_destroy(bcg_ctx* ctx) {
   if (!ctx) return BCG_OK;
   cudaSetDevice(ctx->device);
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+  for (int i = 0; i < 8; ++i)
+    if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
   for (int i = 0; i < 2; ++i)
     if (ctx->pin[i]) { cudaFreeHost(ctx->pin[i]); cudaEventDestroy(ctx->pin_done[i]); }
   cudaStreamDestroy(ctx->stream);
@@ -467,35 +488,40 @@ static int project_common(bcg_dataset* ds, const int64_t* rowidx, int64_t nsel, 
     if (colsum) memset(colsum, 0, (size_t)S * sizeof(double));
     return BCG_OK;
   }
+  const auto t_entry = std::chrono::steady_clock::now();
   cudaStream_t st = ctx->stream;
-  DevBuf<double> dT, dC, d_partial, d_out, d_rows;
-  DevBuf<unsigned long long> d_zero;
-  DevBuf<int64_t> d_idx;
+  double *dT = nullptr, *dC = nullptr, *d_partial = nullptr, *d_out = nullptr;
+  unsigned long long* d_zero = nullptr;
+  int64_t* d_idx = nullptr;
+  DevBuf<double> d_rows;
   if (rowidx) {
-    CK(d_idx.alloc((size_t)n));
+    RET(ctx_scratch(ctx, 0, (size_t)n * sizeof(int64_t), (void**)&d_idx));
     CK(cudaMemcpyAsync(d_idx, rowidx, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, st));
   }
-  CK(dT.alloc((size_t)d * S));
+  RET(ctx_scratch(ctx, 1, (size_t)d * S * sizeof(double), (void**)&dT));
   CK(cudaMemcpyAsync(dT, thetaT, (size_t)d * S * sizeof(double), cudaMemcpyHostToDevice, st));
   if (coff) {
-    CK(dC.alloc(S));
+    RET(ctx_scratch(ctx, 2, (size_t)S * sizeof(double), (void**)&dC));
     CK(cudaMemcpyAsync(dC, coff, (size_t)S * sizeof(double), cudaMemcpyHostToDevice, st));
   }
+  RET(ctx_scratch(ctx, 3, (size_t)(S + 1) * sizeof(double), (void**)&d_out));
+  RET(ctx_scratch(ctx, 4, sizeof(unsigned long long), (void**)&d_zero));
 
   if (!out_vecs && !rows64 && colsum && d >= env_int("BCG_PROJSUM_MIN_D", 24) && n >= 4096) {
     // K3b, GEMM-shaped: register-tiled float64 kernel (project_sum_kernel.cuh)
     const int64_t nrb = (n + kPsBM - 1) / kPsBM;
     const int grid = (int)std::min<int64_t>(nrb, (int64_t)ctx->sm_count);
-    CK(d_partial.alloc((size_t)grid * S));
-    CK(d_out.alloc(S));
+    RET(ctx_scratch(ctx, 5, (size_t)grid * S * sizeof(double), (void**)&d_partial));
     CK(cudaMemsetAsync(d_partial, 0, (size_t)grid * S * sizeof(double), st));
     ProjectSumArgs pa;
-    pa.Z = ds->Z; pa.rowidx = rowidx ? d_idx.p : nullptr; pa.thetaT = dT; pa.coff = dC; pa.partial = d_partial; pa.n = n; pa.zld = ds->zld; pa.d = d; pa.S = S;
+    pa.Z = ds->Z; pa.rowidx = d_idx; pa.thetaT = dT; pa.coff = dC; pa.partial = d_partial; pa.n = n; pa.zld = ds->zld; pa.d = d; pa.S = S;
     pa.model = model;
-    // float64 tensor cores (DMMA) for the pure contraction (Gaussian: 1.8x the FMA-pipe kernel); for LR / Poisson
-    // the link evaluations dominate and the DMMA variant measured slower and erratic (BCG_PROJSUM_MMA=2 forces it)
+    // float64 tensor cores (DMMA) for the contraction by default (ncu, N=1e6 d=200 S=512: LR 15.1 ms vs 17.1 ms on
+    // the FMA pipe; Gaussian 1.8x faster); BCG_PROJSUM_MMA=0 selects the FMA-pipe kernel
     const int mma = env_int("BCG_PROJSUM_MMA", 1);
-    if (mma >= 2 || (mma == 1 && model == MODEL_LINEAR)) {
+    const bool trace = env_int("BCG_PROJ_TRACE", 0) != 0;
+    const auto t_launch = std::chrono::steady_clock::now();
+    if (mma >= 1) {
       if (model == MODEL_LR) project_sum_mma_kernel<MODEL_LR><<<grid, kPsThreads, 0, st>>>(pa);
       else if (model == MODEL_POISSON) project_sum_mma_kernel<MODEL_POISSON><<<grid, kPsThreads, 0, st>>>(pa);
       else project_sum_mma_kernel<MODEL_LINEAR><<<grid, kPsThreads, 0, st>>>(pa);
@@ -509,6 +535,12 @@ static int project_common(bcg_dataset* ds, const int64_t* rowidx, int64_t nsel, 
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(colsum, d_out, (size_t)S * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    if (trace) {
+      const auto t_done = std::chrono::steady_clock::now();
+      fprintf(stderr, "[bcg] project_sum: prep %.3f ms, kernels+readback %.3f ms\n",
+              std::chrono::duration<double, std::milli>(t_launch - t_entry).count(),
+              std::chrono::duration<double, std::milli>(t_done - t_launch).count());
+    }
     return BCG_OK;
   }
 
@@ -525,12 +557,11 @@ static int project_common(bcg_dataset* ds, const int64_t* rowidx, int64_t nsel, 
   bcg_vecs* v = nullptr;
   if (out_vecs) RET(vecs_alloc(ctx, n, S, &v));
   auto body = [&]() -> int {
-    CK(d_partial.alloc((size_t)grid * (S + 1)));
-    CK(d_zero.alloc(1));
+    RET(ctx_scratch(ctx, 5, (size_t)grid * (S + 1) * sizeof(double), (void**)&d_partial));
     CK(cudaMemsetAsync(d_zero, 0, sizeof(unsigned long long), st));
     if (rows64) CK(d_rows.alloc((size_t)n * S));
     ProjectArgs a;
-    a.Z = ds->Z; a.rowidx = rowidx ? d_idx.p : nullptr; a.theta = dT; a.coff = dC; a.An = v ? v->An : nullptr; a.norms = v ? v->norms : nullptr;
+    a.Z = ds->Z; a.rowidx = d_idx; a.theta = dT; a.coff = dC; a.An = v ? v->An : nullptr; a.norms = v ? v->norms : nullptr;
     a.out64 = d_rows; a.partial = d_partial; a.zero_rows = d_zero; a.n = n; a.zld = ds->zld; a.d = d; a.S = S;
     a.ld = ld; a.model = model; a.ktile = ktile;
     switch (j_for_ld(ld)) {
@@ -546,7 +577,6 @@ static int project_common(bcg_dataset* ds, const int64_t* rowidx, int64_t nsel, 
       if (colsum) memcpy(colsum, v->colsum.data(), (size_t)S * sizeof(double));
     } else if (colsum) {
       const int S1 = S + 1;
-      CK(d_out.alloc(S1));
       colsum_reduce_kernel<<<(S1 + 127) / 128, 128, 0, st>>>(d_partial, grid, S1, d_out);
       CK(cudaGetLastError());
       CK(cudaMemcpyAsync(colsum, d_out, (size_t)S * sizeof(double), cudaMemcpyDeviceToHost, st));
