@@ -1133,7 +1133,7 @@ extern "C" int bcg_solver_nnls(bcg_solver* s, int32_t from_scratch) {
   RET(use_device(s->ctx));
   RET(ensure_nnls(s));
   RET(push_state(s));
-  nnls_kernel<<<1, kStepThreads, 0, s->ctx->stream>>>(s->d, s->d_nw, from_scratch ? 1 : 0);
+  nnls_kernel<<<1, kStepThreads, 0, s->ctx->stream>>>(s->d, s->d_nw, from_scratch ? 1 : 0, env_int("BCG_OMP_WIDE", 1));
   CK(cudaGetLastError());
   RET(pull_state(s));
   return BCG_OK;
@@ -1157,21 +1157,21 @@ extern "C" int bcg_solver_build(bcg_solver* s, int32_t itrs, double tol, bcg_ite
   RET(push_state(s));
   const bool loop = s->use_loop && !s->profiling;
   if (h.alg == BCG_ALG_OMP) {
-    // OrthoPursuit: selection scan + on-device NNLS per iteration, no host round trip inside the loop
+    // OrthoPursuit: selection scan + on-device NNLS per iteration (two launches), no host round trip inside the loop
     RET(ensure_nnls(s));
+    const int wide = env_int("BCG_OMP_WIDE", 1);
     CK(cudaEventRecord(s->ev0, st));
-    step_kernel<<<1, kStepThreads, 0, st>>>(s->d, 0, 0, 1);           // reset the per-call retry flag
+    step_kernel<<<1, kStepThreads, 0, st>>>(s->d, 0, 1, 1);           // reset the per-call retry flag; first residual direction
     for (int i = 0; i < itrs; ++i) {
-      step_kernel<<<1, kStepThreads, 0, st>>>(s->d, 0, 1, 0);         // residual direction
       RET(launch_scan(s));
-      omp_iteration_kernel<<<1, kStepThreads, 0, st>>>(s->d, s->d_nw);
+      omp_iteration_kernel<<<1, kStepThreads, 0, st>>>(s->d, s->d_nw, wide, (i + 1 < itrs) ? 1 : 0);
     }
     CK(cudaGetLastError());
     CK(cudaEventRecord(s->ev1, st));
     RET(pull_state(s));
     CK(cudaEventElapsedTime(&s->build_ms, s->ev0, s->ev1));
     s->scan_launches = itrs;
-    s->step_launches = 2 * itrs + 1;
+    s->step_launches = itrs + 1;
     s->loop_launches = 0;
     s->scan_ms = 0.f;
   } else if (loop) {

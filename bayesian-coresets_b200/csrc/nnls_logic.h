@@ -43,43 +43,6 @@ struct NnlsWork {
   int32_t first_removed;           // first P position dropped by the last step-back (block-uniform hand-over)
 };
 
-BCG_HD int blk_lane(const Blk& B) {
-#ifdef __CUDA_ARCH__
-  return B.tid & 31;
-#else
-  (void)B; return 0;
-#endif
-}
-BCG_HD int blk_warp(const Blk& B) {
-#ifdef __CUDA_ARCH__
-  return B.tid >> 5;
-#else
-  (void)B; return 0;
-#endif
-}
-BCG_HD int blk_nwarps(const Blk& B) {
-#ifdef __CUDA_ARCH__
-  return B.nthr >> 5;
-#else
-  (void)B; return 1;
-#endif
-}
-BCG_HD int blk_lanes(const Blk& B) {
-#ifdef __CUDA_ARCH__
-  (void)B; return 32;
-#else
-  (void)B; return 1;
-#endif
-}
-BCG_HD double blk_warp_sum(const Blk& B, double v) {
-#ifdef __CUDA_ARCH__
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-#endif
-  (void)B;
-  return v;
-}
-
 BCG_HD double act_col(const SolverState* st, int slot, int s) {
   return st->act_norm[slot] * (double)st->act_rows[(size_t)slot * st->ld + s];
 }
@@ -87,44 +50,34 @@ BCG_HD double act_col(const SolverState* st, int slot, int s) {
 // append the column of `slot` to the QR of P; returns false when it is numerically dependent
 BCG_HD bool nnls_qr_append(const Blk& B, SolverState* st, NnlsWork* W, int slot) {
   const int S = st->S, p = W->nP, cap = W->cap;
-  const int lane = blk_lane(B), warp = blk_warp(B), nw = blk_nwarps(B), lanes = blk_lanes(B);
   double n0 = 0.;
   for (int s = B.tid; s < S; s += B.nthr) { const double x = act_col(st, slot, s); W->v[s] = x; n0 += x * x; }
   blk_sum<1>(B, &n0);                                   // (also a barrier: v is complete)
+  double* const Q = W->Q;
+  double* const T = W->R;
+  double* const v = W->v;
+  double* const h = W->h;
+  double* const r = W->z + cap;                         // Gram-Schmidt coefficients r = h1 + h2
   for (int pass = 0; pass < 2; ++pass) {
-    for (int i = warp; i < p; i += nw) {                // h_i = q_i . v, one warp per i
-      double part = 0.;
-      const double* q = W->Q + (size_t)i * S;
-      for (int s = lane; s < S; s += lanes) part += q[s] * W->v[s];
-      part = blk_warp_sum(B, part);
-      if (lane == 0) W->h[i] = part;
-    }
-    B.sync();
-    for (int s = B.tid; s < S; s += B.nthr) {           // v -= sum_i h_i q_i
-      double acc = W->v[s];
-      for (int i = 0; i < p; ++i) acc -= W->h[i] * W->Q[(size_t)i * S + s];
-      W->v[s] = acc;
-    }
-    for (int i = B.tid; i < p; i += B.nthr) W->z[cap + i] = (pass == 0 ? 0. : W->z[cap + i]) + W->h[i];   // r = h1 + h2
-    B.sync();
+    // h_i = q_i . v
+    blk_dots<double>(B, p, S, [&](int i) { return (const double*)(Q + (size_t)i * S); }, v,
+                     [&](int i, double d) { h[i] = d; r[i] = (pass == 0 ? 0. : r[i]) + d; });
+    // v -= sum_i h_i q_i
+    blk_combine<double>(B, S, p, [&](int i) { return CombTerm<double>{h[i], Q + (size_t)i * S, S}; },
+                        [&](int s, double acc) { v[s] -= acc; });
   }
   double u[2] = {0., 0.};
-  for (int s = B.tid; s < S; s += B.nthr) { const double x = W->v[s]; u[0] += x * x; u[1] += x * st->b[s]; }
+  for (int s = B.tid; s < S; s += B.nthr) { const double x = v[s]; u[0] += x * x; u[1] += x * st->b[s]; }
   blk_sum<2>(B, u);
   const double rpp = sqrt(u[0]);
   if (!(rpp > 1e-13 * sqrt(n0))) return false;          // (numerically) in the span of P
-  double* q = W->Q + (size_t)p * S;
-  for (int s = B.tid; s < S; s += B.nthr) q[s] = W->v[s] / rpp;
-  // new column of T = R^{-1}:  -(T r) / rho on top of 1 / rho
-  for (int i = B.tid; i < p; i += B.nthr) {
-    double acc = 0.;
-    for (int j = i; j < p; ++j) acc += W->R[(size_t)i + (size_t)j * cap] * W->z[cap + j];
-    W->h[i] = -acc / rpp;
-  }
-  B.sync();
-  for (int i = B.tid; i < p; i += B.nthr) W->R[(size_t)i + (size_t)p * cap] = W->h[i];
+  double* q = Q + (size_t)p * S;
+  for (int s = B.tid; s < S; s += B.nthr) q[s] = v[s] / rpp;
+  // new column of T = R^{-1}:  -(T r) / rho on top of 1 / rho   (column j of T holds rows 0..j)
+  blk_combine<double>(B, p, p, [&](int j) { return CombTerm<double>{r[j], T + (size_t)j * cap, j + 1}; },
+                      [&](int i, double acc) { T[(size_t)i + (size_t)p * cap] = -acc / rpp; });
   if (B.tid == 0) {
-    W->R[(size_t)p + (size_t)p * cap] = 1. / rpp;
+    T[(size_t)p + (size_t)p * cap] = 1. / rpp;
     W->c[p] = u[1] / rpp;
     W->P[p] = slot;
     W->inP[slot] = 1;
@@ -135,15 +88,14 @@ BCG_HD bool nnls_qr_append(const Blk& B, SolverState* st, NnlsWork* W, int slot)
   return true;
 }
 
-// z = R^{-1} c = T c : thread i owns row i (column-major T: coalesced over i), no sequential dependency
+// z = R^{-1} c = T c : no sequential dependency (column j of T is contiguous over its rows 0..j)
 BCG_HD void nnls_solve_R(const Blk& B, NnlsWork* W) {
   const int n = W->nP, cap = W->cap;
-  for (int i = B.tid; i < n; i += B.nthr) {
-    double acc = 0.;
-    for (int j = i; j < n; ++j) acc += W->R[(size_t)i + (size_t)j * cap] * W->c[j];
-    W->z[i] = acc;
-  }
-  B.sync();
+  const double* const T = W->R;
+  const double* const c = W->c;
+  double* const z = W->z;
+  blk_combine<double>(B, n, n, [&](int j) { return CombTerm<double>{c[j], T + (size_t)j * cap, j + 1}; },
+                      [&](int i, double acc) { z[i] = acc; });
 }
 
 // Rebuild the factorisation for the slots currently listed in P (after removals), keeping their weights.
@@ -174,14 +126,17 @@ BCG_HD void nnls_rebuild(const Blk& B, SolverState* st, NnlsWork* W, int from) {
 
 // Solve the NNLS over the slots with act_w > 0.  from_scratch: forget the factorisation (optimize()).
 // On return act_w holds the solution (zeros for the columns left out), st->xw / st->err are refreshed.
-BCG_HD void nnls_solve(const Blk& B, SolverState* st, NnlsWork* W, int from_scratch) {
-  const int S = st->S, nact = st->nact;
-  const int lane = blk_lane(B), warp = blk_warp(B), nw = blk_nwarps(B), lanes = blk_lanes(B);
+// xw_current: st->xw equals A w for the weights the solver was left with by its previous call (true inside the
+// OMP loop) -- then a valid warm start needs no residual pass before the first dual test.
+BCG_HD void nnls_solve(const Blk& B, SolverState* st, NnlsWork* W, int from_scratch, int xw_current = 0) {
+  const int S = st->S, nact = st->nact, ld = st->ld;
   // a passive column whose weight the host zeroed invalidates the warm start
   double bad = 0.;
   for (int p = B.tid; p < W->nP; p += B.nthr) bad += (st->act_w[W->P[p]] > 0.) ? 0. : 1.;
   blk_sum<1>(B, &bad);
-  if (from_scratch || !W->valid || bad > 0.) {
+  const bool warm = !(from_scratch || !W->valid || bad > 0.);
+  B.sync();
+  if (!warm) {
     for (int k = B.tid; k < W->cap; k += B.nthr) W->inP[k] = 0;
     B.sync();
     if (B.tid == 0) { W->nP = 0; }
@@ -201,33 +156,29 @@ BCG_HD void nnls_solve(const Blk& B, SolverState* st, NnlsWork* W, int from_scra
     }
   }
   B.sync();
-  // scale of the dual tolerance
-  double tolscale = 0.;
-  {
-    double m = 0.;
-    for (int s = B.tid; s < S; s += B.nthr) m += st->b[s] * st->b[s];
-    blk_sum<1>(B, &m);
-    tolscale = sqrt(m);
-  }
+  const double tolscale = st->bnorm;                     // scale of the dual tolerance, ||b||
   const int maxit = 3 * (W->nP + W->nZ) + 10;
+  double* const ax = st->xw_new;                              // A_P wP
+  double* const resid = st->xf;                               // b - A_P wP (xf is otherwise unused by OMP)
+  bool ax_is_final = false;                                   // ax == A_P wP for the P / wP the loop ends with
   for (int outer = 0; outer < maxit; ++outer) {
-    // residual b - A_P wP  -> st->xw_new holds A_P wP
-    for (int s = B.tid; s < S; s += B.nthr) {
-      double acc = 0.;
-      for (int p = 0; p < W->nP; ++p) acc += W->wP[p] * act_col(st, W->P[p], s);
-      st->xw_new[s] = acc;
+    if (outer == 0 && warm && xw_current) {
+      for (int s = B.tid; s < S; s += B.nthr) { const double a = st->xw[s]; ax[s] = a; resid[s] = st->b[s] - a; }
+      B.sync();
+    } else {
+      const int nP = W->nP;
+      blk_combine<float>(B, S, nP,
+                         [&](int p) {
+                           const int slot = W->P[p];
+                           return CombTerm<float>{W->wP[p] * st->act_norm[slot], st->act_rows + (size_t)slot * ld, S};
+                         },
+                         [&](int s, double acc) { ax[s] = acc; resid[s] = st->b[s] - acc; });
     }
-    B.sync();
+    ax_is_final = true;
     if (W->nZ == 0) break;
-    // duals of the zero set: d_j = a_j . (b - A w), one warp per column
-    for (int j = warp; j < W->nZ; j += nw) {
-      const int slot = W->Z[j];
-      double part = 0.;
-      for (int s = lane; s < S; s += lanes) part += act_col(st, slot, s) * (st->b[s] - st->xw_new[s]);
-      part = blk_warp_sum(B, part);
-      if (lane == 0) W->h[j] = part / st->act_norm[slot];     // scale-free (cosine-like) dual
-    }
-    B.sync();
+    // duals of the zero set, scale-free (cosine-like): d_j = (a_j / ||a_j||) . (b - A w)
+    blk_dots<float>(B, W->nZ, S, [&](int j) { return (const float*)(st->act_rows + (size_t)W->Z[j] * ld); }, resid,
+                    [&](int j, double d) { W->h[j] = d; });
     double key = -INFINITY; int64_t id = -1; int pl = -1;
     for (int j = B.tid; j < W->nZ; j += B.nthr) {
       const double d = W->h[j];
@@ -235,6 +186,7 @@ BCG_HD void nnls_solve(const Blk& B, SolverState* st, NnlsWork* W, int from_scra
     }
     blk_argbest(B, &key, &id, &pl);
     if (id < 0 || !(key > 1e-13 * tolscale)) break;           // KKT: no zero column has a positive dual
+    ax_is_final = false;
     // move it into P
     if (B.tid == 0) { W->Z[pl] = W->Z[W->nZ - 1]; W->nZ -= 1; W->outer_iters += 1; }
     B.sync();
@@ -288,7 +240,47 @@ BCG_HD void nnls_solve(const Blk& B, SolverState* st, NnlsWork* W, int from_scra
   for (int p = B.tid; p < W->nP; p += B.nthr) st->act_w[W->P[p]] = W->wP[p];
   if (B.tid == 0) W->valid = 1;
   B.sync();
-  refresh_iterate(B, st);
+  if (ax_is_final) {
+    // the last residual pass already is A w for the final weights: error() without another K x S pass
+    double e = 0.;
+    for (int s = B.tid; s < S; s += B.nthr) { st->xw[s] = ax[s]; const double rr = resid[s]; e += rr * rr; }
+    blk_sum<1>(B, &e);
+    if (B.tid == 0) st->err = sqrt(e);
+    B.sync();
+  } else {
+    refresh_iterate(B, st);
+  }
+}
+
+// One OMP iteration behind the selection scan (orthopursuit.py:17-42 inside snnls.py:41-78): selection (+ w[f] = 1),
+// NNLS re-solve on the active set, monotone-error check with revert, event log, retry / latch, and -- when another
+// iteration follows -- the residual direction for its scan (orthopursuit.py:18).
+// act_w_new keeps the weights from before the iteration for the revert.
+BCG_HD void omp_iteration(const Blk& B, SolverState* st, NnlsWork* W, int prep_next) {
+  if (st->halted) return;
+  bool nonempty;
+  count_positive(B, st, &nonempty);
+  const double prev_err = st->err;
+  const int nact0 = st->nact;
+  for (int k = B.tid; k < nact0; k += B.nthr) st->act_w_new[k] = st->act_w[k];
+  B.sync();
+  const int64_t f = omp_select(B, st);
+  if (st->comm_error) return;
+  nnls_solve(B, st, W, 0, 1);
+  const double err = st->err;
+  if (nonempty && err > prev_err) {                      // snnls.py:58-61: revert
+    for (int k = B.tid; k < st->nact; k += B.nthr) st->act_w[k] = (k < nact0) ? st->act_w_new[k] : 0.;
+    B.sync();
+    if (B.tid == 0) W->valid = 0;
+    B.sync();
+    refresh_iterate(B, st);
+    if (B.tid == 0) fail_event(st, BCG_IT_FAIL_MONOTONE, f, err, prev_err);
+  } else if (B.tid == 0) {
+    if (nonempty) st->retried = 0;
+    push_event(st, BCG_IT_OK, f, st->nact, err, 0., 0.);
+  }
+  B.sync();
+  if (prep_next && !st->halted) prepare_select(B, st);
 }
 
 }  // namespace bcg

@@ -80,7 +80,7 @@ __device__ void mail_exchange(const Blk& B, SolverState* st, uint32_t lrow, doub
 __global__ void __launch_bounds__(kStepThreads, 1)
 step_kernel(SolverState* st, int do_finish, int do_prep, int reset_retry) {
   __shared__ double sred[256];
-  Blk B{(int)threadIdx.x, (int)blockDim.x, sred};
+  Blk B{(int)threadIdx.x, (int)blockDim.x, sred, nullptr};
   if (reset_retry) {
     if (threadIdx.x == 0) st->retried = 0;
     __syncthreads();
@@ -94,7 +94,7 @@ step_kernel(SolverState* st, int do_finish, int do_prep, int reset_retry) {
 
 __global__ void __launch_bounds__(kStepThreads, 1) omp_select_kernel(SolverState* st, int64_t* f_out) {
   __shared__ double sred[256];
-  Blk B{(int)threadIdx.x, (int)blockDim.x, sred};
+  Blk B{(int)threadIdx.x, (int)blockDim.x, sred, nullptr};
   const int64_t f = omp_select(B, st);
   if (threadIdx.x == 0) *f_out = f;
 }
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) omp_select_kernel(SolverState
 // local argmax of <unit row, dir> with float64 re-scoring; no state change (SparseVI selection)
 __global__ void __launch_bounds__(kStepThreads, 1) probe_kernel(SolverState* st, int64_t* f_out, double* score_out) {
   __shared__ double sred[256];
-  Blk B{(int)threadIdx.x, (int)blockDim.x, sred};
+  Blk B{(int)threadIdx.x, (int)blockDim.x, sred, nullptr};
   uint32_t lrow; double sc;
   pick_local(B, st, true, &lrow, &sc);
   if (threadIdx.x == 0) {
@@ -112,45 +112,27 @@ __global__ void __launch_bounds__(kStepThreads, 1) probe_kernel(SolverState* st,
 }
 
 // OMP iteration on the device (orthopursuit.py:17-42 inside snnls.py:41-78): selection (+ w[f] = 1), NNLS
-// re-solve on the active set, monotone-error check with revert, event log, retry / latch.
-// act_w_new keeps the weights from before the iteration for the revert.
-__global__ void __launch_bounds__(kStepThreads, 1) omp_iteration_kernel(SolverState* st, NnlsWork* W) {
+// re-solve on the active set, monotone-error check with revert, event log, retry / latch, and -- when another
+// iteration follows -- the residual direction for its scan (orthopursuit.py:18), so that an iteration is two
+// launches (scan + this kernel).  act_w_new keeps the weights from before the iteration for the revert.
+// wide: use the warp-split K x S products (blk_combine through 32 KB of shared scratch).
+__global__ void __launch_bounds__(kStepThreads, 1) omp_iteration_kernel(SolverState* st, NnlsWork* W, int wide, int prep_next) {
   __shared__ double sred[256];
-  Blk B{(int)threadIdx.x, (int)blockDim.x, sred};
-  if (st->halted) return;
-  bool nonempty;
-  count_positive(B, st, &nonempty);
-  const double prev_err = st->err;
-  const int nact0 = st->nact;
-  for (int k = B.tid; k < nact0; k += B.nthr) st->act_w_new[k] = st->act_w[k];
-  B.sync();
-  const int64_t f = omp_select(B, st);
-  if (st->comm_error) return;
-  nnls_solve(B, st, W, 0);
-  const double err = st->err;
-  if (nonempty && err > prev_err) {                      // snnls.py:58-61: revert
-    for (int k = B.tid; k < st->nact; k += B.nthr) st->act_w[k] = (k < nact0) ? st->act_w_new[k] : 0.;
-    B.sync();
-    if (B.tid == 0) W->valid = 0;
-    B.sync();
-    refresh_iterate(B, st);
-    if (B.tid == 0) fail_event(st, BCG_IT_FAIL_MONOTONE, f, err, prev_err);
-  } else if (B.tid == 0) {
-    if (nonempty) st->retried = 0;
-    push_event(st, BCG_IT_OK, f, st->nact, err, 0., 0.);
-  }
-  B.sync();
+  __shared__ double swide[(kStepThreads / 32) * kWideCols];
+  Blk B{(int)threadIdx.x, (int)blockDim.x, sred, wide ? swide : nullptr};
+  omp_iteration(B, st, W, prep_next);
 }
 
-__global__ void __launch_bounds__(kStepThreads, 1) nnls_kernel(SolverState* st, NnlsWork* W, int from_scratch) {
+__global__ void __launch_bounds__(kStepThreads, 1) nnls_kernel(SolverState* st, NnlsWork* W, int from_scratch, int wide) {
   __shared__ double sred[256];
-  Blk B{(int)threadIdx.x, (int)blockDim.x, sred};
+  __shared__ double swide[(kStepThreads / 32) * kWideCols];
+  Blk B{(int)threadIdx.x, (int)blockDim.x, sred, wide ? swide : nullptr};
   nnls_solve(B, st, W, from_scratch);
 }
 
 __global__ void __launch_bounds__(kStepThreads, 1) refresh_kernel(SolverState* st) {
   __shared__ double sred[256];
-  Blk B{(int)threadIdx.x, (int)blockDim.x, sred};
+  Blk B{(int)threadIdx.x, (int)blockDim.x, sred, nullptr};
   refresh_iterate(B, st);
 }
 

@@ -24,10 +24,13 @@
 namespace bcg {
 
 constexpr uint32_t kNoRow = 0xffffffffu;
+constexpr int kWideCols = 256;       // output columns per blk_combine round (8 per lane)
 
 struct Blk {
   int tid, nthr;
   double* sred;      // shared scratch, >= 32 * 8 doubles
+  double* wide;      // device only, optional: (nthr / 32) * kWideCols doubles of shared scratch for blk_combine;
+                     // null selects the one-thread-per-output forms (host build, BCG_OMP_WIDE=0)
   BCG_HD void sync() const {
 #ifdef __CUDA_ARCH__
     __syncthreads();
@@ -84,6 +87,101 @@ BCG_HD void blk_argbest(const Blk& B, double* key, int64_t* id, int* payload) {
   __syncthreads();
 #else
   (void)B; (void)key; (void)id; (void)payload;
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// Two block-wide building blocks for the K x S algebra of the OMP / NNLS iteration.  With one thread per
+// output and a K-step loop behind it every such product was a chain of ~K dependent-latency L2 round trips
+// (ncu: the single-CTA kernel spent its time in long-scoreboard stalls); the wide forms split the K terms
+// over the warps, keep 8-16 independent loads in flight per lane and reduce across warps through shared memory.
+// All threads of the block must call them (they contain barriers); arguments are block-uniform.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct CombTerm { double coef; const T* row; int len; };
+
+// fin(s, sum_{i < n_terms, s < len_i} coef_i * row_i[s]) for every s < n_out, called by exactly one thread per s
+template <typename T, typename TermF, typename FinF>
+BCG_HD void blk_combine(const Blk& B, int n_out, int n_terms, TermF term, FinF fin) {
+#ifdef __CUDA_ARCH__
+  if (B.wide) {
+    const int lane = B.tid & 31, warp = B.tid >> 5, nw = B.nthr >> 5;
+    for (int c0 = 0; c0 < n_out; c0 += kWideCols) {
+      double acc[kWideCols / 32];
+#pragma unroll
+      for (int j = 0; j < kWideCols / 32; ++j) acc[j] = 0.;
+      for (int i = warp; i < n_terms; i += nw) {
+        const CombTerm<T> t = term(i);
+        if (t.coef == 0.) continue;                        // warp-uniform
+#pragma unroll
+        for (int j = 0; j < kWideCols / 32; ++j) {
+          const int s = c0 + lane + 32 * j;
+          if (s < t.len) acc[j] += t.coef * (double)t.row[s];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kWideCols / 32; ++j) B.wide[warp * kWideCols + lane + 32 * j] = acc[j];
+      __syncthreads();
+      if (B.tid < kWideCols && c0 + B.tid < n_out) {
+        double tot = 0.;
+        for (int w = 0; w < nw; ++w) tot += B.wide[w * kWideCols + B.tid];
+        fin(c0 + B.tid, tot);
+      }
+      __syncthreads();
+    }
+    return;
+  }
+#endif
+  for (int s = B.tid; s < n_out; s += B.nthr) {
+    double acc = 0.;
+    for (int i = 0; i < n_terms; ++i) {
+      const CombTerm<T> t = term(i);
+      if (t.coef != 0. && s < t.len) acc += t.coef * (double)t.row[s];
+    }
+    fin(s, acc);
+  }
+  B.sync();
+}
+
+// emit(i, sum_{s < S} row_i[s] * x[s]) for every i < n whose rowf(i) is not null, called by exactly one thread per i
+template <typename T, typename RowF, typename EmitF>
+BCG_HD void blk_dots(const Blk& B, int n, int S, RowF rowf, const double* x, EmitF emit) {
+#ifdef __CUDA_ARCH__
+  {
+    const int lane = B.tid & 31, warp = B.tid >> 5, nw = B.nthr >> 5;
+    constexpr int G = 4;                                   // rows per warp pass: G * S/32 independent loads per lane
+    for (int i0 = warp * G; i0 < n; i0 += nw * G) {
+      const T* r[G];
+      double p[G];
+#pragma unroll
+      for (int k = 0; k < G; ++k) { r[k] = (i0 + k < n) ? rowf(i0 + k) : nullptr; p[k] = 0.; }
+      for (int s = lane; s < S; s += 32) {
+        const double xs = x[s];
+#pragma unroll
+        for (int k = 0; k < G; ++k)
+          if (r[k]) p[k] += (double)r[k][s] * xs;            // warp-uniform predicate
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+        for (int k = 0; k < G; ++k) p[k] += __shfl_xor_sync(0xffffffffu, p[k], off);
+      if (lane == 0)
+#pragma unroll
+        for (int k = 0; k < G; ++k)
+          if (r[k]) emit(i0 + k, p[k]);
+    }
+    __syncthreads();
+    return;
+  }
+#else
+  for (int i = B.tid; i < n; i += B.nthr) {
+    const T* r = rowf(i);
+    if (!r) continue;
+    double p = 0.;
+    for (int s = 0; s < S; ++s) p += (double)r[s] * x[s];
+    emit(i, p);
+  }
+  B.sync();
 #endif
 }
 
@@ -391,28 +489,11 @@ BCG_HD int64_t omp_select(const Blk& B, SolverState* st) {
     frow = st->An + (size_t)lrow * ld;
   }
   if (nonempty) {
-    // negative direction over the active set (w > 0), lowest global index wins ties
-    // -dots over the active rows, one warp per row (coalesced), then the block arg-max
-    {
-#ifdef __CUDA_ARCH__
-      const int lane = B.tid & 31, warp = B.tid >> 5, nwp = B.nthr >> 5, lanes = 32;
-#else
-      const int lane = 0, warp = 0, nwp = 1, lanes = 1;
-#endif
-      for (int k = warp; k < st->nact; k += nwp) {
-        double d = 0.;
-        if (st->act_w[k] > 0.) {
-          const float* row = st->act_rows + (size_t)k * ld;
-          for (int s = lane; s < S; s += lanes) d += (double)row[s] * st->dir64[s];
-#ifdef __CUDA_ARCH__
-#pragma unroll
-          for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
-#endif
-        }
-        if (lane == 0) st->act_tmp[k] = -d;
-      }
-      B.sync();
-    }
+    // negative direction over the active set (w > 0), lowest global index wins ties:
+    // -dots over the active rows (coalesced, several rows in flight per warp), then the block arg-max
+    blk_dots<float>(B, st->nact, S,
+                    [&](int k) { return st->act_w[k] > 0. ? st->act_rows + (size_t)k * ld : (const float*)nullptr; },
+                    st->dir64, [&](int k, double d) { st->act_tmp[k] = -d; });
     double key = -INFINITY; int64_t id = -1; int pl = -1;
     for (int k = B.tid; k < st->nact; k += B.nthr) {
       if (!(st->act_w[k] > 0.)) continue;

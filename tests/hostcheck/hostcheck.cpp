@@ -77,7 +77,7 @@ extern "C" int hostcheck_run(int alg, const float* An, const double* norms, cons
   st.act_norm = H.act_norm.data(); st.act_tmp = H.act_tmp.data(); st.act_rows = H.act_rows.data();
   st.events = H.events.data();
   const int nb = 37;
-  Blk B{0, 1, H.sred};
+  Blk B{0, 1, H.sred, nullptr};
   for (int bld = 0; bld < builds && !st.halted; ++bld) {
     st.retried = 0;                       // snnls.py:40: local to each build() call
     prepare_select(B, &st);
@@ -126,7 +126,7 @@ extern "C" int hostcheck_omp_select(const float* An, const double* norms, const 
     memcpy(&H.act_rows[(size_t)k * ld], &An[(size_t)act_idx[k] * ld], sizeof(float) * ld);
   }
   st.nact = nact;
-  Blk B{0, 1, H.sred};
+  Blk B{0, 1, H.sred, nullptr};
   refresh_iterate(B, &st);
   prepare_select(B, &st);
   scan(H, 37);
@@ -166,6 +166,8 @@ extern "C" int hostcheck_nnls_sequence(const float* An, const double* norms, con
   H.act_rows.assign((size_t)cap * ld, 0.f);
   H.act_w.assign(cap, 0.); H.act_w_new.assign(cap, 0.); H.act_norm.assign(cap, 0.); H.act_tmp.assign(cap, 0.); H.act_idx.assign(cap, -1);
   st.alg = BCG_ALG_OMP; st.S = S; st.ld = ld; st.world = 1; st.n_local = N; st.n_global = N;
+  for (int i = 0; i < S; ++i) st.bnorm += b[i] * b[i];
+  st.bnorm = sqrt(st.bnorm);
   st.An = H.An.data(); st.norms = H.norms.data(); st.b = H.b.data(); st.bn = H.bn.data();
   st.xw = H.xw.data(); st.xw_new = H.xw_new.data(); st.xf = H.xf.data(); st.dir64 = H.dir64.data();
   st.dir32 = H.dir32.data(); st.wrow = H.wrow.data();
@@ -177,7 +179,7 @@ extern "C" int hostcheck_nnls_sequence(const float* An, const double* norms, con
   memset(&W, 0, sizeof(W));
   W.Q = X.Q.data(); W.R = X.R.data(); W.c = X.c.data(); W.z = X.z.data(); W.wP = X.wP.data(); W.h = X.h.data();
   W.v = X.v.data(); W.P = X.P.data(); W.Z = X.Z.data(); W.inP = X.inP.data(); W.cap = cap;
-  Blk B{0, 1, H.sred};
+  Blk B{0, 1, H.sred, nullptr};
   int have = 0, reb = 0;
   for (int t = 0; t < steps; ++t) {
     for (; have < counts[t]; ++have) {
@@ -190,5 +192,60 @@ extern "C" int hostcheck_nnls_sequence(const float* An, const double* norms, con
     for (int k = 0; k < ncols; ++k) w_out[(size_t)t * ncols + k] = k < have ? st.act_w[k] : 0.;
   }
   *rebuilds_out = reb;
+  return 0;
+}
+
+// full OrthoPursuit loop: scan stand-in + omp_iteration (selection, warm-started NNLS, monotone check, events,
+// next direction) exactly as bcg_solver_build drives omp_iteration_kernel
+extern "C" int hostcheck_run_omp(const float* An, const double* norms, const double* b, int S, int ld, int64_t N,
+                                 int itrs, int builds, bcg_iter_event* events_out, int* n_events_out, int64_t* idx_out,
+                                 double* w_out, int* k_out, double* err_out, int* halted_out) {
+  NnlsHost X;
+  Host& H = X.H;
+  memset(&H.st, 0, sizeof(SolverState));
+  SolverState& st = H.st;
+  const int cap = itrs * builds + 8;
+  H.An.assign(An, An + (size_t)N * ld);
+  H.norms.assign(norms, norms + N);
+  H.b.assign(b, b + S);
+  double bnorm = 0.;
+  for (int i = 0; i < S; ++i) bnorm += b[i] * b[i];
+  bnorm = sqrt(bnorm);
+  H.bn.assign(S, 0.); H.xw.assign(S, 0.); H.xw_new.assign(S, 0.); H.xf.assign(S, 0.); H.dir64.assign(2 * S, 0.);
+  H.dir32.assign(2 * ld, 0.f); H.wrow.assign(ld, 0.f);
+  H.act_rows.assign((size_t)cap * ld, 0.f);
+  H.act_w.assign(cap, 0.); H.act_w_new.assign(cap, 0.); H.act_norm.assign(cap, 0.); H.act_tmp.assign(cap, 0.); H.act_idx.assign(cap, -1);
+  H.events.resize((size_t)itrs * builds);
+  st.alg = BCG_ALG_OMP; st.S = S; st.ld = ld; st.world = 1; st.n_local = N; st.n_global = N; st.tol = 1e-12;
+  st.bnorm = bnorm; st.err = bnorm;
+  st.An = H.An.data(); st.norms = H.norms.data(); st.b = H.b.data(); st.bn = H.bn.data();
+  st.xw = H.xw.data(); st.xw_new = H.xw_new.data(); st.xf = H.xf.data(); st.dir64 = H.dir64.data();
+  st.dir32 = H.dir32.data(); st.wrow = H.wrow.data();
+  st.cap = cap; st.act_idx = H.act_idx.data(); st.act_w = H.act_w.data(); st.act_w_new = H.act_w_new.data();
+  st.act_norm = H.act_norm.data(); st.act_tmp = H.act_tmp.data(); st.act_rows = H.act_rows.data();
+  st.events = H.events.data();
+  X.Q.assign((size_t)cap * S, 0.); X.R.assign((size_t)cap * cap, 0.); X.c.assign(cap, 0.); X.z.assign(2 * cap, 0.);
+  X.wP.assign(cap, 0.); X.h.assign(cap, 0.); X.v.assign(S, 0.); X.P.assign(cap, 0); X.Z.assign(cap, 0); X.inP.assign(cap, 0);
+  NnlsWork& W = X.W;
+  memset(&W, 0, sizeof(W));
+  W.Q = X.Q.data(); W.R = X.R.data(); W.c = X.c.data(); W.z = X.z.data(); W.wP = X.wP.data(); W.h = X.h.data();
+  W.v = X.v.data(); W.P = X.P.data(); W.Z = X.Z.data(); W.inP = X.inP.data(); W.cap = cap;
+  Blk B{0, 1, H.sred, nullptr};
+  const int nb = 37;
+  for (int bld = 0; bld < builds && !st.halted; ++bld) {
+    st.retried = 0;
+    prepare_select(B, &st);
+    for (int i = 0; i < itrs; ++i) {
+      scan(H, nb);
+      st.cands = H.cands.data(); st.n_cands = nb;
+      omp_iteration(B, &st, &W, (i + 1 < itrs) ? 1 : 0);
+    }
+  }
+  memcpy(events_out, H.events.data(), sizeof(bcg_iter_event) * st.n_events);
+  *n_events_out = st.n_events;
+  for (int k = 0; k < st.nact; ++k) { idx_out[k] = st.act_idx[k]; w_out[k] = st.act_w[k]; }
+  *k_out = st.nact;
+  *err_out = st.err;
+  *halted_out = st.halted;
   return 0;
 }

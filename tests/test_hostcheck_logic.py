@@ -179,3 +179,56 @@ def test_nnls_logic_matches_scipy(lib, seed, shift):
       active = ref > 0
     if shift >= 2.0:
       assert (out[-1] == 0).any()          # some weights were driven to zero along the way
+
+
+# ---------------------------------------------------------------- full OMP iteration (omp_iteration) vs the oracle
+def run_host_omp(lib, vecs, itrs, builds=1):
+  N, S = vecs.shape
+  An, norms, ld = device_layout(vecs)
+  b = vecs.sum(axis=0)
+  ev = (Event*(itrs*builds))()
+  nev, k, halted = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+  err = ctypes.c_double(0)
+  idx = np.zeros(itrs*builds + 8, dtype=np.int64)
+  w = np.zeros(itrs*builds + 8)
+  P = ctypes.c_void_p
+  lib.hostcheck_run_omp(P(An.ctypes.data), P(norms.ctypes.data), P(b.ctypes.data), ctypes.c_int(S), ctypes.c_int(ld),
+                        ctypes.c_int64(N), ctypes.c_int(itrs), ctypes.c_int(builds), ev, ctypes.byref(nev),
+                        P(idx.ctypes.data), P(w.ctypes.data), ctypes.byref(k), ctypes.byref(err), ctypes.byref(halted))
+  events = [(e.code, e.f, e.error) for e in ev[:nev.value]]
+  wd = np.zeros(N)
+  wd[idx[:k.value]] = w[:k.value]
+  return events, wd, err.value, bool(halted.value)
+
+
+def test_omp_iteration_matches_oracle_c1(lib):
+  """SURVEY 8c known answers for OrthoPursuit on C1 (first selections, err@10) through the warm-started device
+  NNLS logic; stops before K = S, where the residual is rounding noise and selections are not comparable"""
+  L = lib
+  np.random.seed(1)
+  X = np.random.randn(1000, 50)
+  o = greedy.OrthoPursuitOracle(X.T, X.sum(axis=0))
+  oev = o.build(45)
+  ev, w, err, halted = run_host_omp(L, X, 45)
+  assert [e[1] for e in ev][:10] == [582, 668, 335, 58, 733, 196, 200, 629, 823, 949]
+  assert [(e[0], e[1]) for e in ev] == [(e[0], e[1]) for e in oev]
+  assert_errors_close([e[2] for e in ev], [e[2] for e in oev], X, o.w)
+  assert_weights_close(w, o.w)
+  assert_errors_close(err, o.error(), X, o.w)
+  assert not halted
+
+
+def test_omp_iteration_split_builds_and_small_lr(lib):
+  """build(k) repeated == build(n*k) (the direction is prepared per call), on the LR golden projection"""
+  L = lib
+  g = load_golden('lr_small_omp')
+  vecs = load_golden('lr_project_small')['vecs']
+  itrs = int(g['itrs'])
+  ev, w, err, halted = run_host_omp(L, vecs, itrs)
+  assert [e[1] for e in ev if e[0] == 0] == list(g['sel'])
+  assert_weights_close(w, g['w'])
+  assert_errors_close(err, float(g['final_error']), vecs, g['w'])
+  if itrs % 2 == 0:
+    ev2, w2, err2, _ = run_host_omp(L, vecs, itrs//2, builds=2)
+    assert [e[1] for e in ev2] == [e[1] for e in ev]
+    np.testing.assert_allclose(w2, w, rtol=1e-9, atol=1e-12)
