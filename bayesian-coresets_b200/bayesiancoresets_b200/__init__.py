@@ -14,5 +14,5 @@ from . import snnls
 from .projector import (Projector, BlackBoxProjector, LogisticRegressionProjector, GaussianProjector,
                         PoissonProjector)
 from .coreset import Coreset, HilbertCoreset, SparseVICoreset, BatchPSVICoreset
-from ._native import DeviceVecs, Dataset, Context, BcgError
+from ._native import DeviceVecs, Dataset, Context, BcgError, pinned_empty, pinned_copy
 from . import comm

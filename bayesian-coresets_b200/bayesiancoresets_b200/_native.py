@@ -46,6 +46,8 @@ _PROTOTYPES = {
   'bcg_ctx_synchronize': (_c.c_int, [_P]),
   'bcg_ctx_mem_info': (_c.c_int, [_P, _c.POINTER(_c.c_int64), _c.POINTER(_c.c_int64)]),
   'bcg_ctx_flush_l2': (_c.c_int, [_P, _c.c_int64]),
+  'bcg_host_alloc': (_c.c_int, [_c.c_int64, _PP]),
+  'bcg_host_free': (_c.c_int, [_P]),
   'bcg_vecs_from_host_f64': (_c.c_int, [_P, _P, _c.c_int64, _c.c_int32, _c.c_int64, _PP]),
   'bcg_vecs_project_lr': (_c.c_int, [_P, _P, _c.c_int64, _c.c_int32, _P, _c.c_int32, _PP]),
   'bcg_vecs_project_gaussian': (_c.c_int, [_P, _P, _c.c_int64, _c.c_int32, _P, _c.c_int32, _P, _PP]),
@@ -117,6 +119,40 @@ def _f64(a):
 
 def _ptr(a):
   return ctypes.c_void_p(a.ctypes.data)
+
+
+class _PinnedBlock(object):
+  """owner of one bcg_host_alloc block; freed when the last ndarray view of it is collected"""
+  def __init__(self, nbytes):
+    self.ptr = ctypes.c_void_p()
+    check(lib().bcg_host_alloc(int(nbytes), ctypes.byref(self.ptr)))
+    self.nbytes = int(nbytes)
+
+  def __del__(self):
+    try:
+      if self.ptr:
+        lib().bcg_host_free(self.ptr)
+        self.ptr = None
+    except Exception:
+      pass
+
+
+def pinned_empty(shape, dtype=np.float64):
+  """ndarray in page-locked host memory (bcg_host_alloc): uploads from it are DMA copies straight from the array,
+  without the staging memcpy a pageable ndarray needs.  Use it for the data handed to the coreset constructors."""
+  dtype = np.dtype(dtype)
+  shape = (shape,) if np.isscalar(shape) else tuple(shape)
+  nbytes = int(np.prod(shape, dtype=np.int64))*dtype.itemsize
+  blk = _PinnedBlock(max(nbytes, 1))
+  buf = (ctypes.c_char*max(nbytes, 1)).from_address(blk.ptr.value)
+  buf._bcg_owner = blk                                   # the ctypes buffer (base of the ndarray) keeps the block alive
+  return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
+
+
+def pinned_copy(a):
+  out = pinned_empty(np.shape(a), np.asarray(a).dtype)
+  out[...] = a
+  return out
 
 
 class Context(object):

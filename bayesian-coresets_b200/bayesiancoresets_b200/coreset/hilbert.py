@@ -17,7 +17,7 @@ class HilbertCoreset(Coreset):
     self.comm = comm or SerialComm()
     project = getattr(ll_projector, 'project_device', ll_projector.project)
     if n_subsample is None:
-      sub_idcs = np.arange(data.shape[0])
+      sub_idcs = None                                   # identity (the reference's np.arange(N) is an O(N) host array)
       vecs = project(data)
     else:
       if self.comm.world > 1:
@@ -37,9 +37,14 @@ class HilbertCoreset(Coreset):
       b = self.comm.allreduce_sum(b)
       extra['comm'] = self.comm
     self.snnls = snnls(vecs.T, b, **extra)
-    self.sub_idcs = sub_idcs
+    self._sub_idcs = sub_idcs
     self.data = data
     super().__init__(**kw)
+
+  @property
+  def sub_idcs(self):
+    """hilbert.py:11,16 -- materialised on demand in the identity case"""
+    return np.arange(self.data.shape[0]) if self._sub_idcs is None else self._sub_idcs
 
   def reset(self):
     self.snnls.reset()
@@ -53,7 +58,7 @@ class HilbertCoreset(Coreset):
       self.idcs = idx
       self.pts = gather_rows(self.comm, self.data, self.snnls.row_offset, idx)
     else:
-      self.idcs = self.sub_idcs[idx]
+      self.idcs = idx if self._sub_idcs is None else self._sub_idcs[idx]
       self.pts = self.data[self.idcs]
 
   def _build(self, itrs):

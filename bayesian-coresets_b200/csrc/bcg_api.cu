@@ -102,6 +102,7 @@ struct bcg_ctx {
   cudaStream_t copy_stream;   // second stream: uploads that overlap kernels on `stream`
   void* scratch[8];           // per-context device scratch, grown on demand (no malloc/free per projection pass)
   size_t scratch_bytes[8];
+  double* sp_tab;             // softplus table of the fast links (softplus_table.h); null with BCG_FAST_LINK=0
 };
 
 struct bcg_vecs {
@@ -204,6 +205,13 @@ extern "C" int bcg_ctx_create(int device, bcg_ctx** out) {
   c->sm_count = c->prop.multiProcessorCount;
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  c->sp_tab = nullptr;
+  if (env_int("BCG_FAST_LINK", 1)) {
+    std::vector<double> tab(kSpTableDoubles);
+    softplus_table_build(tab.data());
+    CK(cudaMalloc(&c->sp_tab, kSpTableDoubles * sizeof(double)));
+    CK(cudaMemcpy(c->sp_tab, tab.data(), kSpTableDoubles * sizeof(double), cudaMemcpyHostToDevice));
+  }
   *out = c;
   return BCG_OK;
 }
@@ -212,6 +220,7 @@ extern "C" int bcg_ctx_destroy(bcg_ctx* ctx) {
   if (!ctx) return BCG_OK;
   cudaSetDevice(ctx->device);
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+  if (ctx->sp_tab) cudaFree(ctx->sp_tab);
   for (int i = 0; i < 8; ++i)
     if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
   for (int i = 0; i < 2; ++i)
@@ -289,6 +298,38 @@ static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
   for (auto& x : th) x.join();
 }
 
+extern "C" int bcg_host_alloc(int64_t bytes, void** out) {
+  if (!out || bytes < 0) return fail(BCG_ERR_ARG, "bad arguments");
+  *out = nullptr;
+  int n = 0;
+  RET(bcg_device_count(&n));
+  CK(cudaHostAlloc(out, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocPortable));
+  return BCG_OK;
+}
+
+extern "C" int bcg_host_free(void* p) {
+  if (p) CK(cudaFreeHost(p));
+  return BCG_OK;
+}
+
+// page-locked source (bcg_host_alloc / cudaHostRegister): DMA reads it directly, no staging copy
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+
+// the two context-owned pinned staging buffers (kPinChunk bytes each), allocated on first use and kept:
+// cudaMallocHost / cudaFreeHost cost milliseconds per call
+static int ensure_pins(bcg_ctx* ctx) {
+  for (int i = 0; i < 2; ++i)
+    if (!ctx->pin[i]) {
+      CK(cudaMallocHost(&ctx->pin[i], kPinChunk));
+      CK(cudaEventCreateWithFlags(&ctx->pin_done[i], cudaEventDisableTiming));
+    }
+  return BCG_OK;
+}
+
 static int h2d(bcg_ctx* ctx, void* dst, const void* src, size_t bytes) {
   if (bytes == 0) return BCG_OK;
   if (bytes < ((size_t)1 << 20)) {
@@ -296,11 +337,12 @@ static int h2d(bcg_ctx* ctx, void* dst, const void* src, size_t bytes) {
     CK(cudaStreamSynchronize(ctx->stream));   // the source may be a temporary of the caller
     return BCG_OK;
   }
-  for (int i = 0; i < 2; ++i)
-    if (!ctx->pin[i]) {
-      CK(cudaMallocHost(&ctx->pin[i], kPinChunk));
-      CK(cudaEventCreateWithFlags(&ctx->pin_done[i], cudaEventDisableTiming));
-    }
+  if (is_pinned(src)) {
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BCG_OK;
+  }
+  RET(ensure_pins(ctx));
   int c = 0;
   for (size_t off = 0; off < bytes; off += kPinChunk, ++c) {
     const int i = c & 1;
@@ -515,7 +557,7 @@ static int project_common(bcg_dataset* ds, const int64_t* rowidx, int64_t nsel, 
     CK(cudaMemsetAsync(d_partial, 0, (size_t)grid * S * sizeof(double), st));
     ProjectSumArgs pa;
     pa.Z = ds->Z; pa.rowidx = d_idx; pa.thetaT = dT; pa.coff = dC; pa.partial = d_partial; pa.n = n; pa.zld = ds->zld; pa.d = d; pa.S = S;
-    pa.model = model;
+    pa.model = model; pa.sp_tab = ctx->sp_tab;
     // float64 tensor cores (DMMA) for the contraction by default (ncu, N=1e6 d=200 S=512: LR 15.1 ms vs 17.1 ms on
     // the FMA pipe; Gaussian 1.8x faster); BCG_PROJSUM_MMA=0 selects the FMA-pipe kernel
     const int mma = env_int("BCG_PROJSUM_MMA", 1);
@@ -563,7 +605,7 @@ static int project_common(bcg_dataset* ds, const int64_t* rowidx, int64_t nsel, 
     ProjectArgs a;
     a.Z = ds->Z; a.rowidx = d_idx; a.theta = dT; a.coff = dC; a.An = v ? v->An : nullptr; a.norms = v ? v->norms : nullptr;
     a.out64 = d_rows; a.partial = d_partial; a.zero_rows = d_zero; a.n = n; a.zld = ds->zld; a.d = d; a.S = S;
-    a.ld = ld; a.model = model; a.ktile = ktile;
+    a.ld = ld; a.model = model; a.ktile = ktile; a.sp_tab = ctx->sp_tab;
     switch (j_for_ld(ld)) {
       case 1: RET(launch_project<1>(ctx, a, grid, smem)); break;
       case 2: RET(launch_project<2>(ctx, a, grid, smem)); break;
@@ -675,17 +717,23 @@ static int project_host_pipelined(bcg_ctx* ctx, int kmodel, const double* Z, int
       return fail(BCG_ERR_UNSUPPORTED, "projection tile does not fit shared memory for S=%d", S);
     const int ktile = (int)std::min<size_t>(std::min<size_t>(kProjKTile, (size_t)d), (budget - cs_bytes) / ((size_t)S * sizeof(double)));
     const size_t smem = (size_t)ktile * S * sizeof(double) + cs_bytes;
-    const int64_t chunk_rows = std::max<int64_t>(4096, std::min<int64_t>(n, ((int64_t)16 << 20) / ((int64_t)zld * 8)));
+    const int64_t row_bytes = (int64_t)zld * 8;
+    const int64_t rows_cap = (int64_t)kPinChunk / row_bytes;             // rows that fit one staging buffer
+    if (rows_cap < 1) return fail(BCG_ERR_UNSUPPORTED, "a data row of %d doubles exceeds the staging chunk", zld);
+    const int64_t chunk_rows = std::min<int64_t>(n, std::min<int64_t>(rows_cap, std::max<int64_t>(4096, ((int64_t)16 << 20) / row_bytes)));
     const int nchunks = (int)((n + chunk_rows - 1) / chunk_rows);
     const int grid = (int)std::min<int64_t>((chunk_rows + kProjWarps - 1) / kProjWarps, (int64_t)ctx->sm_count);
-    PinBuf<double> pin[2];
-    DevBuf<double> dev[2], dT, dC, d_partial;
+    // staging and chunk buffers are context-owned (no cudaMallocHost / cudaMalloc / cudaFree per call)
+    const bool direct = is_pinned(Z);                                    // page-locked source: no staging copy
+    RET(ensure_pins(ctx));
+    double* pin[2] = {reinterpret_cast<double*>(ctx->pin[0]), reinterpret_cast<double*>(ctx->pin[1])};
+    double* dev[2] = {nullptr, nullptr};
+    DevBuf<double> dT, dC, d_partial;
     DevBuf<unsigned long long> d_zero;
     EventPair copied, kdone;
     const size_t celems = (size_t)chunk_rows * zld;
     for (int i = 0; i < 2; ++i) {
-      CK(pin[i].alloc(celems));
-      CK(dev[i].alloc(celems));
+      RET(ctx_scratch(ctx, 6 + i, celems * sizeof(double), (void**)&dev[i]));
       CK(cudaEventCreateWithFlags(&copied.e[i], cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&kdone.e[i], cudaEventDisableTiming));
     }
@@ -703,14 +751,15 @@ static int project_host_pipelined(bcg_ctx* ctx, int kmodel, const double* Z, int
       const int64_t r0 = (int64_t)c * chunk_rows;
       const int64_t nr = std::min<int64_t>(chunk_rows, n - r0);
       if (c >= 2) CK(cudaEventSynchronize(kdone.e[i]));            // staging + device buffer i are free again
-      parallel_memcpy(pin[i], Z + r0 * zld, (size_t)nr * zld * sizeof(double));
-      CK(cudaMemcpyAsync(dev[i], pin[i], (size_t)nr * zld * sizeof(double), cudaMemcpyHostToDevice, cs));
+      const double* src = Z + r0 * zld;
+      if (!direct) { parallel_memcpy(pin[i], src, (size_t)nr * zld * sizeof(double)); src = pin[i]; }
+      CK(cudaMemcpyAsync(dev[i], src, (size_t)nr * zld * sizeof(double), cudaMemcpyHostToDevice, cs));
       CK(cudaEventRecord(copied.e[i], cs));
       CK(cudaStreamWaitEvent(st, copied.e[i], 0));
       ProjectArgs a;
       a.Z = dev[i]; a.rowidx = nullptr; a.theta = dT; a.coff = dC; a.An = v->An + (size_t)r0 * ld; a.norms = v->norms + r0;
       a.out64 = nullptr; a.partial = d_partial.p + (size_t)c * grid * (S + 1); a.zero_rows = d_zero; a.n = nr; a.zld = zld;
-      a.d = d; a.S = S; a.ld = ld; a.model = kmodel; a.ktile = ktile;
+      a.d = d; a.S = S; a.ld = ld; a.model = kmodel; a.ktile = ktile; a.sp_tab = ctx->sp_tab;
       switch (j_for_ld(ld)) {
         case 1: RET(launch_project<1>(ctx, a, grid, smem)); break;
         case 2: RET(launch_project<2>(ctx, a, grid, smem)); break;

@@ -17,6 +17,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "softplus_table.h"
 
 namespace bcg {
 
@@ -133,6 +134,7 @@ struct ProjectArgs {
   unsigned long long* zero_rows;
   int64_t n;
   int32_t zld, d, S, ld, model, ktile;
+  const double* sp_tab;  // softplus table (softplus_table.h) or null: libdevice exp / log1p links
 };
 
 __device__ __forceinline__ double link_value(int model, double lin, double y) {
@@ -149,6 +151,13 @@ __device__ __forceinline__ double link_value(int model, double lin, double y) {
     if (s > -100.) s = log(fmax(s, 0.) + log1p(exp(-fabs(s))));
     return y * s - exp(s);                               // - gammaln(y+1): constant per row
   }
+  return lin;
+}
+
+// table-driven links (softplus_table.h) when the context carries the table
+__device__ __forceinline__ double link_value_tab(const double* tab, int model, double lin, double y) {
+  if (model == MODEL_LR) return lr_link_fast(tab, lin);
+  if (model == MODEL_POISSON) return poisson_link_fast(tab, lin, y);
   return lin;
 }
 
@@ -208,7 +217,7 @@ __global__ void __launch_bounds__(kProjWarps * 32) project_kernel(const ProjectA
         if (s < S) {
           double lin = acc[j];
           if (a.coff) lin += a.coff[s];
-          acc[j] = link_value(a.model, lin, y);
+          acc[j] = a.sp_tab ? link_value_tab(a.sp_tab, a.model, lin, y) : link_value(a.model, lin, y);
           sum += acc[j];
         }
       }

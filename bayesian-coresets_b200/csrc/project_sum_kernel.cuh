@@ -31,6 +31,7 @@ struct ProjectSumArgs {
   double* partial;       // gridDim.x x S raw column sums
   int64_t n;
   int32_t zld, d, S, model;
+  const double* sp_tab;  // softplus table or null
 };
 
 // out-of-line link: the epilogue applies it to 64 accumulators per thread; inlining 64 copies of the
@@ -39,6 +40,13 @@ template <int MODEL>
 __device__ __noinline__ double link_call(double lin, double y) { return link_value(MODEL, lin, y); }
 template <>
 __device__ __forceinline__ double link_call<MODEL_LINEAR>(double lin, double) { return lin; }
+// table-driven link inline (~20 instructions), libdevice link out of line
+template <int MODEL>
+__device__ __forceinline__ double link_apply(const double* tab, double lin, double y) {
+  if (MODEL == MODEL_LINEAR) return lin;
+  if (tab) return MODEL == MODEL_LR ? lr_link_fast(tab, lin) : poisson_link_fast(tab, lin, y);
+  return link_call<MODEL>(lin, y);
+}
 
 template <int MODEL>
 __global__ void __launch_bounds__(kPsThreads, 1) project_sum_kernel(const ProjectSumArgs a) {
@@ -131,7 +139,7 @@ __global__ void __launch_bounds__(kPsThreads, 1) project_sum_kernel(const Projec
           const int c = col0 + wc * 64 + 16 * (j >> 1) + lc * 2 + (j & 1);
           double lin = acc[i][j];
           if (a.coff && c < S) lin += a.coff[c];
-          const double v = link_call<MODEL>(lin, y);
+          const double v = link_apply<MODEL>(a.sp_tab, lin, y);
           cs[j] += (live && c < S) ? v : 0.;
         }
       }

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(kPsThreads, 1) project_sum_mma_kernel(const Pr
             const int c = col0 + wc * 64 + ni * 8 + tq * 2 + e;
             double lin = acc[mi][ni][e];
             if (a.coff && c < S) lin += a.coff[c];
-            const double v = link_call<MODEL>(lin, y);
+            const double v = link_apply<MODEL>(a.sp_tab, lin, y);
             cs[ni][e] += (live && c < S) ? v : 0.;
           }
       }

@@ -92,6 +92,12 @@ int  bcg_ctx_info(bcg_ctx* ctx, char* name, int name_cap, int* sm_count, int* cc
                   int64_t* total_mem_bytes);
 int  bcg_ctx_synchronize(bcg_ctx* ctx);
 int  bcg_ctx_mem_info(bcg_ctx* ctx, int64_t* free_bytes, int64_t* total_bytes);
+/* Page-locked host memory for the caller's input arrays.  Every host -> device upload of this library checks
+ * whether its source is page-locked (allocated here, or registered by the caller with the CUDA runtime): such a
+ * source is copied by DMA straight from the caller's array, a pageable one is first staged through the library's
+ * pinned buffers with a multi-threaded memcpy. */
+int  bcg_host_alloc(int64_t bytes, void** out);
+int  bcg_host_free(void* p);
 /* write `bytes` of device scratch (evicts L2 between timed iterations) */
 int  bcg_ctx_flush_l2(bcg_ctx* ctx, int64_t bytes);
 

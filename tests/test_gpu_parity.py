@@ -533,3 +533,92 @@ def test_device_row_gather_and_grad_contract(bc):
   pp = bc.PoissonProjector(lambda n, w_, p: th, th.shape[0])
   np.testing.assert_allclose(pp.grad_contract(zp, w, resid), reference(models.poisson_grad_z_loglik_fixed(zp, th)),
                              rtol=1e-10, atol=1e-12)
+
+
+# ---------------------------------------------------------------- round-1 late additions: wide OMP products, table links, pinned sources
+def test_omp_wide_products_equal_narrow(bc, monkeypatch):
+  """the warp-split K x S products of the OMP / NNLS iteration (default) against the one-thread-per-output
+  forms (BCG_OMP_WIDE=0), S above and below one 256-column round, K past S/2"""
+  for N, d, S, itrs in ((20000, 6, 300, 120), (5000, 5, 96, 60)):
+    Z, theta = lr_problem(3, N, d, S)
+    prj = bc.LogisticRegressionProjector(lambda n, w, p: theta, S)
+    a = bc.HilbertCoreset(Z, prj, snnls=bc.snnls.OrthoPursuit)
+    a.build(itrs)
+    monkeypatch.setenv('BCG_OMP_WIDE', '0')
+    b = bc.HilbertCoreset(Z, prj, snnls=bc.snnls.OrthoPursuit)
+    b.build(itrs)
+    monkeypatch.delenv('BCG_OMP_WIDE')
+    assert [(e.code, e.f) for e in a.snnls.last_events] == [(e.code, e.f) for e in b.snnls.last_events]
+    wa, wb = a.snnls.weights(), b.snnls.weights()
+    np.testing.assert_allclose(wa, wb, rtol=1e-7, atol=1e-10*wb.max())
+    assert a.error() == pytest.approx(b.error(), rel=1e-7)
+    a.optimize()
+    b.optimize()
+    np.testing.assert_allclose(a.snnls.weights(), b.snnls.weights(), rtol=1e-7, atol=1e-10*wb.max())
+
+
+def test_omp_medium_vs_oracle(bc):
+  """OrthoPursuit at a size where the oracle (SciPy NNLS per iteration) still finishes in seconds"""
+  N, d, S, itrs = 60000, 8, 256, 60
+  Z, theta = lr_problem(5, N, d, S)
+  vecs = models.project(models.lr_loglik, Z, theta)
+  o = greedy.OrthoPursuitOracle(vecs.T, vecs.sum(axis=0))
+  oev = o.build(itrs)
+  prj = bc.LogisticRegressionProjector(lambda n, w, p: theta, S)
+  cs = bc.HilbertCoreset(Z, prj, snnls=bc.snnls.OrthoPursuit)
+  cs.build(itrs)
+  assert [e.f for e in cs.snnls.last_events] == [e[1] for e in oev]
+  assert_weights_close(cs.snnls.weights(), o.w)
+  assert_errors_close(cs.error(), o.error(), vecs, o.w)
+
+
+def test_table_links_equal_libdevice_links(bc, monkeypatch):
+  """softplus-table links (default) against the libdevice exp / log1p links (BCG_FAST_LINK=0, read when a
+  context is created): materialised rows, float64 read-backs and K3b column sums, LR and Poisson"""
+  fast = bc.Context.default()
+  monkeypatch.setenv('BCG_FAST_LINK', '0')
+  slow = bc.Context(0)
+  monkeypatch.delenv('BCG_FAST_LINK')
+  rng = np.random.RandomState(11)
+  for d, S, n in ((10, 512, 3000), (40, 200, 5000)):
+    X = rng.randn(n, d)*rng.choice([0.3, 1., 8., 60.], size=(n, 1))      # includes saturated rows (|m| >> 37)
+    th = rng.randn(S, d)/np.sqrt(d)
+    y = rng.poisson(2., size=n).astype(np.float64)
+    Zp = np.hstack((X, y[:, None]))
+    for model, Z in ((bc._native.MODEL_LR, X), (bc._native.MODEL_POISSON, Zp)):
+      outs = []
+      for ctx in (fast, slow):
+        ds = bc.Dataset(Z, ctx=ctx)
+        v, rows, cs = ds.project(model, th, vecs=True, rows=True, colsum=True)
+        cs2 = ds.project(model, th, colsum=True)[2]                         # K3b kernels (d >= 24) or K3 without stores
+        outs.append((v.to_numpy(), v.norms(), rows, cs, cs2))
+      a, b = outs
+      scale = np.abs(b[2]).max(axis=1, keepdims=True) + 1e-300
+      assert np.max(np.abs(a[2] - b[2])/scale) < 1e-13                      # float64 centred rows
+      np.testing.assert_allclose(a[1], b[1], rtol=1e-11)
+      assert np.max(np.abs(a[0] - b[0])/(b[1][:, None] + 1e-300)) < 2.**-23
+      for k in (3, 4):
+        np.testing.assert_allclose(a[k], b[k], rtol=1e-11, atol=1e-11*np.abs(b[k]).max())
+      np.testing.assert_allclose(a[4], b[3], rtol=1e-9, atol=1e-9*np.abs(b[3]).max())
+
+
+def test_pinned_source_equals_pageable_source(bc):
+  """page-locked input arrays (bc.pinned_empty / pinned_copy) are uploaded by DMA without staging: same matrix"""
+  Z, theta = lr_problem(9, 700000, 10, 64)                                   # 56 MB: several pipeline chunks
+  Zp = bc.pinned_copy(Z)
+  assert Zp.shape == Z.shape and np.array_equal(Zp, Z)
+  a = bc.DeviceVecs.project_lr(Z, theta)
+  b = bc.DeviceVecs.project_lr(Zp, theta)
+  assert np.array_equal(a.norms(), b.norms())
+  assert np.array_equal(a.sum(axis=0), b.sum(axis=0))
+  assert np.array_equal(a.to_numpy(1000, 50), b.to_numpy(1000, 50))
+  da, db = bc.Dataset(Z), bc.Dataset(Zp)
+  ca = da.project(bc._native.MODEL_LR, theta, colsum=True)[2]
+  cb = db.project(bc._native.MODEL_LR, theta, colsum=True)[2]
+  assert np.array_equal(ca, cb)
+  prj = bc.LogisticRegressionProjector(lambda n, w, p: theta, 64)
+  cs = bc.HilbertCoreset(Zp, prj)
+  cs.build(10)
+  wts, pts, idcs = cs.get()
+  assert np.array_equal(pts, Z[idcs])
+  del Zp, b, db, cs

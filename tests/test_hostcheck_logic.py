@@ -232,3 +232,48 @@ def test_omp_iteration_split_builds_and_small_lr(lib):
     ev2, w2, err2, _ = run_host_omp(L, vecs, itrs//2, builds=2)
     assert [e[1] for e in ev2] == [e[1] for e in ev]
     np.testing.assert_allclose(w2, w, rtol=1e-9, atol=1e-12)
+
+
+# ---------------------------------------------------------------- table-driven link functions (softplus_table.h)
+def _link(lib, model, lin, y=None):
+  lin = np.ascontiguousarray(lin, dtype=np.float64)
+  y = np.zeros_like(lin) if y is None else np.ascontiguousarray(y, dtype=np.float64)
+  out = np.zeros_like(lin)
+  P = ctypes.c_void_p
+  lib.hostcheck_link(ctypes.c_int(model), P(lin.ctypes.data), P(y.ctypes.data), ctypes.c_int64(lin.size), P(out.ctypes.data))
+  return out
+
+
+def test_softplus_table_relative_accuracy(lib):
+  """g(t) = log1p(exp(t)), t <= 0: the table keeps RELATIVE accuracy over the whole range, tail included"""
+  rng = np.random.RandomState(0)
+  t = np.concatenate([-rng.rand(200000)*45., -np.arange(0, 38*8 + 1)/8., -np.arange(0, 38*8)/8. - 1e-13,
+                      [-0.0, 0.0, -36.999999, -37.0, -37.000001, -700., -745.2]])
+  ref = np.log1p(np.exp(t.astype(np.longdouble))).astype(np.float64)
+  got = _link(lib, 0, t)
+  ok = ref > 0
+  assert np.max(np.abs(got[ok]/ref[ok] - 1.)) < 1e-15
+  assert np.all(got[~ok] == 0.)
+  assert np.isnan(_link(lib, 0, np.array([np.nan]))[0])
+
+
+def test_fast_links_match_reference_formulas(lib):
+  """LR and Poisson links against the oracle's NumPy restatement of model_lr.py:25-32 / model_poiss.py:25-38"""
+  from oracle import models
+  rng = np.random.RandomState(1)
+  lin = np.concatenate([rng.randn(100000)*5., rng.randn(20000)*60., [0., -0., 99.9, 100., 100.1, -99.9, -100., -100.1,
+                                                                   -36.9, -37.1, 37., 700., -700., -120.]])
+  # LR: loglik of a 1-d datapoint z = 1 against samples theta = lin  (m = -lin)
+  ref = models.lr_loglik(np.ones((1, 1)), lin[:, None])[0]
+  got = _link(lib, 1, lin)
+  np.testing.assert_allclose(got, ref, rtol=2e-15, atol=0.)
+  # Poisson: y s - exp(s) (the row-constant gammaln(y + 1) is added back for the comparison)
+  from scipy.special import gammaln
+  y = rng.poisson(3., size=lin.size).astype(np.float64)
+  Z = np.array([[1., 0.]])
+  for yy in (0., 1., 7.):
+    Z[0, 1] = yy
+    ref = models.poisson_loglik(Z, lin[:, None])[0] + gammaln(yy + 1.)
+    got = _link(lib, 2, lin, np.full(lin.size, yy))
+    # y s and exp(s) cancel near the mode: absolute rounding of O(10) terms
+    np.testing.assert_allclose(got, ref, rtol=1e-13, atol=5e-14)
