@@ -1075,7 +1075,8 @@ extern "C" int bcg_solver_destroy(bcg_solver* s) {
                   h.act_w_new, h.act_norm, h.act_tmp, h.act_rows, h.events, s->d_fout, s->d, s->mail, s->d_ctl, s->d_cta_cands, s->d_trace, s->d_claims};
   for (void* p : bufs)
     if (p) cudaFree(p);
-  void* nb[] = {s->nw.Q, s->nw.R, s->nw.c, s->nw.z, s->nw.wP, s->nw.h, s->nw.v, s->nw.P, s->nw.Z, s->nw.inP, s->d_nw};
+  if (s->d_nw) cudaMemcpy(&s->nw, s->d_nw, sizeof(NnlsWork), cudaMemcpyDeviceToHost);   // R / R2 may have swapped on the device
+  void* nb[] = {s->nw.Q, s->nw.R, s->nw.R2, s->nw.rot, s->nw.rem, s->nw.c, s->nw.z, s->nw.wP, s->nw.h, s->nw.v, s->nw.P, s->nw.Z, s->nw.inP, s->d_nw};
   for (void* p : nb)
     if (p) cudaFree(p);
   for (cudaEvent_t e : s->scan_ev) cudaEventDestroy(e);
@@ -1144,12 +1145,16 @@ static int ensure_nnls(bcg_solver* s) {
   const int cap = s->h.cap, S = s->h.S;
   if (s->d_nw && s->nw_cap == cap) return BCG_OK;
   NnlsWork& w = s->nw;
-  void* old[] = {w.Q, w.R, w.c, w.z, w.wP, w.h, w.v, w.P, w.Z, w.inP};
+  if (s->d_nw) CK(cudaMemcpy(&w, s->d_nw, sizeof(NnlsWork), cudaMemcpyDeviceToHost));      // R / R2 may have swapped
+  void* old[] = {w.Q, w.R, w.R2, w.rot, w.rem, w.c, w.z, w.wP, w.h, w.v, w.P, w.Z, w.inP};
   for (void* p : old)
     if (p) CK(cudaFree(p));
   memset(&w, 0, sizeof(NnlsWork));
   CK(cudaMalloc(&w.Q, (size_t)cap * S * sizeof(double)));
   CK(cudaMalloc(&w.R, (size_t)cap * cap * sizeof(double)));
+  CK(cudaMalloc(&w.R2, (size_t)cap * cap * sizeof(double)));
+  CK(cudaMalloc(&w.rot, (size_t)3 * cap * sizeof(double)));
+  CK(cudaMalloc(&w.rem, (size_t)cap * sizeof(int32_t)));
   CK(cudaMalloc(&w.c, (size_t)cap * sizeof(double)));
   CK(cudaMalloc(&w.z, (size_t)2 * cap * sizeof(double)));
   CK(cudaMalloc(&w.wP, (size_t)cap * sizeof(double)));
@@ -1161,6 +1166,7 @@ static int ensure_nnls(bcg_solver* s) {
   CK(cudaMemsetAsync(w.inP, 0, (size_t)cap * sizeof(int32_t), s->ctx->stream));
   w.cap = cap;
   w.valid = 0;
+  w.downdate = env_int("BCG_NNLS_DOWNDATE", 1);
   if (!s->d_nw) CK(cudaMalloc(&s->d_nw, sizeof(NnlsWork)));
   CK(cudaMemcpyAsync(s->d_nw, &w, sizeof(NnlsWork), cudaMemcpyHostToDevice, s->ctx->stream));
   CK(cudaStreamSynchronize(s->ctx->stream));
@@ -1209,6 +1215,13 @@ extern "C" int bcg_solver_build(bcg_solver* s, int32_t itrs, double tol, bcg_ite
     // OrthoPursuit: selection scan + on-device NNLS per iteration (two launches), no host round trip inside the loop
     RET(ensure_nnls(s));
     const int wide = env_int("BCG_OMP_WIDE", 1);
+    DevBuf<unsigned long long> d_omp_trace;
+    if (env_int("BCG_OMP_TRACE", 0)) {
+      CK(d_omp_trace.alloc((size_t)itrs * 16));
+      CK(cudaMemsetAsync(d_omp_trace, 0, (size_t)itrs * 16 * sizeof(unsigned long long), st));
+      h.omp_trace = d_omp_trace;
+      RET(push_state(s));
+    }
     CK(cudaEventRecord(s->ev0, st));
     step_kernel<<<1, kStepThreads, 0, st>>>(s->d, 0, 1, 1);           // reset the per-call retry flag; first residual direction
     for (int i = 0; i < itrs; ++i) {
@@ -1219,6 +1232,32 @@ extern "C" int bcg_solver_build(bcg_solver* s, int32_t itrs, double tol, bcg_ite
     CK(cudaEventRecord(s->ev1, st));
     RET(pull_state(s));
     CK(cudaEventElapsedTime(&s->build_ms, s->ev0, s->ev1));
+    if (d_omp_trace.p) {
+      // diagnostics: mean time between the phase marks of omp_iteration (see omp_mark), first / second half of the call
+      std::vector<unsigned long long> tr((size_t)itrs * 16);
+      CK(cudaMemcpy(tr.data(), d_omp_trace, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+      static const char* names[12] = {"start", "count+save", "pick_local", "neg-dir", "select-end", "nnls-setup", "resid+dual",
+                                      "qr-append", "solve", "resid2", "writeback+err", "event+prep"};
+      for (int half = 0; half < 2; ++half) {
+        double acc[12] = {0}, sub[4] = {0}; int cnt = 0;
+        for (int i = half * itrs / 2; i < (half + 1) * itrs / 2; ++i) {
+          const unsigned long long* t = &tr[(size_t)i * 16];
+          bool ok = true;
+          for (int k = 0; k < 12; ++k) ok = ok && t[k] != 0;
+          if (!ok || t[11] - t[0] > 250000) continue;         // skip incomplete (failed / step-back) iterations
+          for (int k = 1; k < 12; ++k) acc[k] += (double)(t[k] - t[k - 1]);
+          sub[0] += (double)(t[12] - t[6]); sub[1] += (double)(t[13] - t[12]); sub[2] += (double)(t[14] - t[13]);
+          sub[3] += (double)(t[7] - t[14]);
+          ++cnt;
+        }
+        fprintf(stderr, "[bcg] omp trace, iterations %d..%d (%d clean):", half * itrs / 2, (half + 1) * itrs / 2, cnt);
+        for (int k = 1; k < 12; ++k) fprintf(stderr, " %s %.1f", names[k], cnt ? acc[k] / cnt / 1e3 : 0.);
+        fprintf(stderr, " us | append: pass0 %.1f pass1 %.1f sums+store %.1f Tcol %.1f us\n", cnt ? sub[0] / cnt / 1e3 : 0.,
+                cnt ? sub[1] / cnt / 1e3 : 0., cnt ? sub[2] / cnt / 1e3 : 0., cnt ? sub[3] / cnt / 1e3 : 0.);
+      }
+      h.omp_trace = nullptr;
+      CK(cudaMemcpy(&s->d->omp_trace, &h.omp_trace, sizeof(void*), cudaMemcpyHostToDevice));
+    }
     s->scan_launches = itrs;
     s->step_launches = itrs + 1;
     s->loop_launches = 0;

@@ -63,6 +63,8 @@ struct SolverState {
   unsigned char* mail_local;        // this rank's mailbox: [2][world] slots
   unsigned char* mail_peer[kMaxWorld];  // mapped mailboxes of all ranks (self included)
   int64_t mail_slot_bytes;
+  // ---- diagnostics ---------------------------------------------------------------------------
+  unsigned long long* omp_trace;    // null, or 16 device timestamps per OMP iteration (BCG_OMP_TRACE=1)
 };
 
 inline int64_t mail_slot_bytes_for(int ld) {

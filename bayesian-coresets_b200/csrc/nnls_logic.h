@@ -9,8 +9,11 @@
 // does) the passive set P and its QR factorisation are kept between iterations.  In the common
 // case the new column enters, one triangular solve gives an all-positive solution, and the
 // iteration costs O(S K) (Gram-Schmidt append) + O(K^2) (back substitution) instead of O(S K^2).
-// When a weight would turn negative the standard step-back / removal loop runs and the QR of the
-// reduced set is rebuilt.
+// When a weight would turn negative the standard step-back / removal loop runs and the dropped column is
+// removed from the factorisation by a sweep of Givens rotations (nnls_qr_remove, O((S + K) K)); the first
+// version rebuilt the factorisation behind the removed position with one Gram-Schmidt append per column,
+// which cost 0.3 - 4 ms on exactly the iterations that drop a column (ncu launch list, N = 1e6, S = 256: 79 of
+// the 97 ms that 205 OMP iterations spent in this kernel).
 //
 // QR: classical Gram-Schmidt applied twice (CGS2, orthogonal to working precision), Q stored as
 // K rows of length S, c = Q^T b maintained incrementally.  Instead of R the factorisation keeps
@@ -38,6 +41,10 @@ struct NnlsWork {
   int32_t* P;     // cap   P position -> active-set slot
   int32_t* Z;     // cap   zero set (slots of the problem that are not in P)
   int32_t* inP;   // cap   slot -> 1 when the slot is in P
+  double* R2;     // cap x cap second buffer of T (a column removal writes the new T there, then the two swap)
+  double* rot;    // 3 cap  Givens rotations of a column removal: c_j, s_j, staged row of T
+  int32_t* rem;   // cap   P positions dropped by the current step-back
+  int32_t nrem, downdate;   // downdate = 1: remove columns by Givens rotations; 0: rebuild behind the first removed
   int32_t nP, nZ, cap, valid;
   int32_t outer_iters, rebuilds;   // diagnostics of the last solve
   int32_t first_removed;           // first P position dropped by the last step-back (block-uniform hand-over)
@@ -65,6 +72,7 @@ BCG_HD bool nnls_qr_append(const Blk& B, SolverState* st, NnlsWork* W, int slot)
     // v -= sum_i h_i q_i
     blk_combine<double>(B, S, p, [&](int i) { return CombTerm<double>{h[i], Q + (size_t)i * S, S}; },
                         [&](int s, double acc) { v[s] -= acc; });
+    omp_mark(B, st, 12 + pass);
   }
   double u[2] = {0., 0.};
   for (int s = B.tid; s < S; s += B.nthr) { const double x = v[s]; u[0] += x * x; u[1] += x * st->b[s]; }
@@ -74,6 +82,7 @@ BCG_HD bool nnls_qr_append(const Blk& B, SolverState* st, NnlsWork* W, int slot)
   double* q = Q + (size_t)p * S;
   for (int s = B.tid; s < S; s += B.nthr) q[s] = v[s] / rpp;
   // new column of T = R^{-1}:  -(T r) / rho on top of 1 / rho   (column j of T holds rows 0..j)
+  omp_mark(B, st, 14);
   blk_combine<double>(B, p, p, [&](int j) { return CombTerm<double>{r[j], T + (size_t)j * cap, j + 1}; },
                       [&](int i, double acc) { T[(size_t)i + (size_t)p * cap] = -acc / rpp; });
   if (B.tid == 0) {
@@ -96,6 +105,67 @@ BCG_HD void nnls_solve_R(const Blk& B, NnlsWork* W) {
   double* const z = W->z;
   blk_combine<double>(B, n, n, [&](int j) { return CombTerm<double>{c[j], T + (size_t)j * cap, j + 1}; },
                       [&](int i, double acc) { z[i] = acc; });
+}
+
+// Remove position k (of p) from the factorisation; positions behind it move down by one.  With A_P = Q R and
+// E = the identity without column k, A_P E = (Q G^T) (G R E) for any orthogonal G; G R E is upper triangular with a
+// zero last row exactly when the last row of G is the normalised row k of T = R^{-1} (that row is orthogonal to
+// every remaining column of R).  Such a G is a sweep of plane rotations (j, j+1), j = k .. p-2, that moves the mass
+// of t = T[k, k:p] into its last component, so the rotations come from ONE row of T by a scalar recurrence; they are
+// then applied to the q vectors (Q G^T), to the columns of T with row k deleted (T_new = (E^T T G^T)[:, :p-1]) and
+// to c = Q^T b.  R itself is never needed.  P / wP are compacted by the caller.
+BCG_HD void nnls_qr_remove(const Blk& B, SolverState* st, NnlsWork* W, int k, int p) {
+  const int S = st->S, cap = W->cap;
+  double* const T = W->R;
+  double* const Tn = W->R2;
+  double* const Q = W->Q;
+  double* const c = W->c;
+  double* const rc = W->rot;
+  double* const rs = W->rot + cap;
+  double* const trow = W->rot + 2 * (size_t)cap;
+  for (int j = k + B.tid; j < p; j += B.nthr) trow[j] = T[(size_t)k + (size_t)j * cap];   // strided row: stage it
+  B.sync();
+  if (B.tid == 0) {
+    double carry = trow[k], ccur = c[k];
+    for (int j = k; j < p - 1; ++j) {
+      const double a = carry, b = trow[j + 1];
+      const double h = sqrt(a * a + b * b);                    // >= |T[k,k]| > 0
+      const double ih = 1. / h;
+      const double cj = b * ih, sj = a * ih;                   // (c a - s b, s a + c b) = (0, h)
+      rc[j] = cj; rs[j] = sj; carry = h;
+      const double y = c[j + 1];
+      c[j] = cj * ccur - sj * y;                               // c[j]'s old value was consumed one step earlier
+      ccur = sj * ccur + cj * y;
+    }
+  }
+  B.sync();
+  // q vectors: thread per component s, the rotation sweep runs down the rows k .. p-1 (in place)
+  for (int s = B.tid; s < S; s += B.nthr) {
+    double cur = Q[(size_t)k * S + s];
+#pragma unroll 4
+    for (int j = k; j < p - 1; ++j) {
+      const double y = Q[(size_t)(j + 1) * S + s];
+      Q[(size_t)j * S + s] = rc[j] * cur - rs[j] * y;
+      cur = rs[j] * cur + rc[j] * y;
+    }
+  }
+  // T: thread per new row i (old row r = i, or i + 1 behind the deleted row), sweep over the columns k .. p-1 into the
+  // second buffer; entries below the diagonal are never stored, so they read as zero
+  for (int i = B.tid; i < p - 1; i += B.nthr) {
+    const int r = i + (i >= k ? 1 : 0);
+    for (int j = i; j < k; ++j) Tn[(size_t)i + (size_t)j * cap] = T[(size_t)i + (size_t)j * cap];   // (only rows above k)
+    const int j0 = (i >= k) ? i : k;                           // first column with a non-zero result
+    double cur = (r <= j0) ? T[(size_t)r + (size_t)j0 * cap] : 0.;
+#pragma unroll 4
+    for (int j = j0; j < p - 1; ++j) {
+      const double y = T[(size_t)r + (size_t)(j + 1) * cap];   // r <= j + 1 always holds here
+      Tn[(size_t)i + (size_t)j * cap] = rc[j] * cur - rs[j] * y;
+      cur = rs[j] * cur + rc[j] * y;
+    }
+  }
+  B.sync();
+  if (B.tid == 0) { W->R = Tn; W->R2 = T; }
+  B.sync();
 }
 
 // Rebuild the factorisation for the slots currently listed in P (after removals), keeping their weights.
@@ -156,6 +226,7 @@ BCG_HD void nnls_solve(const Blk& B, SolverState* st, NnlsWork* W, int from_scra
     }
   }
   B.sync();
+  omp_mark(B, st, 5);
   const double tolscale = st->bnorm;                     // scale of the dual tolerance, ||b||
   const int maxit = 3 * (W->nP + W->nZ) + 10;
   double* const ax = st->xw_new;                              // A_P wP
@@ -185,12 +256,14 @@ BCG_HD void nnls_solve(const Blk& B, SolverState* st, NnlsWork* W, int from_scra
       if (id < 0 || d > key || (d == key && W->Z[j] < id)) { key = d; id = W->Z[j]; pl = j; }
     }
     blk_argbest(B, &key, &id, &pl);
+    if (outer == 0) omp_mark(B, st, 6);
     if (id < 0 || !(key > 1e-13 * tolscale)) break;           // KKT: no zero column has a positive dual
     ax_is_final = false;
     // move it into P
     if (B.tid == 0) { W->Z[pl] = W->Z[W->nZ - 1]; W->nZ -= 1; W->outer_iters += 1; }
     B.sync();
     if (!nnls_qr_append(B, st, W, (int)id)) continue;         // dependent column: stays at zero, dropped
+    if (outer == 0) omp_mark(B, st, 7);
     // inner loop: move towards the unconstrained solution on P, dropping columns that hit zero
     for (int inner = 0; inner < maxit; ++inner) {
       nnls_solve_R(B, W);
@@ -201,6 +274,7 @@ BCG_HD void nnls_solve(const Blk& B, SolverState* st, NnlsWork* W, int from_scra
       if (-neg > 0.) {
         for (int p = B.tid; p < W->nP; p += B.nthr) W->wP[p] = W->z[p];
         B.sync();
+        if (outer == 0 && inner == 0) omp_mark(B, st, 8);
         break;
       }
       // step length alpha = min_{z_p <= 0} w_p / (w_p - z_p)
@@ -217,23 +291,34 @@ BCG_HD void nnls_solve(const Blk& B, SolverState* st, NnlsWork* W, int from_scra
       }
       { int64_t i2 = 0; int p2 = 0; double k2 = wmax; blk_argbest(B, &k2, &i2, &p2); wmax = k2; }
       B.sync();
-      // drop the columns that reached zero (to the zero set), compact P, rebuild the factorisation
+      // drop the columns that reached zero (to the zero set) and compact P
+      const int p_before = W->nP;
       if (B.tid == 0) {
-        int keep = 0, first = -1;
+        int keep = 0, first = -1, nrem = 0;
         for (int p = 0; p < W->nP; ++p) {
           if (W->wP[p] > 1e-15 * wmax) { W->P[keep] = W->P[p]; W->wP[keep] = W->wP[p]; ++keep; }
-          else { if (first < 0) first = p; W->inP[W->P[p]] = 0; W->Z[W->nZ++] = W->P[p]; }
+          else { if (first < 0) first = p; W->rem[nrem++] = p; W->inP[W->P[p]] = 0; W->Z[W->nZ++] = W->P[p]; }
         }
         W->nP = keep;
+        W->nrem = nrem;
         W->first_removed = (first < 0) ? keep : first;
       }
       B.sync();
-      const int first_removed = W->first_removed;
-      nnls_rebuild(B, st, W, first_removed < W->nP ? first_removed : W->nP);
+      if (W->downdate) {
+        // Givens removal, highest position first (the positions below it keep their meaning)
+        const int nrem = W->nrem;
+        for (int q = nrem - 1; q >= 0; --q) nnls_qr_remove(B, st, W, W->rem[q], p_before - (nrem - 1 - q));
+        if (B.tid == 0 && nrem > 0) W->rebuilds += 1;
+        B.sync();
+      } else {
+        const int first_removed = W->first_removed;
+        nnls_rebuild(B, st, W, first_removed < W->nP ? first_removed : W->nP);
+      }
       if (W->nP == 0) break;
     }
   }
   // write the solution back
+  omp_mark(B, st, 9);
   for (int k = B.tid; k < nact; k += B.nthr)
     if (st->act_w[k] > 0.) st->act_w[k] = 0.;
   B.sync();
@@ -258,15 +343,19 @@ BCG_HD void nnls_solve(const Blk& B, SolverState* st, NnlsWork* W, int from_scra
 // act_w_new keeps the weights from before the iteration for the revert.
 BCG_HD void omp_iteration(const Blk& B, SolverState* st, NnlsWork* W, int prep_next) {
   if (st->halted) return;
+  omp_mark(B, st, 0);
   bool nonempty;
   count_positive(B, st, &nonempty);
   const double prev_err = st->err;
   const int nact0 = st->nact;
   for (int k = B.tid; k < nact0; k += B.nthr) st->act_w_new[k] = st->act_w[k];
   B.sync();
+  omp_mark(B, st, 1);
   const int64_t f = omp_select(B, st);
   if (st->comm_error) return;
+  omp_mark(B, st, 4);
   nnls_solve(B, st, W, 0, 1);
+  omp_mark(B, st, 10);
   const double err = st->err;
   if (nonempty && err > prev_err) {                      // snnls.py:58-61: revert
     for (int k = B.tid; k < st->nact; k += B.nthr) st->act_w[k] = (k < nact0) ? st->act_w_new[k] : 0.;
@@ -281,6 +370,13 @@ BCG_HD void omp_iteration(const Blk& B, SolverState* st, NnlsWork* W, int prep_n
   }
   B.sync();
   if (prep_next && !st->halted) prepare_select(B, st);
+#ifdef __CUDA_ARCH__
+  if (st->omp_trace && B.tid == 0) {                     // n_events already counts this iteration
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    st->omp_trace[(size_t)(st->n_events - 1) * 16 + 11] = t;
+  }
+#endif
 }
 
 }  // namespace bcg

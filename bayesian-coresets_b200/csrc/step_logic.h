@@ -38,6 +38,19 @@ struct Blk {
   }
 };
 
+// phase timestamp i of the current OMP iteration (diagnostics: BCG_OMP_TRACE=1); no-op on the host build
+BCG_HD void omp_mark(const Blk& B, SolverState* st, int i) {
+#ifdef __CUDA_ARCH__
+  if (st->omp_trace && B.tid == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    st->omp_trace[(size_t)st->n_events * 16 + i] = t;
+  }
+#else
+  (void)B; (void)st; (void)i;
+#endif
+}
+
 // sum N per-thread values over the block; every thread receives the totals (fixed order)
 template <int N>
 BCG_HD void blk_sum(const Blk& B, double* v) {
@@ -110,14 +123,27 @@ BCG_HD void blk_combine(const Blk& B, int n_out, int n_terms, TermF term, FinF f
       double acc[kWideCols / 32];
 #pragma unroll
       for (int j = 0; j < kWideCols / 32; ++j) acc[j] = 0.;
-      for (int i = warp; i < n_terms; i += nw) {
-        const CombTerm<T> t = term(i);
-        if (t.coef == 0.) continue;                        // warp-uniform
+      constexpr int G = 4;                                 // terms per warp pass: G * 8 independent loads per lane
+      for (int i0 = warp * G; i0 < n_terms; i0 += nw * G) {
+        CombTerm<T> t[G];
 #pragma unroll
-        for (int j = 0; j < kWideCols / 32; ++j) {
-          const int s = c0 + lane + 32 * j;
-          if (s < t.len) acc[j] += t.coef * (double)t.row[s];
+        for (int g = 0; g < G; ++g) {
+          if (i0 + g < n_terms) t[g] = term(i0 + g);
+          else { t[g].coef = 0.; t[g].row = nullptr; t[g].len = 0; }
+          if (t[g].coef == 0.) t[g].len = 0;               // warp-uniform
         }
+        T v[G][kWideCols / 32];
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+          for (int j = 0; j < kWideCols / 32; ++j) {
+            const int s = c0 + lane + 32 * j;
+            v[g][j] = (s < t[g].len) ? t[g].row[s] : (T)0;
+          }
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+          for (int j = 0; j < kWideCols / 32; ++j) acc[j] += t[g].coef * (double)v[g][j];
       }
 #pragma unroll
       for (int j = 0; j < kWideCols / 32; ++j) B.wide[warp * kWideCols + lane + 32 * j] = acc[j];
@@ -474,6 +500,7 @@ BCG_HD int64_t omp_select(const Blk& B, SolverState* st) {
   count_positive(B, st, &nonempty);
   uint32_t lrow; double pos;
   pick_local(B, st, true, &lrow, &pos);
+  omp_mark(B, st, 2);
   int64_t f; double nf_stored; const float* frow;
   if (st->world > 1) {
 #ifdef __CUDA_ARCH__
@@ -502,6 +529,7 @@ BCG_HD int64_t omp_select(const Blk& B, SolverState* st) {
       if (id < 0 || ng > key || (ng == key && gi < id)) { key = ng; id = gi; pl = k; }
     }
     blk_argbest(B, &key, &id, &pl);
+    omp_mark(B, st, 3);
     if (id >= 0 && !(pos >= key)) {          // orthopursuit.py:32-35
       f = id;
       if (B.tid == 0) st->act_w[pl] = 1.;

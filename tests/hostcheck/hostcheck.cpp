@@ -142,8 +142,8 @@ namespace {
 struct NnlsHost {
   Host H;
   NnlsWork W;
-  std::vector<double> Q, R, c, z, wP, h, v;
-  std::vector<int32_t> P, Z, inP;
+  std::vector<double> Q, R, R2, rot, c, z, wP, h, v;
+  std::vector<int32_t> P, Z, inP, rem;
 };
 }  // namespace
 
@@ -152,7 +152,7 @@ struct NnlsHost {
 // w_out: steps x ncols solutions.
 extern "C" int hostcheck_nnls_sequence(const float* An, const double* norms, const double* b, int S, int ld, int64_t N,
                                        const int64_t* cols, int ncols, const int* counts, int steps, int from_scratch,
-                                       double* w_out, int* rebuilds_out) {
+                                       int downdate, double* w_out, int* rebuilds_out) {
   NnlsHost X;
   Host& H = X.H;
   memset(&H.st, 0, sizeof(SolverState));
@@ -179,6 +179,8 @@ extern "C" int hostcheck_nnls_sequence(const float* An, const double* norms, con
   memset(&W, 0, sizeof(W));
   W.Q = X.Q.data(); W.R = X.R.data(); W.c = X.c.data(); W.z = X.z.data(); W.wP = X.wP.data(); W.h = X.h.data();
   W.v = X.v.data(); W.P = X.P.data(); W.Z = X.Z.data(); W.inP = X.inP.data(); W.cap = cap;
+  X.R2.assign((size_t)cap * cap, 0.); X.rot.assign((size_t)3 * cap, 0.); X.rem.assign(cap, 0);
+  W.R2 = X.R2.data(); W.rot = X.rot.data(); W.rem = X.rem.data(); W.downdate = downdate;
   Blk B{0, 1, H.sred, nullptr};
   int have = 0, reb = 0;
   for (int t = 0; t < steps; ++t) {
@@ -198,7 +200,7 @@ extern "C" int hostcheck_nnls_sequence(const float* An, const double* norms, con
 // full OrthoPursuit loop: scan stand-in + omp_iteration (selection, warm-started NNLS, monotone check, events,
 // next direction) exactly as bcg_solver_build drives omp_iteration_kernel
 extern "C" int hostcheck_run_omp(const float* An, const double* norms, const double* b, int S, int ld, int64_t N,
-                                 int itrs, int builds, bcg_iter_event* events_out, int* n_events_out, int64_t* idx_out,
+                                 int itrs, int builds, int downdate, bcg_iter_event* events_out, int* n_events_out, int64_t* idx_out,
                                  double* w_out, int* k_out, double* err_out, int* halted_out) {
   NnlsHost X;
   Host& H = X.H;
@@ -230,6 +232,8 @@ extern "C" int hostcheck_run_omp(const float* An, const double* norms, const dou
   memset(&W, 0, sizeof(W));
   W.Q = X.Q.data(); W.R = X.R.data(); W.c = X.c.data(); W.z = X.z.data(); W.wP = X.wP.data(); W.h = X.h.data();
   W.v = X.v.data(); W.P = X.P.data(); W.Z = X.Z.data(); W.inP = X.inP.data(); W.cap = cap;
+  X.R2.assign((size_t)cap * cap, 0.); X.rot.assign((size_t)3 * cap, 0.); X.rem.assign(cap, 0);
+  W.R2 = X.R2.data(); W.rot = X.rot.data(); W.rem = X.rem.data(); W.downdate = downdate;
   Blk B{0, 1, H.sred, nullptr};
   const int nb = 37;
   for (int bld = 0; bld < builds && !st.halted; ++bld) {

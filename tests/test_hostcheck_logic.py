@@ -141,7 +141,7 @@ def test_omp_select_matches_oracle(lib):
 
 
 # ---------------------------------------------------------------- device NNLS logic vs scipy.optimize.nnls
-def run_nnls_sequence(lib, vecs, b, cols, counts, from_scratch=0):
+def run_nnls_sequence(lib, vecs, b, cols, counts, from_scratch=0, downdate=1):
   An, norms, ld = device_layout(vecs)
   N, S = vecs.shape
   cols = np.asarray(cols, dtype=np.int64)
@@ -151,7 +151,8 @@ def run_nnls_sequence(lib, vecs, b, cols, counts, from_scratch=0):
   P = ctypes.c_void_p
   lib.hostcheck_nnls_sequence(P(An.ctypes.data), P(norms.ctypes.data), P(b.ctypes.data), ctypes.c_int(S), ctypes.c_int(ld),
                               ctypes.c_int64(N), P(cols.ctypes.data), ctypes.c_int(len(cols)), P(counts.ctypes.data),
-                              ctypes.c_int(len(counts)), ctypes.c_int(from_scratch), P(out.ctypes.data), ctypes.byref(reb))
+                              ctypes.c_int(len(counts)), ctypes.c_int(from_scratch), ctypes.c_int(downdate),
+                              P(out.ctypes.data), ctypes.byref(reb))
   A32 = (An[:, :S].astype(np.float64)*norms[:, None])           # the columns exactly as the device holds them
   return out, A32, reb.value
 
@@ -167,8 +168,8 @@ def test_nnls_logic_matches_scipy(lib, seed, shift):
   b = vecs[rng.choice(N, 60)].sum(axis=0) + 0.3*rng.randn(S)
   cols = rng.choice(N, K, replace=False)
   counts = list(range(1, K + 1))
-  for scratch in (0, 1):
-    out, A32, reb = run_nnls_sequence(lib, vecs, b, cols, counts, from_scratch=scratch)
+  for scratch, downdate in ((0, 1), (1, 1), (0, 0)):
+    out, A32, reb = run_nnls_sequence(lib, vecs, b, cols, counts, from_scratch=scratch, downdate=downdate)
     active = np.zeros(K, dtype=bool)
     for t, cnt in enumerate(counts):
       # the problem at step t: columns that were positive after step t-1 plus the new one (orthopursuit.py:38-41)
@@ -179,10 +180,11 @@ def test_nnls_logic_matches_scipy(lib, seed, shift):
       active = ref > 0
     if shift >= 2.0:
       assert (out[-1] == 0).any()          # some weights were driven to zero along the way
+      assert reb > 0                       # ... by the removal path (Givens downdate / rebuild)
 
 
 # ---------------------------------------------------------------- full OMP iteration (omp_iteration) vs the oracle
-def run_host_omp(lib, vecs, itrs, builds=1):
+def run_host_omp(lib, vecs, itrs, builds=1, downdate=1):
   N, S = vecs.shape
   An, norms, ld = device_layout(vecs)
   b = vecs.sum(axis=0)
@@ -193,7 +195,7 @@ def run_host_omp(lib, vecs, itrs, builds=1):
   w = np.zeros(itrs*builds + 8)
   P = ctypes.c_void_p
   lib.hostcheck_run_omp(P(An.ctypes.data), P(norms.ctypes.data), P(b.ctypes.data), ctypes.c_int(S), ctypes.c_int(ld),
-                        ctypes.c_int64(N), ctypes.c_int(itrs), ctypes.c_int(builds), ev, ctypes.byref(nev),
+                        ctypes.c_int64(N), ctypes.c_int(itrs), ctypes.c_int(builds), ctypes.c_int(downdate), ev, ctypes.byref(nev),
                         P(idx.ctypes.data), P(w.ctypes.data), ctypes.byref(k), ctypes.byref(err), ctypes.byref(halted))
   events = [(e.code, e.f, e.error) for e in ev[:nev.value]]
   wd = np.zeros(N)
@@ -277,3 +279,28 @@ def test_fast_links_match_reference_formulas(lib):
     got = _link(lib, 2, lin, np.full(lin.size, yy))
     # y s and exp(s) cancel near the mode: absolute rounding of O(10) terms
     np.testing.assert_allclose(got, ref, rtol=1e-13, atol=5e-14)
+
+
+def test_nnls_givens_removal_stress(lib):
+  """many removals (more candidate columns than dimensions, strongly correlated columns): the Givens column
+  removal keeps the warm-started factorisation consistent with scipy.optimize.nnls over a long sequence"""
+  from scipy.optimize import nnls
+  rng = np.random.RandomState(7)
+  S, N, K = 48, 400, 110
+  vecs = rng.randn(N, S) + 1.5
+  b = vecs[rng.choice(N, 80)].sum(axis=0) + 0.5*rng.randn(S)
+  cols = rng.choice(N, K, replace=False)
+  counts = list(range(1, K + 1))
+  out, A32, reb = run_nnls_sequence(lib, vecs, b, cols, counts, from_scratch=0, downdate=1)
+  assert reb >= 20
+  active = np.zeros(K, dtype=bool)
+  for t, cnt in enumerate(counts):
+    active[cnt - 1] = True
+    ref = np.zeros(K)
+    ref[active] = nnls(A32[cols[active]].T, b, maxiter=100000)[0]
+    res_ref = np.linalg.norm(A32[cols].T.dot(ref) - b)
+    res_got = np.linalg.norm(A32[cols].T.dot(out[t]) - b)
+    assert np.all(out[t] >= 0) and np.all(out[t][~active] == 0)
+    assert res_got <= res_ref*(1. + 1e-9) + 1e-9
+    np.testing.assert_allclose(out[t], ref, rtol=1e-6, atol=1e-7*max(1., np.abs(ref).max()))
+    active = ref > 0
