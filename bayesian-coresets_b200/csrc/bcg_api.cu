@@ -18,6 +18,7 @@
 #include "bcg_state.h"
 #include "kernel_args.h"
 #include "project_kernels.cuh"
+#include "project_fast_kernel.cuh"
 #include "project_sum_kernel.cuh"
 #include "project_sum_mma_kernel.cuh"
 #include "step_kernels.cuh"
@@ -512,6 +513,71 @@ static int launch_project(bcg_ctx* ctx, const ProjectArgs& a, int grid, size_t s
   return BCG_OK;
 }
 
+template <int J2, int MODEL>
+static int launch_project_fast(bcg_ctx* ctx, const ProjectArgs& a, int grid, size_t smem) {
+  CK(cudaFuncSetAttribute(project_fast_kernel<J2, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  project_fast_kernel<J2, MODEL><<<grid, kProjWarps * 32, smem, ctx->stream>>>(a);
+  CK(cudaGetLastError());
+  return BCG_OK;
+}
+
+template <int J2, int MODEL>
+static int launch_project_pair(bcg_ctx* ctx, const ProjectArgs& a, int grid, size_t smem) {
+  CK(cudaFuncSetAttribute(project_pair_kernel<J2, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  project_pair_kernel<J2, MODEL><<<grid, kPairThreads, smem, ctx->stream>>>(a);
+  CK(cudaGetLastError());
+  return BCG_OK;
+}
+
+template <int J2>
+static int launch_project_pair_model(bcg_ctx* ctx, const ProjectArgs& a, int grid, size_t smem) {
+  if (a.model == MODEL_LR) return launch_project_pair<J2, MODEL_LR>(ctx, a, grid, smem);
+  if (a.model == MODEL_POISSON) return launch_project_pair<J2, MODEL_POISSON>(ctx, a, grid, smem);
+  return launch_project_pair<J2, MODEL_LINEAR>(ctx, a, grid, smem);
+}
+
+template <int J2>
+static int launch_project_fast_model(bcg_ctx* ctx, const ProjectArgs& a, int grid, size_t smem) {
+  if (a.model == MODEL_LR) return launch_project_fast<J2, MODEL_LR>(ctx, a, grid, smem);
+  if (a.model == MODEL_POISSON) return launch_project_fast<J2, MODEL_POISSON>(ctx, a, grid, smem);
+  return launch_project_fast<J2, MODEL_LINEAR>(ctx, a, grid, smem);
+}
+
+// K3 launch: the specialised kernels (project_fast_kernel.cuh) for S in {64, 128, 256, 512} with the whole sample tile
+// in shared memory and table links, the general kernel otherwise (BCG_PROJ_FAST=0 forces the general kernel)
+static int dispatch_project(bcg_ctx* ctx, const ProjectArgs& a, int grid, size_t smem) {
+  // 1 (default): one warp per row; 2: two warps per row (measured slower: 0.546 vs 0.506 ms per 209715 x 512 chunk);
+  // 0: general kernel (0.897 ms)
+  const int fast = env_int("BCG_PROJ_FAST", 1);
+  const bool fast_ok = fast && !a.out64 && a.ld == a.S && a.d <= 32 && a.ktile >= a.d &&
+                       (a.model == MODEL_LINEAR || a.sp_tab != nullptr);
+  if (fast_ok && fast >= 2) {
+    switch (a.S) {
+      case 128: return launch_project_pair_model<1>(ctx, a, grid, smem);
+      case 256: return launch_project_pair_model<2>(ctx, a, grid, smem);
+      case 512: return launch_project_pair_model<4>(ctx, a, grid, smem);
+      default: break;
+    }
+  }
+  if (fast_ok) {
+    switch (a.S) {
+      case 64: return launch_project_fast_model<1>(ctx, a, grid, smem);
+      case 128: return launch_project_fast_model<2>(ctx, a, grid, smem);
+      case 256: return launch_project_fast_model<4>(ctx, a, grid, smem);
+      case 512: return launch_project_fast_model<8>(ctx, a, grid, smem);
+      default: break;
+    }
+  }
+  switch (j_for_ld(a.ld)) {
+    case 1: return launch_project<1>(ctx, a, grid, smem);
+    case 2: return launch_project<2>(ctx, a, grid, smem);
+    case 4: return launch_project<4>(ctx, a, grid, smem);
+    case 8: return launch_project<8>(ctx, a, grid, smem);
+    case 16: return launch_project<16>(ctx, a, grid, smem);
+    default: return launch_project<32>(ctx, a, grid, smem);
+  }
+}
+
 // common driver.  thetaT (d x S, already transposed) and coff (S or null) are host arrays.
 // out_vecs: materialise the unit-row matrix; rows64: host n x S float64 centred rows; colsum: host S.
 static int project_common(bcg_dataset* ds, const int64_t* rowidx, int64_t nsel, int32_t d, const double* thetaT,
@@ -606,14 +672,7 @@ static int project_common(bcg_dataset* ds, const int64_t* rowidx, int64_t nsel, 
     a.Z = ds->Z; a.rowidx = d_idx; a.theta = dT; a.coff = dC; a.An = v ? v->An : nullptr; a.norms = v ? v->norms : nullptr;
     a.out64 = d_rows; a.partial = d_partial; a.zero_rows = d_zero; a.n = n; a.zld = ds->zld; a.d = d; a.S = S;
     a.ld = ld; a.model = model; a.ktile = ktile; a.sp_tab = ctx->sp_tab;
-    switch (j_for_ld(ld)) {
-      case 1: RET(launch_project<1>(ctx, a, grid, smem)); break;
-      case 2: RET(launch_project<2>(ctx, a, grid, smem)); break;
-      case 4: RET(launch_project<4>(ctx, a, grid, smem)); break;
-      case 8: RET(launch_project<8>(ctx, a, grid, smem)); break;
-      case 16: RET(launch_project<16>(ctx, a, grid, smem)); break;
-      default: RET(launch_project<32>(ctx, a, grid, smem)); break;
-    }
+    RET(dispatch_project(ctx, a, grid, smem));
     if (v) {
       RET(finish_colsum(v, d_partial, grid, d_zero));
       if (colsum) memcpy(colsum, v->colsum.data(), (size_t)S * sizeof(double));
@@ -760,14 +819,7 @@ static int project_host_pipelined(bcg_ctx* ctx, int kmodel, const double* Z, int
       a.Z = dev[i]; a.rowidx = nullptr; a.theta = dT; a.coff = dC; a.An = v->An + (size_t)r0 * ld; a.norms = v->norms + r0;
       a.out64 = nullptr; a.partial = d_partial.p + (size_t)c * grid * (S + 1); a.zero_rows = d_zero; a.n = nr; a.zld = zld;
       a.d = d; a.S = S; a.ld = ld; a.model = kmodel; a.ktile = ktile; a.sp_tab = ctx->sp_tab;
-      switch (j_for_ld(ld)) {
-        case 1: RET(launch_project<1>(ctx, a, grid, smem)); break;
-        case 2: RET(launch_project<2>(ctx, a, grid, smem)); break;
-        case 4: RET(launch_project<4>(ctx, a, grid, smem)); break;
-        case 8: RET(launch_project<8>(ctx, a, grid, smem)); break;
-        case 16: RET(launch_project<16>(ctx, a, grid, smem)); break;
-        default: RET(launch_project<32>(ctx, a, grid, smem)); break;
-      }
+      RET(dispatch_project(ctx, a, grid, smem));
       CK(cudaEventRecord(kdone.e[i], st));
     }
     RET(finish_colsum(v, d_partial, nchunks * grid, d_zero));

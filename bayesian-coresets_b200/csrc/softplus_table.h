@@ -5,13 +5,17 @@
 //   examples/common/model_poiss.py:25-38   s = log softplus(x.theta),  y s - exp(s)
 // are built on softplus.  Written with libdevice's exp + log1p the link costs ~110 instructions per matrix
 // element and the d = 10 projection kernel spent most of its issue slots there (profiles/r01_final_project_lr_*:
-// 208 instructions per element, 5 % of the HBM write rate).  Here g(t) = log1p(exp(t)), t <= 0, comes from a table:
-// [-37, 0] is cut into 296 intervals of width 1/8, each with the degree-7 polynomial that interpolates g at the
-// interval's 8 Chebyshev nodes (built on the host in long double).  The interpolation error is below
-// |g^(8)| (1/16)^8 / (8! 2^7) ~ 1e-17 g, i.e. below double rounding, RELATIVE to g on every interval (all derivatives
-// of g scale like exp(t) in the tail), so tiny values keep their relative accuracy like the libdevice path.
+// 208 instructions per element, 5 % of the HBM write rate).  Here g(t) = log1p(exp(t)), t <= 0, is a Taylor
+// expansion about the nearest node t_i = -i/32 of a table that holds only (g(t_i), sigma(t_i)): every derivative of
+// softplus is a polynomial in sigma -- with q = sigma (1 - sigma):
+//   g1 = sigma, g2 = q, g3 = q (1 - 2 sigma), g4 = q (1 - 6 q), g5 = q (1 - 2 sigma)(1 - 12 q),
+//   g6 = q (1 - 30 q + 120 q^2)
+// so ONE 16-byte load feeds an order-6 expansion (|delta| <= 1/64: remainder < 1e-16 g; all derivatives scale like
+// exp(t) in the tail, so tiny values keep their RELATIVE accuracy; measured max relative error 2.5e-16 over [-37, 0]).
+// The first version used 64-byte records of degree-7 Chebyshev coefficients: four gathered 16-byte loads per element
+// saturated the L1 data pipe of the projection kernels (ncu: l1tex data-pipe wavefronts 97 % of peak, 13.6 wavefronts per
+// load request), which is why the table shrank to one load per element at the price of ~15 more float64 operations.
 // Below t = -37, log1p(exp(t)) == exp(t) in float64 (the next term is exp(t) * 2^-54): rare out-of-line tail.
-// One evaluation: 4 x 16-byte table loads (one 64-byte record) + ~14 float64 instructions.
 #pragma once
 #include <math.h>
 #include <stddef.h>
@@ -25,45 +29,17 @@
 
 namespace bcg {
 
-constexpr int kSpPerUnit = 8;                            // intervals per unit of t
+constexpr int kSpPerUnit = 32;                           // nodes per unit of t
 constexpr int kSpRange = 37;                             // the table covers [-37, 0]
-constexpr int kSpIntervals = kSpRange * kSpPerUnit;      // 296
-constexpr int kSpStride = 8;                             // coefficients per interval (degree 7): one 64-byte record
-constexpr size_t kSpTableDoubles = (size_t)kSpIntervals * kSpStride;
+constexpr int kSpNodes = kSpRange * kSpPerUnit + 1;      // 1185 nodes t_i = -i / 32
+constexpr size_t kSpTableDoubles = (size_t)kSpNodes * 2; // (g, sigma) per node: 16-byte records, 19 KB
 
-// host: coefficients c_0..c_7 of p(x) = sum c_k x^k, x = 2 (8 t - floor(8 t)) - 1 in [-1, 1), per interval
+// host: tab[2 i] = log1p(exp(t_i)), tab[2 i + 1] = 1 / (1 + exp(-t_i)), evaluated in long double
 inline void softplus_table_build(double* tab) {
-  const int n = kSpStride;
-  const long double pi = 3.14159265358979323846264338327950288L;
-  // monomial coefficients of the Chebyshev polynomials T_0..T_7
-  long double Tm[8][8];
-  for (int k = 0; k < n; ++k)
-    for (int j = 0; j < n; ++j) Tm[k][j] = 0.L;
-  Tm[0][0] = 1.L;
-  Tm[1][1] = 1.L;
-  for (int k = 2; k < n; ++k) {
-    for (int j = 0; j < n; ++j) Tm[k][j] = -Tm[k - 2][j];
-    for (int j = 1; j < n; ++j) Tm[k][j] += 2.L * Tm[k - 1][j - 1];
-  }
-  for (int i = 0; i < kSpIntervals; ++i) {
-    const long double lo = (long double)(i - kSpIntervals) / kSpPerUnit;       // interval [lo, lo + 1/8]
-    const long double half = 0.5L / kSpPerUnit;
-    long double f[8], cheb[8];
-    for (int j = 0; j < n; ++j) {
-      const long double xj = cosl(pi * (j + 0.5L) / n);
-      f[j] = log1pl(expl(lo + half * (xj + 1.L)));
-    }
-    for (int k = 0; k < n; ++k) {
-      long double s = 0.L;
-      for (int j = 0; j < n; ++j) s += f[j] * cosl(pi * k * (j + 0.5L) / n);
-      cheb[k] = s * 2.L / n;
-    }
-    cheb[0] *= 0.5L;
-    for (int j = 0; j < n; ++j) {
-      long double c = 0.L;
-      for (int k = 0; k < n; ++k) c += cheb[k] * Tm[k][j];
-      tab[(size_t)i * kSpStride + j] = (double)c;
-    }
+  for (int i = 0; i < kSpNodes; ++i) {
+    const long double t = -(long double)i / kSpPerUnit;
+    tab[2 * (size_t)i] = (double)log1pl(expl(t));
+    tab[2 * (size_t)i + 1] = (double)(1.L / (1.L + expl(-t)));
   }
 }
 
@@ -77,35 +53,31 @@ inline double exp_tail(double t) { return exp(t); }
 // g(t) = log1p(exp(t)) for t <= 0 (NaN propagates)
 SP_HD double softplus_neg(const double* tab, double t) {
   if (t < -(double)kSpRange) return exp_tail(t);
-  const double u = t * (double)kSpPerUnit;               // exact
 #ifdef __CUDA_ARCH__
-  int i = __double2int_rd(u);                            // floor; NaN -> 0
+  int i = __double2int_rn(t * -(double)kSpPerUnit);      // nearest node; NaN -> 0
 #else
-  int i = (u == u) ? (int)floor(u) : 0;
+  int i = (t == t) ? (int)nearbyint(t * -(double)kSpPerUnit) : 0;
 #endif
-  i += kSpIntervals;
-  i = i < 0 ? 0 : (i > kSpIntervals - 1 ? kSpIntervals - 1 : i);   // t = 0 evaluates the last interval at x = 1
-  const double x = fma(2., u - (double)(i - kSpIntervals), -1.);
-  const double* c = tab + (size_t)i * kSpStride;
+  i = i < 0 ? 0 : (i > kSpNodes - 1 ? kSpNodes - 1 : i);
+  const double dl = fma((double)i, 1. / kSpPerUnit, t);  // t - t_i, |dl| <= 1/64
 #ifdef __CUDA_ARCH__
-  const double2 c01 = __ldg(reinterpret_cast<const double2*>(c));
-  const double2 c23 = __ldg(reinterpret_cast<const double2*>(c) + 1);
-  const double2 c45 = __ldg(reinterpret_cast<const double2*>(c) + 2);
-  const double2 c67 = __ldg(reinterpret_cast<const double2*>(c) + 3);
-  double p = c67.y;
-  p = fma(p, x, c67.x);
-  p = fma(p, x, c45.y);
-  p = fma(p, x, c45.x);
-  p = fma(p, x, c23.y);
-  p = fma(p, x, c23.x);
-  p = fma(p, x, c01.y);
-  p = fma(p, x, c01.x);
-  return p;
+  const double2 n = __ldg(reinterpret_cast<const double2*>(tab) + i);
+  const double g = n.x, s = n.y;
 #else
-  double p = c[7];
-  for (int k = 6; k >= 0; --k) p = fma(p, x, c[k]);
-  return p;
+  const double g = tab[2 * (size_t)i], s = tab[2 * (size_t)i + 1];
 #endif
+  const double q = fma(-s, s, s);                        // sigma (1 - sigma)
+  const double r = fma(-2., s, 1.);
+  const double g3 = q * r;
+  const double g4 = q * fma(-6., q, 1.);
+  const double g5 = g3 * fma(-12., q, 1.);
+  const double g6 = q * fma(fma(120., q, -30.), q, 1.);
+  double p = fma(dl * (1. / 6.), g6, g5);
+  p = fma(dl * 0.2, p, g4);
+  p = fma(dl * 0.25, p, g3);
+  p = fma(dl * (1. / 3.), p, q);
+  p = fma(dl * 0.5, p, s);
+  return fma(dl, p, g);
 }
 
 // model_lr.py:28-31 as -(max(m, 0) + log1p(exp(-|m|))), m = -lin: the same function in float64 (for m >= 100 the

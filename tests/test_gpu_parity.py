@@ -622,3 +622,46 @@ def test_pinned_source_equals_pageable_source(bc):
   wts, pts, idcs = cs.get()
   assert np.array_equal(pts, Z[idcs])
   del Zp, b, db, cs
+
+
+@pytest.mark.parametrize('S,d', [(64, 3), (128, 32), (256, 10), (512, 10), (512, 24)])
+def test_specialised_projection_kernel_vs_general_and_oracle(bc, monkeypatch, S, d):
+  """project_pair_kernel / project_fast_kernel (S in {64,128,256,512}, d <= 32; BCG_PROJ_FAST=2 / 1) against the general
+  kernel (BCG_PROJ_FAST=0) and the oracle:
+  three models, a row count that is no multiple of the CTA batch, a device row gather, column-sum-only passes"""
+  rng = np.random.RandomState(S + d)
+  n = 3001
+  X = rng.randn(n, d)*rng.choice([0.3, 1., 5.], size=(n, 1))
+  th = rng.randn(S, d)/np.sqrt(d)
+  y = rng.poisson(2., size=n).astype(np.float64)
+  Zp = np.hstack((X, y[:, None]))
+  Siginv = np.eye(d) + 0.1*np.ones((d, d))
+  sub = rng.randint(n, size=777)
+  cases = [(bc._native.MODEL_LR, X, None, models.project(models.lr_loglik, X, th)),
+           (bc._native.MODEL_POISSON, Zp, None, models.project(models.poisson_loglik, Zp, th)),
+           (bc._native.MODEL_GAUSSIAN, X, Siginv, models.project(lambda x, t: models.gaussian_loglik(x, t, Siginv, 0.), X, th))]
+  for model, Z, si, ref in cases:
+    ds = bc.Dataset(Z)
+    res = []
+    for fast in ('2', '1', '0'):
+      monkeypatch.setenv('BCG_PROJ_FAST', fast)
+      v = ds.project(model, th, si, vecs=True)[0]
+      vs = ds.project(model, th, si, vecs=True, sub=sub)[0]
+      cs = ds.project(model, th, si, colsum=True)[2]
+      res.append((v.to_numpy(), v.norms(), v.sum(axis=0), vs.to_numpy(), vs.norms(), cs, v.norm_sum(), v.zero_rows()))
+      if fast != '0':
+        check_projection(v, ref)
+        check_projection(vs, ref[sub])
+    monkeypatch.delenv('BCG_PROJ_FAST')
+    for a, b in ((res[0], res[2]), (res[1], res[2])):
+      compare_projection_outputs(a, b, ref)
+
+
+def compare_projection_outputs(a, b, ref):
+    assert np.max(np.abs(a[0] - b[0])) <= 2.**-22 and np.max(np.abs(a[3] - b[3])) <= 2.**-22   # unit rows, float32 rounding
+    np.testing.assert_allclose(a[1], b[1], rtol=1e-12)
+    np.testing.assert_allclose(a[4], b[4], rtol=1e-12)
+    np.testing.assert_allclose(a[2], b[2], rtol=1e-10, atol=1e-10*np.abs(b[2]).max())
+    np.testing.assert_allclose(a[5], b[5], rtol=1e-10, atol=1e-10*np.abs(b[5]).max())
+    np.testing.assert_allclose(a[5], ref.sum(axis=0), rtol=1e-9, atol=1e-9*np.abs(ref).sum(axis=0).max())
+    assert a[6] == pytest.approx(b[6], rel=1e-12) and a[7] == b[7] == 0
