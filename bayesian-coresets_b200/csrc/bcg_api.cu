@@ -392,7 +392,7 @@ static int finish_colsum(bcg_vecs* v, const double* d_partial, int nparts, unsig
   const int S1 = v->S + 1;
   DevBuf<double> d_out;
   CK(d_out.alloc(S1));
-  colsum_reduce_kernel<<<(S1 + 127) / 128, 128, 0, ctx->stream>>>(d_partial, nparts, S1, d_out);
+  colsum_reduce_kernel<<<(S1 + 31) / 32, dim3(32, kCsrSlices), 0, ctx->stream>>>(d_partial, nparts, S1, d_out);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(v->colsum.data(), d_out, S1 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   unsigned long long z = 0;
@@ -678,7 +678,7 @@ static int project_common(bcg_dataset* ds, const int64_t* rowidx, int64_t nsel, 
       if (colsum) memcpy(colsum, v->colsum.data(), (size_t)S * sizeof(double));
     } else if (colsum) {
       const int S1 = S + 1;
-      colsum_reduce_kernel<<<(S1 + 127) / 128, 128, 0, st>>>(d_partial, grid, S1, d_out);
+      colsum_reduce_kernel<<<(S1 + 31) / 32, dim3(32, kCsrSlices), 0, st>>>(d_partial, grid, S1, d_out);
       CK(cudaGetLastError());
       CK(cudaMemcpyAsync(colsum, d_out, (size_t)S * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
