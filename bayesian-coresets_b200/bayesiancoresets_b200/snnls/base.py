@@ -110,6 +110,8 @@ class SparseNNLS(object):
     if self.n_global*self._vecs.shape[1] == 0:
       self.log.warning('there are no data, returning.')
       return
+    if self.comm.world > 1:
+      self.comm.barrier()        # the ranks' solvers share one mailbox per context: no rank may still be in another solver's build
     self.last_events = self._run(int(itrs))
     self._log_events(self.last_events)
     if self.reached_numeric_limit:

@@ -11,6 +11,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <array>
+#include <utility>
 #include <thread>
 #include <vector>
 
@@ -104,6 +106,16 @@ struct bcg_ctx {
   void* scratch[8];           // per-context device scratch, grown on demand (no malloc/free per projection pass)
   size_t scratch_bytes[8];
   double* sp_tab;             // softplus table of the fast links (softplus_table.h); null with BCG_FAST_LINK=0
+  // N-sharding mailbox of this rank and the peers' mailboxes mapped so far.  Owned by the context, not by a solver:
+  // opening a peer's IPC handle (and the lazy peer-access enable behind it) costs ~100 ms, so the mappings are made
+  // once per process and reused by every solver; sized for kMaxWorld ranks and S = 1024 up front (67 KB), so the
+  // allocation -- and with it the handle the peers hold -- never changes
+  unsigned char* mail;
+  int64_t mail_bytes;
+  unsigned long long mail_epoch;   // solvers connected so far: every solver numbers its exchanges from epoch << 32,
+                                   // so a value left in a slot by an earlier solver never matches (ranks connect in
+                                   // the same order, SPMD, hence agree on the epoch)
+  std::vector<std::pair<std::array<unsigned char, 64>, void*>> peer_cache;
 };
 
 struct bcg_vecs {
@@ -134,8 +146,6 @@ struct bcg_solver {
   unsigned long long* d_trace;
   int trace_cap, trace_n;
   int64_t* d_fout;
-  unsigned char* mail;      // this rank's mailbox allocation
-  int64_t mail_bytes;
   void* peer_ptrs[kMaxWorld];
   bool peers_open;
   // timing
@@ -206,6 +216,9 @@ extern "C" int bcg_ctx_create(int device, bcg_ctx** out) {
   c->sm_count = c->prop.multiProcessorCount;
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  c->mail = nullptr;
+  c->mail_bytes = 0;
+  c->mail_epoch = 0;
   c->sp_tab = nullptr;
   if (env_int("BCG_FAST_LINK", 1)) {
     std::vector<double> tab(kSpTableDoubles);
@@ -222,6 +235,8 @@ extern "C" int bcg_ctx_destroy(bcg_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);
   if (ctx->sp_tab) cudaFree(ctx->sp_tab);
+  for (auto& pc : ctx->peer_cache) cudaIpcCloseMemHandle(pc.second);
+  if (ctx->mail) cudaFree(ctx->mail);
   for (int i = 0; i < 8; ++i)
     if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
   for (int i = 0; i < 2; ++i)
@@ -1091,8 +1106,6 @@ extern "C" int bcg_solver_create(bcg_ctx* ctx, bcg_vecs* v, int32_t alg, const d
   s->ev0 = s->ev1 = nullptr;
   s->ctx = ctx;
   s->v = v;
-  s->mail = nullptr;
-  s->mail_bytes = 0;
   s->peers_open = false;
   s->use_loop = false;
   s->d_ctl = nullptr;
@@ -1120,11 +1133,9 @@ extern "C" int bcg_solver_destroy(bcg_solver* s) {
   cudaSetDevice(s->ctx->device);
   cudaStreamSynchronize(s->ctx->stream);
   SolverState& h = s->h;
-  if (s->peers_open)
-    for (int p = 0; p < h.world; ++p)
-      if (p != h.rank && s->peer_ptrs[p]) cudaIpcCloseMemHandle(s->peer_ptrs[p]);
+  // (the mailbox and the peer mappings belong to the context and outlive the solver)
   void* bufs[] = {h.b, h.bn, h.xw, h.xw_new, h.xf, h.dir64, h.dir32, h.wrow, h.cands, h.act_idx, h.act_w,
-                  h.act_w_new, h.act_norm, h.act_tmp, h.act_rows, h.events, s->d_fout, s->d, s->mail, s->d_ctl, s->d_cta_cands, s->d_trace, s->d_claims};
+                  h.act_w_new, h.act_norm, h.act_tmp, h.act_rows, h.events, s->d_fout, s->d, s->d_ctl, s->d_cta_cands, s->d_trace, s->d_claims};
   for (void* p : bufs)
     if (p) cudaFree(p);
   if (s->d_nw) cudaMemcpy(&s->nw, s->d_nw, sizeof(NnlsWork), cudaMemcpyDeviceToHost);   // R / R2 may have swapped on the device
@@ -1139,13 +1150,15 @@ extern "C" int bcg_solver_destroy(bcg_solver* s) {
 }
 
 static int ensure_mailbox(bcg_solver* s, int world) {
-  const int64_t sb = mail_slot_bytes_for(s->h.ld);
-  const int64_t bytes = 2 * (int64_t)world * sb;
-  if (s->mail && s->mail_bytes >= bytes) return BCG_OK;
-  if (s->mail) CK(cudaFree(s->mail));
-  CK(cudaMalloc(&s->mail, bytes));
-  CK(cudaMemset(s->mail, 0, bytes));
-  s->mail_bytes = bytes;
+  (void)world;
+  bcg_ctx* ctx = s->ctx;
+  const int64_t bytes = 2 * (int64_t)kMaxWorld * mail_slot_bytes_for(1024);
+  if (mail_slot_bytes_for(s->h.ld) > mail_slot_bytes_for(1024)) return fail(BCG_ERR_UNSUPPORTED, "row too long for the mailbox");
+  if (!ctx->mail) {
+    CK(cudaMalloc(&ctx->mail, bytes));
+    CK(cudaMemset(ctx->mail, 0, bytes));
+    ctx->mail_bytes = bytes;
+  }
   return BCG_OK;
 }
 
@@ -1155,7 +1168,7 @@ extern "C" int bcg_solver_comm_handle(bcg_solver* s, void* handle64) {
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle must be 64 bytes");
   RET(ensure_mailbox(s, kMaxWorld));
   cudaIpcMemHandle_t hnd;
-  CK(cudaIpcGetMemHandle(&hnd, s->mail));
+  CK(cudaIpcGetMemHandle(&hnd, s->ctx->mail));
   memcpy(handle64, &hnd, 64);
   return BCG_OK;
 }
@@ -1167,16 +1180,24 @@ extern "C" int bcg_solver_comm_connect(bcg_solver* s, int32_t world, int32_t ran
   RET(use_device(s->ctx));
   RET(ensure_mailbox(s, kMaxWorld));
   SolverState& h = s->h;
+  bcg_ctx* ctx = s->ctx;
   for (int p = 0; p < world; ++p) {
     if (p == rank) {
-      s->peer_ptrs[p] = s->mail;
+      s->peer_ptrs[p] = ctx->mail;
     } else {
-      cudaIpcMemHandle_t hnd;
-      memcpy(&hnd, (const char*)handles64 + 64 * p, 64);
+      std::array<unsigned char, 64> key;
+      memcpy(key.data(), (const char*)handles64 + 64 * p, 64);
       void* ptr = nullptr;
-      cudaError_t e = cudaIpcOpenMemHandle(&ptr, hnd, cudaIpcMemLazyEnablePeerAccess);
-      if (e != cudaSuccess)
-        return fail(BCG_ERR_COMM, "cudaIpcOpenMemHandle(rank %d) failed: %s", p, cudaGetErrorString(e));
+      for (auto& pc : ctx->peer_cache)
+        if (pc.first == key) { ptr = pc.second; break; }
+      if (!ptr) {
+        cudaIpcMemHandle_t hnd;
+        memcpy(&hnd, key.data(), 64);
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, hnd, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess)
+          return fail(BCG_ERR_COMM, "cudaIpcOpenMemHandle(rank %d) failed: %s", p, cudaGetErrorString(e));
+        ctx->peer_cache.emplace_back(key, ptr);
+      }
       s->peer_ptrs[p] = ptr;
     }
     h.mail_peer[p] = (unsigned char*)s->peer_ptrs[p];
@@ -1184,9 +1205,9 @@ extern "C" int bcg_solver_comm_connect(bcg_solver* s, int32_t world, int32_t ran
   s->peers_open = true;
   h.world = world;
   h.rank = rank;
-  h.mail_local = s->mail;
+  h.mail_local = ctx->mail;
   h.mail_slot_bytes = mail_slot_bytes_for(h.ld);
-  h.seq = 0;
+  h.seq = (++ctx->mail_epoch) << 32;
   RET(push_state(s));
   CK(cudaStreamSynchronize(s->ctx->stream));
   return BCG_OK;

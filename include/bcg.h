@@ -153,7 +153,10 @@ int  bcg_solver_create(bcg_ctx* ctx, bcg_vecs* v, int32_t alg, const double* b, 
                        int64_t row_offset, int64_t n_global, bcg_solver** out);
 int  bcg_solver_destroy(bcg_solver* s);
 /* N-sharding over GPUs of one node: every rank exports a 64-byte handle of its mailbox, the
- * host exchanges them (any transport), then every rank connects to all `world` handles. */
+ * host exchanges them (any transport), then every rank connects to all `world` handles.  The mailbox and the
+ * mapped peer mailboxes belong to the context and are reused by all its solvers (mapping a peer costs ~100 ms once).
+ * Ranks must connect their solvers in the same order, and must be synchronised (any host barrier) between
+ * bcg_solver_comm_connect and the first bcg_solver_build, and between build calls of DIFFERENT solvers. */
 int  bcg_solver_comm_handle(bcg_solver* s, void* handle64);
 int  bcg_solver_comm_connect(bcg_solver* s, int32_t world, int32_t rank, const void* handles64);
 /* run up to `itrs` greedy iterations entirely on the device (GIGA, FW).  events: host array of
