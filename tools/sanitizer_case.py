@@ -1,0 +1,25 @@
+"""small end-to-end case for compute-sanitizer (memcheck / racecheck): specialised and general projection kernels,
+persistent GIGA loop, OMP iterations with removals, optimize()"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'bayesian-coresets_b200')); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
+import numpy as np
+import bayesiancoresets_b200 as bc
+from conftest import lr_problem
+N, d = int(sys.argv[1]) if len(sys.argv) > 1 else 3000, 6
+for S in (256, 96):
+  Z, theta = lr_problem(1, N, d, S)
+  for fast in ('1', '2', '0'):
+    os.environ['BCG_PROJ_FAST'] = fast
+    prj = bc.LogisticRegressionProjector(lambda n, w, p: theta, S)
+    cs = bc.HilbertCoreset(Z, prj, snnls=bc.snnls.GIGA)
+    cs.build(12)
+  os.environ['BCG_PROJ_FAST'] = '1'
+  y = np.random.RandomState(0).poisson(2., size=(N, 1)).astype(float)
+  pp = bc.PoissonProjector(lambda n, w, p: theta, S)
+  v = pp.project_device(np.hstack((Z, y)))
+  cs = bc.HilbertCoreset(Z, prj, snnls=bc.snnls.OrthoPursuit)
+  cs.build(S//2 + 20)
+  cs.optimize()
+  print('S', S, 'omp size', cs.snnls.size(), 'error', cs.error(), flush=True)
+print('SANITIZER CASE DONE')
