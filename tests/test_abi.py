@@ -53,6 +53,20 @@ def test_no_cpu_fallback(built_lib):
   assert 'oracle' not in re.sub(r'""".*?"""', '', src, flags=re.S)
 
 
+def test_pinned_allocation_needs_a_device_too(built_lib):
+  """bc.pinned_empty is backed by bcg_host_alloc (cudaHostAlloc): without a CUDA device it raises like everything else"""
+  import bayesiancoresets_b200._native as nat
+  n = ctypes.c_int(-1)
+  rc = nat.lib().bcg_device_count(ctypes.byref(n))
+  if rc == 0 and n.value > 0:
+    pytest.skip('a GPU is present')
+  import bayesiancoresets_b200 as bc
+  with pytest.raises(nat.BcgError) as ei:
+    bc.pinned_empty((4, 3))
+  assert ei.value.code == 3
+  assert nat.lib().bcg_host_free(None) == 0
+
+
 def test_product_package_never_imports_oracle():
   for dirpath, _, files in os.walk(os.path.join(PKG_DIR, 'bayesiancoresets_b200')):
     for f in files:
