@@ -799,7 +799,7 @@ static int project_host_pipelined(bcg_ctx* ctx, int kmodel, const double* Z, int
     const int grid = (int)std::min<int64_t>((chunk_rows + kProjWarps - 1) / kProjWarps, (int64_t)ctx->sm_count);
     // staging and chunk buffers are context-owned (no cudaMallocHost / cudaMalloc / cudaFree per call)
     const bool direct = is_pinned(Z);                                    // page-locked source: no staging copy
-    RET(ensure_pins(ctx));
+    if (!direct) RET(ensure_pins(ctx));
     double* pin[2] = {reinterpret_cast<double*>(ctx->pin[0]), reinterpret_cast<double*>(ctx->pin[1])};
     double* dev[2] = {nullptr, nullptr};
     DevBuf<double> dT, dC, d_partial;
