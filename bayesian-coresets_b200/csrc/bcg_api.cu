@@ -23,6 +23,7 @@
 #include "project_fast_kernel.cuh"
 #include "project_sum_kernel.cuh"
 #include "project_sum_mma_kernel.cuh"
+#include "project_sum_mma2_kernel.cuh"
 #include "step_kernels.cuh"
 
 using namespace bcg;
@@ -644,7 +645,16 @@ static int project_common(bcg_dataset* ds, const int64_t* rowidx, int64_t nsel, 
     const int mma = env_int("BCG_PROJSUM_MMA", 1);
     const bool trace = env_int("BCG_PROJ_TRACE", 0) != 0;
     const auto t_launch = std::chrono::steady_clock::now();
-    if (mma >= 1) {
+    if (mma >= 2) {                                      // double-buffered tiles, conflict-free stores (to be measured)
+      auto launch2 = [&](auto kern) -> int {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPm2SmemBytes));
+        kern<<<grid, kPsThreads, kPm2SmemBytes, st>>>(pa);
+        return BCG_OK;
+      };
+      if (model == MODEL_LR) RET(launch2(project_sum_mma2_kernel<MODEL_LR>));
+      else if (model == MODEL_POISSON) RET(launch2(project_sum_mma2_kernel<MODEL_POISSON>));
+      else RET(launch2(project_sum_mma2_kernel<MODEL_LINEAR>));
+    } else if (mma >= 1) {
       if (model == MODEL_LR) project_sum_mma_kernel<MODEL_LR><<<grid, kPsThreads, 0, st>>>(pa);
       else if (model == MODEL_POISSON) project_sum_mma_kernel<MODEL_POISSON><<<grid, kPsThreads, 0, st>>>(pa);
       else project_sum_mma_kernel<MODEL_LINEAR><<<grid, kPsThreads, 0, st>>>(pa);
