@@ -304,3 +304,29 @@ def test_nnls_givens_removal_stress(lib):
     assert res_got <= res_ref*(1. + 1e-9) + 1e-9
     np.testing.assert_allclose(out[t], ref, rtol=1e-6, atol=1e-7*max(1., np.abs(ref).max()))
     active = ref > 0
+
+
+def test_nnls_dependent_columns_keep_the_optimal_residual(lib):
+  """duplicated columns (two data rows with the same vector): the dependent copy is refused by the Gram-Schmidt append
+  and stays at zero; the minimiser is then not unique, so the comparison with scipy.optimize.nnls is on the residual and
+  on feasibility, for the Givens-removal and the rebuild variant alike"""
+  from scipy.optimize import nnls
+  rng = np.random.RandomState(3)
+  S, N, K = 24, 120, 40
+  vecs = rng.randn(N, S) + 0.8
+  vecs[1::3] = vecs[0::3][:vecs[1::3].shape[0]]          # every third row duplicates its predecessor's source row
+  b = vecs[rng.choice(N, 30)].sum(axis=0) + 0.2*rng.randn(S)
+  cols = rng.permutation(N)[:K]
+  counts = list(range(1, K + 1))
+  for downdate in (1, 0):
+    out, A32, reb = run_nnls_sequence(lib, vecs, b, cols, counts, from_scratch=0, downdate=downdate)
+    active = np.zeros(K, dtype=bool)
+    for t, cnt in enumerate(counts):
+      active[cnt - 1] = True
+      ref = np.zeros(K)
+      ref[active] = nnls(A32[cols[active]].T, b, maxiter=100000)[0]
+      res_ref = np.linalg.norm(A32[cols].T.dot(ref) - b)
+      res_got = np.linalg.norm(A32[cols].T.dot(out[t]) - b)
+      assert np.all(out[t] >= 0) and np.all(out[t][~active] == 0)
+      assert res_got <= res_ref*(1. + 1e-8) + 1e-9, (downdate, t, res_got, res_ref)
+      active = out[t] > 0                                  # continue from OUR active set (what the device loop does)
