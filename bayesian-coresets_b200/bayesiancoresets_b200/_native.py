@@ -57,6 +57,7 @@ _PROTOTYPES = {
   'bcg_dataset_destroy': (_c.c_int, [_P]),
   'bcg_dataset_project': (_c.c_int, [_P, _P, _c.c_int64, _c.c_int32, _c.c_int32, _P, _c.c_int32, _P, _PP, _P, _P]),
   'bcg_dataset_project_linear': (_c.c_int, [_P, _P, _c.c_int64, _c.c_int32, _P, _P, _c.c_int32, _PP, _P, _P]),
+  'bcg_dataset_audit': (_c.c_int, [_P, _c.c_int32, _c.c_int32, _P, _c.c_int32, _P, _c.c_int32, _P, _P, _P, _P]),
   'bcg_vecs_shape': (_c.c_int, [_P, _c.POINTER(_c.c_int64), _c.POINTER(_c.c_int32), _c.POINTER(_c.c_int32)]),
   'bcg_vecs_colsum': (_c.c_int, [_P, _P]),
   'bcg_vecs_norm_sum': (_c.c_int, [_P, _c.POINTER(_c.c_double)]),
@@ -222,6 +223,21 @@ class Dataset(object):
     else:
       check(lib().bcg_dataset_project(self.handle, sel[0], sel[1], model, d, _ptr(theta), S, None, *outs))
     return (DeviceVecs(self.ctx, hv) if vecs else None), out_rows, out_cs
+
+  def audit(self, model, theta, Siginv=None, kind=ALG_FW, dirs=None, scores=True, norms=False, colsum=False):
+    """independent float64 re-evaluation of one selection pass from the raw data (bcg_dataset_audit):
+    returns (scores | None, norms | None, colsum | None) as host ndarrays"""
+    theta = _f64(np.atleast_2d(theta))
+    S, d = theta.shape
+    si = None if Siginv is None else _f64(Siginv)
+    dd = None if dirs is None else _f64(np.atleast_2d(dirs))
+    n = self.shape[0]
+    o_sc = np.empty(n) if (scores and dd is not None) else None
+    o_nr = np.empty(n) if norms else None
+    o_cs = np.empty(S) if colsum else None
+    p = lambda x: None if x is None else _ptr(x)
+    check(lib().bcg_dataset_audit(self.handle, model, d, _ptr(theta), S, p(si), kind, p(dd), p(o_sc), p(o_nr), p(o_cs)))
+    return o_sc, o_nr, o_cs
 
   def __del__(self):
     try:

@@ -25,6 +25,7 @@
 #include "project_sum_mma_kernel.cuh"
 #include "project_sum_mma2_kernel.cuh"
 #include "step_kernels.cuh"
+#include "audit_kernel.cuh"
 
 using namespace bcg;
 
@@ -779,6 +780,74 @@ static int prepare_model(int model, int d, const double* theta, int S, const dou
     return BCG_OK;
   }
   return fail(BCG_ERR_ARG, "unknown model %d", model);
+}
+
+// Independent float64 audit of one selection pass, recomputed from the raw data (audit_kernel.cuh).  Outputs are
+// host arrays and optional: scores (n; needs dirs), norms (n), colsum (S).
+template <int J>
+static int launch_audit(bcg_ctx* ctx, const AuditArgs& a) {
+  const int grid = ctx->sm_count * 8;
+  audit_score_kernel<J><<<grid, 256, 0, ctx->stream>>>(a);
+  CK(cudaGetLastError());
+  return BCG_OK;
+}
+
+extern "C" int bcg_dataset_audit(bcg_dataset* ds, int32_t model, int32_t d, const double* theta, int32_t S,
+                                 const double* Siginv, int32_t kind, const double* dirs, double* scores, double* norms,
+                                 double* colsum) {
+  if (!ds || !theta) return fail(BCG_ERR_ARG, "null argument");
+  RET(use_device(ds->ctx));
+  bcg_ctx* ctx = ds->ctx;
+  if (d <= 0 || S <= 0 || S > 1024) return fail(BCG_ERR_ARG, "bad shape d=%d S=%d", d, S);
+  if ((model == BCG_MODEL_POISSON ? d + 1 : d) > ds->zld) return fail(BCG_ERR_ARG, "dataset has too few columns");
+  if (scores && !dirs) return fail(BCG_ERR_ARG, "scores need the direction(s)");
+  const int ndir = kind == BCG_ALG_GIGA ? 2 : 1;
+  std::vector<double> tT, coff;
+  int kmodel = 0;
+  RET(prepare_model(model, d, theta, S, Siginv, tT, coff, &kmodel));
+  (void)kmodel;
+  std::vector<double> tt(S, 0.);
+  for (size_t i = 0; i < coff.size(); ++i) tt[i] = -2. * coff[i];
+  const int64_t n = ds->n;
+  if (n == 0) {
+    if (colsum) memset(colsum, 0, (size_t)S * sizeof(double));
+    return BCG_OK;
+  }
+  cudaStream_t st = ctx->stream;
+  DevBuf<double> dT, dtt, dSi, ddir, dsc, dnr, dcs;
+  CK(dT.alloc((size_t)d * S));
+  CK(cudaMemcpyAsync(dT, tT.data(), (size_t)d * S * sizeof(double), cudaMemcpyHostToDevice, st));
+  AuditArgs a;
+  a.Z = ds->Z; a.n = n; a.zld = ds->zld; a.d = d; a.S = S; a.model = model; a.kind = kind;
+  a.thetaT = dT; a.tt = nullptr; a.Siginv = nullptr; a.dirs = nullptr; a.scores = nullptr; a.norms = nullptr; a.colsum = nullptr;
+  if (model == BCG_MODEL_GAUSSIAN) {
+    CK(dtt.alloc(S));
+    CK(dSi.alloc((size_t)d * d));
+    CK(cudaMemcpyAsync(dtt, tt.data(), (size_t)S * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dSi, Siginv, (size_t)d * d * sizeof(double), cudaMemcpyHostToDevice, st));
+    a.tt = dtt; a.Siginv = dSi;
+  }
+  if (dirs) {
+    CK(ddir.alloc((size_t)ndir * S));
+    CK(cudaMemcpyAsync(ddir, dirs, (size_t)ndir * S * sizeof(double), cudaMemcpyHostToDevice, st));
+    a.dirs = ddir;
+  }
+  if (scores) { CK(dsc.alloc((size_t)n)); a.scores = dsc; }
+  if (norms) { CK(dnr.alloc((size_t)n)); a.norms = dnr; }
+  if (colsum) { CK(dcs.alloc(S)); CK(cudaMemsetAsync(dcs, 0, (size_t)S * sizeof(double), st)); a.colsum = dcs; }
+  switch (pow2ceil((S + 31) / 32)) {
+    case 1: RET(launch_audit<1>(ctx, a)); break;
+    case 2: RET(launch_audit<2>(ctx, a)); break;
+    case 4: RET(launch_audit<4>(ctx, a)); break;
+    case 8: RET(launch_audit<8>(ctx, a)); break;
+    case 16: RET(launch_audit<16>(ctx, a)); break;
+    default: RET(launch_audit<32>(ctx, a)); break;
+  }
+  if (scores) CK(cudaMemcpyAsync(scores, dsc, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (norms) CK(cudaMemcpyAsync(norms, dnr, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (colsum) CK(cudaMemcpyAsync(colsum, dcs, (size_t)S * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return BCG_OK;
 }
 
 // Projection straight from a HOST array, chunked and software-pipelined: while chunk c is being projected on

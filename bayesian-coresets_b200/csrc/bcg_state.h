@@ -16,6 +16,12 @@ struct ScanCand {
 constexpr int kMaxWorld = 8;        // GPUs of one NVSwitch node
 constexpr int kRescoreMax = 8;      // near-tie candidates re-scored in float64 per iteration
 
+// result of one CTA of the exact float64 selection pass (exact_scan_kernel): best local row, lowest row on ties
+struct ExactCand {
+  double score;
+  int64_t row;                      // -1: the CTA saw no comparable row
+};
+
 // mailbox slot written by one peer for one iteration parity (lives in IPC-shared device memory)
 struct MailHeader {
   unsigned long long seq;           // iteration sequence number, written last (release)
@@ -59,6 +65,20 @@ struct SolverState {
   ScanCand* cands;
   int32_t n_cands;
   int32_t comm_error;
+  // ---- exact-selection fallback ----------------------------------------------------------------
+  // The float32 scan publishes a bounded candidate set (one per warp / two per CTA).  Every scan warp also reports
+  // the best float32 score it saw but did NOT publish (cand_lost).  When an unpublished score, or more than
+  // kRescoreMax published ones, lie inside the near-tie window of the maximum, the candidate set may miss the
+  // float64 arg-max: need_exact is raised and the selection is redone by exact_scan_kernel (float64 over all local
+  // rows, lowest index on ties), whose per-CTA results land in exact_cands.
+  float* cand_lost;                 // n_cands (scan_kernel) or null
+  ExactCand* exact_cands;           // n_exact_cands entries
+  int32_t n_exact_cands;
+  int32_t need_exact;               // set by the scan's last CTA / the loop's control warp, cleared by the consumer
+  int32_t n_exact;                  // selections resolved by the exact pass so far (diagnostics)
+  int32_t iters_done;               // iterations consumed by the last persistent-kernel launch
+  unsigned int scan_done;           // CTA completion counter of scan_kernel (last CTA resets it)
+  int32_t check_monotone;           // snnls.py:9 check_error_monotone
   // ---- N-sharding mailboxes ----------------------------------------------------------------
   unsigned char* mail_local;        // this rank's mailbox: [2][world] slots
   unsigned char* mail_peer[kMaxWorld];  // mapped mailboxes of all ranks (self included)

@@ -16,6 +16,7 @@
  *   bcg_vecs_project_gaussian  projector.py:19-21 with examples/common/model_gaussian.py:4-10
  *   bcg_vecs_project_poisson   projector.py:19-21 with examples/common/model_poiss.py:25-38
  *   bcg_vecs_colsum / _rows    hilbert.py:24 / the ndarray returned by Projector.project
+ *   bcg_dataset_audit          projector.py:19-21 + giga.py:31-38 / frankwolfe.py:17 (independent float64 re-evaluation)
  *   bcg_solver_create          snnls/snnls.py:9-16 + giga.py:8-18 / frankwolfe.py:7-13 /
  *                              orthopursuit.py:9-15
  *   bcg_solver_build           snnls/snnls.py:31-79 driving giga.py:20-64 / frankwolfe.py:15-40
@@ -131,6 +132,15 @@ int  bcg_dataset_destroy(bcg_dataset* ds);
 int  bcg_dataset_project(bcg_dataset* ds, const int64_t* rowidx, int64_t nsel, int32_t model, int32_t d,
                          const double* theta, int32_t S, const double* Siginv, bcg_vecs** out_vecs,
                          double* rows64, double* colsum);
+/* Independent float64 AUDIT of one selection pass (csrc/audit_kernel.cuh): every data row's centred log-likelihood
+ * vector is recomputed from Z and theta in float64 with libdevice math (projector.py:19-21 + model_*.log_likelihood),
+ * normalised (giga.py:10-13) and scored against the direction(s) of one greedy iteration -- kind = BCG_ALG_GIGA:
+ * dirs = [cdir | xw] (2 x S), score = masked s0 / sqrt(1 - s1^2) (giga.py:31-38); otherwise dirs = [residual] (S),
+ * score = <a_n / ||a_n||, residual> (frankwolfe.py:17, orthopursuit.py:19, sparsevi.py:51).  Shares no code and no
+ * storage with the production scan.  All outputs are host arrays and optional: scores (n, needs dirs; -inf for zero
+ * rows), norms (n), colsum (S; hilbert.py:24).  Also the first half of the never-materialising select. */
+int  bcg_dataset_audit(bcg_dataset* ds, int32_t model, int32_t d, const double* theta, int32_t S, const double* Siginv,
+                       int32_t kind, const double* dirs, double* scores, double* norms, double* colsum);
 /* ll_ns = x_n . A_s + coff_s : the Gaussian model with A = theta Siginv (host S x d) and
  * coff_s = -0.5 theta_s Siginv theta_s precomputed by the caller */
 int  bcg_dataset_project_linear(bcg_dataset* ds, const int64_t* rowidx, int64_t nsel, int32_t d, const double* A,

@@ -665,3 +665,104 @@ def compare_projection_outputs(a, b, ref):
     np.testing.assert_allclose(a[5], b[5], rtol=1e-10, atol=1e-10*np.abs(b[5]).max())
     np.testing.assert_allclose(a[5], ref.sum(axis=0), rtol=1e-9, atol=1e-9*np.abs(ref).sum(axis=0).max())
     assert a[6] == pytest.approx(b[6], rel=1e-12) and a[7] == b[7] == 0
+
+
+# ---------------------------------------------------------------- independent float64 audit (bcg_dataset_audit)
+def audit_score_fn(nat, ds, model, theta, Siginv=None):
+  def fn(kind, dirs):
+    return ds.audit(model, theta, Siginv, kind=nat.ALG_GIGA if kind == 'giga' else nat.ALG_FW, dirs=dirs)[0]
+  return fn
+
+
+def test_audit_kernel_vs_oracle(bc):
+  """the audit scorer itself against the dense oracle: scores of one GIGA and one FW iteration, norms, column sums"""
+  import bayesiancoresets_b200._native as nat
+  Z, theta = lr_problem(5, 20000, 7, 200)
+  vecs = models.project(models.lr_loglik, Z, theta)
+  ds = nat.Dataset(Z)
+  for alg in ('giga', 'fw'):
+    o = greedy.ORACLES[alg](vecs.T, vecs.sum(axis=0))
+    o.build(7)
+    ref = o.scores()
+    if alg == 'giga':
+      xw, nw = o._unit_iterate()
+      xw = xw/nw
+      cdir = o.bn - o.bn.dot(xw)*xw
+      dirs = np.vstack((cdir/np.sqrt((cdir**2).sum()), xw))
+    else:
+      dirs = (o.b - o.A.dot(o.w))[np.newaxis, :]
+    sc, nr, cs = ds.audit(nat.MODEL_LR, theta, kind=nat.ALG_GIGA if alg == 'giga' else nat.ALG_FW, dirs=dirs, norms=True,
+                          colsum=True)
+    np.testing.assert_allclose(sc, ref, rtol=1e-9, atol=1e-11*np.abs(ref).max())
+    assert sc.argmax() == ref.argmax()
+    np.testing.assert_allclose(nr, np.sqrt((vecs**2).sum(axis=1)), rtol=1e-11)
+    np.testing.assert_allclose(cs, vecs.sum(axis=0), rtol=1e-9, atol=1e-10*np.abs(vecs).sum(axis=0).max())
+  # Gaussian and Poisson models: residual scores against dense NumPy
+  rng = np.random.RandomState(3)
+  x = rng.randn(3000, 9) + 1.
+  th = rng.randn(70, 9)
+  Si = np.eye(9) + 0.2*np.ones((9, 9))
+  vg = models.project(lambda a, t: models.gaussian_loglik(a, t, Si, 0.), x, th)
+  r = rng.randn(70)
+  sc = nat.Dataset(x).audit(nat.MODEL_GAUSSIAN, th, Si, dirs=r[np.newaxis, :])[0]
+  ref = vg.dot(r)/np.sqrt((vg**2).sum(axis=1))
+  np.testing.assert_allclose(sc, ref, rtol=1e-8, atol=1e-10*np.abs(ref).max())
+  g = load_golden('poisson_project_small')
+  vp, thp = g['vecs'], g['theta']
+  r = rng.randn(thp.shape[0])
+  sc = nat.Dataset(g['Z']).audit(nat.MODEL_POISSON, thp, dirs=r[np.newaxis, :])[0]
+  ref = vp.dot(r)/np.sqrt((vp**2).sum(axis=1))
+  np.testing.assert_allclose(sc, ref, rtol=1e-8, atol=1e-10*np.abs(ref).max())
+
+
+FULL_SIZE_REPORT = []
+
+
+@pytest.mark.parametrize('alg,N,S,itrs', [('giga', 1000000, 256, 60), ('fw', 1000000, 256, 60), ('omp', 1000000, 256, 60),
+                                         ('giga', 10000000, 512, 40), ('fw', 10000000, 512, 30), ('omp', 10000000, 512, 30)])
+def test_full_size_selection_equals_float64_audit(bc, alg, N, S, itrs):
+  """BASELINE configs[1] and the north-star / configs[3] size: the engine's whole build against the reference's
+  algorithm replayed in float64 (oracle/replay.py), where every O(N S) scoring pass is the independent audit kernel
+  (float64 from the raw data; no float32 storage, no shared code).  Indices exact, weights / error to 1e-5."""
+  import bayesiancoresets_b200._native as nat
+  from oracle import replay
+  Z, theta = lr_problem(0, N, 10, S)
+  prj = bc.LogisticRegressionProjector(lambda n, w, p: theta, S)
+  cs = bc.HilbertCoreset(Z, prj, snnls=algs(bc)[alg])
+  cs.build(itrs)
+  ev = cs.snnls.last_events
+  ds = nat.Dataset(Z)
+  _, norms, b = ds.audit(nat.MODEL_LR, theta, norms=True, colsum=True)
+  np.testing.assert_allclose(cs.snnls.b, b, rtol=1e-9, atol=1e-9*np.abs(b).max())
+  kw = {'norm_sum': norms.sum()} if alg == 'fw' else {}
+  r = replay.REPLAYS[alg](N, b, audit_score_fn(nat, ds, nat.MODEL_LR, theta),
+                          lambda idx: models.project(models.lr_loglik, Z[idx], theta), **kw)
+  rev = r.build(itrs)
+  gaps = np.array([g[1] for g in r.diag])
+  inwin = np.array([g[2] for g in r.diag])
+  FULL_SIZE_REPORT.append('audit %s N=%d S=%d: %d iterations, min top-2 gap %.3e (median %.3e), max rows inside the '
+                          'float32 near-tie window %d' % (alg, N, S, len(rev), gaps.min(), np.median(gaps), inwin.max()))
+  print(FULL_SIZE_REPORT[-1])
+  assert [(e.code, e.f) for e in ev] == [(e[0], e[1]) for e in rev]
+  w = cs.snnls.weights()
+  assert_weights_close(w, r.w)
+  norms_act = norms[r.idx]
+  atol = 2.**-24*float(np.abs(r.wa).dot(norms_act)) + 1e-300
+  np.testing.assert_allclose([e.error for e in ev], [e[2] for e in rev], rtol=W_RTOL, atol=atol)
+
+
+def test_full_size_vs_dense_host_oracle(bc):
+  """the affordable host test: the dense float64 oracle (= the reference, bit for bit) at N = 1e6, S = 256, 60 GIGA
+  iterations -- indices exact, weights and per-iteration error() to 1e-5 (snnls.py:31-79)"""
+  N, S, itrs = 1000000, 256, 60
+  Z, theta = lr_problem(0, N, 10, S)
+  vecs = models.project(models.lr_loglik, Z, theta)
+  o = greedy.GigaOracle(vecs.T, vecs.sum(axis=0))
+  oev = o.build(itrs)
+  prj = bc.LogisticRegressionProjector(lambda n, w, p: theta, S)
+  cs = bc.HilbertCoreset(Z, prj)
+  cs.build(itrs)
+  ev = cs.snnls.last_events
+  assert [(e.code, e.f) for e in ev] == [(e[0], e[1]) for e in oev]
+  assert_weights_close(cs.snnls.weights(), o.w)
+  assert_errors_close([e.error for e in ev], [e[2] for e in oev], vecs, o.w)
