@@ -82,6 +82,9 @@ _PROTOTYPES = {
   'bcg_solver_reset': (_c.c_int, [_P]),
   'bcg_solver_timing': (_c.c_int, [_P, _c.POINTER(_c.c_float), _c.POINTER(_c.c_float), _c.POINTER(_c.c_int32),
                                    _c.POINTER(_c.c_int32)]),
+  'bcg_solver_set_check_monotone': (_c.c_int, [_P, _c.c_int32]),
+  'bcg_solver_set_force_exact': (_c.c_int, [_P, _c.c_int32]),
+  'bcg_solver_exact_count': (_c.c_int, [_P, _c.POINTER(_c.c_int64)]),
   'bcg_solver_set_profiling': (_c.c_int, [_P, _c.c_int32]),
   'bcg_solver_set_trace': (_c.c_int, [_P, _c.c_int32]),
   'bcg_solver_get_trace': (_c.c_int, [_P, _c.c_int32, _P, _c.POINTER(_c.c_int32)]),
@@ -455,6 +458,17 @@ class NativeSolver(object):
 
   def reset(self):
     check(lib().bcg_solver_reset(self.handle))
+
+  def set_check_monotone(self, on):
+    check(lib().bcg_solver_set_check_monotone(self.handle, 1 if on else 0))
+
+  def set_force_exact(self, on):
+    check(lib().bcg_solver_set_force_exact(self.handle, 1 if on else 0))
+
+  def exact_count(self):
+    v = ctypes.c_int64()
+    check(lib().bcg_solver_exact_count(self.handle, ctypes.byref(v)))
+    return v.value
 
   def set_profiling(self, on):
     check(lib().bcg_solver_set_profiling(self.handle, 1 if on else 0))

@@ -20,9 +20,7 @@ class SparseNNLS(object):
   def __init__(self, A, b, check_error_monotone=True, comm=None):
     self.alg_name = self.__class__.__name__ + '-' + secrets.token_hex(3)
     self.log = logging.LoggerAdapter(logging.getLogger(), {'id': self.alg_name})
-    if not check_error_monotone:
-      raise NotImplementedError('the device loop always checks error monotonicity (snnls.py:56-61)')
-    self.check_error_monotone = True
+    self.check_error_monotone = bool(check_error_monotone)
     self.comm = comm or SerialComm()
     if isinstance(A, nat.DeviceVecsT):
       vecs = A.vecs                                   # already on the device: vecs.T of a GPU projector
@@ -45,6 +43,8 @@ class SparseNNLS(object):
       if e.code == nat.ERR_ZERO_B:
         raise NumericalPrecisionError('norm of b must be > 0')
       raise
+    if not self.check_error_monotone:
+      self._native.set_check_monotone(False)          # snnls.py:46,56: no monotone test, retry flag never cleared
     if self.comm.world > 1:
       handles = self.comm.allgather_object(self._native.comm_handle())
       self._native.comm_connect(self.comm.world, self.comm.rank, handles)

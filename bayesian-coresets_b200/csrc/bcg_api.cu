@@ -139,6 +139,7 @@ struct bcg_solver {
   bool use_loop;            // persistent cooperative kernel available for this shape
   LoopCtl* d_ctl;
   ScanCand* d_cta_cands;
+  float* d_cta_lost;
   unsigned int* d_claims;
   int claims_cap;
   NnlsWork nw;              // device buffers of the NNLS factorisation (host copy of the struct)
@@ -1047,7 +1048,7 @@ static int choose_scan_config(bcg_solver* s) {
   c.stages = std::max(1, env_int("BCG_SCAN_STAGES", 2));
   c.evict_first = env_int("BCG_SCAN_EVICT_FIRST", 0);
   const size_t budget = (size_t)(200 * 1024);
-  const size_t extra = 32 * sizeof(ScanCand) + 4 * (size_t)s->v->S * sizeof(double) + 64 + 16 * 8 * 12 + 128;   // loop kernel only
+  const size_t extra = 64 * sizeof(ScanCand) + 4 * (size_t)s->v->S * sizeof(double) + 64 + 16 * 8 * 12 + 128;   // loop kernel only
   auto ring = [&](int stages, int rps) { return (size_t)c.wpb * stages * rps * row_bytes + (size_t)c.wpb * stages * 8; };
   while (c.stages > 2 && ring(c.stages, c.rps) + extra > budget) --c.stages;
   while (c.rps > c.rb && ring(c.stages, c.rps) + extra > budget) c.rps -= c.rb;
@@ -1081,7 +1082,13 @@ static int launch_scan(bcg_solver* s) {
   a.cands = s->h.cands;
   a.skip0 = &s->d->halted;
   a.skip1 = &s->d->select_failed;
+  a.lost = s->h.cand_lost;
+  a.done = &s->d->scan_done;
+  a.need_exact = &s->d->need_exact;
+  a.force_exact = &s->d->force_exact;
   CK(scan_launch(s->sc, a, s->ctx->stream));
+  // exact float64 selection pass: returns at once unless the scan's last CTA found the candidate set ambiguous
+  CK(exact_scan_launch(s->h.n_exact_cands, s->d, 0, s->ctx->stream));
   return BCG_OK;
 }
 
@@ -1135,6 +1142,8 @@ static int solver_init(bcg_solver* s, bcg_ctx* ctx, bcg_vecs* v, int32_t alg, co
   h.err = bnorm;
   RET(choose_scan_config(s));
   h.n_cands = s->sc.grid * s->sc.wpb;
+  h.n_exact_cands = ctx->sm_count;
+  h.check_monotone = 1;
   cudaStream_t st = ctx->stream;
   std::vector<double> bn(S);
   for (int i = 0; i < S; ++i) bn[i] = bnorm > 0. ? b[i] / bnorm : 0.;
@@ -1151,6 +1160,10 @@ static int solver_init(bcg_solver* s, bcg_ctx* ctx, bcg_vecs* v, int32_t alg, co
   CK(cudaMalloc(&s->d, sizeof(SolverState)));
   CK(cudaMalloc(&s->d_ctl, sizeof(LoopCtl)));
   CK(cudaMalloc(&s->d_cta_cands, (size_t)2 * s->sc.grid * sizeof(ScanCand)));
+  CK(cudaMalloc(&s->d_cta_lost, (size_t)s->sc.grid * sizeof(float)));
+  CK(cudaMalloc(&h.cand_lost, (size_t)h.n_cands * sizeof(float)));
+  CK(cudaMalloc(&h.exact_cands, (size_t)h.n_exact_cands * sizeof(ExactCand)));
+  CK(cudaMemsetAsync(h.cand_lost, 0xff, (size_t)h.n_cands * sizeof(float), st));
   CK(cudaMemcpyAsync(h.b, b, S * sizeof(double), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(h.bn, bn.data(), S * sizeof(double), cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(h.xw, 0, S * sizeof(double), st));
@@ -1189,6 +1202,7 @@ extern "C" int bcg_solver_create(bcg_ctx* ctx, bcg_vecs* v, int32_t alg, const d
   s->use_loop = false;
   s->d_ctl = nullptr;
   s->d_cta_cands = nullptr;
+  s->d_cta_lost = nullptr;
   s->d_claims = nullptr;
   s->claims_cap = 0;
   memset(&s->nw, 0, sizeof(NnlsWork));
@@ -1214,7 +1228,8 @@ extern "C" int bcg_solver_destroy(bcg_solver* s) {
   SolverState& h = s->h;
   // (the mailbox and the peer mappings belong to the context and outlive the solver)
   void* bufs[] = {h.b, h.bn, h.xw, h.xw_new, h.xf, h.dir64, h.dir32, h.wrow, h.cands, h.act_idx, h.act_w,
-                  h.act_w_new, h.act_norm, h.act_tmp, h.act_rows, h.events, s->d_fout, s->d, s->d_ctl, s->d_cta_cands, s->d_trace, s->d_claims};
+                  h.act_w_new, h.act_norm, h.act_tmp, h.act_rows, h.events, s->d_fout, s->d, s->d_ctl, s->d_cta_cands, s->d_trace, s->d_claims,
+                  s->d_cta_lost, h.cand_lost, h.exact_cands};
   for (void* p : bufs)
     if (p) cudaFree(p);
   if (s->d_nw) cudaMemcpy(&s->nw, s->d_nw, sizeof(NnlsWork), cudaMemcpyDeviceToHost);   // R / R2 may have swapped on the device
@@ -1415,18 +1430,21 @@ extern "C" int bcg_solver_build(bcg_solver* s, int32_t itrs, double tol, bcg_ite
     s->loop_launches = 0;
     s->scan_ms = 0.f;
   } else if (loop) {
-    // the whole build call is ONE persistent cooperative kernel (loop_kernel.cuh)
+    // the whole build call is ONE persistent cooperative kernel (loop_kernel.cuh).  Rare exception: when the control
+    // warp finds the float32 candidate set ambiguous (an unpublished score inside the near-tie window) it stops before
+    // that iteration; the selection is redone exactly in float64 (exact_scan_kernel) and the loop is relaunched for the
+    // remaining iterations with that result.
     LoopArgs la;
     la.st = s->d;
     la.ctl = s->d_ctl;
     la.cta_cands = s->d_cta_cands;
+    la.cta_lost = s->d_cta_lost;
     la.g.An = s->v->An;
     la.g.n_rows = s->v->n;
     la.g.ld = s->v->ld;
     la.g.rps = s->sc.rps;
     la.g.stages = s->sc.stages;
     la.g.evict_first = s->sc.evict_first;
-    la.itrs = itrs;
     la.wpb = s->sc.wpb;
     if (s->claims_cap < itrs) {
       if (s->d_claims) CK(cudaFree(s->d_claims));
@@ -1434,7 +1452,6 @@ extern "C" int bcg_solver_build(bcg_solver* s, int32_t itrs, double tol, bcg_ite
       CK(cudaMalloc(&s->d_claims, (size_t)itrs * sizeof(unsigned int)));
       s->claims_cap = itrs;
     }
-    CK(cudaMemsetAsync(s->d_claims, 0, (size_t)itrs * sizeof(unsigned int), st));
     la.claims = s->d_claims;
     la.static_frac = (float)env_int("BCG_STATIC_PCT", 100) / 100.f;   // measured: a larger dynamic share only costs (atomics); the grid is HBM-bound either way
     la.l2_prefetch = env_int("BCG_L2_PREFETCH", 0);
@@ -1448,18 +1465,35 @@ extern "C" int bcg_solver_build(bcg_solver* s, int32_t itrs, double tol, bcg_ite
         s->trace_cap = itrs;
       }
       CK(cudaMemsetAsync(s->d_trace, 0, (size_t)itrs * 8 * sizeof(unsigned long long), st));
-      la.trace = s->d_trace;
       s->trace_n = itrs;
     }
-    CK(cudaMemsetAsync(s->d_ctl, 0, sizeof(LoopCtl), st));
     CK(cudaEventRecord(s->ev0, st));
-    CK(loop_launch(s->sc, la, st));
-    CK(cudaEventRecord(s->ev1, st));
-    RET(pull_state(s));
-    CK(cudaEventElapsedTime(&s->build_ms, s->ev0, s->ev1));
+    int done = 0;
+    s->loop_launches = 0;
     s->scan_launches = 0;
-    s->step_launches = 0;
-    s->loop_launches = 1;
+    la.cont = 0;
+    la.use_pre = 0;
+    for (;;) {
+      la.itrs = itrs - done;
+      la.trace = s->trace_on ? s->d_trace + (size_t)done * 8 : nullptr;
+      CK(cudaMemsetAsync(s->d_claims, 0, (size_t)la.itrs * sizeof(unsigned int), st));
+      CK(cudaMemsetAsync(s->d_ctl, 0, sizeof(LoopCtl), st));
+      CK(loop_launch(s->sc, la, st));
+      CK(cudaEventRecord(s->ev1, st));                                 // (re-recorded per launch: the last one counts)
+      s->loop_launches += 1;
+      RET(pull_state(s));
+      if (!h.need_exact || h.halted || h.comm_error) break;
+      done += h.iters_done;
+      if (done >= itrs) break;                                         // (cannot happen: the stop precedes an iteration)
+      step_kernel<<<1, kStepThreads, 0, st>>>(s->d, 0, 1, 0);          // float64 direction of the pending iteration
+      CK(exact_scan_launch(h.n_exact_cands, s->d, 1, st));
+      CK(cudaGetLastError());
+      s->scan_launches += 1;
+      la.cont = 1;
+      la.use_pre = 1;
+    }
+    CK(cudaEventElapsedTime(&s->build_ms, s->ev0, s->ev1));
+    s->step_launches = s->scan_launches;
     s->scan_ms = 0.f;
   } else {
     if (s->profiling) {
@@ -1653,6 +1687,30 @@ extern "C" int bcg_solver_timing(bcg_solver* s, float* build_ms, float* scan_ms,
   if (scan_ms) *scan_ms = s->scan_ms;
   if (scan_launches) *scan_launches = s->scan_launches;
   if (step_launches) *step_launches = s->step_launches + s->loop_launches;
+  return BCG_OK;
+}
+
+extern "C" int bcg_solver_set_check_monotone(bcg_solver* s, int32_t check) {
+  if (!s) return fail(BCG_ERR_ARG, "null solver");
+  RET(use_device(s->ctx));
+  s->h.check_monotone = check ? 1 : 0;
+  RET(push_state(s));
+  CK(cudaStreamSynchronize(s->ctx->stream));
+  return BCG_OK;
+}
+
+extern "C" int bcg_solver_set_force_exact(bcg_solver* s, int32_t on) {
+  if (!s) return fail(BCG_ERR_ARG, "null solver");
+  RET(use_device(s->ctx));
+  s->h.force_exact = on ? 1 : 0;
+  RET(push_state(s));
+  CK(cudaStreamSynchronize(s->ctx->stream));
+  return BCG_OK;
+}
+
+extern "C" int bcg_solver_exact_count(bcg_solver* s, int64_t* n_exact) {
+  if (!s || !n_exact) return fail(BCG_ERR_ARG, "null argument");
+  *n_exact = s->h.n_exact;
   return BCG_OK;
 }
 

@@ -79,6 +79,7 @@ struct SolverState {
   int32_t iters_done;               // iterations consumed by the last persistent-kernel launch
   unsigned int scan_done;           // CTA completion counter of scan_kernel (last CTA resets it)
   int32_t check_monotone;           // snnls.py:9 check_error_monotone
+  int32_t force_exact;              // testing: treat every candidate set as ambiguous
   // ---- N-sharding mailboxes ----------------------------------------------------------------
   unsigned char* mail_local;        // this rank's mailbox: [2][world] slots
   unsigned char* mail_peer[kMaxWorld];  // mapped mailboxes of all ranks (self included)

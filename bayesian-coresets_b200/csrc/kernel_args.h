@@ -24,6 +24,10 @@ struct ScanArgs {
   ScanCand* cands;        // gridDim.x * warps_per_block
   const int32_t* skip0;   // scan is skipped when *skip0 or *skip1 is non-zero (halted / select failed)
   const int32_t* skip1;
+  float* lost;            // gridDim.x * warps_per_block: best score each warp saw but did not publish
+  unsigned int* done;     // CTA completion counter (zero between launches)
+  int32_t* need_exact;    // raised by the last CTA when the candidate set may miss the float64 arg-max
+  const int32_t* force_exact;
 };
 
 struct LoopCtl {
@@ -37,6 +41,9 @@ struct LoopArgs {
   SolverState* st;
   LoopCtl* ctl;
   ScanCand* cta_cands;   // 2 per CTA: best and runner-up of the CTA's warps
+  float* cta_lost;       // 1 per CTA: best score the CTA saw but did not publish
+  int32_t cont;          // continuation of the same build() call after an exact-selection stop (keeps the retry flag)
+  int32_t use_pre;       // the first iteration takes its local winner from st->exact_cands (exact_scan_kernel)
   ScanGeom g;
   int32_t itrs;
   int32_t wpb;           // scan warps per CTA (blockDim.x = (wpb + 1) * 32)
@@ -64,6 +71,7 @@ bool scan_variant_exists(int ch, int lpr);
 int scan_variant_r(int ch, int lpr);
 cudaError_t scan_set_smem(const ScanConfig& c);
 cudaError_t scan_launch(const ScanConfig& c, const ScanArgs& a, cudaStream_t st);
+cudaError_t exact_scan_launch(int grid, SolverState* st, int force, cudaStream_t s);
 // kernels_loop.cu
 bool loop_variant_exists(int ch, int lpr);
 cudaError_t loop_set_smem(const ScanConfig& c);

@@ -47,4 +47,9 @@ cudaError_t scan_launch(const ScanConfig& c, const ScanArgs& a, cudaStream_t st)
   return cudaErrorInvalidValue;
 }
 
+cudaError_t exact_scan_launch(int grid, SolverState* st, int force, cudaStream_t s) {
+  exact_scan_kernel<<<grid, 512, 0, s>>>(st, force);
+  return cudaGetLastError();
+}
+
 }  // namespace bcg

@@ -286,9 +286,12 @@ __device__ void control_loop(const LoopArgs& a, double* sb, double* sbn, double*
   __syncwarp();
 
   int nact = st->nact;
-  int retried = 0;                       // snnls.py:40: local to the build() call
+  int retried = a.cont ? st->retried : 0;   // snnls.py:40: local to the build() call (kept across an exact-selection stop)
   int halted = 0;
-  int n_events = 0;
+  int stop_exact = 0;
+  int n_events = st->n_events;
+  const bool check_mono = st->check_monotone != 0;
+  const bool force_exact = st->force_exact != 0;
   double err = st->err;
   double sel_aux = 0.;
   int npos = 0;
@@ -349,13 +352,41 @@ __device__ void control_loop(const LoopArgs& a, double* sb, double* sbn, double*
     } else {
       // ---- winner: best fp32 candidate; near ties re-scored in float64 --------------------------
       const int nc = 2 * (int)G;
-      float top, second; uint32_t lrow, row2;
-      warp_top2(a.cta_cands, nc, lane, &top, &lrow, &second, &row2);
-      lscore = (double)top;
+      float top = -INFINITY, second = -INFINITY; uint32_t lrow = kNoRow, row2 = kNoRow;
+      bool ambiguous = false;
+      const bool pre = a.use_pre && it == 0;
+      if (pre) {
+        // this launch continues a build() call that stopped on an ambiguous candidate set: the local winner of its
+        // first iteration is the result of the exact float64 pass (exact_scan_kernel), one candidate per CTA
+        double ks = -INFINITY; long long kr = -1;
+        for (int i = lane; i < st->n_exact_cands; i += 32) {
+          const ExactCand x = st->exact_cands[i];
+          if (x.row >= 0 && (kr < 0 || x.score > ks || (x.score == ks && x.row < kr))) { ks = x.score; kr = x.row; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          const double s2 = __shfl_xor_sync(0xffffffffu, ks, off);
+          const long long r2 = __shfl_xor_sync(0xffffffffu, kr, off);
+          if (r2 >= 0 && (kr < 0 || s2 > ks || (s2 == ks && r2 < kr))) { ks = s2; kr = r2; }
+        }
+        lrow = kr < 0 ? kNoRow : (uint32_t)kr;
+        lscore = ks;
+        if (lane == 0) { st->need_exact = 0; st->n_exact += 1; }
+        __syncwarp();
+      } else {
+        float lostmax = -INFINITY;
+        for (int i = lane; i < (int)G; i += 32) lostmax = fmaxf(lostmax, __ldcg(a.cta_lost + i));
+        warp_top2(a.cta_cands, nc, lane, &top, &lrow, &second, &row2);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) lostmax = fmaxf(lostmax, __shfl_xor_sync(0xffffffffu, lostmax, off));
+        lscore = (double)top;
+        // exactness of the candidate set (SolverState::cand_lost): an unpublished score inside the near-tie window
+        ambiguous = (lrow != kNoRow) && (lostmax >= top - (2e-5f + 1e-5f * fabsf(top)) || force_exact);
+      }
       if (a.trace && lane == 0) a.trace[(size_t)it * 8 + 4] = globaltimer_ns();
       __syncwarp();
       const float thr = top - (2e-5f + 1e-5f * fabsf(top));
-      const bool near_tie = (lrow != kNoRow) && (row2 != kNoRow) && (second >= thr);
+      const bool near_tie = !pre && !ambiguous && (lrow != kNoRow) && (row2 != kNoRow) && (second >= thr);
       if (near_tie) {
         // rare path: gather up to kRescoreMax candidates within the threshold, re-score in float64
         uint32_t chosen[kRescoreMax];
@@ -367,6 +398,11 @@ __device__ void control_loop(const LoopArgs& a, double* sb, double* sbn, double*
           if (r2 == kNoRow || !(s2 >= thr)) break;
           chosen[nch++] = r2;
         }
+        if (nch == kRescoreMax) {               // more published candidates inside the window than are re-scored?
+          float s2; uint32_t r2;
+          warp_pick(a.cta_cands, nc, chosen, nch, lane, &s2, &r2);
+          ambiguous = (r2 != kNoRow) && (s2 >= thr);
+        }
         uint32_t brow = kNoRow; double best = -INFINITY;
         for (int r = 0; r < nch; ++r) {
           double xr[J];
@@ -375,6 +411,13 @@ __device__ void control_loop(const LoopArgs& a, double* sb, double* sbn, double*
           if (brow == kNoRow || sc > best || (sc == best && chosen[r] < brow)) { best = sc; brow = chosen[r]; }
         }
         lrow = brow; lscore = best;
+      }
+      if (ambiguous) {
+        // stop BEFORE this iteration: the host runs the exact float64 pass and relaunches (rare; bcg_solver_build)
+        if (lane == 0) st->need_exact = 1;
+        __syncwarp();
+        stop_exact = 1;
+        break;
       }
       const bool have = lrow != kNoRow;
       if (world == 1 && !have) {                 // no comparable score at all (non-finite matrix)
@@ -493,7 +536,7 @@ __device__ void control_loop(const LoopArgs& a, double* sb, double* sbn, double*
       wsum<3>(v);
       n2n = v[0]; bxn = v[1]; e2n = v[2];
       const double err_new = sqrt(e2n);
-      if (nonempty && err_new > err) {         // snnls.py:58-61
+      if (check_mono && nonempty && err_new > err) {         // snnls.py:56-61
         failed = true; fcode = BCG_IT_FAIL_MONOTONE; fa0 = err_new; fa1 = err;
       }
     }
@@ -517,7 +560,7 @@ __device__ void control_loop(const LoopArgs& a, double* sb, double* sbn, double*
     for (int j = 0; j < J; ++j) xw[j] = alpha * xw[j] + delta * xf[j];
     err = sqrt(e2n);
     n2 = n2n; bx = bxn; e2 = e2n;
-    if (nonempty) retried = 0;                  // snnls.py:62
+    if (check_mono && nonempty) retried = 0;    // snnls.py:62 (inside the monotone branch)
     const bool last = (it + 1 == a.itrs);
     if (a.trace && lane == 0) a.trace[(size_t)it * 8 + 7] = globaltimer_ns() + (unsigned long long)(err == 12345.678);
     __syncwarp();
@@ -587,6 +630,7 @@ __device__ void control_loop(const LoopArgs& a, double* sb, double* sbn, double*
     st->select_failed = sel_ok ? 0 : 1;
     st->sel_aux = sel_aux;
     st->seq = mc.seq;
+    st->iters_done = stop_exact ? it : a.itrs;
   }
 }
 
@@ -604,8 +648,8 @@ __global__ void __launch_bounds__(384, 1) greedy_loop_kernel(const LoopArgs a) {
   const uint32_t stage_floats = (uint32_t)q.rps * (uint32_t)q.ld;
   const size_t ring_bytes = (size_t)wpb * q.stages * stage_floats * sizeof(float);
   uint64_t* bars_all = reinterpret_cast<uint64_t*>(smem_raw + ring_bytes);
-  ScanCand* cta_c = reinterpret_cast<ScanCand*>(bars_all + wpb * q.stages);
-  double* sb = reinterpret_cast<double*>(cta_c + 32);
+  ScanCand* cta_c = reinterpret_cast<ScanCand*>(bars_all + wpb * q.stages);   // 64 slots (see the end of the scan loop)
+  double* sb = reinterpret_cast<double*>(cta_c + 64);
   double* sbn = sb + a.st->S;
 
   // shared memory after the rings: barriers | per-warp candidates | b, bn (2 S) | float64 directions (2 S) |
@@ -708,7 +752,7 @@ __global__ void __launch_bounds__(384, 1) greedy_loop_kernel(const LoopArgs a) {
     float4 d1[CH];
     Core::load_dirs(a.st->dir32, q.ld, nchunk, g, d0, d1);
 
-    float best = -INFINITY;
+    float best = -INFINITY, lost = -INFINITY;
     uint32_t brow = kNoRowU;
     while (outstanding > 0 && sm_it[slot] == it) {   // uniform: shared-memory broadcast reads
       mbar_wait(&bars[slot], parity);
@@ -717,7 +761,7 @@ __global__ void __launch_bounds__(384, 1) greedy_loop_kernel(const LoopArgs a) {
       const int nr = (int)(left < q.rps ? left : q.rps);
       const float* tile = wbuf + (size_t)slot * stage_floats;
       for (int b0 = 0; b0 < nr; b0 += Core::RB)
-        Core::batch(tile + (size_t)b0 * q.ld, q.ld, nchunk, g, grp, nr - b0, (uint32_t)(row0 + b0), d0, d1, best, brow);
+        Core::batch(tile + (size_t)b0 * q.ld, q.ld, nchunk, g, grp, nr - b0, (uint32_t)(row0 + b0), d0, d1, best, brow, lost);
       __syncwarp();   // every lane's shared-memory reads of this stage (and of its slot record) are complete
       --outstanding;
       issue_next();
@@ -739,23 +783,33 @@ __global__ void __launch_bounds__(384, 1) greedy_loop_kernel(const LoopArgs a) {
         tma_prefetch_l2(q.An + (size_t)row0 * q.ld, (uint32_t)q.rps * (uint32_t)q.ld * 4u, leader);
       }
     }
-    Core::warp_merge(best, brow);
-    if (lane == 0) { cta_c[warp].score = best; cta_c[warp].row = brow; }
+    Core::warp_merge_lost(best, brow, lost);
+    // per-warp results, double-buffered on the iteration parity: a warp that runs ahead into iteration it + 1 writes
+    // the other half, and its write of iteration it + 2 is ordered behind the barrier of it + 1, which warp 0 only
+    // joins after it has read iteration it.  Slots [par*16 + w]: candidate; [32 + par*16 + w].score: lost score.
+    ScanCand* cc = cta_c + (it & 1) * 16;
+    if (lane == 0) { cc[warp].score = best; cc[warp].row = brow; cc[32 + warp].score = lost; }
     named_bar_sync(1, wpb * 32);
     if (warp == 0) {
       // best and runner-up of the CTA's warps -> global, then arrive (release)
-      float s1 = -INFINITY; uint32_t r1 = kNoRowU;
-      if (lane < wpb) { s1 = cta_c[lane].score; r1 = cta_c[lane].row; }
+      float s1 = -INFINITY, l1 = -INFINITY; uint32_t r1 = kNoRowU;
+      if (lane < wpb) { s1 = cc[lane].score; r1 = cc[lane].row; l1 = cc[32 + lane].score; }
+      const float s_mine = s1; const uint32_t r_mine = r1;
       float bs = s1; uint32_t br = r1;
       Core::warp_merge(bs, br);
       if (r1 == br) { s1 = -INFINITY; r1 = kNoRowU; }     // exclude the winner, then second best
       float ss = s1; uint32_t sr = r1;
       Core::warp_merge(ss, sr);
+      // what the CTA does not publish: the warps' lost scores and every warp best other than the two above
+      if (r_mine != kNoRowU && r_mine != br && r_mine != sr) l1 = fmaxf(l1, s_mine);
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) l1 = fmaxf(l1, __shfl_xor_sync(0xffffffffu, l1, off));
       if (lane == 0) {
         ScanCand c0; c0.score = bs; c0.row = br;
         ScanCand c1; c1.score = ss; c1.row = sr;
         a.cta_cands[2 * blockIdx.x] = c0;
         a.cta_cands[2 * blockIdx.x + 1] = c1;
+        a.cta_lost[blockIdx.x] = l1;
         __threadfence();
         red_release_gpu_add(&ctl->arrive, 1u);
       }

@@ -357,7 +357,7 @@ BCG_HD void omp_iteration(const Blk& B, SolverState* st, NnlsWork* W, int prep_n
   nnls_solve(B, st, W, 0, 1);
   omp_mark(B, st, 10);
   const double err = st->err;
-  if (nonempty && err > prev_err) {                      // snnls.py:58-61: revert
+  if (st->check_monotone && nonempty && err > prev_err) {  // snnls.py:56-61: revert
     for (int k = B.tid; k < st->nact; k += B.nthr) st->act_w[k] = (k < nact0) ? st->act_w_new[k] : 0.;
     B.sync();
     if (B.tid == 0) W->valid = 0;
@@ -365,7 +365,7 @@ BCG_HD void omp_iteration(const Blk& B, SolverState* st, NnlsWork* W, int prep_n
     refresh_iterate(B, st);
     if (B.tid == 0) fail_event(st, BCG_IT_FAIL_MONOTONE, f, err, prev_err);
   } else if (B.tid == 0) {
-    if (nonempty) st->retried = 0;
+    if (st->check_monotone && nonempty) st->retried = 0;
     push_event(st, BCG_IT_OK, f, st->nact, err, 0., 0.);
   }
   B.sync();

@@ -147,7 +147,7 @@ struct ScanCore {
   // tile row 0 is row_base
   static __device__ __forceinline__ void batch(const float* tile, int ld, int nchunk, int g, int grp, int nvalid,
                                                uint32_t row_base, const float4 (&d0)[CH], const float4 (&d1)[CH],
-                                               float& best, uint32_t& brow) {
+                                               float& best, uint32_t& brow, float& lost) {
     float a0[R];
     float a1[R];
 #pragma unroll
@@ -184,8 +184,26 @@ struct ScanCore {
       } else {
         score = a0[t];
       }
-      if (rin < nvalid && score > best) { best = score; brow = row_base + (uint32_t)rin; }
+      // running best per lane; `lost` = the best score this lane saw and does NOT carry (exactness check of the
+      // candidate set: see SolverState::cand_lost)
+      if (rin < nvalid) {
+        if (score > best) { lost = fmaxf(lost, best); best = score; brow = row_base + (uint32_t)rin; }
+        else lost = fmaxf(lost, score);
+      }
     }
+  }
+
+  // merge the per-lane running bests of a warp and fold what the merge drops into `lost` (lanes that scored the
+  // same row -- LPR > R leaves several lanes with the complete sums of one row -- are not "dropped")
+  static __device__ __forceinline__ void warp_merge_lost(float& best, uint32_t& brow, float& lost) {
+    const float mine = best;
+    const uint32_t myrow = brow;
+    warp_merge(best, brow);
+    float l = lost;
+    if (myrow != brow && myrow != kNoRowU) l = fmaxf(l, mine);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) l = fmaxf(l, __shfl_xor_sync(0xffffffffu, l, off));
+    lost = l;
   }
 
   // merge the per-lane running bests of a warp

@@ -65,6 +65,11 @@ __device__ void mail_exchange(const Blk& B, SolverState* st, uint32_t lrow, doub
     if (gi < 0) continue;
     if (win < 0 || sc > best || (sc == best && gi < bidx)) { win = p; best = sc; bidx = gi; }
   }
+  if (win < 0) {                             // no rank has a comparable row (non-finite matrix entries)
+    if (B.tid == 0) { st->comm_error = 2; st->halted = 1; st->seq = seq; }
+    __syncthreads();
+    return;
+  }
   const unsigned char* wslot = st->mail_local + (int64_t)(par * W + win) * sb;
   const float* wsrc = reinterpret_cast<const float*>(wslot + sizeof(MailHeader));
   for (int s = B.tid; s < ld; s += B.nthr) st->wrow[s] = __ldcg(wsrc + s);

@@ -250,6 +250,23 @@ BCG_HD double row_score64(const Blk& B, const SolverState* st, const float* row)
 // ndarray.argmax).  force_rescore: always produce the float64 score (needed for cross-rank and
 // OMP comparisons).
 BCG_HD void pick_local(const Blk& B, SolverState* st, bool force_rescore, uint32_t* row_out, double* score_out) {
+  if (st->need_exact) {
+    // the float32 candidate set was ambiguous (SolverState::cand_lost): the local winner is the result of the exact
+    // float64 pass over all local rows (exact_scan_kernel), one candidate per CTA -> best score, lowest row on ties
+    double key = -INFINITY; int64_t id = -1; int pl = 0;
+    for (int i = B.tid; i < st->n_exact_cands; i += B.nthr) {
+      const ExactCand x = st->exact_cands[i];
+      if (x.row < 0) continue;
+      if (id < 0 || x.score > key || (x.score == key && x.row < id)) { key = x.score; id = x.row; }
+    }
+    blk_argbest(B, &key, &id, &pl);
+    B.sync();
+    if (B.tid == 0) { st->need_exact = 0; st->n_exact += 1; }
+    B.sync();
+    *row_out = id < 0 ? kNoRow : (uint32_t)id;
+    *score_out = key;
+    return;
+  }
   ScanCand* c = st->cands;
   const int n = st->n_cands;
   uint32_t chosen[kRescoreMax];
@@ -338,6 +355,12 @@ BCG_HD void finish_iteration(const Blk& B, SolverState* st) {
 
   uint32_t lrow; double lscore;
   pick_local(B, st, st->world > 1, &lrow, &lscore);
+  if (st->world == 1 && lrow == kNoRow) {    // no comparable score at all (non-finite matrix entries)
+    B.sync();
+    if (B.tid == 0) { st->comm_error = 2; st->halted = 1; }
+    B.sync();
+    return;
+  }
 
   int64_t f; double nf_stored; const float* frow;
   if (st->world > 1) {
@@ -427,7 +450,7 @@ BCG_HD void finish_iteration(const Blk& B, SolverState* st) {
 
   const double err_new = recompute_iterate(B, st, st->act_w_new, nact_new, st->xw_new);
 
-  if (nonempty && err_new > prev_err) {      // snnls.py:58-61: revert (nothing was committed)
+  if (st->check_monotone && nonempty && err_new > prev_err) {      // snnls.py:56-61: revert (nothing was committed)
     if (B.tid == 0) fail_event(st, BCG_IT_FAIL_MONOTONE, f, err_new, prev_err);
     B.sync();
     return;
@@ -438,7 +461,7 @@ BCG_HD void finish_iteration(const Blk& B, SolverState* st) {
   if (B.tid == 0) {
     st->nact = nact_new;
     st->err = err_new;
-    if (nonempty) st->retried = 0;           // snnls.py:62
+    if (st->check_monotone && nonempty) st->retried = 0;           // snnls.py:62 (inside the monotone branch)
     push_event(st, BCG_IT_OK, f, nact_new, err_new, lscore, 0.);
   }
   B.sync();
@@ -501,6 +524,12 @@ BCG_HD int64_t omp_select(const Blk& B, SolverState* st) {
   uint32_t lrow; double pos;
   pick_local(B, st, true, &lrow, &pos);
   omp_mark(B, st, 2);
+  if (st->world == 1 && lrow == kNoRow) {    // no comparable score at all (non-finite matrix entries)
+    B.sync();
+    if (B.tid == 0) { st->comm_error = 2; st->halted = 1; }
+    B.sync();
+    return -1;
+  }
   int64_t f; double nf_stored; const float* frow;
   if (st->world > 1) {
 #ifdef __CUDA_ARCH__

@@ -192,6 +192,15 @@ int  bcg_solver_active_rows(bcg_solver* s, int64_t first, int64_t count, double*
 /* overwrite the weights of the stored active rows (k must equal n_stored); recomputes A w and error */
 int  bcg_solver_set_weights(bcg_solver* s, const double* w, int64_t k);
 int  bcg_solver_reset(bcg_solver* s);
+/* snnls.py:9 `check_error_monotone` (default 1): with 0 the monotone-error test of snnls.py:56-61 is skipped -- and, as in
+ * the reference, the retry flag is then never cleared by a successful step */
+int  bcg_solver_set_check_monotone(bcg_solver* s, int32_t check);
+/* Exactness of the selection.  The float32 scan publishes a bounded candidate set and every scan warp reports the best
+ * score it did not publish; whenever such a score, or more than 8 published ones, lie inside the near-tie window of the
+ * float32 maximum, the selection is redone by an exact float64 pass over all local rows (lowest index on ties).
+ * exact_count: selections resolved that way so far.  set_force_exact(1): every selection takes the exact pass (tests). */
+int  bcg_solver_exact_count(bcg_solver* s, int64_t* n_exact);
+int  bcg_solver_set_force_exact(bcg_solver* s, int32_t on);
 /* device time of the last bcg_solver_build: total, and summed over the scan kernel launches */
 int  bcg_solver_timing(bcg_solver* s, float* build_ms, float* scan_ms, int32_t* scan_launches,
                        int32_t* step_launches);

@@ -19,6 +19,8 @@ struct Host {
   std::vector<double> norms, b, bn, xw, xw_new, xf, dir64, act_w, act_w_new, act_norm, act_tmp;
   std::vector<int64_t> act_idx;
   std::vector<ScanCand> cands;
+  std::vector<float> lost;
+  ExactCand exact;
   std::vector<bcg_iter_event> events;
   double sred[256];
 };
@@ -28,6 +30,9 @@ struct Host {
 void scan(Host& H, int nb) {
   SolverState& st = H.st;
   H.cands.assign(nb, ScanCand{-INFINITY, kNoRow});
+  H.lost.assign(nb, -INFINITY);
+  st.check_monotone = 1;
+  st.exact_cands = &H.exact; st.n_exact_cands = 1;
   if (st.halted || st.select_failed) return;
   for (int64_t r = 0; r < st.n_local; ++r) {
     const float* row = &H.An[(size_t)r * st.ld];
@@ -42,7 +47,29 @@ void scan(Host& H, int nb) {
       score = (a1 > -1.f && den > 0.f) ? a0 / sqrtf(den) : 0.f;
     }
     ScanCand& c = H.cands[r % nb];
-    if (c.row == kNoRow || score > c.score) { c.score = score; c.row = (uint32_t)r; }
+    float& lost = H.lost[r % nb];
+    if (c.row == kNoRow || score > c.score) { if (c.row != kNoRow) lost = fmaxf(lost, c.score); c.score = score; c.row = (uint32_t)r; }
+    else lost = fmaxf(lost, score);
+  }
+  // the exactness check of scan_kernel's last CTA and, when it fires, the exact float64 pass (exact_scan_kernel)
+  float top = -INFINITY, lm = -INFINITY;
+  for (int i = 0; i < nb; ++i) { if (H.cands[i].row != kNoRow) top = fmaxf(top, H.cands[i].score); lm = fmaxf(lm, H.lost[i]); }
+  const float thr = top - (2e-5f + 1e-5f * fabsf(top));
+  int cnt = 0;
+  for (int i = 0; i < nb; ++i) cnt += (H.cands[i].row != kNoRow && H.cands[i].score >= thr) ? 1 : 0;
+  if (top > -INFINITY && (lm >= thr || cnt > kRescoreMax || st.force_exact)) {
+    st.need_exact = 1;
+    H.exact.score = -INFINITY; H.exact.row = -1;
+    for (int64_t r = 0; r < st.n_local; ++r) {
+      const float* row = &H.An[(size_t)r * st.ld];
+      double v0 = 0., v1 = 0.;
+      for (int s = 0; s < st.S; ++s) {
+        v0 += (double)row[s] * H.dir64[s];
+        if (st.alg == BCG_ALG_GIGA) v1 += (double)row[s] * H.dir64[st.S + s];
+      }
+      const double sc = st.alg == BCG_ALG_GIGA ? giga_score64(v0, v1) : v0;
+      if (sc > H.exact.score) { H.exact.score = sc; H.exact.row = r; }
+    }
   }
 }
 }  // namespace

@@ -766,3 +766,91 @@ def test_full_size_vs_dense_host_oracle(bc):
   assert [(e.code, e.f) for e in ev] == [(e[0], e[1]) for e in oev]
   assert_weights_close(cs.snnls.weights(), o.w)
   assert_errors_close([e.error for e in ev], [e[2] for e in oev], vecs, o.w)
+
+
+# ---------------------------------------------------------------- exactness of the selection, API holes
+@pytest.mark.parametrize('alg,engine', [('giga', '2'), ('fw', '2'), ('omp', '2'), ('giga', '1')])
+def test_forced_exact_selection_equals_normal_path(bc, monkeypatch, alg, engine):
+  """every selection through the exact float64 pass (exact_scan_kernel; for GIGA / FW the persistent kernel stops and
+  is relaunched at every iteration) gives the same events as the float32 candidate path"""
+  monkeypatch.setenv('BCG_ENGINE', engine)
+  Z, theta = lr_problem(13, 30000, 6, 128)
+  prj = bc.LogisticRegressionProjector(lambda n, w, p: theta, 128)
+  a = bc.HilbertCoreset(Z, prj, snnls=algs(bc)[alg])
+  a.build(25)
+  b = bc.HilbertCoreset(Z, prj, snnls=algs(bc)[alg])
+  b.snnls._native.set_force_exact(True)
+  b.build(12)
+  b.build(13)                                   # incremental: the retry flag / state survive the relaunches
+  eva = [(e.code, e.f) for e in a.snnls.last_events]
+  assert b.snnls._native.exact_count() == 25
+  assert a.snnls._native.exact_count() == 0
+  np.testing.assert_allclose(b.snnls.weights(), a.snnls.weights(), rtol=1e-12, atol=0)
+  assert b.error() == pytest.approx(a.error(), rel=1e-12)
+  assert eva[12:] == [(e.code, e.f) for e in b.snnls.last_events]
+
+
+def test_near_ties_beyond_the_candidate_set_take_the_exact_pass(bc):
+  """13 rows whose scores differ by ~1e-6 (well inside the float32 near-tie window of 2e-5 + 1e-5 |top|, well above the
+  ~4e-9 noise of float32 storage), 12 of them adjacent: one warp scans them and publishes ONE candidate.  The engine
+  must notice the unpublished in-window scores and return the float64 arg-max (= the oracle's selection)."""
+  rng = np.random.RandomState(4)
+  N, S = 40000, 96
+  X = rng.randn(N, S)
+  f0 = greedy.GigaOracle(X.T, X.sum(axis=0)).select()
+  r = X[f0].copy()
+  X[20000:20012] = r
+  b = X.sum(axis=0)
+  bh, rh = b/np.linalg.norm(b), r/np.linalg.norm(r)
+  p = bh - bh.dot(rh)*rh
+  p /= np.linalg.norm(p)
+  for k in range(12):                             # cos(row, b) grows by ~1e-6 per step; the best one comes last
+    X[20000 + k] = np.linalg.norm(r)*(rh + 1e-6*(k + 1)*p)
+  for alg in ('giga', 'fw'):
+    o = greedy.ORACLES[alg](X.T, X.sum(axis=0))
+    oev = o.build(6)
+    assert oev[0][1] == 20011
+    s = algs(bc)[alg](X.T, X.sum(axis=0))
+    s.build(6)
+    assert [e.f for e in s.last_events] == [e[1] for e in oev]
+    assert s._native.exact_count() >= 1
+
+
+@pytest.mark.parametrize('alg', ['giga', 'fw', 'omp'])
+def test_check_error_monotone_false_follows_the_reference(bc, alg):
+  """snnls.py:9,46,56: without the monotone test the retry flag is never cleared by a successful step"""
+  X = np.eye(12)
+  o = greedy.ORACLES[alg](X.T, X.sum(axis=0), check_error_monotone=False)
+  oev = o.build(20)
+  s = algs(bc)[alg](X.T, X.sum(axis=0), check_error_monotone=False)
+  s.build(20)
+  # (FW: once all 12 axes are in, the residual is round-off noise and so is the next selection)
+  nsel = 12 if alg == 'fw' else len(oev)
+  assert [(e.code, e.f) for e in s.last_events][:nsel] == [(e[0], e[1]) for e in oev][:nsel]
+  if alg != 'fw':
+    assert s.reached_numeric_limit == o.reached_numeric_limit
+  np.random.seed(3)
+  Y = np.random.randn(3000, 40)
+  o = greedy.ORACLES[alg](Y.T, Y.sum(axis=0), check_error_monotone=False)
+  oev = o.build(60)
+  s = algs(bc)[alg](Y.T, Y.sum(axis=0), check_error_monotone=False)
+  s.build(60)
+  nsel = len(oev) if alg != 'omp' else 24
+  assert [(e.code, e.f) for e in s.last_events][:nsel] == [(e[0], e[1]) for e in oev][:nsel]
+
+
+@pytest.mark.parametrize('alg,engine', [('omp', '2'), ('giga', '1'), ('giga', '2'), ('fw', '1')])
+def test_non_finite_rows_fail_cleanly(bc, monkeypatch, alg, engine):
+  """NaN in the data: b and the direction become NaN, the scan yields no candidate.  Every engine must report an
+  error (BCG_ERR_STATE) instead of reading out of bounds; the context stays usable afterwards."""
+  monkeypatch.setenv('BCG_ENGINE', engine)
+  rng = np.random.RandomState(0)
+  X = rng.randn(5000, 32)
+  X[17, 3] = np.nan
+  s = algs(bc)[alg](X.T, X.sum(axis=0))
+  with pytest.raises(bc.BcgError):
+    s.build(5)
+  Y = rng.randn(500, 32)
+  t = bc.snnls.GIGA(Y.T, Y.sum(axis=0))
+  t.build(5)
+  assert t.size() > 0
