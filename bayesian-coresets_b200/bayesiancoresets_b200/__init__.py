@@ -13,6 +13,6 @@ from . import util
 from . import snnls
 from .projector import (Projector, BlackBoxProjector, LogisticRegressionProjector, GaussianProjector,
                         PoissonProjector)
-from .coreset import Coreset, HilbertCoreset, SparseVICoreset, BatchPSVICoreset
+from .coreset import Coreset, HilbertCoreset, SparseVICoreset, BatchPSVICoreset, UniformSamplingCoreset
 from ._native import DeviceVecs, Dataset, Context, BcgError, pinned_empty, pinned_copy
 from . import comm

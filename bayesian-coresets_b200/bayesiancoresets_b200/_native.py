@@ -67,6 +67,7 @@ _PROTOTYPES = {
   'bcg_vecs_destroy': (_c.c_int, [_P]),
   'bcg_solver_create': (_c.c_int, [_P, _P, _c.c_int32, _P, _c.c_double, _c.c_int64, _c.c_int64, _PP]),
   'bcg_solver_destroy': (_c.c_int, [_P]),
+  'bcg_ctx_comm_handle': (_c.c_int, [_P, _P]),
   'bcg_solver_comm_handle': (_c.c_int, [_P, _P]),
   'bcg_solver_comm_connect': (_c.c_int, [_P, _c.c_int32, _c.c_int32, _P]),
   'bcg_solver_build': (_c.c_int, [_P, _c.c_int32, _c.c_double, _c.POINTER(IterEvent), _c.POINTER(_c.c_int32)]),
@@ -79,6 +80,7 @@ _PROTOTYPES = {
   'bcg_solver_active': (_c.c_int, [_P, _c.c_int64, _P, _P, _c.POINTER(_c.c_int64)]),
   'bcg_solver_active_rows': (_c.c_int, [_P, _c.c_int64, _c.c_int64, _P]),
   'bcg_solver_set_weights': (_c.c_int, [_P, _P, _c.c_int64]),
+  'bcg_solver_set_active': (_c.c_int, [_P, _P, _P, _c.c_int64]),
   'bcg_solver_reset': (_c.c_int, [_P]),
   'bcg_solver_timing': (_c.c_int, [_P, _c.POINTER(_c.c_float), _c.POINTER(_c.c_float), _c.POINTER(_c.c_int32),
                                    _c.POINTER(_c.c_int32)]),
@@ -88,6 +90,12 @@ _PROTOTYPES = {
   'bcg_solver_set_profiling': (_c.c_int, [_P, _c.c_int32]),
   'bcg_solver_set_trace': (_c.c_int, [_P, _c.c_int32]),
   'bcg_solver_get_trace': (_c.c_int, [_P, _c.c_int32, _P, _c.POINTER(_c.c_int32)]),
+  'bcg_comm_create': (_c.c_int, [_c.c_char_p, _c.c_int32, _c.c_int32, _c.c_int32, _c.c_int32, _PP]),
+  'bcg_comm_destroy': (_c.c_int, [_P]),
+  'bcg_comm_rank': (_c.c_int, [_P, _c.POINTER(_c.c_int32), _c.POINTER(_c.c_int32)]),
+  'bcg_comm_allgather': (_c.c_int, [_P, _P, _c.c_int64, _P]),
+  'bcg_comm_allreduce_f64': (_c.c_int, [_P, _P, _c.c_int64, _c.c_int32]),
+  'bcg_comm_barrier': (_c.c_int, [_P]),
 }
 EXPORTED_SYMBOLS = sorted(_PROTOTYPES)
 
@@ -190,6 +198,12 @@ class Context(object):
     f, t = ctypes.c_int64(), ctypes.c_int64()
     check(lib().bcg_ctx_mem_info(self.handle, ctypes.byref(f), ctypes.byref(t)))
     return f.value, t.value
+
+  def comm_handle(self):
+    """64-byte IPC handle of this context's N-sharding mailbox"""
+    buf = ctypes.create_string_buffer(64)
+    check(lib().bcg_ctx_comm_handle(self.handle, buf))
+    return buf.raw
 
   def flush_l2(self, nbytes=256 << 20):
     check(lib().bcg_ctx_flush_l2(self.handle, int(nbytes)))
@@ -455,6 +469,11 @@ class NativeSolver(object):
   def set_weights(self, w):
     w = _f64(w)
     check(lib().bcg_solver_set_weights(self.handle, _ptr(w), w.shape[0]))
+
+  def set_active(self, idx, w):
+    idx = np.ascontiguousarray(idx, dtype=np.int64)
+    w = _f64(w)
+    check(lib().bcg_solver_set_active(self.handle, _ptr(idx), _ptr(w), idx.shape[0]))
 
   def reset(self):
     check(lib().bcg_solver_reset(self.handle))

@@ -5,7 +5,7 @@ column-sum-only projection on the device, the N x S matrix is never written -- p
 projection and (K, S, d) gradients of the K pseudo-points, which are K-sized host algebra."""
 import numpy as np
 from ..util import nn_opt
-from ..comm import SerialComm, shard_layout
+from ..comm import SerialComm, shard_layout, local_part
 from .coreset import Coreset
 
 
@@ -16,12 +16,10 @@ class BatchPSVICoreset(Coreset):
     # (one S-vector per gradient step); the K pseudo-points and their optimiser state are replicated
     self.comm = comm or SerialComm()
     self.row_offset, self.n_global, _ = shard_layout(self.comm, data.shape[0])
-    if self.comm.world > 1 and n_subsample_opt is not None:
-      raise NotImplementedError('subsampling with N-sharding is not supported')
     self.data = data
     self.ll_projector = ll_projector
     self.opt_itrs = opt_itrs
-    self.n_subsample_opt = None if n_subsample_opt is None else min(data.shape[0], n_subsample_opt)
+    self.n_subsample_opt = None if n_subsample_opt is None else min(self.n_global, n_subsample_opt)
     self.step_sched = step_sched
     super().__init__(**kw)
 
@@ -42,8 +40,11 @@ class BatchPSVICoreset(Coreset):
     prj.update(w, p)
     sub, scaling = None, 1.
     if self.n_subsample_opt is not None:
-      sub = np.random.randint(self.data.shape[0], size=self.n_subsample_opt)
-      scaling = self.data.shape[0]/self.n_subsample_opt
+      # drawn over the GLOBAL index range, identically on every rank (SPMD); each rank projects its part
+      sub = np.random.randint(self.n_global, size=self.n_subsample_opt)
+      scaling = self.n_global/self.n_subsample_opt
+      if self.comm.world > 1:
+        sub = local_part(sub, self.row_offset, self.data.shape[0])[1]
     if hasattr(prj, 'project_sum'):
       local = prj.project_sum(self.data, cache=True, sub=sub)      # rows gathered on the device
     else:

@@ -7,7 +7,7 @@ once, the greedy loop exchanges candidates over NVLink inside the step kernel, a
 ends with the same (wts, idcs, pts)."""
 import numpy as np
 from ..snnls.giga import GIGA
-from ..comm import SerialComm, gather_rows
+from ..comm import SerialComm, gather_rows, shard_layout, local_part
 from .. import _native as nat
 from .coreset import Coreset
 
@@ -20,17 +20,23 @@ class HilbertCoreset(Coreset):
       sub_idcs = None                                   # identity (the reference's np.arange(N) is an O(N) host array)
       vecs = project(data)
     else:
-      if self.comm.world > 1:
-        raise NotImplementedError('n_subsample with N-sharding is not supported')
-      # hilbert.py:13-22: sorted, de-duplicated subsample from the global RNG, zero rows removed
-      sub_idcs = np.unique(np.random.randint(data.shape[0], size=n_subsample))
-      on_device = hasattr(ll_projector, 'project_device')
-      sub_project = (lambda idx: project(data, sub=idx)) if on_device else (lambda idx: project(data[idx]))
-      vecs = sub_project(sub_idcs)
+      # hilbert.py:13-22: sorted, de-duplicated subsample from the global RNG, zero rows removed.  With N-sharding
+      # every rank draws the SAME subsample of the global index range (SPMD: identical seeded RNG state on the
+      # ranks) and keeps the part that falls into its shard; the solver then shards the subsample.
+      self._data_offset, n_total, _ = shard_layout(self.comm, data.shape[0])
+      sub_global = np.unique(np.random.randint(n_total, size=n_subsample))
+      _, mine = local_part(sub_global, self._data_offset, data.shape[0])
+      # (the subsample is gathered on the host and projected once: uploading all of `data` for it would be wasted)
+      sub_project = lambda idx: project(data[idx])
+      vecs = sub_project(mine)
       nonzero = (vecs.norms() > 0.) if isinstance(vecs, nat.DeviceVecs) else (np.sqrt((vecs**2).sum(axis=1)) > 0.)
       if not nonzero.all():
-        sub_idcs = sub_idcs[nonzero]
-        vecs = sub_project(sub_idcs)
+        mine = mine[nonzero]
+        vecs = sub_project(mine)
+      if self.comm.world > 1:
+        sub_idcs = np.concatenate(self.comm.allgather_object(mine + self._data_offset))
+      else:
+        sub_idcs = mine
     b = vecs.sum(axis=0)
     extra = {}
     if self.comm.world > 1:
@@ -44,7 +50,7 @@ class HilbertCoreset(Coreset):
   @property
   def sub_idcs(self):
     """hilbert.py:11,16 -- materialised on demand in the identity case"""
-    return np.arange(self.data.shape[0]) if self._sub_idcs is None else self._sub_idcs
+    return np.arange(self.snnls.n_global) if self._sub_idcs is None else self._sub_idcs
 
   def reset(self):
     self.snnls.reset()
@@ -55,8 +61,9 @@ class HilbertCoreset(Coreset):
     idx, w = self.snnls.weights_sparse()
     self.wts = w
     if self.comm.world > 1:
-      self.idcs = idx
-      self.pts = gather_rows(self.comm, self.data, self.snnls.row_offset, idx)
+      self.idcs = idx if self._sub_idcs is None else self._sub_idcs[idx]
+      off = self.snnls.row_offset if self._sub_idcs is None else self._data_offset
+      self.pts = gather_rows(self.comm, self.data, off, self.idcs)
     else:
       self.idcs = idx if self._sub_idcs is None else self._sub_idcs[idx]
       self.pts = self.data[self.idcs]

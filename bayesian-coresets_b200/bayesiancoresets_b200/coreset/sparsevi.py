@@ -10,7 +10,7 @@ Host-side pieces (sampler, nn_opt, the K-sized algebra) stay NumPy, in the refer
 order, so seeded runs consume the global RNG identically."""
 import numpy as np
 from ..util import nn_opt
-from ..comm import SerialComm, shard_layout
+from ..comm import SerialComm, shard_layout, local_part
 from .. import _native as nat
 from .coreset import Coreset
 
@@ -22,12 +22,10 @@ class SparseVICoreset(Coreset):
     # the selection arg-max is resolved over the ranks (lowest global index wins ties), indices are global
     self.comm = comm or SerialComm()
     self.row_offset, self.n_global, _ = shard_layout(self.comm, data.shape[0])
-    if self.comm.world > 1 and (n_subsample_select is not None or n_subsample_opt is not None):
-      raise NotImplementedError('subsampling with N-sharding is not supported')
     self.data = data
     self.ll_projector = ll_projector
-    self.n_subsample_select = None if n_subsample_select is None else min(data.shape[0], n_subsample_select)
-    self.n_subsample_opt = None if n_subsample_opt is None else min(data.shape[0], n_subsample_opt)
+    self.n_subsample_select = None if n_subsample_select is None else min(self.n_global, n_subsample_select)
+    self.n_subsample_opt = None if n_subsample_opt is None else min(self.n_global, n_subsample_opt)
     self.step_sched = step_sched
     self.opt_itrs = opt_itrs
     super().__init__(**kw)
@@ -43,8 +41,18 @@ class SparseVICoreset(Coreset):
     self.ll_projector.update(w, p)
     if n_subsample is None:
       return 1., None
-    sub = np.random.randint(self.data.shape[0], size=n_subsample)
-    return self.data.shape[0]/n_subsample, sub
+    # the draw is over the GLOBAL index range; with N-sharding every rank draws the same indices (SPMD: identical
+    # seeded RNG state) and projects the ones that fall into its shard
+    sub = np.random.randint(self.n_global, size=n_subsample)
+    return self.n_global/n_subsample, sub
+
+  def _local(self, sub):
+    """(positions within the draw, local rows) of this rank's part of a global draw; (None, None) without subsampling"""
+    if sub is None:
+      return None, None
+    if self.comm.world == 1:
+      return np.arange(sub.shape[0]), sub
+    return local_part(sub, self.row_offset, self.data.shape[0])
 
   def _corevecs(self, S):
     if self.pts.size > 0:
@@ -77,7 +85,8 @@ class SparseVICoreset(Coreset):
   # ---- sparsevi.py:44-67 -------------------------------------------------------------------------
   def _select(self):
     scaling, sub = self._draw(self.n_subsample_select, self.wts, self.pts)
-    vecs = self._device_vecs(sub)
+    pos, loc = self._local(sub)
+    vecs = self._device_vecs(loc)
     S = vecs.shape[1]
     corevecs = self._corevecs(S)
     total = vecs.sum(axis=0)
@@ -85,9 +94,12 @@ class SparseVICoreset(Coreset):
       total = self.comm.allreduce_sum(total)
     resid = scaling*total - self.wts.dot(corevecs)
     # corrs = vecs.dot(resid)/||vecs_n||/S : arg-max and maximum on the device
+    # (np.argmax over the subsample: the lowest POSITION in the draw wins ties; without subsampling position = index)
     best, dot = vecs.argmax_dot(resid)
+    if best >= 0:
+      best = int(pos[best]) if pos is not None else self.row_offset + best
     if self.comm.world > 1:
-      cands = [c for c in self.comm.allgather_object((dot, self.row_offset + best if best >= 0 else -1)) if c[1] >= 0]
+      cands = [c for c in self.comm.allgather_object((dot, best)) if c[1] >= 0]
       dot, best = max(cands, key=lambda c: (c[0], -c[1]))
     corr_max = dot/S
     corecorrs = np.fabs(corevecs.dot(resid)/np.sqrt((corevecs**2).sum(axis=1)))/S
@@ -103,7 +115,7 @@ class SparseVICoreset(Coreset):
   def _optimize(self):
     def grd(w):
       scaling, sub = self._draw(self.n_subsample_opt, w, self.pts)
-      colsum = self._sum(sub)
+      colsum = self._sum(self._local(sub)[1])
       corevecs = self._corevecs(colsum.shape[0])
       resid = scaling*colsum - w.dot(corevecs)
       return -corevecs.dot(resid)/corevecs.shape[1]

@@ -1,5 +1,6 @@
-"""Greedy sparse-NNLS solvers (reference: bayesiancoresets/snnls/__init__.py:1-4).  The
-sampling baselines of the reference (snnls/sampling.py) are out of scope of this engine."""
+"""Sparse-NNLS solvers (reference: bayesiancoresets/snnls/__init__.py:1-4): the greedy solvers run on the device; the
+sampling baselines are O(1) per iteration and only use the device for error() / optimize()."""
 from .base import SparseNNLS
 from .giga import GIGA, FrankWolfe
 from .orthopursuit import OrthoPursuit
+from .sampling import ImportanceSampling, UniformSampling

@@ -3,15 +3,14 @@
 optimize / reset, attributes w / A / b / reached_numeric_limit -- with the greedy loop running
 on the device through the C-ABI (bcg_solver_build)."""
 import logging
-import os
 import secrets
+import struct
 import numpy as np
-from scipy.optimize import nnls
 
 from .. import util
 from ..util import NumericalPrecisionError
 from .. import _native as nat
-from ..comm import SerialComm, shard_layout
+from ..comm import SerialComm
 
 
 class SparseNNLS(object):
@@ -33,10 +32,23 @@ class SparseNNLS(object):
     self.b = np.asarray(b, dtype=np.float64)
     self._vecs = vecs
     self.reached_numeric_limit = False
-    if vecs.zero_rows() > 0:
-      raise ValueError(self.alg_name + '.__init__(): A must not have any 0 columns')
-    self.row_offset, self.n_global, self._counts = shard_layout(self.comm, vecs.shape[0])
-    norm_sum = float(self.comm.allreduce_sum(np.array([vecs.norm_sum()]))[0])
+    # One collective for the whole bootstrap: (local rows, zero rows, sum of local norms, mailbox handle) of every
+    # rank in a fixed-size blob.  Every rank derives the same layout / totals from it (sums in rank order), and a
+    # zero column anywhere raises on EVERY rank -- no rank is left waiting in a collective.
+    nloc, zloc, nsum_loc = vecs.shape[0], vecs.zero_rows(), vecs.norm_sum()
+    if self.comm.world > 1:
+      blob = struct.pack('<qqd', nloc, zloc, nsum_loc) + vecs.ctx.comm_handle()
+      parts = self.comm.allgather_bytes(blob)
+      meta = [struct.unpack('<qqd', p[:24]) for p in parts]
+      handles = [p[24:88] for p in parts]
+    else:
+      meta, handles = [(nloc, zloc, nsum_loc)], None
+    self._counts = [int(m[0]) for m in meta]
+    self.row_offset, self.n_global = sum(self._counts[:self.comm.rank]), sum(self._counts)
+    self._check_zero_columns(sum(int(m[1]) for m in meta))
+    norm_sum = 0.
+    for m in meta:
+      norm_sum += m[2]
     try:
       self._native = nat.NativeSolver(vecs, self._alg, self.b, norm_sum, self.row_offset, self.n_global)
     except nat.BcgError as e:
@@ -46,9 +58,12 @@ class SparseNNLS(object):
     if not self.check_error_monotone:
       self._native.set_check_monotone(False)          # snnls.py:46,56: no monotone test, retry flag never cleared
     if self.comm.world > 1:
-      handles = self.comm.allgather_object(self._native.comm_handle())
       self._native.comm_connect(self.comm.world, self.comm.rank, handles)
-      self.comm.barrier()
+      # (build() starts with a barrier: no rank scans before every rank has connected)
+
+  def _check_zero_columns(self, total):
+    if total > 0:                                     # giga.py:11-12, frankwolfe.py:11-12, orthopursuit.py:13-14
+      raise ValueError(self.alg_name + '.__init__(): A must not have any 0 columns')
 
   # ---- state ---------------------------------------------------------------------------------
   def reset(self):
@@ -72,6 +87,15 @@ class SparseNNLS(object):
   @property
   def w(self):
     return self.weights()
+
+  @w.setter
+  def w(self, value):
+    """assigning the dense weight vector (the reference's `self.w = ...`) becomes a sparse active-set write"""
+    if self.comm.world > 1:
+      raise NotImplementedError('assigning w is single-process only')
+    value = np.asarray(value, dtype=np.float64)
+    idx = np.flatnonzero(value != 0)
+    self._native.set_active(idx, value[idx])
 
   def size(self):
     return int((self._native.active()[1] > 0).sum())
@@ -124,28 +148,12 @@ class SparseNNLS(object):
     return events
 
   # ---- NNLS re-solve on the active set (snnls.py:82-97) --------------------------------------
-  def _active_problem(self):
-    """stored indices/weights and the float64 S x k matrix of the active (w > 0) columns in
-    ascending index order -- what `self.A[:, w > 0]` is in the reference"""
-    idx, w = self._native.active()
-    rows = self._native.active_rows(0, idx.shape[0])
-    pos = np.flatnonzero(w > 0)
-    pos = pos[np.argsort(idx[pos], kind='stable')]
-    return idx, w, pos, np.ascontiguousarray(rows[pos].T)
-
   def optimize(self):
     prev_cost = self.error()
     idx, w = self._native.active()
     if not (w > 0).any():
       return
-    if os.environ.get('BCG_NNLS', 'device') == 'scipy':
-      idx, w, pos, Aact = self._active_problem()
-      res = nnls(Aact, self.b, maxiter=100*self.n_global)
-      w_new = w.copy()
-      w_new[pos] = res[0]
-      self._native.set_weights(w_new)
-    else:
-      self._native.nnls(from_scratch=True)          # float64 Lawson-Hanson on the device (csrc/nnls_logic.h)
+    self._native.nnls(from_scratch=True)            # float64 Lawson-Hanson on the device (csrc/nnls_logic.h)
     new_cost = self.error()
     if new_cost > prev_cost*(1. + util.TOL):
       self.log.warning('self.optimize() returned a solution with increasing error. Numeric limit possibly '

@@ -21,9 +21,8 @@
 #include "kernel_args.h"
 #include "project_kernels.cuh"
 #include "project_fast_kernel.cuh"
-#include "project_sum_kernel.cuh"
 #include "project_sum_mma_kernel.cuh"
-#include "project_sum_mma2_kernel.cuh"
+#include "project_mma_kernel.cuh"
 #include "step_kernels.cuh"
 #include "audit_kernel.cuh"
 
@@ -35,6 +34,15 @@ using namespace bcg;
 static thread_local char g_err[512] = "";
 
 static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+// error setter for the other translation units of the library (bcg_comm.cu)
+int bcg_set_error(int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
@@ -148,6 +156,7 @@ struct bcg_solver {
   int trace_on;
   unsigned long long* d_trace;
   int trace_cap, trace_n;
+  int events_cap;           // capacity of h.events (kept across build calls)
   int64_t* d_fout;
   void* peer_ptrs[kMaxWorld];
   bool peers_open;
@@ -211,24 +220,31 @@ extern "C" int bcg_ctx_create(int device, bcg_ctx** out) {
   c->flush_bytes = 0;
   c->pin[0] = c->pin[1] = nullptr;
   for (int i = 0; i < 8; ++i) { c->scratch[i] = nullptr; c->scratch_bytes[i] = 0; }
-  CK(cudaSetDevice(device));
-  CK(cudaGetDeviceProperties(&c->prop, device));
-  if (c->prop.major < 10)
-    return fail(BCG_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
-                c->prop.major, c->prop.minor);
-  c->sm_count = c->prop.multiProcessorCount;
-  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  c->stream = nullptr;
+  c->copy_stream = nullptr;
   c->mail = nullptr;
   c->mail_bytes = 0;
   c->mail_epoch = 0;
   c->sp_tab = nullptr;
-  if (env_int("BCG_FAST_LINK", 1)) {
-    std::vector<double> tab(kSpTableDoubles);
-    softplus_table_build(tab.data());
-    CK(cudaMalloc(&c->sp_tab, kSpTableDoubles * sizeof(double)));
-    CK(cudaMemcpy(c->sp_tab, tab.data(), kSpTableDoubles * sizeof(double), cudaMemcpyHostToDevice));
-  }
+  auto body = [&]() -> int {
+    CK(cudaSetDevice(device));
+    CK(cudaGetDeviceProperties(&c->prop, device));
+    if (c->prop.major < 10)
+      return fail(BCG_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                  c->prop.major, c->prop.minor);
+    c->sm_count = c->prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    if (env_int("BCG_FAST_LINK", 1)) {
+      std::vector<double> tab(kSpTableDoubles);
+      softplus_table_build(tab.data());
+      CK(cudaMalloc(&c->sp_tab, kSpTableDoubles * sizeof(double)));
+      CK(cudaMemcpy(c->sp_tab, tab.data(), kSpTableDoubles * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    return BCG_OK;
+  };
+  const int rc = body();
+  if (rc != BCG_OK) { bcg_ctx_destroy(c); return rc; }    // (bcg_ctx_destroy leaves the error message alone)
   *out = c;
   return BCG_OK;
 }
@@ -244,8 +260,8 @@ extern "C" int bcg_ctx_destroy(bcg_ctx* ctx) {
     if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
   for (int i = 0; i < 2; ++i)
     if (ctx->pin[i]) { cudaFreeHost(ctx->pin[i]); cudaEventDestroy(ctx->pin_done[i]); }
-  cudaStreamDestroy(ctx->stream);
-  cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
   return BCG_OK;
 }
@@ -539,21 +555,6 @@ static int launch_project_fast(bcg_ctx* ctx, const ProjectArgs& a, int grid, siz
   return BCG_OK;
 }
 
-template <int J2, int MODEL>
-static int launch_project_pair(bcg_ctx* ctx, const ProjectArgs& a, int grid, size_t smem) {
-  CK(cudaFuncSetAttribute(project_pair_kernel<J2, MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  project_pair_kernel<J2, MODEL><<<grid, kPairThreads, smem, ctx->stream>>>(a);
-  CK(cudaGetLastError());
-  return BCG_OK;
-}
-
-template <int J2>
-static int launch_project_pair_model(bcg_ctx* ctx, const ProjectArgs& a, int grid, size_t smem) {
-  if (a.model == MODEL_LR) return launch_project_pair<J2, MODEL_LR>(ctx, a, grid, smem);
-  if (a.model == MODEL_POISSON) return launch_project_pair<J2, MODEL_POISSON>(ctx, a, grid, smem);
-  return launch_project_pair<J2, MODEL_LINEAR>(ctx, a, grid, smem);
-}
-
 template <int J2>
 static int launch_project_fast_model(bcg_ctx* ctx, const ProjectArgs& a, int grid, size_t smem) {
   if (a.model == MODEL_LR) return launch_project_fast<J2, MODEL_LR>(ctx, a, grid, smem);
@@ -561,22 +562,52 @@ static int launch_project_fast_model(bcg_ctx* ctx, const ProjectArgs& a, int gri
   return launch_project_fast<J2, MODEL_LINEAR>(ctx, a, grid, smem);
 }
 
+template <int MODEL, int MI>
+static int launch_project_mma(bcg_ctx* ctx, const ProjectArgs& a, int grid) {
+  const size_t smem = project_mma_smem(a.S, MI);
+  CK(cudaFuncSetAttribute(project_mma_kernel<MODEL, MI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  project_mma_kernel<MODEL, MI><<<grid, kPjThreads, smem, ctx->stream>>>(a);   // (CTAs without rows write zero partial sums)
+  CK(cudaGetLastError());
+  return BCG_OK;
+}
+
+template <int MI>
+static int launch_project_mma_model(bcg_ctx* ctx, const ProjectArgs& a, int grid) {
+  if (a.model == MODEL_LR) return launch_project_mma<MODEL_LR, MI>(ctx, a, grid);
+  if (a.model == MODEL_POISSON) return launch_project_mma<MODEL_POISSON, MI>(ctx, a, grid);
+  return launch_project_mma<MODEL_LINEAR, MI>(ctx, a, grid);
+}
+
+// the DMMA materialising projection (project_mma_kernel.cuh) applies when the unit-row matrix is written, S is 64, 128,
+// 256 or 512 and the links come from the table; the partial column sums need room for its grid (see project_mma_grid_cap)
+static bool project_mma_ok(const ProjectArgs& a) {
+  return env_int("BCG_PROJ_MMA", 1) && a.An && !a.out64 && a.ld == a.S &&
+         (a.S == 64 || a.S == 128 || a.S == 256 || a.S == 512) && (a.model == MODEL_LINEAR || a.sp_tab != nullptr);
+}
+
+// CTAs (= rows of the partial column-sum buffer) of a projection launch over at most a.n rows
+static int project_grid(bcg_ctx* ctx, const ProjectArgs& a) {
+  if (project_mma_ok(a)) {
+    const int WR = 8 / (a.S / 64);
+    const bool resident = a.d <= kPjKT;
+    const int bm = (resident ? 8 : 32) * WR;
+    return (int)std::min<int64_t>((a.n + bm - 1) / bm, (int64_t)ctx->sm_count * (resident ? 2 : 1));
+  }
+  return (int)std::min<int64_t>((a.n + kProjWarps - 1) / kProjWarps, (int64_t)ctx->sm_count);
+}
+
 // K3 launch: the specialised kernels (project_fast_kernel.cuh) for S in {64, 128, 256, 512} with the whole sample tile
 // in shared memory and table links, the general kernel otherwise (BCG_PROJ_FAST=0 forces the general kernel)
 static int dispatch_project(bcg_ctx* ctx, const ProjectArgs& a, int grid, size_t smem) {
-  // 1 (default): one warp per row; 2: two warps per row (measured slower: 0.546 vs 0.506 ms per 209715 x 512 chunk);
-  // 0: general kernel (0.897 ms)
+  if (project_mma_ok(a)) {
+    // MI = 1: the whole sample tile resident (d <= 16); MI = 4: streamed k tiles, 32-row blocks (any d)
+    if (a.d <= kPjKT) return launch_project_mma_model<1>(ctx, a, grid);
+    return launch_project_mma_model<4>(ctx, a, grid);
+  }
+  // BCG_PROJ_FAST=0 forces the general kernel
   const int fast = env_int("BCG_PROJ_FAST", 1);
   const bool fast_ok = fast && !a.out64 && a.ld == a.S && a.d <= 32 && a.ktile >= a.d &&
                        (a.model == MODEL_LINEAR || a.sp_tab != nullptr);
-  if (fast_ok && fast >= 2) {
-    switch (a.S) {
-      case 128: return launch_project_pair_model<1>(ctx, a, grid, smem);
-      case 256: return launch_project_pair_model<2>(ctx, a, grid, smem);
-      case 512: return launch_project_pair_model<4>(ctx, a, grid, smem);
-      default: break;
-    }
-  }
   if (fast_ok) {
     switch (a.S) {
       case 64: return launch_project_fast_model<1>(ctx, a, grid, smem);
@@ -634,7 +665,7 @@ static int project_common(bcg_dataset* ds, const int64_t* rowidx, int64_t nsel, 
   RET(ctx_scratch(ctx, 4, sizeof(unsigned long long), (void**)&d_zero));
 
   if (!out_vecs && !rows64 && colsum && d >= env_int("BCG_PROJSUM_MIN_D", 24) && n >= 4096) {
-    // K3b, GEMM-shaped: register-tiled float64 kernel (project_sum_kernel.cuh)
+    // K3b, GEMM-shaped: float64 tensor-core kernel (project_sum_mma_kernel.cuh)
     const int64_t nrb = (n + kPsBM - 1) / kPsBM;
     const int grid = (int)std::min<int64_t>(nrb, (int64_t)ctx->sm_count);
     RET(ctx_scratch(ctx, 5, (size_t)grid * S * sizeof(double), (void**)&d_partial));
@@ -642,29 +673,16 @@ static int project_common(bcg_dataset* ds, const int64_t* rowidx, int64_t nsel, 
     ProjectSumArgs pa;
     pa.Z = ds->Z; pa.rowidx = d_idx; pa.thetaT = dT; pa.coff = dC; pa.partial = d_partial; pa.n = n; pa.zld = ds->zld; pa.d = d; pa.S = S;
     pa.model = model; pa.sp_tab = ctx->sp_tab;
-    // float64 tensor cores (DMMA) for the contraction by default (ncu, N=1e6 d=200 S=512: LR 15.1 ms vs 17.1 ms on
-    // the FMA pipe; Gaussian 1.8x faster); BCG_PROJSUM_MMA=0 selects the FMA-pipe kernel
-    const int mma = env_int("BCG_PROJSUM_MMA", 1);
     const bool trace = env_int("BCG_PROJ_TRACE", 0) != 0;
     const auto t_launch = std::chrono::steady_clock::now();
-    if (mma >= 2) {                                      // double-buffered tiles, conflict-free stores (to be measured)
-      auto launch2 = [&](auto kern) -> int {
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPm2SmemBytes));
-        kern<<<grid, kPsThreads, kPm2SmemBytes, st>>>(pa);
-        return BCG_OK;
-      };
-      if (model == MODEL_LR) RET(launch2(project_sum_mma2_kernel<MODEL_LR>));
-      else if (model == MODEL_POISSON) RET(launch2(project_sum_mma2_kernel<MODEL_POISSON>));
-      else RET(launch2(project_sum_mma2_kernel<MODEL_LINEAR>));
-    } else if (mma >= 1) {
-      if (model == MODEL_LR) project_sum_mma_kernel<MODEL_LR><<<grid, kPsThreads, 0, st>>>(pa);
-      else if (model == MODEL_POISSON) project_sum_mma_kernel<MODEL_POISSON><<<grid, kPsThreads, 0, st>>>(pa);
-      else project_sum_mma_kernel<MODEL_LINEAR><<<grid, kPsThreads, 0, st>>>(pa);
-    } else {                                             // float64 FMA pipe
-      if (model == MODEL_LR) project_sum_kernel<MODEL_LR><<<grid, kPsThreads, 0, st>>>(pa);
-      else if (model == MODEL_POISSON) project_sum_kernel<MODEL_POISSON><<<grid, kPsThreads, 0, st>>>(pa);
-      else project_sum_kernel<MODEL_LINEAR><<<grid, kPsThreads, 0, st>>>(pa);
-    }
+    auto launch_sum = [&](auto kern) -> int {
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPm2SmemBytes));
+      kern<<<grid, kPsThreads, kPm2SmemBytes, st>>>(pa);
+      return BCG_OK;
+    };
+    if (model == MODEL_LR) RET(launch_sum(project_sum_mma_kernel<MODEL_LR>));
+    else if (model == MODEL_POISSON) RET(launch_sum(project_sum_mma_kernel<MODEL_POISSON>));
+    else RET(launch_sum(project_sum_mma_kernel<MODEL_LINEAR>));
     CK(cudaGetLastError());
     project_sum_finish_kernel<<<1, 256, 0, st>>>(d_partial, grid, S, d_out);
     CK(cudaGetLastError());
@@ -687,18 +705,19 @@ static int project_common(bcg_dataset* ds, const int64_t* rowidx, int64_t nsel, 
     return fail(BCG_ERR_UNSUPPORTED, "projection tile does not fit shared memory for S=%d", S);
   const int ktile = (int)std::min<size_t>(std::min<size_t>(kProjKTile, (size_t)d), (budget - cs_bytes) / ((size_t)S * sizeof(double)));
   const size_t smem = (size_t)ktile * S * sizeof(double) + cs_bytes;
-  const int64_t nbatch = (n + kProjWarps - 1) / kProjWarps;
-  const int grid = (int)std::min<int64_t>(nbatch, (int64_t)ctx->sm_count);
   bcg_vecs* v = nullptr;
   if (out_vecs) RET(vecs_alloc(ctx, n, S, &v));
+  int grid = 0;
   auto body = [&]() -> int {
-    RET(ctx_scratch(ctx, 5, (size_t)grid * (S + 1) * sizeof(double), (void**)&d_partial));
     CK(cudaMemsetAsync(d_zero, 0, sizeof(unsigned long long), st));
     if (rows64) CK(d_rows.alloc((size_t)n * S));
     ProjectArgs a;
     a.Z = ds->Z; a.rowidx = d_idx; a.theta = dT; a.coff = dC; a.An = v ? v->An : nullptr; a.norms = v ? v->norms : nullptr;
-    a.out64 = d_rows; a.partial = d_partial; a.zero_rows = d_zero; a.n = n; a.zld = ds->zld; a.d = d; a.S = S;
+    a.out64 = d_rows; a.partial = nullptr; a.zero_rows = d_zero; a.n = n; a.zld = ds->zld; a.d = d; a.S = S;
     a.ld = ld; a.model = model; a.ktile = ktile; a.sp_tab = ctx->sp_tab;
+    grid = project_grid(ctx, a);
+    RET(ctx_scratch(ctx, 5, (size_t)grid * (S + 1) * sizeof(double), (void**)&d_partial));
+    a.partial = d_partial;
     RET(dispatch_project(ctx, a, grid, smem));
     if (v) {
       RET(finish_colsum(v, d_partial, grid, d_zero));
@@ -876,7 +895,10 @@ static int project_host_pipelined(bcg_ctx* ctx, int kmodel, const double* Z, int
     if (rows_cap < 1) return fail(BCG_ERR_UNSUPPORTED, "a data row of %d doubles exceeds the staging chunk", zld);
     const int64_t chunk_rows = std::min<int64_t>(n, std::min<int64_t>(rows_cap, std::max<int64_t>(4096, ((int64_t)16 << 20) / row_bytes)));
     const int nchunks = (int)((n + chunk_rows - 1) / chunk_rows);
-    const int grid = (int)std::min<int64_t>((chunk_rows + kProjWarps - 1) / kProjWarps, (int64_t)ctx->sm_count);
+    ProjectArgs proto;                                                   // what decides the kernel and its grid
+    proto.An = v->An; proto.out64 = nullptr; proto.n = chunk_rows; proto.d = d; proto.S = S; proto.ld = ld; proto.model = kmodel;
+    proto.sp_tab = ctx->sp_tab;
+    const int grid = project_grid(ctx, proto);
     // staging and chunk buffers are context-owned (no cudaMallocHost / cudaMalloc / cudaFree per call)
     const bool direct = is_pinned(Z);                                    // page-locked source: no staging copy
     if (!direct) RET(ensure_pins(ctx));
@@ -1070,7 +1092,7 @@ static int choose_scan_config(bcg_solver* s) {
   return BCG_OK;
 }
 
-static int launch_scan(bcg_solver* s) {
+static int launch_scan(bcg_solver* s, cudaEvent_t e0 = nullptr, cudaEvent_t e1 = nullptr) {
   ScanArgs a;
   a.g.An = s->v->An;
   a.g.n_rows = s->v->n;
@@ -1086,7 +1108,9 @@ static int launch_scan(bcg_solver* s) {
   a.done = &s->d->scan_done;
   a.need_exact = &s->d->need_exact;
   a.force_exact = &s->d->force_exact;
+  if (e0) CK(cudaEventRecord(e0, s->ctx->stream));
   CK(scan_launch(s->sc, a, s->ctx->stream));
+  if (e1) CK(cudaEventRecord(e1, s->ctx->stream));
   // exact float64 selection pass: returns at once unless the scan's last CTA found the candidate set ambiguous
   CK(exact_scan_launch(s->h.n_exact_cands, s->d, 0, s->ctx->stream));
   return BCG_OK;
@@ -1146,7 +1170,7 @@ static int solver_init(bcg_solver* s, bcg_ctx* ctx, bcg_vecs* v, int32_t alg, co
   h.check_monotone = 1;
   cudaStream_t st = ctx->stream;
   std::vector<double> bn(S);
-  for (int i = 0; i < S; ++i) bn[i] = bnorm > 0. ? b[i] / bnorm : 0.;
+  for (int i = 0; i < S; ++i) bn[i] = bnorm == 0. ? 0. : b[i] / bnorm;   // (a non-finite b propagates, as in giga.py:18)
   CK(cudaMalloc(&h.b, S * sizeof(double)));
   CK(cudaMalloc(&h.bn, S * sizeof(double)));
   CK(cudaMalloc(&h.xw, S * sizeof(double)));
@@ -1211,6 +1235,7 @@ extern "C" int bcg_solver_create(bcg_ctx* ctx, bcg_vecs* v, int32_t alg, const d
   s->trace_on = 0;
   s->d_trace = nullptr;
   s->trace_cap = s->trace_n = 0;
+  s->events_cap = 0;
   s->profiling = 0;
   s->build_ms = s->scan_ms = 0.f;
   s->scan_launches = s->step_launches = s->loop_launches = 0;
@@ -1240,6 +1265,28 @@ extern "C" int bcg_solver_destroy(bcg_solver* s) {
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   delete s;
+  return BCG_OK;
+}
+
+static int ensure_ctx_mailbox(bcg_ctx* ctx) {
+  const int64_t bytes = 2 * (int64_t)kMaxWorld * mail_slot_bytes_for(1024);
+  if (!ctx->mail) {
+    CK(cudaMalloc(&ctx->mail, bytes));
+    CK(cudaMemset(ctx->mail, 0, bytes));
+    ctx->mail_bytes = bytes;
+  }
+  return BCG_OK;
+}
+
+// the mailbox belongs to the context: its handle can be exported before any solver exists, so the host can fold the
+// handle exchange into the same all-gather as the row counts
+extern "C" int bcg_ctx_comm_handle(bcg_ctx* ctx, void* handle64) {
+  if (!ctx || !handle64) return fail(BCG_ERR_ARG, "null argument");
+  RET(use_device(ctx));
+  RET(ensure_ctx_mailbox(ctx));
+  cudaIpcMemHandle_t hnd;
+  CK(cudaIpcGetMemHandle(&hnd, ctx->mail));
+  memcpy(handle64, &hnd, 64);
   return BCG_OK;
 }
 
@@ -1369,9 +1416,14 @@ extern "C" int bcg_solver_build(bcg_solver* s, int32_t itrs, double tol, bcg_ite
   cudaStream_t st = s->ctx->stream;
   SolverState& h = s->h;
   RET(ensure_capacity(s, itrs + 1));
-  if (h.events) CK(cudaFree(h.events));
-  h.events = nullptr;
-  CK(cudaMalloc(&h.events, (size_t)itrs * sizeof(bcg_iter_event)));
+  if (s->events_cap < itrs) {
+    if (h.events) CK(cudaFree(h.events));
+    h.events = nullptr;
+    s->events_cap = 0;
+    const int want = std::max(itrs, 256);
+    CK(cudaMalloc(&h.events, (size_t)want * sizeof(bcg_iter_event)));
+    s->events_cap = want;
+  }
   CK(cudaMemsetAsync(h.events, 0, (size_t)itrs * sizeof(bcg_iter_event), st));
   h.n_events = 0;
   h.tol = tol;
@@ -1389,10 +1441,18 @@ extern "C" int bcg_solver_build(bcg_solver* s, int32_t itrs, double tol, bcg_ite
       h.omp_trace = d_omp_trace;
       RET(push_state(s));
     }
+    if (s->profiling) {
+      while ((int)s->scan_ev.size() < 2 * itrs) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        s->scan_ev.push_back(e);
+      }
+    }
     CK(cudaEventRecord(s->ev0, st));
     step_kernel<<<1, kStepThreads, 0, st>>>(s->d, 0, 1, 1);           // reset the per-call retry flag; first residual direction
     for (int i = 0; i < itrs; ++i) {
-      RET(launch_scan(s));
+      if (s->profiling) RET(launch_scan(s, s->scan_ev[2 * i], s->scan_ev[2 * i + 1]));
+      else RET(launch_scan(s));
       omp_iteration_kernel<<<1, kStepThreads, 0, st>>>(s->d, s->d_nw, wide, (i + 1 < itrs) ? 1 : 0);
     }
     CK(cudaGetLastError());
@@ -1429,6 +1489,13 @@ extern "C" int bcg_solver_build(bcg_solver* s, int32_t itrs, double tol, bcg_ite
     s->step_launches = itrs + 1;
     s->loop_launches = 0;
     s->scan_ms = 0.f;
+    if (s->profiling) {
+      for (int i = 0; i < itrs; ++i) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, s->scan_ev[2 * i], s->scan_ev[2 * i + 1]));
+        s->scan_ms += ms;
+      }
+    }
   } else if (loop) {
     // the whole build call is ONE persistent cooperative kernel (loop_kernel.cuh).  Rare exception: when the control
     // warp finds the float32 candidate set ambiguous (an unpublished score inside the near-tie window) it stops before
@@ -1506,9 +1573,8 @@ extern "C" int bcg_solver_build(bcg_solver* s, int32_t itrs, double tol, bcg_ite
     CK(cudaEventRecord(s->ev0, st));
     step_kernel<<<1, kStepThreads, 0, st>>>(s->d, 0, 1, 1);
     for (int i = 0; i < itrs; ++i) {
-      if (s->profiling) CK(cudaEventRecord(s->scan_ev[2 * i], st));
-      RET(launch_scan(s));
-      if (s->profiling) CK(cudaEventRecord(s->scan_ev[2 * i + 1], st));
+      if (s->profiling) RET(launch_scan(s, s->scan_ev[2 * i], s->scan_ev[2 * i + 1]));
+      else RET(launch_scan(s));
       step_kernel<<<1, kStepThreads, 0, st>>>(s->d, 1, (i + 1 < itrs) ? 1 : 0, 0);
     }
     CK(cudaGetLastError());
@@ -1657,6 +1723,45 @@ extern "C" int bcg_solver_set_weights(bcg_solver* s, const double* w, int64_t k)
   RET(use_device(s->ctx));
   cudaStream_t st = s->ctx->stream;
   if (k > 0) CK(cudaMemcpyAsync(s->h.act_w, w, (size_t)k * sizeof(double), cudaMemcpyHostToDevice, st));
+  RET(invalidate_nnls(s));
+  refresh_kernel<<<1, kStepThreads, 0, st>>>(s->d);
+  CK(cudaGetLastError());
+  RET(pull_state(s));
+  return BCG_OK;
+}
+
+// Replace the stored active set: rows `idx` (GLOBAL indices owned by this rank) with weights `w`; their unit rows and
+// norms are gathered on the device, A w and the error are recomputed.  This is the sparse form of assigning the dense
+// weight vector `self.w = ...` (what the sampling solvers of snnls/sampling.py:33-35 do after every draw).
+__global__ void gather_active_kernel(SolverState* st, int k) {
+  const int ld = st->ld;
+  for (int r = blockIdx.x; r < k; r += gridDim.x) {
+    const int64_t lrow = st->act_idx[r] - st->row_offset;
+    const float* src = st->An + (size_t)lrow * ld;
+    for (int c = threadIdx.x; c < ld; c += blockDim.x) st->act_rows[(size_t)r * ld + c] = src[c];
+    if (threadIdx.x == 0) st->act_norm[r] = st->norms[lrow];
+  }
+}
+
+extern "C" int bcg_solver_set_active(bcg_solver* s, const int64_t* idx, const double* w, int64_t k) {
+  if (!s || k < 0 || (k > 0 && (!idx || !w))) return fail(BCG_ERR_ARG, "bad arguments");
+  RET(use_device(s->ctx));
+  SolverState& h = s->h;
+  for (int64_t i = 0; i < k; ++i)
+    if (idx[i] < h.row_offset || idx[i] >= h.row_offset + h.n_local)
+      return fail(BCG_ERR_ARG, "row %lld is not owned by this rank", (long long)idx[i]);
+  cudaStream_t st = s->ctx->stream;
+  if (k > h.cap) { h.nact = 0; RET(ensure_capacity(s, (int)k)); }
+  if (k > 0) {
+    CK(cudaMemcpyAsync(h.act_idx, idx, (size_t)k * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h.act_w, w, (size_t)k * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  h.nact = (int32_t)k;
+  RET(push_state(s));
+  if (k > 0) {
+    gather_active_kernel<<<(unsigned)std::min<int64_t>(k, 1024), 128, 0, st>>>(s->d, (int)k);
+    CK(cudaGetLastError());
+  }
   RET(invalidate_nnls(s));
   refresh_kernel<<<1, kStepThreads, 0, st>>>(s->d);
   CK(cudaGetLastError());

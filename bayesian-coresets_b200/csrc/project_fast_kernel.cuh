@@ -127,145 +127,8 @@ __global__ void __launch_bounds__(kProjWarps * 32, 1) project_fast_kernel(const 
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Two warps per row -- an experiment that did NOT pay off, kept selectable (BCG_PROJ_FAST=2).  With the first link
-// table project_fast_kernel ran with issue slots 24 % busy at 16 warps per SM (the 64 registers of per-lane state --
-// 16 accumulators + 16 column sums in float64 -- pin it at 128 registers per thread), which looked latency-bound.  It
-// was not: doubling the warps doubled the stall cycles per issue and ncu showed the L1 data pipe at 97 % of its
-// wavefront rate (gathered table loads + sample-tile LDS); the fix was the one-load link table (softplus_table.h), after
-// which one warp per row takes 0.506 ms per 209715 x 512 chunk and this kernel 0.546 ms.  Here a row is shared by a PAIR of warps, each owning half
-// of the columns (8 + 8 float64 of state at S = 512), so 32 warps fit on an SM at 64 registers; the two row-wide
-// reductions (mean over the S samples, row norm) are completed across the pair through shared memory and an
-// mbarrier per exchange (lane 0 of each warp arrives, all lanes wait; the two exchanges of a row alternate, so a slot
-// is never overwritten before the partner has read it).  Both warps add the two halves in the same order: they hold
-// bit-identical means and norms.  S = 128 * J2 in {128, 256, 512}.
-// ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t pk_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ double pair_total(double part, double* slot, uint64_t* bar, int half, int lane, uint32_t parity) {
-  const uint32_t addr = pk_smem_u32(bar);
-  if (lane == 0) {
-    slot[half] = part;
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(addr) : "memory");
-  }
-  uint32_t done;
-  do {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-  } while (!done);
-  const volatile double* vs = slot;
-  return vs[0] + vs[1];
-}
-
-constexpr int kPairThreads = 1024;                       // 32 warps = kProjWarps row pairs
-
-template <int J2, int MODEL>
-__global__ void __launch_bounds__(kPairThreads, 1) project_pair_kernel(const ProjectArgs a) {
-  extern __shared__ __align__(16) double smem[];
-  constexpr int S = 128 * J2, H = S / 2;
-  __shared__ double xval[kProjWarps][2][2];              // [pair][exchange][half]
-  __shared__ __align__(8) uint64_t xbar[kProjWarps][2];
-  double* th = smem;                                     // [d][S]
-  double* smem_cs = smem + (size_t)a.d * S;              // [pairs][S + 1]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int pair = warp >> 1, half = warp & 1;
-  const int d = a.d;
-  const double* __restrict__ tab = a.sp_tab;
-  for (int i = threadIdx.x; i < d * S; i += blockDim.x) th[i] = a.theta[i];
-  double* coff_s = smem_cs;                              // idle until the flush (see project_fast_kernel)
-  if (MODEL == MODEL_LINEAR)
-    for (int i = threadIdx.x; i < S; i += blockDim.x) coff_s[i] = a.coff ? a.coff[i] : 0.;
-  if (threadIdx.x < 2 * kProjWarps) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pk_smem_u32(&xbar[threadIdx.x >> 1][threadIdx.x & 1])), "r"(2) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  double colsum[J2][2];
-#pragma unroll
-  for (int j = 0; j < J2; ++j) colsum[j][0] = colsum[j][1] = 0.;
-  double normsum = 0.;
-
-  const int64_t gp = (int64_t)blockIdx.x * kProjWarps + pair, GP = (int64_t)gridDim.x * kProjWarps;
-  auto fetch = [&](int64_t row, double& z, double& y) {
-    z = 0.; y = 0.;
-    if (row < a.n) {
-      const int64_t zr = a.rowidx ? a.rowidx[row] : row;
-      if (lane < d) z = a.Z[zr * a.zld + lane];
-      if (MODEL == MODEL_POISSON) y = a.Z[zr * a.zld + d];
-    }
-  };
-  double zreg, y;
-  fetch(gp, zreg, y);
-  uint32_t parity = 0;
-  for (int64_t row = gp; row < a.n; row += GP) {
-    double znext, ynext;
-    fetch(row + GP, znext, ynext);
-    double acc[J2][2];
-#pragma unroll
-    for (int j = 0; j < J2; ++j) {
-      if (MODEL == MODEL_LINEAR) {
-        const double2 c = reinterpret_cast<const double2*>(coff_s + half * H)[32 * j + lane];
-        acc[j][0] = c.x; acc[j][1] = c.y;
-      } else {
-        acc[j][0] = acc[j][1] = 0.;
-      }
-    }
-    for (int k = 0; k < d; ++k) {
-      const double zk = __shfl_sync(0xffffffffu, zreg, k);
-      const double2* tk = reinterpret_cast<const double2*>(th + (size_t)k * S + half * H) + lane;
-#pragma unroll
-      for (int j = 0; j < J2; ++j) {
-        const double2 t = tk[32 * j];
-        acc[j][0] = fma(zk, t.x, acc[j][0]);
-        acc[j][1] = fma(zk, t.y, acc[j][1]);
-      }
-    }
-    double sum = 0.;
-#pragma unroll
-    for (int j = 0; j < J2; ++j) {
-      acc[j][0] = fast_link<MODEL>(tab, acc[j][0], y);
-      acc[j][1] = fast_link<MODEL>(tab, acc[j][1], y);
-      sum += acc[j][0] + acc[j][1];
-    }
-    const double mean = pair_total(warp_sum(sum), xval[pair][0], &xbar[pair][0], half, lane, parity) * (1. / (double)S);
-    double ss = 0.;
-#pragma unroll
-    for (int j = 0; j < J2; ++j) {
-      acc[j][0] -= mean; acc[j][1] -= mean;
-      ss = fma(acc[j][0], acc[j][0], ss);
-      ss = fma(acc[j][1], acc[j][1], ss);
-      colsum[j][0] += acc[j][0]; colsum[j][1] += acc[j][1];
-    }
-    ss = pair_total(warp_sum(ss), xval[pair][1], &xbar[pair][1], half, lane, parity);
-    parity ^= 1u;
-    const double norm = sqrt(ss);
-    const double inv = norm > 0. ? 1. / norm : 0.;
-    if (a.An) {
-      float2* out = reinterpret_cast<float2*>(a.An + (size_t)row * S + half * H) + lane;
-#pragma unroll
-      for (int j = 0; j < J2; ++j) out[32 * j] = make_float2((float)(acc[j][0] * inv), (float)(acc[j][1] * inv));
-      if (lane == 0 && half == 0) a.norms[row] = norm;
-    }
-    if (lane == 0 && half == 0) {
-      normsum += norm;
-      if (norm == 0.) atomicAdd(a.zero_rows, 1ull);
-    }
-    zreg = znext; y = ynext;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int j = 0; j < J2; ++j) {
-    smem_cs[(size_t)pair * (S + 1) + half * H + 64 * j + 2 * lane] = colsum[j][0];
-    smem_cs[(size_t)pair * (S + 1) + half * H + 64 * j + 2 * lane + 1] = colsum[j][1];
-  }
-  if (lane == 0 && half == 0) smem_cs[(size_t)pair * (S + 1) + S] = normsum;
-  __syncthreads();
-  for (int s = threadIdx.x; s < S + 1; s += blockDim.x) {
-    double t = 0.;
-    for (int w = 0; w < kProjWarps; ++w) t += smem_cs[(size_t)w * (S + 1) + s];
-    a.partial[(size_t)blockIdx.x * (S + 1) + s] = t;
-  }
-}
+// (A two-warps-per-row variant -- half the per-lane state, 32 warps per SM, row reductions completed across the pair
+// through shared memory and an mbarrier -- was measured at 0.546 ms per 209715 x 512 chunk against 0.506 ms for this kernel and
+// removed: the bound was the L1 data pipe, not latency.  The DMMA kernel of project_mma_kernel.cuh is what relieved it.)
 
 }  // namespace bcg

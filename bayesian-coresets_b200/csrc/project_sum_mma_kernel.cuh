@@ -1,23 +1,61 @@
-// K3b on the float64 tensor cores: the same computation as project_sum_kernel.cuh (column sums of the
-// row-centred log-likelihood matrix without materialising it; sparsevi.py:71-72, bpsvi.py:49-51 with
-// projector.py:19-21), but the (rows x d) . (d x S) contraction is issued as DMMA
-// (mma.sync.m8n8k4.f64: 256 FMA per warp instruction instead of 32), which is the only tensor-core path
-// that keeps float64 accumulation -- tcgen05 has no f64 kind, and these sums feed gradients that are
-// differences of O(N) sums, so float32 accumulators (TF32 / BF16 splits) are not an option.
+// K3b for large feature dimension on the float64 tensor cores: column sums of the row-centred log-likelihood matrix
+// WITHOUT materialising it -- the project(data).sum(axis=0) inside every SparseVI / BatchPSVI optimisation step
+// (reference: coreset/sparsevi.py:71-72, coreset/bpsvi.py:49-51 with projector.py:19-21).
 //
-// CTA tile 128 rows x 128 columns, 8 warps as 4 x 2, warp tile 32 x 64 = 4 x 8 MMA tiles, 2 accumulators per
-// lane and tile (64 doubles per lane).  Operand tiles live in shared memory as zs[k][row], ts[k][col] with a
-// row length of 132 doubles, which makes the fragment loads (lane = 4 g + t reads [k0 + t][base + g])
-// bank-conflict free.  Link, row masking and the column reduction are the epilogue, as in the CUDA-core kernel.
+//   colsum_s = sum_n (ll_ns - mean_t ll_nt) = rawsum_s - (1/S) sum_t rawsum_t ,  rawsum_s = sum_n ll_ns
+// so no per-row centring pass is needed: the kernel is a float64 GEMM (rows x d) . (d x S) with the model's link
+// applied to the accumulators in registers and a column reduction as its epilogue.  The contraction is issued as DMMA
+// (mma.sync.m8n8k4.f64: 256 FMA per warp instruction instead of 32), the only tensor-core path that keeps float64
+// accumulation -- tcgen05 has no f64 kind, and these sums feed gradients that are differences of O(N) sums.
+//
+// CTA tile 128 rows x 128 columns, 8 warps as 4 x 2, warp tile 32 x 64 = 4 x 8 DMMA tiles, 2 accumulators per lane and
+// tile (64 doubles per lane).  History (profiles/r01_analysis.md, r01b_projsum_*): a register-tiled kernel on the FMA
+// pipe reached 50 % of the float64 pipe; the first DMMA version 22.9 TFLOP/s with single-buffered operand tiles (DMMA
+// pipe 64 % active, 0.9 barrier-stall cycles per issue, 208 M shared-memory bank conflicts); this version:
+//   * operand tiles double-buffered in dynamic shared memory: the stores of k tile kt+1 go to the other buffer while
+//     tile kt is being multiplied, ONE block barrier per k tile;
+//   * conflict-free tile stores: the z loader is warp-uniform in k (threads 0-127 carry k 0-7 of rows 0-127, threads
+//     128-255 carry k 8-15), so a warp writes 32 consecutive doubles of one k row; the theta loader takes columns
+//     (t & 15) + 16 q of k row t >> 4, so a half-warp writes 16 consecutive doubles;
+//   * fragment loads from rows of 132 doubles: lane = 4 g + t reads [k0 + t][base + g], conflict-free per half-warp.
+// Measured back to back on one box (profiles/r01b_projsum_mma2.txt): 9.1 / 11.1 / 15.8 ms per pass (Gaussian / LR /
+// Poisson, N = 1e6, d = 200, S = 512) against 9.9 / 12.0 / 16.7 ms for the single-buffered version, which it replaced.
+// Bound: float64 tensor pipe (2 N d S flops) plus N S link evaluations (LR / Poisson).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
-#include "project_sum_kernel.cuh"
+#include "project_kernels.cuh"
 
 namespace bcg {
 
+constexpr int kPsBM = 128, kPsBN = 128, kPsThreads = 256;
 constexpr int kPmKT = 16;            // k per shared-memory tile (4 MMA k-steps)
 constexpr int kPmLd = 132;           // padded row length of both operand tiles (doubles)
+
+struct ProjectSumArgs {
+  const double* Z;       // rows x zld
+  const int64_t* rowidx; // optional gather (n entries)
+  const double* thetaT;  // d x S
+  const double* coff;    // S or null
+  double* partial;       // gridDim.x x S raw column sums
+  int64_t n;
+  int32_t zld, d, S, model;
+  const double* sp_tab;  // softplus table or null
+};
+
+// out-of-line link: the epilogue applies it to 64 accumulators per thread; inlining 64 copies of the
+// float64 exp/log1p bodies made the kernel ~600 KB of SASS and instruction-fetch bound
+template <int MODEL>
+__device__ __noinline__ double link_call(double lin, double y) { return link_value(MODEL, lin, y); }
+template <>
+__device__ __forceinline__ double link_call<MODEL_LINEAR>(double lin, double) { return lin; }
+// table-driven link inline (~20 instructions), libdevice link out of line
+template <int MODEL>
+__device__ __forceinline__ double link_apply(const double* tab, double lin, double y) {
+  if (MODEL == MODEL_LINEAR) return lin;
+  if (tab) return MODEL == MODEL_LR ? lr_link_fast(tab, lin) : poisson_link_fast(tab, lin, y);
+  return link_call<MODEL>(lin, y);
+}
 
 __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
@@ -25,21 +63,27 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
                : "d"(a), "d"(b));
 }
 
+constexpr size_t kPm2TileDoubles = (size_t)kPmKT * kPmLd;                       // one operand tile
+constexpr size_t kPm2SmemBytes = (4 * kPm2TileDoubles + kPsBM + 4 * kPsBN) * sizeof(double);   // 2 x (z, theta) + ys + colacc
+
 template <int MODEL>
 __global__ void __launch_bounds__(kPsThreads, 1) project_sum_mma_kernel(const ProjectSumArgs a) {
-  __shared__ __align__(16) double zs[kPmKT][kPmLd];
-  __shared__ __align__(16) double ts[kPmKT][kPmLd];
-  __shared__ double ys[kPsBM];
-  __shared__ double colacc[4][kPsBN];
+  extern __shared__ __align__(16) double pm2_smem[];
+  double* zs0 = pm2_smem;                               // [2][kPmKT][kPmLd]
+  double* ts0 = pm2_smem + 2 * kPm2TileDoubles;         // [2][kPmKT][kPmLd]
+  double* ys = pm2_smem + 4 * kPm2TileDoubles;          // [kPsBM]
+  double* colacc = ys + kPsBM;                          // [4][kPsBN]
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int wr = warp >> 1, wc = warp & 1;
-  const int g = lane >> 2, tq = lane & 3;             // MMA fragment coordinates
+  const int g = lane >> 2, tq = lane & 3;               // MMA fragment coordinates
   const int S = a.S, d = a.d;
   const int ncoltiles = (S + kPsBN - 1) / kPsBN;
   const int64_t nrowblocks = (a.n + kPsBM - 1) / kPsBM;
-  // loader roles: z tile 128 rows x 16 k (8 doubles per thread), theta tile 16 k x 128 cols (8 per thread)
-  const int zrow = t >> 1, zhalf = t & 1;
-  const int tk = t >> 4, tcol = (t & 15) * 8;
+  const int nk = (d + kPmKT - 1) / kPmKT;
+  // loader roles: z tile 128 rows x 16 k (8 consecutive k of one row per thread, warp-uniform k half),
+  // theta tile 16 k x 128 columns (k row t >> 4, columns (t & 15) + 16 q)
+  const int zrow = t & 127, zhalf = t >> 7;
+  const int tk = t >> 4, tc0 = t & 15;
 
   double mysum[4] = {0., 0., 0., 0.};
 
@@ -69,31 +113,40 @@ __global__ void __launch_bounds__(kPsThreads, 1) project_sum_mma_kernel(const Pr
         const int k = k0 + tk;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const int c = col0 + tcol + q;
+          const int c = col0 + tc0 + 16 * q;
           treg[q] = (k < d && c < S) ? a.thetaT[(size_t)k * S + c] : 0.;
         }
       };
+      auto sstore = [&](int buf) {
+        double* zs = zs0 + (size_t)buf * kPm2TileDoubles;
+        double* ts = ts0 + (size_t)buf * kPm2TileDoubles;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) zs[(size_t)(zhalf * 8 + q) * kPmLd + zrow] = zreg[q];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) ts[(size_t)tk * kPmLd + tc0 + 16 * q] = treg[q];
+      };
       gload(0);
-      for (int k0 = 0; k0 < d; k0 += kPmKT) {
-        __syncthreads();
-#pragma unroll
-        for (int q = 0; q < 8; ++q) zs[zhalf * 8 + q][zrow] = zreg[q];
-#pragma unroll
-        for (int q = 0; q < 8; q += 2) *reinterpret_cast<double2*>(&ts[tk][tcol + q]) = make_double2(treg[q], treg[q + 1]);
-        __syncthreads();
-        if (k0 + kPmKT < d) gload(k0 + kPmKT);
+      sstore(0);
+      __syncthreads();
+      for (int kt = 0; kt < nk; ++kt) {
+        const bool more = kt + 1 < nk;
+        if (more) gload((kt + 1) * kPmKT);                // global loads in flight during this tile's DMMAs
+        const double* zs = zs0 + (size_t)(kt & 1) * kPm2TileDoubles;
+        const double* ts = ts0 + (size_t)(kt & 1) * kPm2TileDoubles;
 #pragma unroll
         for (int kk = 0; kk < kPmKT; kk += 4) {
           double af[4], bf[8];
 #pragma unroll
-          for (int mi = 0; mi < 4; ++mi) af[mi] = zs[kk + tq][wr * 32 + mi * 8 + g];
+          for (int mi = 0; mi < 4; ++mi) af[mi] = zs[(size_t)(kk + tq) * kPmLd + wr * 32 + mi * 8 + g];
 #pragma unroll
-          for (int ni = 0; ni < 8; ++ni) bf[ni] = ts[kk + tq][wc * 64 + ni * 8 + g];
+          for (int ni = 0; ni < 8; ++ni) bf[ni] = ts[(size_t)(kk + tq) * kPmLd + wc * 64 + ni * 8 + g];
 #pragma unroll
           for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
             for (int ni = 0; ni < 8; ++ni) dmma_m8n8k4(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
         }
+        if (more) sstore((kt + 1) & 1);                   // the other buffer: last read before the previous barrier
+        __syncthreads();
       }
 
       // ---- epilogue: accumulator (mi, ni, e) is row wr*32 + mi*8 + g, column wc*64 + ni*8 + tq*2 + e
@@ -130,13 +183,13 @@ __global__ void __launch_bounds__(kPsThreads, 1) project_sum_mma_kernel(const Pr
       if (g == 0) {
 #pragma unroll
         for (int ni = 0; ni < 8; ++ni) {
-          colacc[wr][wc * 64 + ni * 8 + tq * 2] = cs[ni][0];
-          colacc[wr][wc * 64 + ni * 8 + tq * 2 + 1] = cs[ni][1];
+          colacc[wr * kPsBN + wc * 64 + ni * 8 + tq * 2] = cs[ni][0];
+          colacc[wr * kPsBN + wc * 64 + ni * 8 + tq * 2 + 1] = cs[ni][1];
         }
       }
       __syncthreads();
       if (t < kPsBN) {
-        const double v = colacc[0][t] + colacc[1][t] + colacc[2][t] + colacc[3][t];
+        const double v = colacc[t] + colacc[kPsBN + t] + colacc[2 * kPsBN + t] + colacc[3 * kPsBN + t];
         if (ct < 4) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) if (q == ct) mysum[q] += v;
@@ -153,6 +206,27 @@ __global__ void __launch_bounds__(kPsThreads, 1) project_sum_mma_kernel(const Pr
       if (q < ncoltiles && c < S) a.partial[(size_t)blockIdx.x * S + c] = mysum[q];
     }
   }
+}
+
+// rawsum -> centred column sums: out_s = sum_b partial[b][s] - (1/S) sum_t sum_b partial[b][t]
+__global__ void project_sum_finish_kernel(const double* partial, int nblocks, int S, double* out) {
+  __shared__ double tot[1024];
+  __shared__ double red[32];
+  const int t = threadIdx.x;
+  double mine = 0.;
+  for (int s = t; s < S; s += blockDim.x) {
+    double v = 0.;
+    for (int b = 0; b < nblocks; ++b) v += partial[(size_t)b * S + s];
+    tot[s] = v;
+    mine += v;
+  }
+  mine = warp_sum(mine);
+  if ((t & 31) == 0) red[t >> 5] = mine;
+  __syncthreads();
+  double all = 0.;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) all += red[w];
+  const double mean = all / (double)S;
+  for (int s = t; s < S; s += blockDim.x) out[s] = tot[s] - mean;
 }
 
 }  // namespace bcg

@@ -168,6 +168,7 @@ int  bcg_solver_destroy(bcg_solver* s);
  * Ranks must connect their solvers in the same order, and must be synchronised (any host barrier) between
  * bcg_solver_comm_connect and the first bcg_solver_build, and between build calls of DIFFERENT solvers. */
 int  bcg_solver_comm_handle(bcg_solver* s, void* handle64);
+int  bcg_ctx_comm_handle(bcg_ctx* ctx, void* handle64);       /* the same handle, available before a solver exists */
 int  bcg_solver_comm_connect(bcg_solver* s, int32_t world, int32_t rank, const void* handles64);
 /* run up to `itrs` greedy iterations entirely on the device (GIGA, FW).  events: host array of
  * `itrs` entries; n_events receives how many iterations were attempted. */
@@ -191,6 +192,9 @@ int  bcg_solver_active(bcg_solver* s, int64_t cap, int64_t* idx, double* w, int6
 int  bcg_solver_active_rows(bcg_solver* s, int64_t first, int64_t count, double* out);
 /* overwrite the weights of the stored active rows (k must equal n_stored); recomputes A w and error */
 int  bcg_solver_set_weights(bcg_solver* s, const double* w, int64_t k);
+/* replace the stored active set by rows idx (global indices owned by this rank) with weights w: rows / norms are gathered
+ * on the device, A w and error() recomputed -- the sparse form of `self.w = ...` (snnls/sampling.py:33-35) */
+int  bcg_solver_set_active(bcg_solver* s, const int64_t* idx, const double* w, int64_t k);
 int  bcg_solver_reset(bcg_solver* s);
 /* snnls.py:9 `check_error_monotone` (default 1): with 0 the monotone-error test of snnls.py:56-61 is skipped -- and, as in
  * the reference, the retry flag is then never cleared by a successful step */
@@ -210,6 +214,22 @@ int  bcg_solver_set_profiling(bcg_solver* s, int32_t per_kernel_events);
  * then 4 control-warp milestones (candidates reduced, row fetched, line search done, committed) */
 int  bcg_solver_set_trace(bcg_solver* s, int32_t enable);
 int  bcg_solver_get_trace(bcg_solver* s, int32_t cap_iters, uint64_t* out, int32_t* n_iters);
+
+/* ---- process group for N-sharding (torch-free) ------------------------------------------------ */
+/* One process per GPU of one node.  Used for bootstrap (row counts, the 64-byte mailbox handles of
+ * bcg_solver_comm_handle) and for the one-off / per-pass reductions of S-vectors (b = vecs.sum(axis=0) of hilbert.py:24
+ * over all shards, sum ||a_n|| of frankwolfe.py:21, the column sums of sparsevi.py:48 / bpsvi.py:51); the per-iteration
+ * candidate exchange of the greedy loop is fused into the kernels over NVLink peer memory and never comes here.
+ * TCP on addr:port (rank 0 listens, the others connect; addr = "127.0.0.1" under torchrun), star topology.
+ * All-reduces gather the contributions and reduce them in rank order on every rank: bit-identical results. */
+typedef struct bcg_comm bcg_comm;
+int  bcg_comm_create(const char* addr, int32_t port, int32_t rank, int32_t world, int32_t timeout_ms, bcg_comm** out);
+int  bcg_comm_destroy(bcg_comm* c);
+int  bcg_comm_rank(bcg_comm* c, int32_t* rank, int32_t* world);
+/* recv: world * bytes, contribution of rank r at offset r * bytes; bytes = 0 is a barrier */
+int  bcg_comm_allgather(bcg_comm* c, const void* send, int64_t bytes, void* recv);
+int  bcg_comm_allreduce_f64(bcg_comm* c, double* data, int64_t n, int32_t op /* 0 sum, 1 max */);
+int  bcg_comm_barrier(bcg_comm* c);
 
 #ifdef __cplusplus
 }

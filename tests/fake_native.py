@@ -6,12 +6,20 @@ global index, and the GIGA reweight is replicated on every rank."""
 import numpy as np
 
 
+RANK = [0]      # set by the worker: the fake mailbox handle carries the rank
+
+
+class FakeCtx(object):
+  def comm_handle(self):
+    return bytes([RANK[0]])*64
+
+
 class FakeVecs(object):
   def __init__(self, rows):
     self.rows = np.array(rows, dtype=np.float64)
     self.shape = self.rows.shape
     self.size = self.rows.size
-    self.ctx = None
+    self.ctx = FakeCtx()
 
   @classmethod
   def from_host(cls, rows, ctx=None):

@@ -1,7 +1,9 @@
-"""Multi-GPU parity check, launched under torchrun (one rank per GPU):
+"""Multi-GPU parity check, one process per GPU.  Any launcher that exports RANK / LOCAL_RANK / WORLD_SIZE / MASTER_ADDR /
+MASTER_PORT works (tests/test_gpu_multi.py spawns the ranks itself; torchrun also does):
    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_check.py
 Every rank holds a contiguous shard of the rows; the result (selection sequence, weights, error, points)
-must equal the single-process oracle on the full data, on every rank."""
+must equal the single-process oracle on the full data, on every rank.  The workers never import torch: the process
+group is the library's own (bcg_comm_*)."""
 import os
 import sys
 import numpy as np
@@ -13,15 +15,10 @@ sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
 
 def main():
-  import torch
-  import torch.distributed as dist
-  local_rank = int(os.environ['LOCAL_RANK'])
-  torch.cuda.set_device(local_rank)
-  dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
   import bayesiancoresets_b200 as bc
   from oracle import greedy, models
   from conftest import lr_problem
-  comm = bc.comm.TorchComm()
+  comm = bc.comm.default_comm()
   rank, world = comm.rank, comm.world
   algs = {'giga': bc.snnls.GIGA, 'fw': bc.snnls.FrankWolfe, 'omp': bc.snnls.OrthoPursuit}
 
@@ -89,10 +86,28 @@ def main():
     print('mgpu sparsevi / bpsvi world=%d: identical to the oracle' % world, flush=True)
   os.environ['BCG_ENGINE'] = '1'          # launch-per-iteration engine with the block-wide exchange
   check(20000, 6, 128, 30, 'giga')
+  # subsampling under N-sharding (hilbert.py:13-22): every rank draws the same global subsample
+  os.environ['BCG_ENGINE'] = '2'
+  Zs, ths = lr_problem(31, 12000, 5, 64)
+  np.random.seed(17)
+  ref_idx = np.unique(np.random.randint(12000, size=3000))
+  vs = models.project(models.lr_loglik, Zs[ref_idx], ths)
+  o = greedy.GigaOracle(vs.T, vs.sum(axis=0))
+  o.build(20)
+  np.random.seed(17)
+  lo, hi = bc.comm.even_shard(12000, rank, world)
+  cs = bc.HilbertCoreset(Zs[lo:hi], bc.LogisticRegressionProjector(lambda n, w, p: ths, 64), n_subsample=3000, comm=comm)
+  cs.build(20)
+  wts, pts, idcs = cs.get()
+  assert np.array_equal(idcs, ref_idx[o.w > 0]), (rank, idcs[:5], ref_idx[o.w > 0][:5])
+  assert np.allclose(wts, o.w[o.w > 0], rtol=1e-5) and np.array_equal(pts, Zs[idcs])
+  if rank == 0:
+    print('mgpu subsampled Hilbert world=%d: identical to the oracle' % world, flush=True)
+  assert 'torch' not in sys.modules, 'the workers must not need torch'
+  comm.barrier()
   if rank == 0:
     print('MGPU OK', flush=True)
-  dist.barrier()
-  dist.destroy_process_group()
+  comm.close()
 
 
 if __name__ == '__main__':

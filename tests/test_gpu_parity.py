@@ -429,11 +429,10 @@ def test_device_nnls_equals_scipy_path(bc, monkeypatch):
   prj = bc.LogisticRegressionProjector(lambda n, w, p: g['theta'], int(g['S']))
   a = bc.HilbertCoreset(g['Z'], prj, snnls=bc.snnls.OrthoPursuit)
   a.build(50)
-  monkeypatch.setenv('BCG_NNLS', 'scipy')
+  from scipy_omp import run_scipy_omp
   b = bc.HilbertCoreset(g['Z'], prj, snnls=bc.snnls.OrthoPursuit)
-  b.build(50)
-  monkeypatch.delenv('BCG_NNLS')
-  assert [e.f for e in a.snnls.last_events] == [e.f for e in b.snnls.last_events]
+  bev = run_scipy_omp(b.snnls, 50)
+  assert [e.f for e in a.snnls.last_events] == [e[1] for e in bev]
   np.testing.assert_allclose(a.snnls.weights(), b.snnls.weights(), rtol=1e-6, atol=1e-9*b.snnls.weights().max())
   assert a.error() == pytest.approx(b.error(), rel=1e-6)
   # incremental builds continue from the kept factorisation
@@ -624,35 +623,40 @@ def test_pinned_source_equals_pageable_source(bc):
   del Zp, b, db, cs
 
 
-@pytest.mark.parametrize('S,d', [(64, 3), (128, 32), (256, 10), (512, 10), (512, 24)])
-def test_specialised_projection_kernel_vs_general_and_oracle(bc, monkeypatch, S, d):
-  """project_pair_kernel / project_fast_kernel (S in {64,128,256,512}, d <= 32; BCG_PROJ_FAST=2 / 1) against the general
-  kernel (BCG_PROJ_FAST=0) and the oracle:
-  three models, a row count that is no multiple of the CTA batch, a device row gather, column-sum-only passes"""
+@pytest.mark.parametrize('S,d', [(64, 3), (128, 32), (256, 10), (512, 10), (512, 24), (256, 200), (512, 70), (128, 16)])
+def test_specialised_projection_kernels_vs_general_and_oracle(bc, monkeypatch, S, d):
+  """the three materialising projection kernels -- project_mma_kernel (DMMA; default for S in {64,128,256,512}: sample tile
+  resident for d <= 16, streamed k tiles above), project_fast_kernel (BCG_PROJ_MMA=0; d <= 32) and the general kernel
+  (BCG_PROJ_MMA=0 BCG_PROJ_FAST=0) -- against each other and the oracle: three models, a row count that is no multiple of
+  any row block, a device row gather, column-sum-only passes"""
   rng = np.random.RandomState(S + d)
   n = 3001
-  X = rng.randn(n, d)*rng.choice([0.3, 1., 5.], size=(n, 1))
+  X = rng.randn(n, d)*rng.choice([0.3, 1., 5.], size=(n, 1))/max(1., np.sqrt(d/10.))
   th = rng.randn(S, d)/np.sqrt(d)
   y = rng.poisson(2., size=n).astype(np.float64)
   Zp = np.hstack((X, y[:, None]))
-  Siginv = np.eye(d) + 0.1*np.ones((d, d))
+  Siginv = np.eye(d) + 0.1*np.ones((d, d))/d
   sub = rng.randint(n, size=777)
   cases = [(bc._native.MODEL_LR, X, None, models.project(models.lr_loglik, X, th)),
            (bc._native.MODEL_POISSON, Zp, None, models.project(models.poisson_loglik, Zp, th)),
            (bc._native.MODEL_GAUSSIAN, X, Siginv, models.project(lambda x, t: models.gaussian_loglik(x, t, Siginv, 0.), X, th))]
+  variants = [{'BCG_PROJ_MMA': '1'}, {'BCG_PROJ_MMA': '0', 'BCG_PROJ_FAST': '1'}, {'BCG_PROJ_MMA': '0', 'BCG_PROJ_FAST': '0'}]
   for model, Z, si, ref in cases:
     ds = bc.Dataset(Z)
     res = []
-    for fast in ('2', '1', '0'):
-      monkeypatch.setenv('BCG_PROJ_FAST', fast)
+    for env in variants:
+      for k, val in env.items():
+        monkeypatch.setenv(k, val)
       v = ds.project(model, th, si, vecs=True)[0]
       vs = ds.project(model, th, si, vecs=True, sub=sub)[0]
       cs = ds.project(model, th, si, colsum=True)[2]
+      vh = bc.DeviceVecs.project_host(model, Z, th, si)            # pipelined host path (chunked launches)
       res.append((v.to_numpy(), v.norms(), v.sum(axis=0), vs.to_numpy(), vs.norms(), cs, v.norm_sum(), v.zero_rows()))
-      if fast != '0':
-        check_projection(v, ref)
-        check_projection(vs, ref[sub])
-    monkeypatch.delenv('BCG_PROJ_FAST')
+      check_projection(v, ref)
+      check_projection(vs, ref[sub])
+      check_projection(vh, ref)
+      for k in env:
+        monkeypatch.delenv(k)
     for a, b in ((res[0], res[2]), (res[1], res[2])):
       compare_projection_outputs(a, b, ref)
 
@@ -839,6 +843,36 @@ def test_check_error_monotone_false_follows_the_reference(bc, alg):
   assert [(e.code, e.f) for e in s.last_events][:nsel] == [(e[0], e[1]) for e in oev][:nsel]
 
 
+def test_sampling_baselines_follow_the_reference(bc):
+  """snnls/sampling.py and coreset/sampling.py: same draws (global RNG), same weights, error() from the device"""
+  ref, _ = _reference_package()
+  rng = np.random.RandomState(0)
+  X = rng.randn(500, 30)*rng.uniform(0.2, 4., size=(500, 1))
+  for name in ('ImportanceSampling', 'UniformSampling'):
+    np.random.seed(7)
+    r = getattr(ref.snnls, name)(X.T, X.sum(axis=0))
+    r.build(40); r.build(25)
+    np.random.seed(7)
+    s = getattr(bc.snnls, name)(X.T, X.sum(axis=0))
+    s.build(40); s.build(25)
+    np.testing.assert_allclose(s.weights(), r.weights(), rtol=1e-12)
+    assert s.error() == pytest.approx(r.error(), rel=1e-6) and s.size() == r.size()
+    r.optimize(); s.optimize()
+    assert s.error() == pytest.approx(r.error(), rel=1e-5)
+  np.random.seed(3)
+  a = ref.UniformSamplingCoreset(X); a.build(60)
+  np.random.seed(3)
+  b = bc.UniformSamplingCoreset(X); b.build(60)
+  for u, v in zip(a.get(), b.get()):
+    assert np.array_equal(u, v)
+  # assigning the dense weight vector is a sparse active-set write
+  g = bc.snnls.GIGA(X.T, X.sum(axis=0))
+  w = np.zeros(500); w[[3, 77, 400]] = [1.5, 0.25, 2.]
+  g.w = w
+  assert np.array_equal(g.weights(), w)
+  assert g.error() == pytest.approx(np.linalg.norm(w.dot(X) - X.sum(axis=0)), rel=1e-6)
+
+
 @pytest.mark.parametrize('alg,engine', [('omp', '2'), ('giga', '1'), ('giga', '2'), ('fw', '1')])
 def test_non_finite_rows_fail_cleanly(bc, monkeypatch, alg, engine):
   """NaN in the data: b and the direction become NaN, the scan yields no candidate.  Every engine must report an
@@ -854,3 +888,93 @@ def test_non_finite_rows_fail_cleanly(bc, monkeypatch, alg, engine):
   t = bc.snnls.GIGA(Y.T, Y.sum(axis=0))
   t.build(5)
   assert t.size() > 0
+
+
+# ---------------------------------------------------------------- the drop-in boundary, exercised from the REFERENCE side
+def _reference_package(tmp_path=None):
+  """the unmodified reference installed under baseline/_ref (it travels to the GPU box); a private copy when the test
+  adds the INTEGRATION.md stub to its tree"""
+  import importlib
+  import shutil
+  import sys
+  from conftest import ROOT
+  import os
+  src = os.path.join(ROOT, 'baseline', '_ref')
+  if not os.path.isdir(os.path.join(src, 'bayesiancoresets')):
+    src = '/root/reference'
+  if not os.path.isdir(os.path.join(src, 'bayesiancoresets')):
+    pytest.skip('the reference package is not available on this box')
+  if tmp_path is not None:
+    shutil.copytree(os.path.join(src, 'bayesiancoresets'), os.path.join(str(tmp_path), 'bayesiancoresets'))
+    src = str(tmp_path)
+  for m in [m for m in sys.modules if m == 'bayesiancoresets' or m.startswith('bayesiancoresets.')]:
+    del sys.modules[m]
+  sys.path.insert(0, src)
+  try:
+    return importlib.import_module('bayesiancoresets'), src
+  finally:
+    sys.path.remove(src)
+
+
+@pytest.mark.parametrize('alg', ['GIGA', 'FrankWolfe', 'OrthoPursuit'])
+def test_reference_hilbert_coreset_runs_on_this_repos_snnls(bc, alg):
+  """the literal drop-in of hilbert.py:7,24: the REFERENCE's own HilbertCoreset (and BlackBoxProjector) with this repo's
+  solver class passed as `snnls=` -- build / get / error / optimize / reset -- against the pure reference run"""
+  ref, _ = _reference_package()
+  Z, theta = lr_problem(2, 4000, 5, 64)
+  prj = ref.BlackBoxProjector(lambda n, w, p: theta, 64, models.lr_loglik)
+  pure = ref.HilbertCoreset(Z, prj, snnls=getattr(ref.snnls, alg))
+  ours = ref.HilbertCoreset(Z, prj, snnls=getattr(bc.snnls, alg))
+  for cs in (pure, ours):
+    cs.build(20)
+    cs.build(15)
+  (w0, p0, i0), (w1, p1, i1) = pure.get(), ours.get()
+  assert np.array_equal(i0, i1) and np.array_equal(p0, p1)
+  np.testing.assert_allclose(w1, w0, rtol=1e-5, atol=1e-5*np.abs(w0).max())
+  assert ours.error() == pytest.approx(pure.error(), rel=1e-5, abs=1e-7*np.sqrt((models.project(models.lr_loglik, Z, theta)**2).sum()))
+  pure.optimize(); ours.optimize()
+  assert ours.error() == pytest.approx(pure.error(), rel=1e-4, abs=1e-7*np.sqrt((models.project(models.lr_loglik, Z, theta)**2).sum()))
+  ours.reset()
+  assert ours.size() == 0
+
+
+def test_integration_md_stub_runs_inside_the_reference_tree(bc, tmp_path):
+  """INTEGRATION.md section 2 verbatim: the ctypes stub a maintainer would add as bayesiancoresets/snnls/_b200.py,
+  dropped into a copy of the reference tree and used as `snnls=` of the reference's HilbertCoreset"""
+  import importlib
+  import os
+  import re
+  import sys
+  from conftest import ROOT
+  from bayesiancoresets_b200 import _native as nat
+  text = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+  sec = text[text.index('## 2.'):text.index('## 3.')]
+  code = re.search(r'```python\n(.*?)```', sec, re.S).group(1)
+  assert "ctypes.CDLL('libbcg_b200.so')" in code
+  code = code.replace("ctypes.CDLL('libbcg_b200.so')", 'ctypes.CDLL(%r)' % nat.LIB_PATH)
+  ref, src = _reference_package(tmp_path)
+  with open(os.path.join(src, 'bayesiancoresets', 'snnls', '_b200.py'), 'w') as f:
+    f.write(code)
+  sys.path.insert(0, src)
+  try:
+    stub = importlib.import_module('bayesiancoresets.snnls._b200')
+  finally:
+    sys.path.remove(src)
+  np.random.seed(1)
+  X = np.random.randn(1000, 50)
+
+  class IDP(ref.Projector):
+    def project(self, pts, grad=False):
+      return pts
+
+    def update(self, wts, pts):
+      pass
+  a = ref.HilbertCoreset(X, IDP(), snnls=stub.GIGA)
+  a.build(100)
+  wts, pts, idcs = a.get()
+  g = load_golden('c1_normal_giga')
+  o = greedy.GigaOracle(X.T, X.sum(axis=0))
+  o.build(100)
+  assert np.array_equal(idcs, np.flatnonzero(o.w > 0))
+  np.testing.assert_allclose(wts, o.w[o.w > 0], rtol=1e-5)
+  assert a.error() == pytest.approx(o.error(), rel=1e-5, abs=1e-6)

@@ -9,12 +9,14 @@ from conftest import lr_problem
 N, d = int(sys.argv[1]) if len(sys.argv) > 1 else 3000, 6
 for S in (256, 96):
   Z, theta = lr_problem(1, N, d, S)
-  for fast in ('1', '2', '0'):
-    os.environ['BCG_PROJ_FAST'] = fast
+  for mma, fast in (('1', '1'), ('0', '1'), ('0', '0')):            # DMMA / warp-per-row / general projection kernels
+    os.environ['BCG_PROJ_MMA'], os.environ['BCG_PROJ_FAST'] = mma, fast
     prj = bc.LogisticRegressionProjector(lambda n, w, p: theta, S)
     cs = bc.HilbertCoreset(Z, prj, snnls=bc.snnls.GIGA)
     cs.build(12)
-  os.environ['BCG_PROJ_FAST'] = '1'
+    cs.snnls._native.set_force_exact(True)                          # exact float64 selection pass + relaunch
+    cs.build(3)
+  os.environ['BCG_PROJ_MMA'], os.environ['BCG_PROJ_FAST'] = '1', '1'
   y = np.random.RandomState(0).poisson(2., size=(N, 1)).astype(float)
   pp = bc.PoissonProjector(lambda n, w, p: theta, S)
   v = pp.project_device(np.hstack((Z, y)))
