@@ -581,8 +581,14 @@ static int launch_project_mma_model(bcg_ctx* ctx, const ProjectArgs& a, int grid
 // the DMMA materialising projection (project_mma_kernel.cuh) applies when the unit-row matrix is written, S is 64, 128,
 // 256 or 512 and the links come from the table; the partial column sums need room for its grid (see project_mma_grid_cap)
 static bool project_mma_ok(const ProjectArgs& a) {
-  return env_int("BCG_PROJ_MMA", 1) && a.An && !a.out64 && a.ld == a.S &&
-         (a.S == 64 || a.S == 128 || a.S == 256 || a.S == 512) && (a.model == MODEL_LINEAR || a.sp_tab != nullptr);
+  // BCG_PROJ_MMA: 0 never, 2 whenever the shape allows, 1 (default) where it measured faster than the warp-per-row kernel
+  // (profiles/r02_k3_timing.txt: d > 32, where only the general kernel applies otherwise -- 20.9 vs 43.1 ms at d = 200,
+  // S = 512, N = 1e6 -- and S <= 256 -- 1.18 vs 1.25 ms at d = 10, S = 256; at S = 512, d = 10 it is 22.9 vs 21.9 ms)
+  const int mode = env_int("BCG_PROJ_MMA", 1);
+  const bool shape_ok = a.An && !a.out64 && a.ld == a.S && (a.S == 64 || a.S == 128 || a.S == 256 || a.S == 512) &&
+                        (a.model == MODEL_LINEAR || a.sp_tab != nullptr);
+  if (!mode || !shape_ok) return false;
+  return mode >= 2 || a.d > 32 || a.S <= 256;
 }
 
 // CTAs (= rows of the partial column-sum buffer) of a projection launch over at most a.n rows
@@ -718,6 +724,19 @@ static int project_common(bcg_dataset* ds, const int64_t* rowidx, int64_t nsel, 
     grid = project_grid(ctx, a);
     RET(ctx_scratch(ctx, 5, (size_t)grid * (S + 1) * sizeof(double), (void**)&d_partial));
     a.partial = d_partial;
+    if (env_int("BCG_PROJ_TRACE", 0)) {               // diagnostics: device time of the projection kernel alone
+      cudaEvent_t e0, e1;
+      CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+      CK(cudaEventRecord(e0, st));
+      RET(dispatch_project(ctx, a, grid, smem));
+      CK(cudaEventRecord(e1, st));
+      CK(cudaEventSynchronize(e1));
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      fprintf(stderr, "[bcg] projection kernel: n=%lld d=%d S=%d model=%d mma=%d grid=%d: %.3f ms\n", (long long)n, d, S, model,
+              (int)project_mma_ok(a), grid, ms);
+      cudaEventDestroy(e0); cudaEventDestroy(e1);
+    } else
     RET(dispatch_project(ctx, a, grid, smem));
     if (v) {
       RET(finish_colsum(v, d_partial, grid, d_zero));

@@ -61,32 +61,52 @@ __global__ void __launch_bounds__(kProjWarps * 32, 1) project_fast_kernel(const 
     double znext, ynext;
     fetch(row + GW, znext, ynext);                       // in flight during this row's math
     double acc[J2][2];
-#pragma unroll
-    for (int j = 0; j < J2; ++j) {
-      if (MODEL == MODEL_LINEAR) {
-        const double2 c = reinterpret_cast<const double2*>(coff_s)[32 * j + lane];
-        acc[j][0] = c.x; acc[j][1] = c.y;
-      } else {
-        acc[j][0] = acc[j][1] = 0.;
-      }
-    }
-    for (int k = 0; k < d; ++k) {
-      const double zk = __shfl_sync(0xffffffffu, zreg, k);
-      const double2* tk = reinterpret_cast<const double2*>(th + (size_t)k * S) + lane;
+    auto contract = [&]() {
 #pragma unroll
       for (int j = 0; j < J2; ++j) {
-        const double2 t = tk[32 * j];
-        acc[j][0] = fma(zk, t.x, acc[j][0]);
-        acc[j][1] = fma(zk, t.y, acc[j][1]);
+        if (MODEL == MODEL_LINEAR) {
+          const double2 c = reinterpret_cast<const double2*>(coff_s)[32 * j + lane];
+          acc[j][0] = c.x; acc[j][1] = c.y;
+        } else {
+          acc[j][0] = acc[j][1] = 0.;
+        }
+      }
+      for (int k = 0; k < d; ++k) {
+        const double zk = __shfl_sync(0xffffffffu, zreg, k);
+        const double2* tk = reinterpret_cast<const double2*>(th + (size_t)k * S) + lane;
+#pragma unroll
+        for (int j = 0; j < J2; ++j) {
+          const double2 t = tk[32 * j];
+          acc[j][0] = fma(zk, t.x, acc[j][0]);
+          acc[j][1] = fma(zk, t.y, acc[j][1]);
+        }
+      }
+    };
+    contract();
+    double sum = 0.;
+    if (MODEL != MODEL_LINEAR) {
+      // branch-free links first (independent chains the compiler can interleave, softplus_table.h); a row with an
+      // argument beyond their range (|lin| > 37: rare) is contracted again and evaluated with the branching links
+      bool tail = false;
+#pragma unroll
+      for (int j = 0; j < J2; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const double lin = acc[j][e];
+          tail |= link_needs_tail(lin);
+          acc[j][e] = MODEL == MODEL_LR ? lr_link_nb(tab, lin) : poisson_link_nb(tab, lin, y);
+        }
+      if (__any_sync(0xffffffffu, tail)) {
+        contract();
+#pragma unroll
+        for (int j = 0; j < J2; ++j) {
+          acc[j][0] = fast_link<MODEL>(tab, acc[j][0], y);
+          acc[j][1] = fast_link<MODEL>(tab, acc[j][1], y);
+        }
       }
     }
-    double sum = 0.;
 #pragma unroll
-    for (int j = 0; j < J2; ++j) {
-      acc[j][0] = fast_link<MODEL>(tab, acc[j][0], y);
-      acc[j][1] = fast_link<MODEL>(tab, acc[j][1], y);
-      sum += acc[j][0] + acc[j][1];
-    }
+    for (int j = 0; j < J2; ++j) sum += acc[j][0] + acc[j][1];
     const double mean = warp_sum(sum) * (1. / (double)S);   // projector.py:21 (S is a power of two: exact reciprocal)
     double ss = 0.;
 #pragma unroll

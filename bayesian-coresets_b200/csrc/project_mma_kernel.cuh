@@ -61,9 +61,10 @@ __global__ void __launch_bounds__(kPjThreads, MI == 1 ? 2 : 1) project_mma_kerne
 
   auto load_tile = [&](int buf, int k0) {          // sample rows k0 .. k0+15 (zero beyond d) -> shared
     double* dst = ths + (size_t)buf * kPjKT * ld;
-    for (int i = t; i < kPjKT * S; i += kPjThreads) {
-      const int k = i / S, c = i - k * S;
-      dst[(size_t)k * ld + c] = (k0 + k < d) ? a.theta[(size_t)(k0 + k) * S + c] : 0.;
+#pragma unroll 4
+    for (int k = 0; k < kPjKT; ++k) {
+      const bool in = k0 + k < d;
+      for (int c = t; c < S; c += kPjThreads) dst[(size_t)k * ld + c] = in ? __ldg(a.theta + (size_t)(k0 + k) * S + c) : 0.;
     }
   };
   if (MI == 1) {
@@ -76,6 +77,23 @@ __global__ void __launch_bounds__(kPjThreads, MI == 1 ? 2 : 1) project_mma_kerne
   for (int ni = 0; ni < 8; ++ni) cs[ni][0] = cs[ni][1] = 0.;
   double normsum = 0.;
 
+  // MI == 1: the A fragments (and y) of the NEXT row block are fetched while the current block's links are evaluated
+  double afn[kPjKT / 4], yn = 0.;
+  auto fetch_block = [&](int64_t rb) {
+#pragma unroll
+    for (int q = 0; q < kPjKT / 4; ++q) afn[q] = 0.;
+    yn = 0.;
+    const int64_t r = rb * BM + wr * 8 + g;
+    if (rb < nblocks && r < a.n) {
+      const int64_t z = a.rowidx ? a.rowidx[r] : r;
+#pragma unroll
+      for (int q = 0; q < kPjKT / 4; ++q)
+        if (q * 4 + tq < d) afn[q] = __ldg(a.Z + z * a.zld + q * 4 + tq);
+      if (MODEL == MODEL_POISSON) yn = __ldg(a.Z + z * a.zld + d);
+    }
+  };
+  if (MI == 1) fetch_block(blockIdx.x);
+
   for (int64_t rb = blockIdx.x; rb < nblocks; rb += gridDim.x) {
     const int64_t row0 = rb * BM;
     int64_t zr[MI];
@@ -84,7 +102,7 @@ __global__ void __launch_bounds__(kPjThreads, MI == 1 ? 2 : 1) project_mma_kerne
     for (int mi = 0; mi < MI; ++mi) {
       const int64_t r = row0 + wr * (8 * MI) + mi * 8 + g;
       live[mi] = r < a.n;
-      zr[mi] = live[mi] ? (a.rowidx ? a.rowidx[r] : r) : 0;
+      zr[mi] = (live[mi] && MI > 1) ? (a.rowidx ? a.rowidx[r] : r) : 0;
     }
     double acc[MI][8][2];
 #pragma unroll
@@ -98,21 +116,34 @@ __global__ void __launch_bounds__(kPjThreads, MI == 1 ? 2 : 1) project_mma_kerne
       for (int mi = 0; mi < MI; ++mi) { acc[mi][ni][0] = c0; acc[mi][ni][1] = c1; }
     }
     // ---- contraction ---------------------------------------------------------------------------
-    if (MI == 1) {
+    double ycur = 0.;
+    double afc[kPjKT / 4];                                           // (MI == 1) this block's A fragments, kept for the tail path
+    auto contract_resident = [&]() {
 #pragma unroll
       for (int kk = 0; kk < kPjKT; kk += 4) {
         if (kk < d) {                                                // block-uniform
-          const int k = kk + tq;
-          const double af = (live[0] && k < d) ? __ldg(a.Z + zr[0] * a.zld + k) : 0.;
-          const double* brow = ths + (size_t)k * ld + col0 + g;
+          const double* brow = ths + (size_t)(kk + tq) * ld + col0 + g;
 #pragma unroll
-          for (int ni = 0; ni < 8; ++ni) dmma_m8n8k4(acc[0][ni][0], acc[0][ni][1], af, brow[ni * 8]);
+          for (int ni = 0; ni < 8; ++ni) dmma_m8n8k4(acc[0][ni][0], acc[0][ni][1], afc[kk / 4], brow[ni * 8]);
         }
       }
+    };
+    if (MI == 1) {
+#pragma unroll
+      for (int q = 0; q < kPjKT / 4; ++q) afc[q] = afn[q];
+      contract_resident();
+      ycur = yn;
+      fetch_block(rb + gridDim.x);                                   // in flight during this block's epilogue
     } else {
       __syncthreads();                                               // previous block's tiles are no longer read
       load_tile(0, 0);
       __syncthreads();
+      double afq[MI];                                                // A fragments, fetched one k step ahead
+      auto fetch_a = [&](int k) {
+#pragma unroll
+        for (int mi = 0; mi < MI; ++mi) afq[mi] = (live[mi] && k < d) ? __ldg(a.Z + zr[mi] * a.zld + k) : 0.;
+      };
+      fetch_a(tq);
       for (int kt = 0; kt < nk; ++kt) {
         const int k0 = kt * kPjKT;
         if (kt + 1 < nk) load_tile((kt + 1) & 1, k0 + kPjKT);        // the other buffer: last read before the previous barrier
@@ -120,10 +151,10 @@ __global__ void __launch_bounds__(kPjThreads, MI == 1 ? 2 : 1) project_mma_kerne
 #pragma unroll
         for (int kk = 0; kk < kPjKT; kk += 4) {
           if (k0 + kk < d) {
-            const int k = k0 + kk + tq;
             double af[MI];
 #pragma unroll
-            for (int mi = 0; mi < MI; ++mi) af[mi] = (live[mi] && k < d) ? __ldg(a.Z + zr[mi] * a.zld + k) : 0.;
+            for (int mi = 0; mi < MI; ++mi) af[mi] = afq[mi];
+            fetch_a(k0 + kk + 4 + tq);
             const double* brow = tile + (size_t)(kk + tq) * ld + col0 + g;
 #pragma unroll
             for (int ni = 0; ni < 8; ++ni) {
@@ -139,25 +170,51 @@ __global__ void __launch_bounds__(kPjThreads, MI == 1 ? 2 : 1) project_mma_kerne
     // ---- link + row mean (projector.py:20-21) ----------------------------------------------------
 #pragma unroll
     for (int mi = 0; mi < MI; ++mi) {
-      const double y = (MODEL == MODEL_POISSON && live[mi]) ? __ldg(a.Z + zr[mi] * a.zld + d) : 0.;
+      const double y = MODEL != MODEL_POISSON ? 0. : (MI == 1 ? ycur : (live[mi] ? __ldg(a.Z + zr[mi] * a.zld + d) : 0.));
       double sum = 0.;
+      if (MI == 1 && MODEL != MODEL_LINEAR) {
+        // branch-free links: 16 independent evaluations the compiler can interleave (softplus_table.h); when any lane of
+        // the warp met |lin| > 37 (rare) the tile is contracted again and evaluated with the branching links
+        bool tail = false;
 #pragma unroll
-      for (int ni = 0; ni < 8; ++ni) {
-        acc[mi][ni][0] = fast_link<MODEL>(tab, acc[mi][ni][0], y);
-        acc[mi][ni][1] = fast_link<MODEL>(tab, acc[mi][ni][1], y);
-        sum += acc[mi][ni][0] + acc[mi][ni][1];
+        for (int ni = 0; ni < 8; ++ni)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const double lin = acc[mi][ni][e];
+            tail |= link_needs_tail(lin);
+            acc[mi][ni][e] = MODEL == MODEL_LR ? lr_link_nb(tab, lin) : poisson_link_nb(tab, lin, y);
+          }
+        if (__any_sync(0xffffffffu, tail)) {
+#pragma unroll
+          for (int ni = 0; ni < 8; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.;
+          contract_resident();
+#pragma unroll
+          for (int ni = 0; ni < 8; ++ni) {
+            acc[mi][ni][0] = fast_link<MODEL>(tab, acc[mi][ni][0], y);
+            acc[mi][ni][1] = fast_link<MODEL>(tab, acc[mi][ni][1], y);
+          }
+        }
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) sum += acc[mi][ni][0] + acc[mi][ni][1];
+      } else {
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) {
+          acc[mi][ni][0] = fast_link<MODEL>(tab, acc[mi][ni][0], y);
+          acc[mi][ni][1] = fast_link<MODEL>(tab, acc[mi][ni][1], y);
+          sum += acc[mi][ni][0] + acc[mi][ni][1];
+        }
       }
       sum += __shfl_xor_sync(0xffffffffu, sum, 1);
       sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-      if (tq == 0) red[(size_t)(wr * (8 * MI) + mi * 8 + g) * WC + wc] = sum;
+      if (tq == 0) red[(size_t)wc * BM + wr * (8 * MI) + mi * 8 + g] = sum;      // [strip][row]: conflict-free
     }
     __syncthreads();
     double* red1 = red + (size_t)BM * WC;
 #pragma unroll
     for (int mi = 0; mi < MI; ++mi) {
-      const double* rr = red + (size_t)(wr * (8 * MI) + mi * 8 + g) * WC;
+      const double* rr = red + wr * (8 * MI) + mi * 8 + g;
       double tot = 0.;
-      for (int w = 0; w < WC; ++w) tot += rr[w];
+      for (int w = 0; w < WC; ++w) tot += rr[(size_t)w * BM];
       const double mean = tot * (1. / (double)S);                    // S is a power of two: exact reciprocal
       double ss = 0.;
 #pragma unroll
@@ -169,15 +226,15 @@ __global__ void __launch_bounds__(kPjThreads, MI == 1 ? 2 : 1) project_mma_kerne
       }
       ss += __shfl_xor_sync(0xffffffffu, ss, 1);
       ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-      if (tq == 0) red1[(size_t)(wr * (8 * MI) + mi * 8 + g) * WC + wc] = ss;
+      if (tq == 0) red1[(size_t)wc * BM + wr * (8 * MI) + mi * 8 + g] = ss;
     }
     __syncthreads();
     // ---- norm, unit float32 row (giga.py:10-13) ----------------------------------------------------
 #pragma unroll
     for (int mi = 0; mi < MI; ++mi) {
-      const double* rr = red1 + (size_t)(wr * (8 * MI) + mi * 8 + g) * WC;
+      const double* rr = red1 + wr * (8 * MI) + mi * 8 + g;
       double tot = 0.;
-      for (int w = 0; w < WC; ++w) tot += rr[w];
+      for (int w = 0; w < WC; ++w) tot += rr[(size_t)w * BM];
       const double norm = sqrt(tot);
       const double inv = norm > 0. ? 1. / norm : 0.;
       if (live[mi]) {

@@ -149,25 +149,39 @@ __global__ void __launch_bounds__(kPsThreads, 1) project_sum_mma_kernel(const Pr
         __syncthreads();
       }
 
-      // ---- epilogue: accumulator (mi, ni, e) is row wr*32 + mi*8 + g, column wc*64 + ni*8 + tq*2 + e
+      // ---- epilogue: accumulator (mi, ni, e) is row wr*32 + mi*8 + g, column wc*64 + ni*8 + tq*2 + e.  First with the
+      // branch-free links (64 independent evaluations the compiler can interleave); when any lane of the warp met an
+      // argument outside their range (|lin| > 37: rare) the tile's sums are redone with the branching links.
       double cs[8][2];
+      auto epilogue = [&](auto link) {
 #pragma unroll
-      for (int ni = 0; ni < 8; ++ni) { cs[ni][0] = 0.; cs[ni][1] = 0.; }
+        for (int ni = 0; ni < 8; ++ni) { cs[ni][0] = 0.; cs[ni][1] = 0.; }
 #pragma unroll
-      for (int mi = 0; mi < 4; ++mi) {
-        const int rl = wr * 32 + mi * 8 + g;
-        const bool live = row0 + rl < a.n;
-        const double y = (MODEL == MODEL_POISSON) ? ys[rl] : 0.;
+        for (int mi = 0; mi < 4; ++mi) {
+          const int rl = wr * 32 + mi * 8 + g;
+          const bool live = row0 + rl < a.n;
+          const double y = (MODEL == MODEL_POISSON) ? ys[rl] : 0.;
 #pragma unroll
-        for (int ni = 0; ni < 8; ++ni)
+          for (int ni = 0; ni < 8; ++ni)
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int c = col0 + wc * 64 + ni * 8 + tq * 2 + e;
-            double lin = acc[mi][ni][e];
-            if (a.coff && c < S) lin += a.coff[c];
-            const double v = link_apply<MODEL>(a.sp_tab, lin, y);
-            cs[ni][e] += (live && c < S) ? v : 0.;
-          }
+            for (int e = 0; e < 2; ++e) {
+              const int c = col0 + wc * 64 + ni * 8 + tq * 2 + e;
+              double lin = acc[mi][ni][e];
+              if (a.coff && c < S) lin += a.coff[c];
+              const double v = link(lin, y);
+              cs[ni][e] += (live && c < S) ? v : 0.;
+            }
+        }
+      };
+      if (MODEL == MODEL_LINEAR || !a.sp_tab) {
+        epilogue([&](double lin, double y) { return link_apply<MODEL>(a.sp_tab, lin, y); });
+      } else {
+        bool tail = false;
+        epilogue([&](double lin, double y) {
+          tail |= link_needs_tail(lin);
+          return MODEL == MODEL_LR ? lr_link_nb(a.sp_tab, lin) : poisson_link_nb(a.sp_tab, lin, y);
+        });
+        if (__any_sync(0xffffffffu, tail)) epilogue([&](double lin, double y) { return link_apply<MODEL>(a.sp_tab, lin, y); });
       }
 #pragma unroll
       for (int ni = 0; ni < 8; ++ni)

@@ -80,6 +80,54 @@ SP_HD double softplus_neg(const double* tab, double t) {
   return fma(dl, p, g);
 }
 
+// ---- branch-free forms ---------------------------------------------------------------------------------------------
+// A projection kernel evaluates 16-64 links per lane back to back.  With the tail test of softplus_neg inside, every
+// evaluation is its own branch region (SASS: BSSY / @P BRA / CALL / BSYNC around ~55 instructions) and the compiler
+// cannot interleave the independent Horner chains: the float64 pipe sees a dependent chain at a time and the warps sit
+// in fixed-latency "wait" stalls (ncu, profiles/r02_k3_mma_vs_fast_lr_N2e6_S512.csv: 2.1-2.5 wait-stall cycles per
+// issue, float64 pipe 37-53 % busy).  The *_nb forms have no branch: they are exact for |lin| <= 37 and return
+// garbage beyond; the caller ORs link_needs_tail() over its elements and, when any lane of the warp saw one (rare:
+// |z.theta| > 37), re-evaluates that batch with the branching forms below.
+SP_HD bool link_needs_tail(double lin) { return fabs(lin) > (double)kSpRange; }
+
+SP_HD double softplus_neg_nb(const double* tab, double t) {
+#ifdef __CUDA_ARCH__
+  int i = __double2int_rn(t * -(double)kSpPerUnit);
+#else
+  int i = (t == t) ? (int)nearbyint(fmax(fmin(t * -(double)kSpPerUnit, 1e9), -1e9)) : 0;
+#endif
+  i = i < 0 ? 0 : (i > kSpNodes - 1 ? kSpNodes - 1 : i);
+  const double dl = fma((double)i, 1. / kSpPerUnit, t);
+#ifdef __CUDA_ARCH__
+  const double2 n = __ldg(reinterpret_cast<const double2*>(tab) + i);
+  const double g = n.x, s = n.y;
+#else
+  const double g = tab[2 * (size_t)i], s = tab[2 * (size_t)i + 1];
+#endif
+  const double q = fma(-s, s, s);
+  const double r = fma(-2., s, 1.);
+  const double g3 = q * r;
+  const double g4 = q * fma(-6., q, 1.);
+  const double g5 = g3 * fma(-12., q, 1.);
+  const double g6 = q * fma(fma(120., q, -30.), q, 1.);
+  double p = fma(dl * (1. / 6.), g6, g5);
+  p = fma(dl * 0.2, p, g4);
+  p = fma(dl * 0.25, p, g3);
+  p = fma(dl * (1. / 3.), p, q);
+  p = fma(dl * 0.5, p, s);
+  return fma(dl, p, g);
+}
+
+SP_HD double lr_link_nb(const double* tab, double lin) {
+  const double m = -lin;
+  return -(fmax(m, 0.) + softplus_neg_nb(tab, -fabs(m)));
+}
+
+SP_HD double poisson_link_nb(const double* tab, double lin, double y) {
+  const double sp = fmax(lin, 0.) + softplus_neg_nb(tab, -fabs(lin));
+  return y * log(sp) - sp;
+}
+
 // model_lr.py:28-31 as -(max(m, 0) + log1p(exp(-|m|))), m = -lin: the same function in float64 (for m >= 100 the
 // log1p term is < 4e-44 and vanishes against m, which is the reference's linear branch)
 SP_HD double lr_link_fast(const double* tab, double lin) {

@@ -18,7 +18,20 @@ KEEP = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__
         'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio',
-        'smsp__average_warps_issue_stalled_sleeping_per_issue_active.ratio']
+        'smsp__average_warps_issue_stalled_sleeping_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio',
+        # pipe utilisation: what the diagnosis of the projection kernels rests on (L1 data pipe vs float64 pipe vs issue)
+        'l1tex__data_pipe_lsu_wavefronts.sum', 'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_elapsed', 'l1tex__throughput.avg.pct_of_peak_sustained_elapsed',
+        'smsp__inst_executed_pipe_fp64.sum', 'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active',
+        'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_lsu.sum',
+        'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_tensor.sum',
+        'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__pipe_tensor_op_dmma_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active', 'smsp__cycles_active.avg', 'sm__cycles_elapsed.max']
 
 
 def main(rep, out):
@@ -31,6 +44,10 @@ def main(rep, out):
     for k in KEEP:
       if k in hdr:
         i = hdr.index(k)
+        w.writerow([k, units[i]] + [r[i] for r in data])
+    # every fp64 / dmma / pipe metric the capture holds (names differ between ncu versions)
+    for i, k in enumerate(hdr):
+      if k not in KEEP and any(t in k for t in ('fp64', 'dmma', 'pipe_tensor', 'data_pipe_lsu')):
         w.writerow([k, units[i]] + [r[i] for r in data])
   print(open(out).read())
 

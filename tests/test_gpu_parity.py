@@ -625,7 +625,7 @@ def test_pinned_source_equals_pageable_source(bc):
 
 @pytest.mark.parametrize('S,d', [(64, 3), (128, 32), (256, 10), (512, 10), (512, 24), (256, 200), (512, 70), (128, 16)])
 def test_specialised_projection_kernels_vs_general_and_oracle(bc, monkeypatch, S, d):
-  """the three materialising projection kernels -- project_mma_kernel (DMMA; default for S in {64,128,256,512}: sample tile
+  """the three materialising projection kernels -- project_mma_kernel (DMMA; BCG_PROJ_MMA=2 forces it for every S in {64,128,256,512}: sample tile
   resident for d <= 16, streamed k tiles above), project_fast_kernel (BCG_PROJ_MMA=0; d <= 32) and the general kernel
   (BCG_PROJ_MMA=0 BCG_PROJ_FAST=0) -- against each other and the oracle: three models, a row count that is no multiple of
   any row block, a device row gather, column-sum-only passes"""
@@ -640,7 +640,7 @@ def test_specialised_projection_kernels_vs_general_and_oracle(bc, monkeypatch, S
   cases = [(bc._native.MODEL_LR, X, None, models.project(models.lr_loglik, X, th)),
            (bc._native.MODEL_POISSON, Zp, None, models.project(models.poisson_loglik, Zp, th)),
            (bc._native.MODEL_GAUSSIAN, X, Siginv, models.project(lambda x, t: models.gaussian_loglik(x, t, Siginv, 0.), X, th))]
-  variants = [{'BCG_PROJ_MMA': '1'}, {'BCG_PROJ_MMA': '0', 'BCG_PROJ_FAST': '1'}, {'BCG_PROJ_MMA': '0', 'BCG_PROJ_FAST': '0'}]
+  variants = [{'BCG_PROJ_MMA': '2'}, {'BCG_PROJ_MMA': '0', 'BCG_PROJ_FAST': '1'}, {'BCG_PROJ_MMA': '0', 'BCG_PROJ_FAST': '0'}]
   for model, Z, si, ref in cases:
     ds = bc.Dataset(Z)
     res = []
@@ -976,5 +976,5 @@ def test_integration_md_stub_runs_inside_the_reference_tree(bc, tmp_path):
   o = greedy.GigaOracle(X.T, X.sum(axis=0))
   o.build(100)
   assert np.array_equal(idcs, np.flatnonzero(o.w > 0))
-  np.testing.assert_allclose(wts, o.w[o.w > 0], rtol=1e-5)
-  assert a.error() == pytest.approx(o.error(), rel=1e-5, abs=1e-6)
+  assert_weights_close(wts, o.w[o.w > 0])
+  assert_errors_close(a.error(), o.error(), X, o.w)

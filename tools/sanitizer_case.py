@@ -9,7 +9,7 @@ from conftest import lr_problem
 N, d = int(sys.argv[1]) if len(sys.argv) > 1 else 3000, 6
 for S in (256, 96):
   Z, theta = lr_problem(1, N, d, S)
-  for mma, fast in (('1', '1'), ('0', '1'), ('0', '0')):            # DMMA / warp-per-row / general projection kernels
+  for mma, fast in (('2', '1'), ('0', '1'), ('0', '0')):            # DMMA / warp-per-row / general projection kernels
     os.environ['BCG_PROJ_MMA'], os.environ['BCG_PROJ_FAST'] = mma, fast
     prj = bc.LogisticRegressionProjector(lambda n, w, p: theta, S)
     cs = bc.HilbertCoreset(Z, prj, snnls=bc.snnls.GIGA)
