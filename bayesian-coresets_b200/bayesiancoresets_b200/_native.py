@@ -57,6 +57,8 @@ _PROTOTYPES = {
   'bcg_dataset_destroy': (_c.c_int, [_P]),
   'bcg_dataset_project': (_c.c_int, [_P, _P, _c.c_int64, _c.c_int32, _c.c_int32, _P, _c.c_int32, _P, _PP, _P, _P]),
   'bcg_dataset_project_linear': (_c.c_int, [_P, _P, _c.c_int64, _c.c_int32, _P, _P, _c.c_int32, _PP, _P, _P]),
+  'bcg_dataset_project_lazy': (_c.c_int, [_P, _c.c_int32, _c.c_int32, _P, _c.c_int32, _P, _PP]),
+  'bcg_pseudo_grad': (_c.c_int, [_P, _c.c_int32, _P, _c.c_int64, _c.c_int32, _c.c_int32, _P, _c.c_int32, _P, _P, _P, _P, _P]),
   'bcg_dataset_audit': (_c.c_int, [_P, _c.c_int32, _c.c_int32, _P, _c.c_int32, _P, _c.c_int32, _P, _P, _P, _P]),
   'bcg_vecs_shape': (_c.c_int, [_P, _c.POINTER(_c.c_int64), _c.POINTER(_c.c_int32), _c.POINTER(_c.c_int32)]),
   'bcg_vecs_colsum': (_c.c_int, [_P, _P]),
@@ -209,6 +211,24 @@ class Context(object):
     check(lib().bcg_ctx_flush_l2(self.handle, int(nbytes)))
 
 
+def pseudo_grad(model, pts, theta, Siginv=None, w=None, resid=None, full=False, ctx=None):
+  """device evaluation of the pseudo-point gradients (bcg_pseudo_grad): returns (glls (K, S, dz) | None, ugrad (K, dz) | None);
+  ugrad is computed when w and resid are given"""
+  ctx = ctx or Context.default()
+  pts, theta = _f64(np.atleast_2d(pts)), _f64(np.atleast_2d(theta))
+  S, d = theta.shape
+  K, zld = pts.shape
+  dz = d + 1 if model == MODEL_POISSON else d
+  si = None if Siginv is None else _f64(Siginv)
+  g = np.empty((K, S, dz)) if full else None
+  u = np.empty((K, dz)) if w is not None else None
+  ww = None if w is None else _f64(w)
+  rr = None if resid is None else _f64(resid)
+  p = lambda x: None if x is None else _ptr(x)
+  check(lib().bcg_pseudo_grad(ctx.handle, model, _ptr(pts), K, zld, d, _ptr(theta), S, p(si), p(ww), p(rr), p(g), p(u)))
+  return g, u
+
+
 class Dataset(object):
   """bcg_dataset: the (n, d) data uploaded once and projected many times."""
   def __init__(self, Z, ctx=None):
@@ -240,6 +260,18 @@ class Dataset(object):
     else:
       check(lib().bcg_dataset_project(self.handle, sel[0], sel[1], model, d, _ptr(theta), S, None, *outs))
     return (DeviceVecs(self.ctx, hv) if vecs else None), out_rows, out_cs
+
+  def project_lazy(self, model, theta, Siginv=None):
+    """the never-materialising projection: a DeviceVecs without a matrix (norms / column sums only); solvers built over it
+    re-evaluate the rows from this dataset at every selection pass"""
+    theta = _f64(np.atleast_2d(theta))
+    S, d = theta.shape
+    si = None if Siginv is None else _f64(Siginv)
+    hv = ctypes.c_void_p()
+    check(lib().bcg_dataset_project_lazy(self.handle, model, d, _ptr(theta), S, None if si is None else _ptr(si), ctypes.byref(hv)))
+    v = DeviceVecs(self.ctx, hv)
+    v._source = self                                   # the dataset must outlive the lazy projection
+    return v
 
   def audit(self, model, theta, Siginv=None, kind=ALG_FW, dirs=None, scores=True, norms=False, colsum=False):
     """independent float64 re-evaluation of one selection pass from the raw data (bcg_dataset_audit):

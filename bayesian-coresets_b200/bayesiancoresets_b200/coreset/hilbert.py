@@ -13,9 +13,13 @@ from .coreset import Coreset
 
 
 class HilbertCoreset(Coreset):
-  def __init__(self, data, ll_projector, n_subsample=None, snnls=GIGA, comm=None, **kw):
+  def __init__(self, data, ll_projector, n_subsample=None, snnls=GIGA, comm=None, materialize=True, **kw):
     self.comm = comm or SerialComm()
     project = getattr(ll_projector, 'project_device', ll_projector.project)
+    if not materialize:
+      # never-materialising solver: the N x S matrix is not built; every selection pass re-evaluates
+      # the rows from the raw data in float64 (8 N d bytes resident instead of 4 N S, ~10x the time per iteration)
+      project = ll_projector.project_lazy
     if n_subsample is None:
       sub_idcs = None                                   # identity (the reference's np.arange(N) is an O(N) host array)
       vecs = project(data)

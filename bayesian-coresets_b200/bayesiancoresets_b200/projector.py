@@ -82,61 +82,40 @@ class _DeviceModelProjector(Projector):
     return self._dataset(pts, cache or sub is not None).project(self._model, self.samples, self._siginv(), vecs=True,
                                                                 sub=sub)[0]
 
+  def project_lazy(self, pts):
+    """the never-materialising projection (`HilbertCoreset(..., materialize=False)`): only norms and column sums are
+    computed now; the solver re-evaluates the rows from the raw data at every selection pass"""
+    return self._dataset(pts, False).project_lazy(self._model, self.samples, self._siginv())
+
   def project_sum(self, pts, cache=True, sub=None):
     return self._dataset(pts, cache or sub is not None).project(self._model, self.samples, self._siginv(), colsum=True,
                                                                 sub=sub)[2]
 
   def grad_contract(self, pts, w, resid):
     """-(1/S) sum_s w_k resid_s (glls[k,s,:] - mean_d glls[k,s,:]) for the K pseudo-points (bpsvi.py:53 with the
-    centring of projector.py:26), without materialising the (K, S, d) array: glls[k,s,:] = g[k,s] * v_s for the GLM
-    models, so the contraction is one (K x S) . (S x d) product.  K-sized host algebra."""
-    glls = self._grad(np.atleast_2d(pts))
-    glls -= glls.mean(axis=2)[:, :, np.newaxis]
-    return -(w[:, np.newaxis, np.newaxis]*glls*resid[np.newaxis, :, np.newaxis]).sum(axis=1)/glls.shape[1]
+    centring of projector.py:26), on the device, without materialising the (K, S, d) array (csrc/pseudo_grad_kernel.cuh)"""
+    return nat.pseudo_grad(self._model, np.atleast_2d(pts), self.samples, self._siginv(), w=w, resid=resid, ctx=self.ctx)[1]
 
-  def _grad(self, pts):
-    raise ValueError('grad_loglikelihood was requested but is not available for this projector')
+  def _grad_centred(self, pts):
+    """(n, S, d) gradients, centred over the LAST axis as projector.py:26 does, evaluated on the device"""
+    return nat.pseudo_grad(self._model, pts, self.samples, self._siginv(), full=True, ctx=self.ctx)[0]
 
   def project(self, pts, grad=False):
     pts2 = np.atleast_2d(pts)
     lls = self._dataset(pts2, False).project(self._model, self.samples, self._siginv(), rows=True)[1]
     if not grad:
       return lls
-    # (n, S, d) gradients are only ever requested for the K pseudo-points of BatchPSVI
-    # (bpsvi.py:37); K*S*d host arithmetic, centred over the LAST axis as projector.py:26 does
-    glls = self._grad(pts2)
-    glls -= glls.mean(axis=2)[:, :, np.newaxis]
-    return lls, glls
+    # (n, S, d) gradients are only ever requested for the K pseudo-points of BatchPSVI (bpsvi.py:37)
+    return lls, self._grad_centred(pts2)
 
 
 class LogisticRegressionProjector(_DeviceModelProjector):
-  """log-likelihood of examples/common/model_lr.py:25-32 with z_n = y_n x_n."""
+  """log-likelihood of examples/common/model_lr.py:25-32 with z_n = y_n x_n (gradients: model_lr.py:50-57)."""
   _model = nat.MODEL_LR
-
-  def _sig(self, z):
-    m = -z.dot(self.samples.T)                           # model_lr.py:50-56
-    small = m < 100
-    sig = np.ones_like(m)
-    em = np.exp(m[small])
-    sig[small] = em/(1. + em)
-    return sig
-
-  def grad_contract(self, pts, w, resid):
-    th = self.samples
-    g = self._sig(np.atleast_2d(pts))*resid[np.newaxis, :]
-    return -(w[:, np.newaxis]*g.dot(th - th.mean(axis=1)[:, np.newaxis]))/th.shape[0]
-
-  def _grad(self, z):
-    m = -z.dot(self.samples.T)                           # model_lr.py:50-57
-    small = m < 100
-    sig = np.ones_like(m)
-    em = np.exp(m[small])
-    sig[small] = em/(1. + em)
-    return sig[:, :, np.newaxis]*self.samples[np.newaxis, :, :]
 
 
 class GaussianProjector(_DeviceModelProjector):
-  """log-likelihood of examples/common/model_gaussian.py:4-10 (known covariance)."""
+  """log-likelihood of examples/common/model_gaussian.py:4-10, known covariance (gradients: model_gaussian.py:12-15)."""
   _model = nat.MODEL_GAUSSIAN
 
   def __init__(self, sampler, projection_dimension, Siginv, ctx=None):
@@ -146,51 +125,8 @@ class GaussianProjector(_DeviceModelProjector):
   def _siginv(self):
     return self.Siginv
 
-  def _grad(self, x):
-    return self.samples.dot(self.Siginv)[np.newaxis, :, :] - x.dot(self.Siginv)[:, np.newaxis, :]
-
-  def grad_contract(self, pts, w, resid):
-    A = self.samples.dot(self.Siginv)
-    B = np.atleast_2d(pts).dot(self.Siginv)
-    A = A - A.mean(axis=1)[:, np.newaxis]
-    B = B - B.mean(axis=1)[:, np.newaxis]
-    return -(w[:, np.newaxis]*(resid.dot(A)[np.newaxis, :] - resid.sum()*B))/self.samples.shape[0]
-
 
 class PoissonProjector(_DeviceModelProjector):
-  """log-likelihood of examples/common/model_poiss.py:25-38, z_n = [x_n, y_n]."""
+  """log-likelihood of examples/common/model_poiss.py:25-38, z_n = [x_n, y_n] (gradients: model_poiss.py:58-67 with the
+  reference's broadcast defect repaired and a zero d/dy column, as documented in SURVEY.md section 8c)."""
   _model = nat.MODEL_POISSON
-
-  def _grad(self, z):
-    # model_poiss.py:58-67 with the reference's broadcast defect repaired (th[np.newaxis,:,:]) and a zero
-    # d/dy column, as documented in SURVEY.md section 8c
-    x, y = z[:, :-1], z[:, -1][:, np.newaxis]
-    s = x.dot(self.samples.T)
-    big = s > -100
-    s[big] = np.log(np.maximum(s[big], 0) + np.log1p(np.exp(-np.fabs(s[big]))))
-    g = y - np.exp(s)
-    nz = np.exp(s) > 1e-15
-    yy = np.broadcast_to(y, s.shape)
-    g[nz] = (yy[nz]*np.exp(-s[nz]) - 1.)*(1. - np.exp(-np.exp(s[nz])))
-    gx = g[:, :, np.newaxis]*self.samples[np.newaxis, :, :]
-    return np.concatenate((gx, np.zeros(gx.shape[:2] + (1,))), axis=2)
-
-  def _g(self, z):
-    x, y = z[:, :-1], z[:, -1][:, np.newaxis]
-    s = x.dot(self.samples.T)
-    big = s > -100
-    s[big] = np.log(np.maximum(s[big], 0) + np.log1p(np.exp(-np.fabs(s[big]))))
-    g = y - np.exp(s)
-    nz = np.exp(s) > 1e-15
-    yy = np.broadcast_to(y, s.shape)
-    g[nz] = (yy[nz]*np.exp(-s[nz]) - 1.)*(1. - np.exp(-np.exp(s[nz])))
-    return g
-
-  def grad_contract(self, pts, w, resid):
-    th = self.samples
-    d = th.shape[1]
-    g = self._g(np.atleast_2d(pts))*resid[np.newaxis, :]
-    mean = th.sum(axis=1)/(d + 1.)                       # the zero d/dy column takes part in the centring
-    gx = g.dot(th - mean[:, np.newaxis])
-    gy = -g.dot(mean)
-    return -(w[:, np.newaxis]*np.hstack((gx, gy[:, np.newaxis])))/th.shape[0]

@@ -45,93 +45,109 @@ __device__ __forceinline__ double audit_warp_sum(double v) {
   return v;
 }
 
+// centred log-likelihood vector of data row `row` (lane owns columns lane + 32 j) and its norm; shared by the audit
+// scorer and the never-materialising select
+template <int J>
+__device__ __forceinline__ double audit_row(const AuditArgs& a, int64_t row, int lane, double (&v)[J]) {
+  const int S = a.S, d = a.d;
+  const double* z = a.Z + row * a.zld;
+#pragma unroll
+  for (int j = 0; j < J; ++j) v[j] = 0.;
+  for (int k = 0; k < d; ++k) {
+    const double zk = z[k];
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int s = lane + 32 * j;
+      if (s < S) v[j] = fma(zk, __ldg(a.thetaT + (size_t)k * S + s), v[j]);
+    }
+  }
+  double xsx = 0., y = 0., lg = 0.;
+  if (a.model == BCG_MODEL_GAUSSIAN) {
+    // x Siginv x (row constant; kept because the reference evaluates it before centring)
+    double part = 0.;
+    for (int i = lane; i < d; i += 32) {
+      double t = 0.;
+      for (int k = 0; k < d; ++k) t = fma(__ldg(a.Siginv + (size_t)i * d + k), z[k], t);
+      part = fma(z[i], t, part);
+    }
+    xsx = audit_warp_sum(part);
+  } else if (a.model == BCG_MODEL_POISSON) {
+    y = z[d];
+    lg = lgamma(y + 1.);
+  }
+  double sum = 0.;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int s = lane + 32 * j;
+    if (s < S) {
+      double ll;
+      if (a.model == BCG_MODEL_LR) {
+        const double m = -v[j];
+        ll = (m < 100.) ? -log1p(exp(m)) : -m;
+      } else if (a.model == BCG_MODEL_POISSON) {
+        double t = v[j];
+        if (t > -100.) t = log(fmax(t, 0.) + log1p(exp(-fabs(t))));
+        ll = y * t - lg - exp(t);
+      } else {
+        ll = -0.5 * (xsx + __ldg(a.tt + s) - 2. * v[j]);
+      }
+      v[j] = ll;
+      sum += ll;
+    }
+  }
+  const double mean = audit_warp_sum(sum) / (double)S;
+  double ss = 0.;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int s = lane + 32 * j;
+    if (s < S) { v[j] -= mean; ss = fma(v[j], v[j], ss); } else v[j] = 0.;
+  }
+  return sqrt(audit_warp_sum(ss));
+}
+
+// score of a centred row against the direction(s): giga.py:33-38 / frankwolfe.py:17
+template <int J>
+__device__ __forceinline__ double audit_score(const double (&v)[J], double norm, const double* dirs, int S, bool giga, int lane) {
+  double p0 = 0., p1 = 0.;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int s = lane + 32 * j;
+    if (s < S) {
+      p0 = fma(v[j], dirs[s], p0);
+      if (giga) p1 = fma(v[j], dirs[S + s], p1);
+    }
+  }
+  p0 = audit_warp_sum(p0);
+  double score;
+  if (giga) {
+    p1 = audit_warp_sum(p1);
+    const double s0 = p0 / norm, s1 = p1 / norm;
+    const bool ok = (s1 > -1. + 1e-14) && (1. - s1 * s1 > 0.);            // giga.py:33
+    score = ok ? s0 / sqrt(1. - s1 * s1) : s0 / INFINITY;                 // giga.py:34-38
+  } else {
+    score = p0 / norm;
+  }
+  if (!(norm > 0.)) score = -INFINITY;      // the reference rejects zero rows at construction (giga.py:11-12)
+  return score;
+}
+
 template <int J>
 __global__ void __launch_bounds__(256) audit_score_kernel(const AuditArgs a) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int S = a.S, d = a.d;
+  const int S = a.S;
   double cs[J];
 #pragma unroll
   for (int j = 0; j < J; ++j) cs[j] = 0.;
-
   for (int64_t row = warp; row < a.n; row += nwarps) {
-    const double* z = a.Z + row * a.zld;
     double v[J];
+    const double norm = audit_row<J>(a, row, lane, v);
 #pragma unroll
-    for (int j = 0; j < J; ++j) v[j] = 0.;
-    for (int k = 0; k < d; ++k) {
-      const double zk = z[k];
-#pragma unroll
-      for (int j = 0; j < J; ++j) {
-        const int s = lane + 32 * j;
-        if (s < S) v[j] = fma(zk, __ldg(a.thetaT + (size_t)k * S + s), v[j]);
-      }
-    }
-    double xsx = 0., y = 0., lg = 0.;
-    if (a.model == BCG_MODEL_GAUSSIAN) {
-      // x Siginv x (row constant; kept because the reference evaluates it before centring)
-      double part = 0.;
-      for (int i = lane; i < d; i += 32) {
-        double t = 0.;
-        for (int k = 0; k < d; ++k) t = fma(__ldg(a.Siginv + (size_t)i * d + k), z[k], t);
-        part = fma(z[i], t, part);
-      }
-      xsx = audit_warp_sum(part);
-    } else if (a.model == BCG_MODEL_POISSON) {
-      y = z[d];
-      lg = lgamma(y + 1.);
-    }
-    double sum = 0.;
-#pragma unroll
-    for (int j = 0; j < J; ++j) {
-      const int s = lane + 32 * j;
-      if (s < S) {
-        double ll;
-        if (a.model == BCG_MODEL_LR) {
-          const double m = -v[j];
-          ll = (m < 100.) ? -log1p(exp(m)) : -m;
-        } else if (a.model == BCG_MODEL_POISSON) {
-          double t = v[j];
-          if (t > -100.) t = log(fmax(t, 0.) + log1p(exp(-fabs(t))));
-          ll = y * t - lg - exp(t);
-        } else {
-          ll = -0.5 * (xsx + __ldg(a.tt + s) - 2. * v[j]);
-        }
-        v[j] = ll;
-        sum += ll;
-      }
-    }
-    const double mean = audit_warp_sum(sum) / (double)S;
-    double ss = 0., p0 = 0., p1 = 0.;
-#pragma unroll
-    for (int j = 0; j < J; ++j) {
-      const int s = lane + 32 * j;
-      if (s < S) {
-        v[j] -= mean;
-        ss = fma(v[j], v[j], ss);
-        cs[j] += v[j];
-        if (a.dirs) {
-          p0 = fma(v[j], __ldg(a.dirs + s), p0);
-          if (a.kind == BCG_ALG_GIGA) p1 = fma(v[j], __ldg(a.dirs + S + s), p1);
-        }
-      }
-    }
-    ss = audit_warp_sum(ss);
-    const double norm = sqrt(ss);
+    for (int j = 0; j < J; ++j) cs[j] += v[j];
     if (a.norms && lane == 0) a.norms[row] = norm;
     if (a.scores) {
-      p0 = audit_warp_sum(p0);
-      double score;
-      if (a.kind == BCG_ALG_GIGA) {
-        p1 = audit_warp_sum(p1);
-        const double s0 = p0 / norm, s1 = p1 / norm;
-        const bool ok = (s1 > -1. + 1e-14) && (1. - s1 * s1 > 0.);            // giga.py:33
-        score = ok ? s0 / sqrt(1. - s1 * s1) : s0 / INFINITY;                 // giga.py:34-38
-      } else {
-        score = p0 / norm;
-      }
-      if (!(norm > 0.)) score = -INFINITY;      // the reference rejects zero rows at construction (giga.py:11-12)
+      const double score = audit_score<J>(v, norm, a.dirs, S, a.kind == BCG_ALG_GIGA, lane);
       if (lane == 0) a.scores[row] = score;
     }
   }

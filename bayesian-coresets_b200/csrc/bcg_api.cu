@@ -25,6 +25,8 @@
 #include "project_mma_kernel.cuh"
 #include "step_kernels.cuh"
 #include "audit_kernel.cuh"
+#include "lazy_select_kernel.cuh"
+#include "pseudo_grad_kernel.cuh"
 
 using namespace bcg;
 
@@ -136,6 +138,10 @@ struct bcg_vecs {
   double* norms;
   std::vector<double> colsum;   // S sums + [S] = sum of norms
   uint64_t zero_rows;
+  // never-materialising form (bcg_dataset_project_lazy): An == null, rows are re-evaluated from the dataset on demand
+  bcg_dataset* lazy_ds;         // borrowed: must outlive this object
+  int32_t lazy_model, lazy_d;
+  double *lazy_thetaT, *lazy_tt, *lazy_Siginv;   // owned device copies of the samples
 };
 
 struct bcg_solver {
@@ -399,7 +405,7 @@ static int j_for_ld(int ld) {
   return j;
 }
 
-static int vecs_alloc(bcg_ctx* ctx, int64_t n, int32_t S, bcg_vecs** out) {
+static int vecs_alloc(bcg_ctx* ctx, int64_t n, int32_t S, bcg_vecs** out, bool lazy = false) {
   if (n < 0 || S <= 0) return fail(BCG_ERR_ARG, "bad shape n=%lld S=%d", (long long)n, S);
   if (S > 1024) return fail(BCG_ERR_UNSUPPORTED, "S=%d > 1024 is not supported", S);
   if (n >= (1ll << 32) - 1) return fail(BCG_ERR_UNSUPPORTED, "more than 2^32-2 local rows");
@@ -412,8 +418,11 @@ static int vecs_alloc(bcg_ctx* ctx, int64_t n, int32_t S, bcg_vecs** out) {
   v->norms = nullptr;
   v->zero_rows = 0;
   v->colsum.assign(S + 1, 0.);
+  v->lazy_ds = nullptr;
+  v->lazy_model = v->lazy_d = 0;
+  v->lazy_thetaT = v->lazy_tt = v->lazy_Siginv = nullptr;
   if (n > 0) {
-    CK(cudaMalloc(&v->An, (size_t)n * v->ld * sizeof(float)));
+    if (!lazy) CK(cudaMalloc(&v->An, (size_t)n * v->ld * sizeof(float)));
     CK(cudaMalloc(&v->norms, (size_t)n * sizeof(double)));
   }
   *out = v;
@@ -889,6 +898,137 @@ extern "C" int bcg_dataset_audit(bcg_dataset* ds, int32_t model, int32_t d, cons
   return BCG_OK;
 }
 
+// The never-materialising projection: nothing but the row norms, the column sums b and the zero-row count are computed
+// (one float64 pass of the audit kernel); the returned bcg_vecs has no matrix.  A solver created over it re-evaluates the
+// rows from the dataset at every selection pass (lazy_select_kernel.cuh).  `ds` must outlive the result.
+extern "C" int bcg_dataset_project_lazy(bcg_dataset* ds, int32_t model, int32_t d, const double* theta, int32_t S,
+                                        const double* Siginv, bcg_vecs** out) {
+  if (!ds || !theta || !out) return fail(BCG_ERR_ARG, "null argument");
+  *out = nullptr;
+  RET(use_device(ds->ctx));
+  bcg_ctx* ctx = ds->ctx;
+  if (d <= 0 || S <= 0) return fail(BCG_ERR_ARG, "d and S must be positive");
+  if ((model == BCG_MODEL_POISSON ? d + 1 : d) > ds->zld) return fail(BCG_ERR_ARG, "dataset has too few columns");
+  std::vector<double> tT, coff;
+  int kmodel = 0;
+  RET(prepare_model(model, d, theta, S, Siginv, tT, coff, &kmodel));
+  bcg_vecs* v = nullptr;
+  RET(vecs_alloc(ctx, ds->n, S, &v, true));
+  auto body = [&]() -> int {
+    cudaStream_t st = ctx->stream;
+    v->lazy_ds = ds; v->lazy_model = model; v->lazy_d = d;
+    CK(cudaMalloc(&v->lazy_thetaT, (size_t)d * S * sizeof(double)));
+    CK(cudaMemcpyAsync(v->lazy_thetaT, tT.data(), (size_t)d * S * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (model == BCG_MODEL_GAUSSIAN) {
+      std::vector<double> tt(S);
+      for (int i = 0; i < S; ++i) tt[i] = -2. * coff[i];
+      CK(cudaMalloc(&v->lazy_tt, (size_t)S * sizeof(double)));
+      CK(cudaMalloc(&v->lazy_Siginv, (size_t)d * d * sizeof(double)));
+      CK(cudaMemcpyAsync(v->lazy_tt, tt.data(), (size_t)S * sizeof(double), cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(v->lazy_Siginv, Siginv, (size_t)d * d * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    if (ds->n == 0) return BCG_OK;
+    DevBuf<double> dcs;
+    CK(dcs.alloc(S));
+    CK(cudaMemsetAsync(dcs, 0, (size_t)S * sizeof(double), st));
+    AuditArgs a;
+    a.Z = ds->Z; a.n = ds->n; a.zld = ds->zld; a.d = d; a.S = S; a.model = model; a.kind = BCG_ALG_FW;
+    a.thetaT = v->lazy_thetaT; a.tt = v->lazy_tt; a.Siginv = v->lazy_Siginv; a.dirs = nullptr; a.scores = nullptr;
+    a.norms = v->norms; a.colsum = dcs;
+    switch (pow2ceil((S + 31) / 32)) {
+      case 1: RET(launch_audit<1>(ctx, a)); break;
+      case 2: RET(launch_audit<2>(ctx, a)); break;
+      case 4: RET(launch_audit<4>(ctx, a)); break;
+      case 8: RET(launch_audit<8>(ctx, a)); break;
+      case 16: RET(launch_audit<16>(ctx, a)); break;
+      default: RET(launch_audit<32>(ctx, a)); break;
+    }
+    std::vector<double> nr((size_t)ds->n);
+    CK(cudaMemcpyAsync(v->colsum.data(), dcs, (size_t)S * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(nr.data(), v->norms, (size_t)ds->n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    double ns = 0.;
+    uint64_t z = 0;
+    for (double x : nr) { ns += x; z += !(x > 0.) ? 1 : 0; }
+    v->colsum[S] = ns;
+    v->zero_rows = z;
+    return BCG_OK;
+  };
+  const int rc = body();
+  if (rc != BCG_OK) { bcg_vecs_destroy(v); return rc; }
+  *out = v;
+  return BCG_OK;
+}
+
+// (K, S, dz) datapoint gradients of the K pseudo-points and / or their contraction with (w, resid) -- pseudo_grad_kernel.cuh.
+// pts: host K x zld; theta: host S x d; outputs: host arrays, either may be null.
+extern "C" int bcg_pseudo_grad(bcg_ctx* ctx, int32_t model, const double* pts, int64_t K, int32_t zld, int32_t d,
+                               const double* theta, int32_t S, const double* Siginv, const double* w, const double* resid,
+                               double* glls, double* ugrad) {
+  RET(use_device(ctx));
+  if (!pts || !theta || K < 0 || d <= 0 || S <= 0) return fail(BCG_ERR_ARG, "bad arguments");
+  if (ugrad && (!w || !resid)) return fail(BCG_ERR_ARG, "the contraction needs w and resid");
+  if (model == BCG_MODEL_GAUSSIAN && !Siginv) return fail(BCG_ERR_ARG, "Siginv is required for the Gaussian model");
+  if ((model == BCG_MODEL_POISSON ? d + 1 : d) > zld) return fail(BCG_ERR_ARG, "points have too few columns");
+  if (K == 0) return BCG_OK;
+  const int dz = model == BCG_MODEL_POISSON ? d + 1 : d;
+  // glls[k,s,:] = g_ks U_s + V_k, centred over the last axis (projector.py:26): centre the rows of U and V
+  std::vector<double> U((size_t)S * dz, 0.), V;
+  if (model == BCG_MODEL_GAUSSIAN) {
+    V.assign((size_t)K * dz, 0.);
+    for (int s = 0; s < S; ++s)
+      for (int j = 0; j < d; ++j) {
+        double acc = 0.;
+        for (int i = 0; i < d; ++i) acc += theta[(size_t)s * d + i] * Siginv[(size_t)i * d + j];
+        U[(size_t)s * dz + j] = acc;
+      }
+    for (int64_t k = 0; k < K; ++k)
+      for (int j = 0; j < d; ++j) {
+        double acc = 0.;
+        for (int i = 0; i < d; ++i) acc += pts[(size_t)k * zld + i] * Siginv[(size_t)i * d + j];
+        V[(size_t)k * dz + j] = -acc;
+      }
+  } else {
+    for (int s = 0; s < S; ++s)
+      for (int j = 0; j < d; ++j) U[(size_t)s * dz + j] = theta[(size_t)s * d + j];      // Poisson: zero d/dy column
+  }
+  auto centre = [&](std::vector<double>& M, int64_t rows) {
+    for (int64_t r = 0; r < rows; ++r) {
+      double m = 0.;
+      for (int j = 0; j < dz; ++j) m += M[(size_t)r * dz + j];
+      m /= (double)dz;
+      for (int j = 0; j < dz; ++j) M[(size_t)r * dz + j] -= m;
+    }
+  };
+  centre(U, S);
+  if (!V.empty()) centre(V, K);
+  cudaStream_t st = ctx->stream;
+  DevBuf<double> dP, dT, dU, dV, dW, dR, dG, dO;
+  auto up = [&](DevBuf<double>& b, const double* src, size_t n) -> int {
+    CK(b.alloc(n));
+    CK(cudaMemcpyAsync(b, src, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    return BCG_OK;
+  };
+  RET(up(dP, pts, (size_t)K * zld));
+  RET(up(dT, theta, (size_t)S * d));
+  RET(up(dU, U.data(), U.size()));
+  if (!V.empty()) RET(up(dV, V.data(), V.size()));
+  if (ugrad) { RET(up(dW, w, (size_t)K)); RET(up(dR, resid, (size_t)S)); CK(dO.alloc((size_t)K * dz)); }
+  if (glls) CK(dG.alloc((size_t)K * S * dz));
+  PseudoGradArgs a;
+  a.pts = dP; a.theta = dT; a.Uc = dU; a.Vc = V.empty() ? nullptr : dV.p; a.w = dW; a.resid = dR; a.glls = dG; a.ugrad = dO;
+  a.K = (int32_t)K; a.zld = zld; a.d = d; a.dz = dz; a.S = S; a.model = model;
+  const size_t smem = ((size_t)S + d + 2) * sizeof(double);
+  CK(cudaFuncSetAttribute(pseudo_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pseudo_grad_kernel<<<(unsigned)K, 256, smem, st>>>(a);
+  CK(cudaGetLastError());
+  if (glls) CK(cudaMemcpyAsync(glls, dG, (size_t)K * S * dz * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (ugrad) CK(cudaMemcpyAsync(ugrad, dO, (size_t)K * dz * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return BCG_OK;
+}
+
 // Projection straight from a HOST array, chunked and software-pipelined: while chunk c is being projected on
 // `stream`, chunk c+1 is staged (multi-threaded memcpy into pinned memory) and copied on `copy_stream`.  The
 // data are not kept on the device (HilbertCoreset projects once).  thetaT: d x S, coff: S or null (host).
@@ -1041,6 +1181,7 @@ extern "C" int bcg_vecs_norms(bcg_vecs* v, int64_t row0, int64_t nrows, double* 
 extern "C" int bcg_vecs_rows_f64(bcg_vecs* v, int64_t row0, int64_t nrows, double* out) {
   if (!v || !out) return fail(BCG_ERR_ARG, "null argument");
   if (row0 < 0 || nrows < 0 || row0 + nrows > v->n) return fail(BCG_ERR_ARG, "row range out of bounds");
+  if (v->n > 0 && !v->An) return fail(BCG_ERR_UNSUPPORTED, "a never-materialised projection has no stored rows");
   RET(use_device(v->ctx));
   const int64_t chunk = std::max<int64_t>(1, (64ll << 20) / ((int64_t)v->S * 8));
   DevBuf<double> tmp;
@@ -1062,6 +1203,9 @@ extern "C" int bcg_vecs_destroy(bcg_vecs* v) {
   cudaSetDevice(v->ctx->device);
   if (v->An) cudaFree(v->An);
   if (v->norms) cudaFree(v->norms);
+  if (v->lazy_thetaT) cudaFree(v->lazy_thetaT);
+  if (v->lazy_tt) cudaFree(v->lazy_tt);
+  if (v->lazy_Siginv) cudaFree(v->lazy_Siginv);
   delete v;
   return BCG_OK;
 }
@@ -1111,7 +1255,34 @@ static int choose_scan_config(bcg_solver* s) {
   return BCG_OK;
 }
 
+template <int J>
+static int launch_lazy(bcg_solver* s, const LazyArgs& L) {
+  lazy_select_kernel<J><<<s->h.n_exact_cands, 256, 0, s->ctx->stream>>>(L);
+  CK(cudaGetLastError());
+  return BCG_OK;
+}
+
 static int launch_scan(bcg_solver* s, cudaEvent_t e0 = nullptr, cudaEvent_t e1 = nullptr) {
+  if (s->h.lazy) {
+    // never-materialising solver: the selection pass re-evaluates every row from the raw data (lazy_select_kernel.cuh)
+    const bcg_vecs* v = s->v;
+    LazyArgs L;
+    L.a.Z = v->lazy_ds->Z; L.a.n = v->n; L.a.zld = v->lazy_ds->zld; L.a.d = v->lazy_d; L.a.S = v->S; L.a.model = v->lazy_model;
+    L.a.kind = s->h.alg; L.a.thetaT = v->lazy_thetaT; L.a.tt = v->lazy_tt; L.a.Siginv = v->lazy_Siginv;
+    L.a.dirs = nullptr; L.a.scores = nullptr; L.a.norms = nullptr; L.a.colsum = nullptr;
+    L.st = s->d;
+    if (e0) CK(cudaEventRecord(e0, s->ctx->stream));
+    switch (pow2ceil((v->S + 31) / 32)) {
+      case 1: RET(launch_lazy<1>(s, L)); break;
+      case 2: RET(launch_lazy<2>(s, L)); break;
+      case 4: RET(launch_lazy<4>(s, L)); break;
+      case 8: RET(launch_lazy<8>(s, L)); break;
+      case 16: RET(launch_lazy<16>(s, L)); break;
+      default: RET(launch_lazy<32>(s, L)); break;
+    }
+    if (e1) CK(cudaEventRecord(e1, s->ctx->stream));
+    return BCG_OK;
+  }
   ScanArgs a;
   a.g.An = s->v->An;
   a.g.n_rows = s->v->n;
@@ -1185,7 +1356,10 @@ static int solver_init(bcg_solver* s, bcg_ctx* ctx, bcg_vecs* v, int32_t alg, co
   h.err = bnorm;
   RET(choose_scan_config(s));
   h.n_cands = s->sc.grid * s->sc.wpb;
-  h.n_exact_cands = ctx->sm_count;
+  h.lazy = (v->n > 0 && !v->An) ? 1 : 0;
+  h.n_exact_cands = h.lazy ? ctx->sm_count * 8 : ctx->sm_count;
+  h.fused_row = -1;
+  if (h.lazy) s->use_loop = false;                       // the persistent kernel streams the resident matrix
   h.check_monotone = 1;
   cudaStream_t st = ctx->stream;
   std::vector<double> bn(S);

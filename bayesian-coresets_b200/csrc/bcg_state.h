@@ -80,6 +80,11 @@ struct SolverState {
   unsigned int scan_done;           // CTA completion counter of scan_kernel (last CTA resets it)
   int32_t check_monotone;           // snnls.py:9 check_error_monotone
   int32_t force_exact;              // testing: treat every candidate set as ambiguous
+  // ---- never-materialising select (lazy_select_kernel.cuh): An == null ---------------------------
+  int32_t lazy;                     // 1: rows are recomputed from the raw data; the selection pass leaves its result below
+  int64_t fused_row;                // local winner of the last selection pass (-1: none)
+  double fused_score;               // its float64 score
+  double wnorm;                     // its norm (its unit row is in wrow)
   // ---- N-sharding mailboxes ----------------------------------------------------------------
   unsigned char* mail_local;        // this rank's mailbox: [2][world] slots
   unsigned char* mail_peer[kMaxWorld];  // mapped mailboxes of all ranks (self included)

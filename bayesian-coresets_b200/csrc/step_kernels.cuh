@@ -24,9 +24,10 @@ __device__ void mail_exchange(const Blk& B, SolverState* st, uint32_t lrow, doub
   const int par = (int)(seq & 1ull);
   const int64_t sb = st->mail_slot_bytes;
   const bool have = lrow != kNoRow;
-  const float* src = have ? st->An + (size_t)lrow * ld : nullptr;
+  const float* src = nullptr;
+  double nrm = 0.;
+  if (have) local_row(st, lrow, &src, &nrm);
   const int64_t gidx = have ? st->row_offset + (int64_t)lrow : -1;
-  const double nrm = have ? st->norms[lrow] : 0.;
 
   for (int p = 0; p < W; ++p) {
     unsigned char* slot = st->mail_peer[p] + (int64_t)(par * W + me) * sb;

@@ -249,7 +249,20 @@ BCG_HD double row_score64(const Blk& B, const SolverState* st, const float* row)
 // is within delta of the maximum are re-scored in float64 (ties -> lowest row index, as
 // ndarray.argmax).  force_rescore: always produce the float64 score (needed for cross-rank and
 // OMP comparisons).
+// unit row and norm of LOCAL row lrow: a row of the resident matrix, or -- never-materialising solver -- the row the
+// selection pass just re-evaluated (it can only be the winner)
+BCG_HD void local_row(const SolverState* st, uint32_t lrow, const float** row, double* norm) {
+  if (st->lazy) { *row = st->wrow; *norm = st->wnorm; return; }
+  *row = st->An + (size_t)lrow * st->ld;
+  *norm = st->norms[lrow];
+}
+
 BCG_HD void pick_local(const Blk& B, SolverState* st, bool force_rescore, uint32_t* row_out, double* score_out) {
+  if (st->lazy) {                     // lazy_select_kernel already reduced the grid in float64
+    *row_out = st->fused_row < 0 ? kNoRow : (uint32_t)st->fused_row;
+    *score_out = st->fused_score;
+    return;
+  }
   if (st->need_exact) {
     // the float32 candidate set was ambiguous (SolverState::cand_lost): the local winner is the result of the exact
     // float64 pass over all local rows (exact_scan_kernel), one candidate per CTA -> best score, lowest row on ties
@@ -372,8 +385,7 @@ BCG_HD void finish_iteration(const Blk& B, SolverState* st) {
 #endif
   } else {
     f = st->row_offset + (int64_t)lrow;
-    nf_stored = st->norms[lrow];
-    frow = st->An + (size_t)lrow * ld;
+    local_row(st, lrow, &frow, &nf_stored);
   }
 
   for (int s = B.tid; s < S; s += B.nthr) st->xf[s] = nf_stored * (double)frow[s];
@@ -541,8 +553,7 @@ BCG_HD int64_t omp_select(const Blk& B, SolverState* st) {
 #endif
   } else {
     f = st->row_offset + (int64_t)lrow;
-    nf_stored = st->norms[lrow];
-    frow = st->An + (size_t)lrow * ld;
+    local_row(st, lrow, &frow, &nf_stored);
   }
   if (nonempty) {
     // negative direction over the active set (w > 0), lowest global index wins ties:

@@ -16,6 +16,8 @@
  *   bcg_vecs_project_gaussian  projector.py:19-21 with examples/common/model_gaussian.py:4-10
  *   bcg_vecs_project_poisson   projector.py:19-21 with examples/common/model_poiss.py:25-38
  *   bcg_vecs_colsum / _rows    hilbert.py:24 / the ndarray returned by Projector.project
+ *   bcg_pseudo_grad            projector.py:23-28 + model_lr.py:50-57 / model_poiss.py:58-67 / model_gaussian.py:12-15, bpsvi.py:53
+ *   bcg_dataset_project_lazy   the same projection without storing it (norms, b only); rows re-evaluated per selection pass
  *   bcg_dataset_audit          projector.py:19-21 + giga.py:31-38 / frankwolfe.py:17 (independent float64 re-evaluation)
  *   bcg_solver_create          snnls/snnls.py:9-16 + giga.py:8-18 / frankwolfe.py:7-13 /
  *                              orthopursuit.py:9-15
@@ -141,6 +143,19 @@ int  bcg_dataset_project(bcg_dataset* ds, const int64_t* rowidx, int64_t nsel, i
  * rows), norms (n), colsum (S; hilbert.py:24).  Also the first half of the never-materialising select. */
 int  bcg_dataset_audit(bcg_dataset* ds, int32_t model, int32_t d, const double* theta, int32_t S, const double* Siginv,
                        int32_t kind, const double* dirs, double* scores, double* norms, double* colsum);
+/* The NEVER-MATERIALISING projection: only the row norms, b = the column sums and the zero-row count are
+ * computed; the result has no N x S matrix (bcg_vecs_rows_f64 fails on it).  A solver created over it re-evaluates every
+ * row from the dataset in float64 at each selection pass (csrc/lazy_select_kernel.cuh): 8 N d_in bytes resident instead of
+ * 4 N S, at ~10x the time per iteration.  `ds` must outlive the result and every solver created over it. */
+int  bcg_dataset_project_lazy(bcg_dataset* ds, int32_t model, int32_t d, const double* theta, int32_t S,
+                              const double* Siginv, bcg_vecs** out);
+/* Datapoint gradients of the log-likelihood for the K pseudo-points of BatchPSVI, on the device (csrc/pseudo_grad_kernel.cuh):
+ * glls (host K x S x dz, dz = d, or d + 1 for Poisson) = grad_z log-likelihood (model_lr.py:50-57, model_poiss.py:58-67 with the
+ * documented repair, model_gaussian.py:12-15) centred over the last axis (projector.py:26), and / or its contraction
+ * ugrad (host K x dz) = -(1/S) sum_s w_k resid_s glls[k,s,:] (bpsvi.py:53) without forming the (K, S, dz) array.
+ * pts: host K x zld; theta: host S x d. */
+int  bcg_pseudo_grad(bcg_ctx* ctx, int32_t model, const double* pts, int64_t K, int32_t zld, int32_t d, const double* theta,
+                     int32_t S, const double* Siginv, const double* w, const double* resid, double* glls, double* ugrad);
 /* ll_ns = x_n . A_s + coff_s : the Gaussian model with A = theta Siginv (host S x d) and
  * coff_s = -0.5 theta_s Siginv theta_s precomputed by the caller */
 int  bcg_dataset_project_linear(bcg_dataset* ds, const int64_t* rowidx, int64_t nsel, int32_t d, const double* A,

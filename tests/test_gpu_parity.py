@@ -978,3 +978,51 @@ def test_integration_md_stub_runs_inside_the_reference_tree(bc, tmp_path):
   assert np.array_equal(idcs, np.flatnonzero(o.w > 0))
   assert_weights_close(wts, o.w[o.w > 0])
   assert_errors_close(a.error(), o.error(), X, o.w)
+
+
+# ---------------------------------------------------------------- never-materialising solver
+@pytest.mark.parametrize('alg', ['giga', 'fw', 'omp'])
+def test_never_materialising_solver_equals_materialised_and_oracle(bc, alg):
+  """HilbertCoreset(..., materialize=False): no N x S matrix; every selection pass re-evaluates the rows from the raw data
+  in float64 (lazy_select_kernel).  Same events / weights / error as the oracle and as the resident-matrix engine."""
+  Z, theta = lr_problem(6, 30000, 7, 160)
+  vecs = models.project(models.lr_loglik, Z, theta)
+  o = greedy.ORACLES[alg](vecs.T, vecs.sum(axis=0))
+  oev = o.build(30)
+  prj = bc.LogisticRegressionProjector(lambda n, w, p: theta, 160)
+  a = bc.HilbertCoreset(Z, prj, snnls=algs(bc)[alg], materialize=False)
+  free0 = bc.Context.default().mem_info()[0]
+  assert a.snnls._vecs.shape == (30000, 160)
+  np.testing.assert_allclose(a.snnls.b, vecs.sum(axis=0), rtol=1e-9, atol=1e-9*np.abs(vecs).sum(axis=0).max())
+  a.build(18)
+  a.build(12)
+  ev = [(e.code, e.f) for e in a.snnls.last_events]
+  assert ev == [(e[0], e[1]) for e in oev][18:]
+  assert_weights_close(a.snnls.weights(), o.w)
+  assert_errors_close(a.error(), o.error(), vecs, o.w)
+  wts, pts, idcs = a.get()
+  assert np.array_equal(idcs, np.flatnonzero(o.w > 0)) and np.array_equal(pts, Z[idcs])
+  a.optimize()
+  o.optimize()
+  assert a.error() == pytest.approx(o.error(), rel=1e-5)
+  with pytest.raises(bc.BcgError):
+    a.snnls._vecs.to_numpy(0, 1)                    # there are no stored rows
+
+
+def test_never_materialising_solver_other_models(bc):
+  g = load_golden('poisson_project_small')
+  prj = bc.PoissonProjector(lambda n, w, p: g['theta'], g['theta'].shape[0])
+  o = greedy.GigaOracle(g['vecs'].T, g['vecs'].sum(axis=0))
+  oev = o.build(15)
+  a = bc.HilbertCoreset(g['Z'], prj, materialize=False)
+  a.build(15)
+  assert [e.f for e in a.snnls.last_events] == [e[1] for e in oev]
+  assert_weights_close(a.snnls.weights(), o.w)
+  g = load_golden('gaussian_project_small')
+  prj = bc.GaussianProjector(lambda n, w, p: g['theta'], g['theta'].shape[0], g['Siginv'])
+  o = greedy.FrankWolfeOracle(g['vecs'].T, g['vecs'].sum(axis=0))
+  oev = o.build(15)
+  a = bc.HilbertCoreset(g['x'], prj, snnls=bc.snnls.FrankWolfe, materialize=False)
+  a.build(15)
+  assert [e.f for e in a.snnls.last_events] == [e[1] for e in oev]
+  assert_weights_close(a.snnls.weights(), o.w)
