@@ -1547,36 +1547,46 @@ extern "C" int bcg_solver_comm_connect(bcg_solver* s, int32_t world, int32_t ran
   return BCG_OK;
 }
 
-// (re)allocate the NNLS work space for the current active-set capacity; a fresh work space is invalid
+// NNLS work space for the current active-set capacity.  The factorisation buffers (Q, T = R^-1 and its double) are sized
+// by min(cap, S + 1) -- the passive set holds independent columns, nP <= S -- so once the capacity exceeds S they keep
+// their shape: growing the active set then only extends the small per-slot arrays and the warm start SURVIVES the growth.
 static int ensure_nnls(bcg_solver* s) {
   const int cap = s->h.cap, S = s->h.S;
   if (s->d_nw && s->nw_cap == cap) return BCG_OK;
   NnlsWork& w = s->nw;
+  cudaStream_t st = s->ctx->stream;
   if (s->d_nw) CK(cudaMemcpy(&w, s->d_nw, sizeof(NnlsWork), cudaMemcpyDeviceToHost));      // R / R2 may have swapped
-  void* old[] = {w.Q, w.R, w.R2, w.rot, w.rem, w.c, w.z, w.wP, w.h, w.v, w.P, w.Z, w.inP};
-  for (void* p : old)
-    if (p) CK(cudaFree(p));
-  memset(&w, 0, sizeof(NnlsWork));
-  CK(cudaMalloc(&w.Q, (size_t)cap * S * sizeof(double)));
-  CK(cudaMalloc(&w.R, (size_t)cap * cap * sizeof(double)));
-  CK(cudaMalloc(&w.R2, (size_t)cap * cap * sizeof(double)));
-  CK(cudaMalloc(&w.rot, (size_t)3 * cap * sizeof(double)));
-  CK(cudaMalloc(&w.rem, (size_t)cap * sizeof(int32_t)));
-  CK(cudaMalloc(&w.c, (size_t)cap * sizeof(double)));
-  CK(cudaMalloc(&w.z, (size_t)2 * cap * sizeof(double)));
-  CK(cudaMalloc(&w.wP, (size_t)cap * sizeof(double)));
-  CK(cudaMalloc(&w.h, (size_t)cap * sizeof(double)));
-  CK(cudaMalloc(&w.v, (size_t)S * sizeof(double)));
-  CK(cudaMalloc(&w.P, (size_t)cap * sizeof(int32_t)));
-  CK(cudaMalloc(&w.Z, (size_t)cap * sizeof(int32_t)));
-  CK(cudaMalloc(&w.inP, (size_t)cap * sizeof(int32_t)));
-  CK(cudaMemsetAsync(w.inP, 0, (size_t)cap * sizeof(int32_t), s->ctx->stream));
+  const int old_cap = s->d_nw ? s->nw_cap : 0;
+  const int tld = std::min(cap, S + 1);
+  const bool keep = s->d_nw && w.Q && w.tld == tld;
+  if (!keep) {
+    void* old[] = {w.Q, w.R, w.R2};
+    for (void* p : old)
+      if (p) CK(cudaFree(p));
+    w.Q = w.R = w.R2 = nullptr;
+    CK(cudaMalloc(&w.Q, (size_t)tld * S * sizeof(double)));
+    CK(cudaMalloc(&w.R, (size_t)tld * tld * sizeof(double)));
+    CK(cudaMalloc(&w.R2, (size_t)tld * tld * sizeof(double)));
+    w.valid = 0;
+    w.nP = w.nZ = 0;
+  }
+  // per-slot / per-position arrays: extended with their contents (zero beyond the old capacity)
+  RET(grow(&w.rot, (size_t)3 * old_cap, (size_t)3 * cap, st));
+  RET(grow(&w.rem, (size_t)old_cap, (size_t)cap, st));
+  RET(grow(&w.c, (size_t)old_cap, (size_t)cap, st));
+  RET(grow(&w.z, (size_t)2 * old_cap, (size_t)2 * cap, st));
+  RET(grow(&w.wP, (size_t)old_cap, (size_t)cap, st));
+  RET(grow(&w.h, (size_t)old_cap, (size_t)cap, st));
+  RET(grow(&w.P, (size_t)old_cap, (size_t)cap, st));
+  RET(grow(&w.Z, (size_t)old_cap, (size_t)cap, st));
+  RET(grow(&w.inP, (size_t)old_cap, (size_t)cap, st));
+  if (!w.v) CK(cudaMalloc(&w.v, (size_t)S * sizeof(double)));
   w.cap = cap;
-  w.valid = 0;
+  w.tld = tld;
   w.downdate = env_int("BCG_NNLS_DOWNDATE", 1);
   if (!s->d_nw) CK(cudaMalloc(&s->d_nw, sizeof(NnlsWork)));
-  CK(cudaMemcpyAsync(s->d_nw, &w, sizeof(NnlsWork), cudaMemcpyHostToDevice, s->ctx->stream));
-  CK(cudaStreamSynchronize(s->ctx->stream));
+  CK(cudaMemcpyAsync(s->d_nw, &w, sizeof(NnlsWork), cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));
   s->nw_cap = cap;
   return BCG_OK;
 }
@@ -1628,6 +1638,15 @@ extern "C" int bcg_solver_build(bcg_solver* s, int32_t itrs, double tol, bcg_ite
     RET(ensure_nnls(s));
     const int wide = env_int("BCG_OMP_WIDE", 1);
     DevBuf<unsigned long long> d_omp_trace;
+    struct TraceGuard {                       // the state must not keep a pointer to the trace buffer once it is freed
+      bcg_solver* s;
+      ~TraceGuard() {
+        if (s->h.omp_trace) {
+          s->h.omp_trace = nullptr;
+          cudaMemcpy(&s->d->omp_trace, &s->h.omp_trace, sizeof(void*), cudaMemcpyHostToDevice);
+        }
+      }
+    } trace_guard{s};
     if (env_int("BCG_OMP_TRACE", 0)) {
       CK(d_omp_trace.alloc((size_t)itrs * 16));
       CK(cudaMemsetAsync(d_omp_trace, 0, (size_t)itrs * 16 * sizeof(unsigned long long), st));
@@ -1675,8 +1694,6 @@ extern "C" int bcg_solver_build(bcg_solver* s, int32_t itrs, double tol, bcg_ite
         fprintf(stderr, " us | append: pass0 %.1f pass1 %.1f sums+store %.1f Tcol %.1f us\n", cnt ? sub[0] / cnt / 1e3 : 0.,
                 cnt ? sub[1] / cnt / 1e3 : 0., cnt ? sub[2] / cnt / 1e3 : 0., cnt ? sub[3] / cnt / 1e3 : 0.);
       }
-      h.omp_trace = nullptr;
-      CK(cudaMemcpy(&s->d->omp_trace, &h.omp_trace, sizeof(void*), cudaMemcpyHostToDevice));
     }
     s->scan_launches = itrs;
     s->step_launches = itrs + 1;

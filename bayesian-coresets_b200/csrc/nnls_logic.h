@@ -46,6 +46,7 @@ struct NnlsWork {
   int32_t* rem;   // cap   P positions dropped by the current step-back
   int32_t nrem, downdate;   // downdate = 1: remove columns by Givens rotations; 0: rebuild behind the first removed
   int32_t nP, nZ, cap, valid;
+  int32_t tld;                     // leading dimension of T and row capacity of Q: min(cap, S + 1) -- P holds independent columns, nP <= S
   int32_t outer_iters, rebuilds;   // diagnostics of the last solve
   int32_t first_removed;           // first P position dropped by the last step-back (block-uniform hand-over)
 };
@@ -56,7 +57,7 @@ BCG_HD double act_col(const SolverState* st, int slot, int s) {
 
 // append the column of `slot` to the QR of P; returns false when it is numerically dependent
 BCG_HD bool nnls_qr_append(const Blk& B, SolverState* st, NnlsWork* W, int slot) {
-  const int S = st->S, p = W->nP, cap = W->cap;
+  const int S = st->S, p = W->nP, cap = W->cap, tld = W->tld;
   double n0 = 0.;
   for (int s = B.tid; s < S; s += B.nthr) { const double x = act_col(st, slot, s); W->v[s] = x; n0 += x * x; }
   blk_sum<1>(B, &n0);                                   // (also a barrier: v is complete)
@@ -78,15 +79,15 @@ BCG_HD bool nnls_qr_append(const Blk& B, SolverState* st, NnlsWork* W, int slot)
   for (int s = B.tid; s < S; s += B.nthr) { const double x = v[s]; u[0] += x * x; u[1] += x * st->b[s]; }
   blk_sum<2>(B, u);
   const double rpp = sqrt(u[0]);
-  if (!(rpp > 1e-13 * sqrt(n0))) return false;          // (numerically) in the span of P
+  if (!(rpp > 1e-13 * sqrt(n0)) || p >= tld) return false;   // (numerically) in the span of P (P holds at most S columns)
   double* q = Q + (size_t)p * S;
   for (int s = B.tid; s < S; s += B.nthr) q[s] = v[s] / rpp;
   // new column of T = R^{-1}:  -(T r) / rho on top of 1 / rho   (column j of T holds rows 0..j)
   omp_mark(B, st, 14);
-  blk_combine<double>(B, p, p, [&](int j) { return CombTerm<double>{r[j], T + (size_t)j * cap, j + 1}; },
-                      [&](int i, double acc) { T[(size_t)i + (size_t)p * cap] = -acc / rpp; });
+  blk_combine<double>(B, p, p, [&](int j) { return CombTerm<double>{r[j], T + (size_t)j * tld, j + 1}; },
+                      [&](int i, double acc) { T[(size_t)i + (size_t)p * tld] = -acc / rpp; });
   if (B.tid == 0) {
-    T[(size_t)p + (size_t)p * cap] = 1. / rpp;
+    T[(size_t)p + (size_t)p * tld] = 1. / rpp;
     W->c[p] = u[1] / rpp;
     W->P[p] = slot;
     W->inP[slot] = 1;
@@ -99,11 +100,11 @@ BCG_HD bool nnls_qr_append(const Blk& B, SolverState* st, NnlsWork* W, int slot)
 
 // z = R^{-1} c = T c : no sequential dependency (column j of T is contiguous over its rows 0..j)
 BCG_HD void nnls_solve_R(const Blk& B, NnlsWork* W) {
-  const int n = W->nP, cap = W->cap;
+  const int n = W->nP, tld = W->tld;
   const double* const T = W->R;
   const double* const c = W->c;
   double* const z = W->z;
-  blk_combine<double>(B, n, n, [&](int j) { return CombTerm<double>{c[j], T + (size_t)j * cap, j + 1}; },
+  blk_combine<double>(B, n, n, [&](int j) { return CombTerm<double>{c[j], T + (size_t)j * tld, j + 1}; },
                       [&](int i, double acc) { z[i] = acc; });
 }
 
@@ -115,7 +116,7 @@ BCG_HD void nnls_solve_R(const Blk& B, NnlsWork* W) {
 // then applied to the q vectors (Q G^T), to the columns of T with row k deleted (T_new = (E^T T G^T)[:, :p-1]) and
 // to c = Q^T b.  R itself is never needed.  P / wP are compacted by the caller.
 BCG_HD void nnls_qr_remove(const Blk& B, SolverState* st, NnlsWork* W, int k, int p) {
-  const int S = st->S, cap = W->cap;
+  const int S = st->S, cap = W->cap, tld = W->tld;
   double* const T = W->R;
   double* const Tn = W->R2;
   double* const Q = W->Q;
@@ -123,7 +124,7 @@ BCG_HD void nnls_qr_remove(const Blk& B, SolverState* st, NnlsWork* W, int k, in
   double* const rc = W->rot;
   double* const rs = W->rot + cap;
   double* const trow = W->rot + 2 * (size_t)cap;
-  for (int j = k + B.tid; j < p; j += B.nthr) trow[j] = T[(size_t)k + (size_t)j * cap];   // strided row: stage it
+  for (int j = k + B.tid; j < p; j += B.nthr) trow[j] = T[(size_t)k + (size_t)j * tld];   // strided row: stage it
   B.sync();
   if (B.tid == 0) {
     double carry = trow[k], ccur = c[k];
@@ -153,13 +154,13 @@ BCG_HD void nnls_qr_remove(const Blk& B, SolverState* st, NnlsWork* W, int k, in
   // second buffer; entries below the diagonal are never stored, so they read as zero
   for (int i = B.tid; i < p - 1; i += B.nthr) {
     const int r = i + (i >= k ? 1 : 0);
-    for (int j = i; j < k; ++j) Tn[(size_t)i + (size_t)j * cap] = T[(size_t)i + (size_t)j * cap];   // (only rows above k)
+    for (int j = i; j < k; ++j) Tn[(size_t)i + (size_t)j * tld] = T[(size_t)i + (size_t)j * tld];   // (only rows above k)
     const int j0 = (i >= k) ? i : k;                           // first column with a non-zero result
-    double cur = (r <= j0) ? T[(size_t)r + (size_t)j0 * cap] : 0.;
+    double cur = (r <= j0) ? T[(size_t)r + (size_t)j0 * tld] : 0.;
 #pragma unroll 4
     for (int j = j0; j < p - 1; ++j) {
-      const double y = T[(size_t)r + (size_t)(j + 1) * cap];   // r <= j + 1 always holds here
-      Tn[(size_t)i + (size_t)j * cap] = rc[j] * cur - rs[j] * y;
+      const double y = T[(size_t)r + (size_t)(j + 1) * tld];   // r <= j + 1 always holds here
+      Tn[(size_t)i + (size_t)j * tld] = rc[j] * cur - rs[j] * y;
       cur = rs[j] * cur + rc[j] * y;
     }
   }

@@ -205,7 +205,7 @@ extern "C" int hostcheck_nnls_sequence(const float* An, const double* norms, con
   NnlsWork& W = X.W;
   memset(&W, 0, sizeof(W));
   W.Q = X.Q.data(); W.R = X.R.data(); W.c = X.c.data(); W.z = X.z.data(); W.wP = X.wP.data(); W.h = X.h.data();
-  W.v = X.v.data(); W.P = X.P.data(); W.Z = X.Z.data(); W.inP = X.inP.data(); W.cap = cap;
+  W.v = X.v.data(); W.P = X.P.data(); W.Z = X.Z.data(); W.inP = X.inP.data(); W.cap = cap; W.tld = cap;
   X.R2.assign((size_t)cap * cap, 0.); X.rot.assign((size_t)3 * cap, 0.); X.rem.assign(cap, 0);
   W.R2 = X.R2.data(); W.rot = X.rot.data(); W.rem = X.rem.data(); W.downdate = downdate;
   Blk B{0, 1, H.sred, nullptr};
@@ -258,7 +258,7 @@ extern "C" int hostcheck_run_omp(const float* An, const double* norms, const dou
   NnlsWork& W = X.W;
   memset(&W, 0, sizeof(W));
   W.Q = X.Q.data(); W.R = X.R.data(); W.c = X.c.data(); W.z = X.z.data(); W.wP = X.wP.data(); W.h = X.h.data();
-  W.v = X.v.data(); W.P = X.P.data(); W.Z = X.Z.data(); W.inP = X.inP.data(); W.cap = cap;
+  W.v = X.v.data(); W.P = X.P.data(); W.Z = X.Z.data(); W.inP = X.inP.data(); W.cap = cap; W.tld = cap;
   X.R2.assign((size_t)cap * cap, 0.); X.rot.assign((size_t)3 * cap, 0.); X.rem.assign(cap, 0);
   W.R2 = X.R2.data(); W.rot = X.rot.data(); W.rem = X.rem.data(); W.downdate = downdate;
   Blk B{0, 1, H.sred, nullptr};

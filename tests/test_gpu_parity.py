@@ -1026,3 +1026,22 @@ def test_never_materialising_solver_other_models(bc):
   a.build(15)
   assert [e.f for e in a.snnls.last_events] == [e[1] for e in oev]
   assert_weights_close(a.snnls.weights(), o.w)
+
+
+def test_omp_capacity_growth_keeps_the_warm_start_and_stays_small(bc):
+  """the NNLS factorisation is sized by min(capacity, S + 1) and survives the growth of the active-set capacity: several
+  build() calls that cross the growth points give the one-shot result, and build(20000) does not ask for gigabytes"""
+  Z, theta = lr_problem(9, 20000, 6, 96)
+  prj = bc.LogisticRegressionProjector(lambda n, w, p: theta, 96)
+  one = bc.HilbertCoreset(Z, prj, snnls=bc.snnls.OrthoPursuit)
+  one.build(130)
+  inc = bc.HilbertCoreset(Z, prj, snnls=bc.snnls.OrthoPursuit)
+  for k in (30, 30, 30, 40):
+    inc.build(k)
+  ev1 = [e.f for e in one.snnls.last_events]
+  assert [e.f for e in inc.snnls.last_events] == ev1[90:]
+  np.testing.assert_allclose(inc.snnls.weights(), one.snnls.weights(), rtol=1e-9, atol=1e-12*one.snnls.weights().max())
+  free0 = bc.Context.default().mem_info()[0]
+  big = bc.HilbertCoreset(Z, prj, snnls=bc.snnls.OrthoPursuit)
+  big.build(20000)                                   # stops at the numeric limit long before; the work space is what matters
+  assert free0 - bc.Context.default().mem_info()[0] < (1 << 30)
