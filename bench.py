@@ -164,15 +164,22 @@ def measured_f64_peak(device):
 
 def measured_traffic_ratio(kernel, S):
   """DRAM bytes / algorithmic bytes of the dominant kernel from the committed `ncu --set full` capture
-  (profiles/r0*_loop_traffic.json, written by profiles/extract_traffic.py); None when there is no capture"""
-  for name in ('r02_loop_traffic.json', 'r01_loop_traffic.json'):
-    try:
-      with open(os.path.join(ROOT, 'profiles', name)) as f:
-        t = json.load(f)
-      if t.get('kernel') == kernel and int(t.get('S', -1)) == int(S):
-        return float(t['dram_bytes']) / float(t['algorithmic_bytes']), name
-    except Exception:
-      pass
+  (profiles/r02_loop_traffic.json, written by profiles/extract_traffic.py from tools/ncu_traffic_case.py; the round-1
+  capture as a fallback); None when there is no capture of this kernel at this S"""
+  try:
+    with open(os.path.join(ROOT, 'profiles', 'r02_loop_traffic.json')) as f:
+      for c in json.load(f)['captures']:
+        if c['kernel'] == kernel and int(c['S']) == int(S):
+          return float(c['dram_bytes'])/float(c['algorithmic_bytes']), 'r02_loop_traffic.json'
+  except Exception:
+    pass
+  try:
+    with open(os.path.join(ROOT, 'profiles', 'r01_loop_traffic.json')) as f:
+      t = json.load(f)
+    if t.get('kernel') == kernel and int(t.get('S', -1)) == int(S):
+      return float(t['dram_bytes'])/float(t['algorithmic_bytes']), 'r01_loop_traffic.json'
+  except Exception:
+    pass
   return None, None
 
 
