@@ -58,6 +58,7 @@ _PROTOTYPES = {
   'bcg_dataset_project': (_c.c_int, [_P, _P, _c.c_int64, _c.c_int32, _c.c_int32, _P, _c.c_int32, _P, _PP, _P, _P]),
   'bcg_dataset_project_linear': (_c.c_int, [_P, _P, _c.c_int64, _c.c_int32, _P, _P, _c.c_int32, _PP, _P, _P]),
   'bcg_dataset_project_lazy': (_c.c_int, [_P, _c.c_int32, _c.c_int32, _P, _c.c_int32, _P, _PP]),
+  'bcg_sampler_gaussian_post': (_c.c_int, [_P, _c.c_int32, _P, _P, _P, _P, _P, _c.c_int64, _P, _c.c_int32, _P, _P, _P]),
   'bcg_pseudo_grad': (_c.c_int, [_P, _c.c_int32, _P, _c.c_int64, _c.c_int32, _c.c_int32, _P, _c.c_int32, _P, _P, _P, _P, _P]),
   'bcg_dataset_audit': (_c.c_int, [_P, _c.c_int32, _c.c_int32, _P, _c.c_int32, _P, _c.c_int32, _P, _P, _P, _P]),
   'bcg_vecs_shape': (_c.c_int, [_P, _c.POINTER(_c.c_int64), _c.POINTER(_c.c_int32), _c.POINTER(_c.c_int32)]),
@@ -209,6 +210,22 @@ class Context(object):
 
   def flush_l2(self, nbytes=256 << 20):
     check(lib().bcg_ctx_flush_l2(self.handle, int(nbytes)))
+
+
+def gaussian_post_sample(th0, Sig0inv, Siginv, pts, wts, E, want_post=False, ctx=None):
+  """device evaluation of theta = mup + E U^T, (mup, U) = weighted_post(...) (bcg_sampler_gaussian_post)"""
+  ctx = ctx or Context.default()
+  th0, S0, Si, E = _f64(th0), _f64(Sig0inv), _f64(Siginv), _f64(np.atleast_2d(E))
+  d = th0.shape[0]
+  pts = _f64(np.reshape(pts, (-1, d))) if pts is not None and np.size(pts) else np.zeros((0, d))
+  wts = _f64(np.reshape(wts, (-1,))) if wts is not None and np.size(wts) else np.zeros(0)
+  theta = np.empty((E.shape[0], d))
+  mup = np.empty(d) if want_post else None
+  U = np.empty((d, d)) if want_post else None
+  p = lambda x: None if x is None or x.size == 0 else _ptr(x)
+  check(lib().bcg_sampler_gaussian_post(ctx.handle, d, _ptr(th0), _ptr(S0), _ptr(Si), p(pts), p(wts), pts.shape[0], p(E), E.shape[0],
+                                        p(theta), p(mup), p(U)))
+  return (theta, mup, U) if want_post else theta
 
 
 def pseudo_grad(model, pts, theta, Siginv=None, w=None, resid=None, full=False, ctx=None):

@@ -27,6 +27,7 @@
 #include "audit_kernel.cuh"
 #include "lazy_select_kernel.cuh"
 #include "pseudo_grad_kernel.cuh"
+#include "sampler_kernels.cuh"
 
 using namespace bcg;
 
@@ -1026,6 +1027,64 @@ extern "C" int bcg_pseudo_grad(bcg_ctx* ctx, int32_t model, const double* pts, i
   if (glls) CK(cudaMemcpyAsync(glls, dG, (size_t)K * S * dz * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (ugrad) CK(cudaMemcpyAsync(ugrad, dO, (size_t)K * dz * sizeof(double), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  return BCG_OK;
+}
+
+// Weighted Gaussian posterior sampler on the device (sampler_kernels.cuh): theta = mup + E U^T with (mup, U) =
+// weighted_post(th0, Sig0inv, Siginv, pts, w) (model_gaussian.py:23-30; gaussian/main.py:107-113).  E: host S x d standard
+// normals drawn by the caller.  Outputs (host): theta S x d, optionally mup (d) and U (d x d, upper: Sigp = U U^T).
+extern "C" int bcg_sampler_gaussian_post(bcg_ctx* ctx, int32_t d, const double* th0, const double* Sig0inv, const double* Siginv,
+                                         const double* pts, const double* w, int64_t K, const double* E, int32_t S, double* theta,
+                                         double* mup, double* U) {
+  RET(use_device(ctx));
+  if (!th0 || !Sig0inv || !Siginv || d <= 0 || K < 0 || S < 0 || (K > 0 && (!pts || !w)) || (S > 0 && (!E || !theta)))
+    return fail(BCG_ERR_ARG, "bad arguments");
+  cudaStream_t st = ctx->stream;
+  // one carve-out of a context-owned scratch slot (no cudaMalloc / cudaFree per call: SparseVI calls this 101 times per
+  // build iteration)
+  const size_t dd = (size_t)d * d;
+  const size_t n_doubles = d + 2 * dd + (size_t)K * d + K + (size_t)S * d + 2 * dd + 2 * d + d + (size_t)S * d + 2;
+  double* base = nullptr;
+  RET(ctx_scratch(ctx, 0, n_doubles * sizeof(double), (void**)&base));
+  double* cur = base;
+  auto take = [&](size_t n) { double* p = cur; cur += n; return p; };
+  auto up = [&](double** dst, const double* src, size_t n) -> int {
+    *dst = take(n);
+    if (n) CK(cudaMemcpyAsync(*dst, src, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    return BCG_OK;
+  };
+  double *dth0, *dS0, *dS, *dP, *dW, *dE;
+  RET(up(&dth0, th0, (size_t)d));
+  RET(up(&dS0, Sig0inv, dd));
+  RET(up(&dS, Siginv, dd));
+  RET(up(&dP, pts, (size_t)K * d));
+  RET(up(&dW, w, (size_t)K));
+  RET(up(&dE, E, (size_t)S * d));
+  double* dL = take(dd); double* dLi = take(dd); double* dR = take((size_t)2 * d); double* dM = take((size_t)d);
+  double* dT = take((size_t)S * d);
+  int32_t* dStat = reinterpret_cast<int32_t*>(take(1));
+  CK(cudaMemsetAsync(dStat, 0, sizeof(int32_t), st));
+  GaussPostArgs a;
+  a.th0 = dth0; a.Sig0inv = dS0; a.Siginv = dS; a.pts = dP; a.w = dW; a.E = dE; a.L = dL; a.Linv = dLi; a.rhs = dR; a.mup = dM;
+  a.theta = dT; a.d = d; a.K = (int32_t)K; a.S = S; a.status = dStat;
+  gauss_post_factor_kernel<<<1, 1024, 0, st>>>(a);
+  CK(cudaGetLastError());
+  if (S > 0) {
+    const int64_t tot = (int64_t)S * d;
+    gauss_post_sample_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(a);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(theta, dT, (size_t)tot * sizeof(double), cudaMemcpyDeviceToHost, st));
+  }
+  int32_t stat = 0;
+  CK(cudaMemcpyAsync(&stat, dStat, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (mup) CK(cudaMemcpyAsync(mup, dM, (size_t)d * sizeof(double), cudaMemcpyDeviceToHost, st));
+  std::vector<double> li;
+  if (U) { li.resize((size_t)d * d); CK(cudaMemcpyAsync(li.data(), dLi, (size_t)d * d * sizeof(double), cudaMemcpyDeviceToHost, st)); }
+  CK(cudaStreamSynchronize(st));
+  if (stat) return fail(BCG_ERR_ARG, "Sig0inv + sum(w) Siginv is not positive definite");
+  if (U)
+    for (int i = 0; i < d; ++i)
+      for (int j = 0; j < d; ++j) U[(size_t)i * d + j] = li[(size_t)j * d + i];       // U = (L^-1)^T
   return BCG_OK;
 }
 

@@ -1,0 +1,116 @@
+// Device side of the host-side samplers that feed Projector.update().
+//
+// Weighted Gaussian posterior (examples/common/model_gaussian.py:23-30 `weighted_post`, used by the SparseVI / BatchPSVI
+// sampler of examples/gaussian/main.py:107-113):
+//   L = chol(Sig0inv + sum(w) Siginv)                      (lower)
+//   U = (L^-1)^T                                           Sigp = U U^T
+//   mup = U U^T (Sig0inv th0 + Siginv sum_k w_k x_k)       (th0 when there are no points)
+//   theta = mup + E U^T = mup + E L^-1                     E = the caller's standard normals (drawn on the HOST, in the
+//                                                          reference's order, so seeded runs consume the global RNG alike)
+// d is the parameter dimension (200 in the Gaussian example): the d x d factorisation is latency-bound single-CTA work, the
+// point of doing it here is that at d = 200 NumPy spends ~3 ms per call in inv / cholesky / the S x d x d product, 101
+// times per SparseVI build iteration.  All float64.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace bcg {
+
+struct GaussPostArgs {
+  const double* th0;      // d
+  const double* Sig0inv;  // d x d
+  const double* Siginv;   // d x d
+  const double* pts;      // K x d (K may be 0)
+  const double* w;        // K
+  const double* E;        // S x d standard normals
+  double* L;              // d x d work: precision -> its lower Cholesky factor
+  double* Linv;           // d x d work: L^-1 (lower)
+  double* rhs;            // 2 d work
+  double* mup;            // d   out
+  double* theta;          // S x d out
+  int32_t d, K, S;
+  int32_t* status;        // 0 ok, 1 precision not positive definite
+};
+
+// one CTA: precision, right-hand side, Cholesky, triangular inverse, posterior mean
+__global__ void __launch_bounds__(1024) gauss_post_factor_kernel(const GaussPostArgs a) {
+  __shared__ double s_red[32];
+  __shared__ double s_piv;
+  const int d = a.d, t = threadIdx.x, nt = blockDim.x;
+  // wsum (fixed order) and xw = sum_k w_k x_k
+  double wsum = 0.;
+  for (int k = 0; k < a.K; ++k) wsum += a.w[k];
+  for (int i = t; i < d * d; i += nt) a.L[i] = a.Sig0inv[i] + wsum * a.Siginv[i];
+  double* xw = a.rhs + d;
+  for (int j = t; j < d; j += nt) {
+    double acc = 0.;
+    for (int k = 0; k < a.K; ++k) acc += a.w[k] * a.pts[(size_t)k * d + j];
+    xw[j] = acc;
+  }
+  __syncthreads();
+  for (int i = t; i < d; i += nt) {
+    double acc = 0.;
+    for (int j = 0; j < d; ++j) acc += a.Sig0inv[(size_t)i * d + j] * a.th0[j] + a.Siginv[(size_t)i * d + j] * xw[j];
+    a.rhs[i] = acc;
+  }
+  // right-looking Cholesky, lower, in place (column j: scale, then rank-1 update of the trailing block)
+  for (int j = 0; j < d; ++j) {
+    __syncthreads();
+    if (t == 0) {
+      const double p = a.L[(size_t)j * d + j];
+      s_piv = p > 0. ? sqrt(p) : 0.;
+      if (!(p > 0.)) *a.status = 1;
+    }
+    __syncthreads();
+    const double piv = s_piv;
+    if (piv == 0.) return;
+    for (int i = j + t; i < d; i += nt) a.L[(size_t)i * d + j] = (i == j) ? piv : a.L[(size_t)i * d + j] / piv;
+    __syncthreads();
+    const int m = d - j - 1;
+    for (int q = t; q < m * m; q += nt) {
+      const int r = j + 1 + q / m, c = j + 1 + q % m;
+      if (c <= r) a.L[(size_t)r * d + c] -= a.L[(size_t)r * d + j] * a.L[(size_t)c * d + j];
+    }
+  }
+  __syncthreads();
+  for (int q = t; q < d * d; q += nt) { const int r = q / d, c = q % d; if (c > r) a.L[q] = 0.; }
+  __syncthreads();
+  // Linv: column c of L^-1 by forward substitution, one thread per column
+  for (int c = t; c < d; c += nt) {
+    for (int r = 0; r < d; ++r) {
+      double acc = (r == c) ? 1. : 0.;
+      for (int k = c; k < r; ++k) acc -= a.L[(size_t)r * d + k] * a.Linv[(size_t)k * d + c];
+      a.Linv[(size_t)r * d + c] = (r < c) ? 0. : acc / a.L[(size_t)r * d + r];
+    }
+  }
+  __syncthreads();
+  // mup = Linv^T (Linv rhs)
+  double* y = a.rhs + d;
+  for (int i = t; i < d; i += nt) {
+    double acc = 0.;
+    for (int j = 0; j <= i; ++j) acc += a.Linv[(size_t)i * d + j] * a.rhs[j];
+    y[i] = acc;
+  }
+  __syncthreads();
+  for (int i = t; i < d; i += nt) {
+    double acc = 0.;
+    for (int j = i; j < d; ++j) acc += a.Linv[(size_t)j * d + i] * y[j];
+    a.mup[i] = a.K > 0 ? acc : a.th0[i];                   // model_gaussian.py:26-29
+  }
+  (void)s_red;
+}
+
+// theta = mup + E Linv     (E U^T with U^T = L^-1); one thread per output element, coalesced over the columns
+__global__ void gauss_post_sample_kernel(const GaussPostArgs a) {
+  const int d = a.d;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)a.S * d) return;
+  const int s = (int)(i / d), c = (int)(i - (int64_t)s * d);
+  const double* e = a.E + (size_t)s * d;
+  double acc = 0.;
+  for (int k = c; k < d; ++k) acc = fma(e[k], a.Linv[(size_t)k * d + c], acc);
+  a.theta[i] = a.mup[c] + acc;
+}
+
+}  // namespace bcg

@@ -481,13 +481,9 @@ def main():
     x = rng.randn(n3, d3) + 1.                                   # examples/gaussian/main.py:72,82: N(1_d, I)
     th0, Sig0inv, Siginv = np.zeros(d3), np.eye(d3), np.eye(d3)
 
-    def sampler_w(n, wts, pts):                                  # examples/gaussian/main.py:107-113 (weighted_post)
-      if wts is None or pts is None or pts.shape[0] == 0:
-        wts, pts = np.zeros(1), np.zeros((1, d3))
-      prec = Sig0inv + wts.sum() * Siginv
-      cov = np.linalg.inv(prec)
-      mu = cov.dot(Sig0inv.dot(th0) + Siginv.dot((wts[:, None] * pts).sum(axis=0)))
-      return mu + np.random.randn(n, d3).dot(np.linalg.cholesky(cov).T)
+    # the sampler_w of examples/gaussian/main.py:107-113 (weighted_post, model_gaussian.py:23-30): normals drawn on the
+    # host in the reference's order, factorisation and sample transform on the device (csrc/sampler_kernels.cuh)
+    sampler_w = bc.GaussianPosteriorSampler(th0, Sig0inv, Siginv, ctx=ctx)
     np.random.seed(0)
     prj = bc.GaussianProjector(sampler_w, S3, Siginv, ctx=ctx)
     prj.project_sum(x)                                           # one-off upload of x + warm-up

@@ -16,6 +16,7 @@
  *   bcg_vecs_project_gaussian  projector.py:19-21 with examples/common/model_gaussian.py:4-10
  *   bcg_vecs_project_poisson   projector.py:19-21 with examples/common/model_poiss.py:25-38
  *   bcg_vecs_colsum / _rows    hilbert.py:24 / the ndarray returned by Projector.project
+ *   bcg_sampler_gaussian_post  examples/common/model_gaussian.py:23-30 + examples/gaussian/main.py:107-113 (sampler feeding Projector.update)
  *   bcg_pseudo_grad            projector.py:23-28 + model_lr.py:50-57 / model_poiss.py:58-67 / model_gaussian.py:12-15, bpsvi.py:53
  *   bcg_dataset_project_lazy   the same projection without storing it (norms, b only); rows re-evaluated per selection pass
  *   bcg_dataset_audit          projector.py:19-21 + giga.py:31-38 / frankwolfe.py:17 (independent float64 re-evaluation)
@@ -156,6 +157,14 @@ int  bcg_dataset_project_lazy(bcg_dataset* ds, int32_t model, int32_t d, const d
  * pts: host K x zld; theta: host S x d. */
 int  bcg_pseudo_grad(bcg_ctx* ctx, int32_t model, const double* pts, int64_t K, int32_t zld, int32_t d, const double* theta,
                      int32_t S, const double* Siginv, const double* w, const double* resid, double* glls, double* ugrad);
+/* Weighted Gaussian posterior SAMPLER on the device (csrc/sampler_kernels.cuh): theta = mup + E U^T with
+ * (mup, U) = weighted_post(th0, Sig0inv, Siginv, pts, w) of examples/common/model_gaussian.py:23-30 -- the sampler_w of
+ * examples/gaussian/main.py:107-113 that SparseVI / BatchPSVI call before every projection.  E: host S x d standard normals
+ * drawn by the CALLER (the reference's np.random.randn call, so seeded runs consume the global RNG identically).
+ * Outputs (host): theta S x d; optional mup (d) and U (d x d upper, Sigp = U U^T). */
+int  bcg_sampler_gaussian_post(bcg_ctx* ctx, int32_t d, const double* th0, const double* Sig0inv, const double* Siginv,
+                               const double* pts, const double* w, int64_t K, const double* E, int32_t S, double* theta,
+                               double* mup, double* U);
 /* ll_ns = x_n . A_s + coff_s : the Gaussian model with A = theta Siginv (host S x d) and
  * coff_s = -0.5 theta_s Siginv theta_s precomputed by the caller */
 int  bcg_dataset_project_linear(bcg_dataset* ds, const int64_t* rowidx, int64_t nsel, int32_t d, const double* A,

@@ -180,6 +180,20 @@ def main():
   bp.build(8)
   save('bpsvi_lr', seed=8, build_seed=9, N=500, d=4, S=32, sz=8, opt_itrs=10, wts=bp.wts, pts=bp.pts)
 
+  # ---- weighted Gaussian posterior + the sampler_w draw (model_gaussian.py:23-30, gaussian/main.py:107-113)
+  rng = np.random.RandomState(12)
+  d = 9
+  B0, B1 = rng.randn(d, d), rng.randn(d, d)
+  S0inv, S1inv = B0.dot(B0.T) + d*np.eye(d), B1.dot(B1.T) + d*np.eye(d)
+  mu0 = rng.randn(d)
+  ptsw, ww = rng.randn(6, d), rng.uniform(0.2, 3., size=6)
+  mup, USigp, LSigpInv = model_gaussian.weighted_post(mu0, S0inv, S1inv, ptsw, ww)
+  np.random.seed(21)
+  draw = mup + np.random.randn(40, d).dot(USigp.T)
+  mup0, USigp0, _ = model_gaussian.weighted_post(mu0, S0inv, S1inv, np.zeros((0, d)), np.zeros(0))
+  save('gaussian_weighted_post', mu0=mu0, Sig0inv=S0inv, Siginv=S1inv, pts=ptsw, wts=ww, mup=mup, USigp=USigp, draw_seed=21,
+       draw=draw, mup_empty=mup0, USigp_empty=USigp0)
+
 
 if __name__ == '__main__':
   main()

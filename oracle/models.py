@@ -52,6 +52,28 @@ def gaussian_grad_x_loglik(x, th, Siginv):
   return th.dot(Siginv)[np.newaxis, :, :] - x.dot(Siginv)[:, np.newaxis, :]
 
 
+def gaussian_weighted_post(th0, Sig0inv, Siginv, x, w):
+  """model_gaussian.py:23-30: posterior mean and the upper factor U of the covariance (Sigp = U U^T)"""
+  import scipy.linalg as sl
+  LSigpInv = np.linalg.cholesky(Sig0inv + w.sum()*Siginv)
+  USigp = sl.solve_triangular(LSigpInv, np.eye(LSigpInv.shape[0]), lower=True, overwrite_b=True, check_finite=False).T
+  if w.shape[0] > 0:
+    mup = np.dot(USigp.dot(USigp.T), np.dot(Sig0inv, th0) + np.dot(Siginv, (w[:, np.newaxis]*x).sum(axis=0)))
+  else:
+    mup = th0
+  return mup, USigp, LSigpInv
+
+
+def gaussian_sampler_w(th0, Sig0inv, Siginv):
+  """examples/gaussian/main.py:107-113"""
+  def sampler_w(n, wts, pts):
+    if wts is None or pts is None or pts.shape[0] == 0:
+      wts, pts = np.zeros(1), np.zeros((1, th0.shape[0]))
+    muw, USigw, _ = gaussian_weighted_post(th0, Sig0inv, Siginv, pts, wts)
+    return muw + np.random.randn(n, muw.shape[0]).dot(USigw.T)
+  return sampler_w
+
+
 # ---------------------------------------------------------------- Poisson regression
 def poisson_log_rate(th, x):
   """model_poiss.py:25-30: s = log(softplus(x.th)), with s ~= x.th when x.th <= -100."""

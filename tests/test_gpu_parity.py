@@ -1045,3 +1045,44 @@ def test_omp_capacity_growth_keeps_the_warm_start_and_stays_small(bc):
   big = bc.HilbertCoreset(Z, prj, snnls=bc.snnls.OrthoPursuit)
   big.build(20000)                                   # stops at the numeric limit long before; the work space is what matters
   assert free0 - bc.Context.default().mem_info()[0] < (1 << 30)
+
+
+# ---------------------------------------------------------------- device sampler
+def test_gaussian_posterior_sampler_on_the_device(bc):
+  """bc.GaussianPosteriorSampler = the sampler_w of examples/gaussian/main.py:107-113 with weighted_post
+  (model_gaussian.py:23-30) on the device: posterior mean / factor against the reference-generated fixture, the seeded
+  draw (host RNG, reference order) to 1e-10, and the SparseVI golden run reproduced with it"""
+  g = load_golden('gaussian_weighted_post')
+  smp = bc.GaussianPosteriorSampler(g['mu0'], g['Sig0inv'], g['Siginv'])
+  mup, U = smp.weighted_post(g['pts'], g['wts'])
+  np.testing.assert_allclose(mup, g['mup'], rtol=1e-11, atol=1e-13)
+  np.testing.assert_allclose(U, g['USigp'], rtol=1e-11, atol=1e-14)
+  mup0, U0 = smp.weighted_post(np.zeros((0, 9)), np.zeros(0))
+  np.testing.assert_allclose(mup0, g['mup_empty'], rtol=1e-12, atol=0)
+  np.testing.assert_allclose(U0, g['USigp_empty'], rtol=1e-11, atol=1e-14)
+  np.random.seed(int(g['draw_seed']))
+  draw = smp(40, g['wts'], g['pts'])
+  np.testing.assert_allclose(draw, g['draw'], rtol=1e-10, atol=1e-12)
+  # larger dimension against the oracle restatement (d = 200 is the Gaussian example's size)
+  rng = np.random.RandomState(1)
+  d = 200
+  B = rng.randn(d, d)/np.sqrt(d)
+  Si = B.dot(B.T) + np.eye(d)
+  pts, w = rng.randn(30, d), rng.uniform(0.1, 50., size=30)
+  big = bc.GaussianPosteriorSampler(rng.randn(d), np.eye(d), Si)
+  rm, rU, _ = models.gaussian_weighted_post(big.mu0, big.Sig0inv, big.Siginv, pts, w)
+  mup, U = big.weighted_post(pts, w)
+  np.testing.assert_allclose(mup, rm, rtol=1e-9, atol=1e-11)
+  np.testing.assert_allclose(U, rU, rtol=1e-9, atol=1e-12)
+  # the SparseVI fixture (generated by the reference with its own sampler_w) reproduced with the device sampler
+  g = load_golden('sparsevi_gaussian')
+  d = int(g['d'])
+  np.random.seed(int(g['seed']))
+  xs = np.random.multivariate_normal(np.ones(d), np.eye(d), int(g['N']))
+  prj = bc.GaussianProjector(bc.GaussianPosteriorSampler(np.zeros(d), np.eye(d), np.eye(d)), int(g['S']), np.eye(d))
+  svi = bc.SparseVICoreset(xs, prj, opt_itrs=int(g['opt_itrs']))
+  svi.build(int(g['itrs']))
+  assert np.array_equal(svi.idcs, g['raw_idcs'])
+  np.testing.assert_allclose(svi.wts, g['raw_wts'], rtol=1e-6, atol=1e-9)
+  with pytest.raises(bc.BcgError):
+    bc.GaussianPosteriorSampler(np.zeros(3), -np.eye(3), np.eye(3))(4, np.zeros(1), np.zeros((1, 3)))
