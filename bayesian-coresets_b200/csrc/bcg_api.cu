@@ -1357,6 +1357,9 @@ static int launch_scan(bcg_solver* s, cudaEvent_t e0 = nullptr, cudaEvent_t e1 =
   a.done = &s->d->scan_done;
   a.need_exact = &s->d->need_exact;
   a.force_exact = &s->d->force_exact;
+  a.top = &s->d->scan_top;
+  a.top_row = &s->d->scan_top_row;
+  a.top_cnt = &s->d->scan_cnt;
   if (e0) CK(cudaEventRecord(e0, s->ctx->stream));
   CK(scan_launch(s->sc, a, s->ctx->stream));
   if (e1) CK(cudaEventRecord(e1, s->ctx->stream));
@@ -1992,6 +1995,8 @@ extern "C" int bcg_solver_set_weights(bcg_solver* s, const double* w, int64_t k)
   RET(use_device(s->ctx));
   cudaStream_t st = s->ctx->stream;
   if (k > 0) CK(cudaMemcpyAsync(s->h.act_w, w, (size_t)k * sizeof(double), cudaMemcpyHostToDevice, st));
+  s->h.kkt_valid = 0;
+  RET(push_state(s));
   RET(invalidate_nnls(s));
   refresh_kernel<<<1, kStepThreads, 0, st>>>(s->d);
   CK(cudaGetLastError());
@@ -2026,6 +2031,7 @@ extern "C" int bcg_solver_set_active(bcg_solver* s, const int64_t* idx, const do
     CK(cudaMemcpyAsync(h.act_w, w, (size_t)k * sizeof(double), cudaMemcpyHostToDevice, st));
   }
   h.nact = (int32_t)k;
+  h.kkt_valid = 0;
   RET(push_state(s));
   if (k > 0) {
     gather_active_kernel<<<(unsigned)std::min<int64_t>(k, 1024), 128, 0, st>>>(s->d, (int)k);
@@ -2046,6 +2052,8 @@ extern "C" int bcg_solver_reset(bcg_solver* s) {
   h.halted = 0;
   h.retried = 0;
   h.select_failed = 0;
+  h.kkt_valid = 0;
+  h.scan_cnt = 0;
   h.err = h.bnorm;
   RET(invalidate_nnls(s));
   CK(cudaMemsetAsync(h.xw, 0, h.S * sizeof(double), s->ctx->stream));

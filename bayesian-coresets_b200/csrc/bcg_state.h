@@ -78,6 +78,12 @@ struct SolverState {
   int32_t n_exact;                  // selections resolved by the exact pass so far (diagnostics)
   int32_t iters_done;               // iterations consumed by the last persistent-kernel launch
   unsigned int scan_done;           // CTA completion counter of scan_kernel (last CTA resets it)
+  // summary of the last scan by its last CTA: float32 maximum, the lowest row that attains it, published candidates inside
+  // the near-tie window (0 = no summary).  With exactly one candidate in the window pick_local takes it without any reduction.
+  float scan_top;
+  uint32_t scan_top_row;
+  int32_t scan_cnt;
+  int32_t kkt_valid;                // OMP: the weights are the NNLS optimum of the active set (gradient ~ 0 on it)
   int32_t check_monotone;           // snnls.py:9 check_error_monotone
   int32_t force_exact;              // testing: treat every candidate set as ambiguous
   // ---- never-materialising select (lazy_select_kernel.cuh): An == null ---------------------------

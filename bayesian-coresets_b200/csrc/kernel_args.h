@@ -28,6 +28,9 @@ struct ScanArgs {
   unsigned int* done;     // CTA completion counter (zero between launches)
   int32_t* need_exact;    // raised by the last CTA when the candidate set may miss the float64 arg-max
   const int32_t* force_exact;
+  float* top;             // summary of this scan (SolverState::scan_top / scan_top_row / scan_cnt)
+  uint32_t* top_row;
+  int32_t* top_cnt;
 };
 
 struct LoopCtl {

@@ -324,7 +324,7 @@ BCG_HD void nnls_solve(const Blk& B, SolverState* st, NnlsWork* W, int from_scra
     if (st->act_w[k] > 0.) st->act_w[k] = 0.;
   B.sync();
   for (int p = B.tid; p < W->nP; p += B.nthr) st->act_w[W->P[p]] = W->wP[p];
-  if (B.tid == 0) W->valid = 1;
+  if (B.tid == 0) { W->valid = 1; st->kkt_valid = 1; }
   B.sync();
   if (ax_is_final) {
     // the last residual pass already is A w for the final weights: error() without another K x S pass
@@ -361,7 +361,7 @@ BCG_HD void omp_iteration(const Blk& B, SolverState* st, NnlsWork* W, int prep_n
   if (st->check_monotone && nonempty && err > prev_err) {  // snnls.py:56-61: revert
     for (int k = B.tid; k < st->nact; k += B.nthr) st->act_w[k] = (k < nact0) ? st->act_w_new[k] : 0.;
     B.sync();
-    if (B.tid == 0) W->valid = 0;
+    if (B.tid == 0) { W->valid = 0; st->kkt_valid = 0; }
     B.sync();
     refresh_iterate(B, st);
     if (B.tid == 0) fail_event(st, BCG_IT_FAIL_MONOTONE, f, err, prev_err);

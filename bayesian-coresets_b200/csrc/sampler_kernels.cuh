@@ -54,24 +54,34 @@ __global__ void __launch_bounds__(1024) gauss_post_factor_kernel(const GaussPost
     for (int j = 0; j < d; ++j) acc += a.Sig0inv[(size_t)i * d + j] * a.th0[j] + a.Siginv[(size_t)i * d + j] * xw[j];
     a.rhs[i] = acc;
   }
-  // right-looking Cholesky, lower, in place (column j: scale, then rank-1 update of the trailing block)
+  // left-looking Cholesky (Cholesky-Crout), lower, in place: column j needs the dot products of row i (i >= j) with row j
+  // over the finished columns k < j -- both rows are contiguous, so a WARP per row reads them coalesced and reduces by
+  // shuffles; two block barriers per column (the first version -- a right-looking rank-1 update of the trailing block by
+  // all threads with a div/mod per element -- took ~4 ms at d = 200, slower than NumPy)
+  const int lane = t & 31, warp = t >> 5, nw = nt >> 5;
   for (int j = 0; j < d; ++j) {
     __syncthreads();
-    if (t == 0) {
-      const double p = a.L[(size_t)j * d + j];
-      s_piv = p > 0. ? sqrt(p) : 0.;
-      if (!(p > 0.)) *a.status = 1;
+    const double* rj = a.L + (size_t)j * d;
+    for (int i = j + warp; i < d; i += nw) {
+      double* ri = a.L + (size_t)i * d;
+      double acc = 0.;
+      for (int k = lane; k < j; k += 32) acc = fma(ri[k], rj[k], acc);
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+      if (lane == 0) {
+        const double v = ri[j] - acc;
+        if (i == j) {
+          s_piv = v > 0. ? sqrt(v) : 0.;
+          if (!(v > 0.)) *a.status = 1;
+        } else {
+          ri[j] = v;                                          // scaled by the pivot after the barrier
+        }
+      }
     }
     __syncthreads();
     const double piv = s_piv;
     if (piv == 0.) return;
     for (int i = j + t; i < d; i += nt) a.L[(size_t)i * d + j] = (i == j) ? piv : a.L[(size_t)i * d + j] / piv;
-    __syncthreads();
-    const int m = d - j - 1;
-    for (int q = t; q < m * m; q += nt) {
-      const int r = j + 1 + q / m, c = j + 1 + q % m;
-      if (c <= r) a.L[(size_t)r * d + c] -= a.L[(size_t)r * d + j] * a.L[(size_t)c * d + j];
-    }
   }
   __syncthreads();
   for (int q = t; q < d * d; q += nt) { const int r = q / d, c = q % d; if (c > r) a.L[q] = 0.; }

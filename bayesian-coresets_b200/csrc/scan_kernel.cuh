@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const ScanArgs a) {
   __shared__ unsigned int s_last;
   __shared__ float s_top[32];
   __shared__ int s_cnt[32];
+  __shared__ uint32_t s_row[32];
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -112,22 +113,31 @@ __global__ void __launch_bounds__(512, 1) scan_kernel(const ScanArgs a) {
   const float thr = top - (2e-5f + 1e-5f * fabsf(top));
   int cnt = 0;
   float lm = -INFINITY;
+  uint32_t trow = kNoRowU;                                // lowest row among the candidates that attain the maximum
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const unsigned long long raw = __ldcg(reinterpret_cast<const unsigned long long*>(a.cands + i));
-    if ((uint32_t)(raw >> 32) != kNoRowU && __uint_as_float((unsigned int)(raw & 0xffffffffull)) >= thr) ++cnt;
+    const uint32_t rw = (uint32_t)(raw >> 32);
+    const float sc = __uint_as_float((unsigned int)(raw & 0xffffffffull));
+    if (rw != kNoRowU && sc >= thr) ++cnt;
+    if (rw != kNoRowU && sc == top && rw < trow) trow = rw;
     lm = fmaxf(lm, __ldcg(a.lost + i));
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
     cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
     lm = fmaxf(lm, __shfl_xor_sync(0xffffffffu, lm, off));
+    trow = min(trow, __shfl_xor_sync(0xffffffffu, trow, off));
   }
-  if (lane == 0) { s_cnt[warp] = cnt; s_top[warp] = lm; }
+  if (lane == 0) { s_cnt[warp] = cnt; s_top[warp] = lm; s_row[warp] = trow; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    cnt = 0; lm = -INFINITY;
-    for (int w = 0; w < wpb; ++w) { cnt += s_cnt[w]; lm = fmaxf(lm, s_top[w]); }
-    if (top > -INFINITY && (lm >= thr || cnt > kRescoreMax || *a.force_exact)) *a.need_exact = 1;
+    cnt = 0; lm = -INFINITY; trow = kNoRowU;
+    for (int w = 0; w < wpb; ++w) { cnt += s_cnt[w]; lm = fmaxf(lm, s_top[w]); trow = min(trow, s_row[w]); }
+    const bool ambiguous = top > -INFINITY && (lm >= thr || cnt > kRescoreMax || *a.force_exact);
+    if (ambiguous) *a.need_exact = 1;
+    *a.top = top;
+    *a.top_row = trow;
+    *a.top_cnt = ambiguous ? 0 : cnt;
     *a.done = 0u;
   }
 }

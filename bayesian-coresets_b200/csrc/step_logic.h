@@ -280,6 +280,17 @@ BCG_HD void pick_local(const Blk& B, SolverState* st, bool force_rescore, uint32
     *score_out = key;
     return;
   }
+  if (st->scan_cnt == 1) {
+    // the scan's last CTA found exactly ONE published candidate inside the near-tie window (and no unpublished one):
+    // it is the arg-max -- no block-wide reduction over the candidates (~7 us of an OMP iteration)
+    const uint32_t r = st->scan_top_row;
+    const double sc = force_rescore ? row_score64(B, st, st->An + (size_t)r * st->ld) : (double)st->scan_top;
+    B.sync();
+    if (B.tid == 0) st->scan_cnt = 0;                     // consumed
+    B.sync();
+    *row_out = r; *score_out = sc;
+    return;
+  }
   ScanCand* c = st->cands;
   const int n = st->n_cands;
   uint32_t chosen[kRescoreMax];
@@ -555,7 +566,12 @@ BCG_HD int64_t omp_select(const Blk& B, SolverState* st) {
     f = st->row_offset + (int64_t)lrow;
     local_row(st, lrow, &frow, &nf_stored);
   }
-  if (nonempty) {
+  // orthopursuit.py:26-35 compares pos with neg = max over the active set of -<a_k, residual>.  Right after an NNLS solve the
+  // weights are the optimum of the active set, so those inner products are zero up to the backward error of the solve
+  // (<= ~1e-9 of the unit residual while ||r|| > 1e-6 ||b||): with pos > 1e-3 the comparison is decided and the K x S pass is
+  // skipped (7-15 us of the iteration).  Any other state (host-written weights, reverted step, near convergence) takes it.
+  const bool neg_decided = st->kkt_valid && pos > 1e-3 && st->err > 1e-6 * st->bnorm;
+  if (nonempty && !neg_decided) {
     // negative direction over the active set (w > 0), lowest global index wins ties:
     // -dots over the active rows (coalesced, several rows in flight per warp), then the block arg-max
     blk_dots<float>(B, st->nact, S,
@@ -577,6 +593,7 @@ BCG_HD int64_t omp_select(const Blk& B, SolverState* st) {
       return f;
     }
   }
+  if (!nonempty || neg_decided) omp_mark(B, st, 3);
   int slot = find_slot(B, st, f);
   if (slot < 0) {
     slot = st->nact;

@@ -57,6 +57,10 @@ void scan(Host& H, int nb) {
   const float thr = top - (2e-5f + 1e-5f * fabsf(top));
   int cnt = 0;
   for (int i = 0; i < nb; ++i) cnt += (H.cands[i].row != kNoRow && H.cands[i].score >= thr) ? 1 : 0;
+  st.scan_top = top; st.scan_cnt = 0; st.scan_top_row = kNoRow;
+  for (int i = 0; i < nb; ++i)
+    if (H.cands[i].row != kNoRow && H.cands[i].score == top && H.cands[i].row < st.scan_top_row) st.scan_top_row = H.cands[i].row;
+  if (!(top > -INFINITY && (lm >= thr || cnt > kRescoreMax || st.force_exact))) st.scan_cnt = cnt;
   if (top > -INFINITY && (lm >= thr || cnt > kRescoreMax || st.force_exact)) {
     st.need_exact = 1;
     H.exact.score = -INFINITY; H.exact.row = -1;
