@@ -1793,7 +1793,6 @@ extern "C" int bcg_solver_build(bcg_solver* s, int32_t itrs, double tol, bcg_ite
     }
     la.claims = s->d_claims;
     la.static_frac = (float)env_int("BCG_STATIC_PCT", 100) / 100.f;   // measured: a larger dynamic share only costs (atomics); the grid is HBM-bound either way
-    la.l2_prefetch = env_int("BCG_L2_PREFETCH", 0);
     la.trace = nullptr;
     s->trace_n = 0;
     if (s->trace_on) {

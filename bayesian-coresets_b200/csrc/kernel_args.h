@@ -52,7 +52,6 @@ struct LoopArgs {
   int32_t wpb;           // scan warps per CTA (blockDim.x = (wpb + 1) * 32)
   unsigned int* claims;  // itrs zero-initialised counters: dynamically claimed chunks per iteration
   float static_frac;     // share of the chunks that is statically assigned (rest: dynamic tail)
-  int32_t l2_prefetch;   // chunks per warp prefetched into L2 while the iteration is being resolved
   // optional device timestamps (globaltimer ns), null when tracing is off:
   //   trace[it*8 + 0] control: grid arrived      trace[it*8 + 1] control: next direction published
   //   trace[it*8 + 2] CTA 0 warp 0: go observed   trace[it*8 + 3] CTA 0 warp 0: its scan finished

@@ -771,18 +771,8 @@ __global__ void __launch_bounds__(384, 1) greedy_loop_kernel(const LoopArgs a) {
 
     if (a.trace && gw == 0 && lane == 0) a.trace[(size_t)it * 8 + 3] = globaltimer_ns();
     __syncwarp();
-    // Experiment (BCG_L2_PREFETCH, default 0 = off): while the control warp resolves this iteration the
-    // shared-memory rings are full and HBM idles for ~5 us; pulling the next chunks into L2 meanwhile was
-    // measured to be slightly SLOWER (N=1e6, S=256: 154.4 us/iter off, 155.5 / 156.7 / 157.7 with 2 / 4 / 8
-    // chunks per warp), so it stays off.
-    if (issue_it < a.itrs) {
-      for (int p = 0; p < a.l2_prefetch; ++p) {
-        const int64_t kpf = issue_k + p;
-        if (kpf >= n_s) break;
-        const int64_t row0 = (gw + kpf * GW) * q.rps;
-        tma_prefetch_l2(q.An + (size_t)row0 * q.ld, (uint32_t)q.rps * (uint32_t)q.ld * 4u, leader);
-      }
-    }
+    // (Pulling the next chunks into L2 while the control warp resolves the iteration -- the rings are full and HBM idles for
+    // ~5 us -- was measured slightly SLOWER, 155.5-157.7 vs 154.4 us per iteration at N = 1e6, S = 256, and was removed.)
     Core::warp_merge_lost(best, brow, lost);
     // per-warp results, double-buffered on the iteration parity: a warp that runs ahead into iteration it + 1 writes
     // the other half, and its write of iteration it + 2 is ordered behind the barrier of it + 1, which warp 0 only

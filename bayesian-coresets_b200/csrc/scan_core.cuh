@@ -69,17 +69,6 @@ __device__ __forceinline__ void tma_load_rows(uint64_t* bar, float* dst, const f
       : "memory");
 }
 
-// ask the memory system to bring `bytes` at `src` into L2 (no shared-memory destination, no completion event)
-__device__ __forceinline__ void tma_prefetch_l2(const float* src, uint32_t bytes, bool leader) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.u32 p, %2, 0;\n\t"
-      "@p cp.async.bulk.prefetch.L2.global [%0], %1;\n\t"
-      "}"
-      ::"l"(src), "r"(bytes), "r"((uint32_t)leader)
-      : "memory");
-}
-
 __device__ __forceinline__ uint64_t l2_policy(int evict_first) {
   uint64_t policy;
   if (evict_first)

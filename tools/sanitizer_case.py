@@ -24,4 +24,21 @@ for S in (256, 96):
   cs.build(S//2 + 20)
   cs.optimize()
   print('S', S, 'omp size', cs.snnls.size(), 'error', cs.error(), flush=True)
+# round-2 kernels: never-materialising solver, audit scorer, pseudo-point gradients, device sampler, streamed DMMA projection
+from bayesiancoresets_b200 import _native as nat
+Z, theta = lr_problem(2, N, d, 128)
+prj = bc.LogisticRegressionProjector(lambda n, w, p: theta, 128)
+for alg in (bc.snnls.GIGA, bc.snnls.OrthoPursuit):
+  cs = bc.HilbertCoreset(Z, prj, snnls=alg, materialize=False)
+  cs.build(8)
+ds = nat.Dataset(Z)
+sc, nr, csum = ds.audit(nat.MODEL_LR, theta, kind=nat.ALG_GIGA, dirs=np.random.RandomState(0).randn(2, 128), norms=True, colsum=True)
+g, u = nat.pseudo_grad(nat.MODEL_POISSON, np.hstack((Z[:7], np.ones((7, 1)))), theta, w=np.ones(7), resid=np.ones(128), full=True)
+rng = np.random.RandomState(3)
+x = rng.randn(N, 40)
+os.environ['BCG_PROJ_MMA'] = '2'
+gp = bc.GaussianProjector(bc.GaussianPosteriorSampler(np.zeros(40), np.eye(40), np.eye(40)), 64, np.eye(40))
+svi = bc.SparseVICoreset(x, gp, opt_itrs=3)
+svi.build(2)
+print('r2 kernels ok', float(sc.max()), float(u.sum()), svi.size(), flush=True)
 print('SANITIZER CASE DONE')
