@@ -16,4 +16,4 @@ from .projector import (Projector, BlackBoxProjector, LogisticRegressionProjecto
 from .coreset import Coreset, HilbertCoreset, SparseVICoreset, BatchPSVICoreset, UniformSamplingCoreset
 from ._native import DeviceVecs, Dataset, Context, BcgError, pinned_empty, pinned_copy
 from . import comm
-from .samplers import GaussianPosteriorSampler
+from .samplers import GaussianPosteriorSampler, LaplaceSampler

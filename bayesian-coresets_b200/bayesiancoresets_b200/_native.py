@@ -59,6 +59,7 @@ _PROTOTYPES = {
   'bcg_dataset_project_linear': (_c.c_int, [_P, _P, _c.c_int64, _c.c_int32, _P, _P, _c.c_int32, _PP, _P, _P]),
   'bcg_dataset_project_lazy': (_c.c_int, [_P, _c.c_int32, _c.c_int32, _P, _c.c_int32, _P, _PP]),
   'bcg_sampler_gaussian_post': (_c.c_int, [_P, _c.c_int32, _P, _P, _P, _P, _P, _c.c_int64, _P, _c.c_int32, _P, _P, _P]),
+  'bcg_glm_joint': (_c.c_int, [_P, _c.c_int32, _P, _P, _c.c_int64, _c.c_int32, _c.c_int32, _P, _P, _P, _P]),
   'bcg_pseudo_grad': (_c.c_int, [_P, _c.c_int32, _P, _c.c_int64, _c.c_int32, _c.c_int32, _P, _c.c_int32, _P, _P, _P, _P, _P]),
   'bcg_dataset_audit': (_c.c_int, [_P, _c.c_int32, _c.c_int32, _P, _c.c_int32, _P, _c.c_int32, _P, _P, _P, _P]),
   'bcg_vecs_shape': (_c.c_int, [_P, _c.POINTER(_c.c_int64), _c.POINTER(_c.c_int32), _c.POINTER(_c.c_int32)]),
@@ -226,6 +227,21 @@ def gaussian_post_sample(th0, Sig0inv, Siginv, pts, wts, E, want_post=False, ctx
   check(lib().bcg_sampler_gaussian_post(ctx.handle, d, _ptr(th0), _ptr(S0), _ptr(Si), p(pts), p(wts), pts.shape[0], p(E), E.shape[0],
                                         p(theta), p(mup), p(U)))
   return (theta, mup, U) if want_post else theta
+
+
+def glm_joint(model, Z, w, theta, hess=False, ctx=None):
+  """device evaluation of (log_joint, grad_th_log_joint[, hess_th_log_joint]) over the rows of Z (bcg_glm_joint)"""
+  ctx = ctx or Context.default()
+  theta = _f64(np.reshape(theta, (-1,)))
+  d = theta.shape[0]
+  Z = _f64(np.atleast_2d(Z)) if np.size(Z) else np.zeros((0, d + (1 if model == MODEL_POISSON else 0)))
+  w = _f64(np.reshape(w, (-1,)))
+  v = ctypes.c_double()
+  g = np.empty(d)
+  H = np.empty((d, d)) if hess else None
+  check(lib().bcg_glm_joint(ctx.handle, model, _ptr(Z) if Z.size else None, _ptr(w) if w.size else None, Z.shape[0], Z.shape[1], d,
+                            _ptr(theta), ctypes.byref(v), _ptr(g), None if H is None else _ptr(H)))
+  return (v.value, g, H) if hess else (v.value, g)
 
 
 def pseudo_grad(model, pts, theta, Siginv=None, w=None, resid=None, full=False, ctx=None):

@@ -1088,6 +1088,38 @@ extern "C" int bcg_sampler_gaussian_post(bcg_ctx* ctx, int32_t d, const double* 
   return BCG_OK;
 }
 
+// Weighted log-joint, gradient and Hessian of the GLM example models over K points (sampler_kernels.cuh: glm_joint_kernel):
+// the reductions of the Laplace sampler.  Z: host K x zld, w: host K, theta: host d; outputs host (any may be null).
+extern "C" int bcg_glm_joint(bcg_ctx* ctx, int32_t model, const double* Z, const double* w, int64_t K, int32_t zld, int32_t d,
+                             const double* theta, double* value, double* grad, double* hess) {
+  RET(use_device(ctx));
+  if (!theta || d <= 0 || K < 0 || (K > 0 && (!Z || !w))) return fail(BCG_ERR_ARG, "bad arguments");
+  if (model != BCG_MODEL_LR && model != BCG_MODEL_POISSON) return fail(BCG_ERR_ARG, "the Laplace reductions exist for the LR and Poisson models");
+  if ((model == BCG_MODEL_POISSON ? d + 1 : d) > zld && K > 0) return fail(BCG_ERR_ARG, "points have too few columns");
+  const size_t smem = ((size_t)d + 3 * (size_t)K) * sizeof(double);
+  if (smem > 200 * 1024) return fail(BCG_ERR_UNSUPPORTED, "too many points for the single-CTA Laplace reduction (K = %lld)", (long long)K);
+  cudaStream_t st = ctx->stream;
+  const size_t dd = (size_t)d * d;
+  double* base = nullptr;
+  RET(ctx_scratch(ctx, 0, ((size_t)K * zld + K + d + 1 + d + dd + 4) * sizeof(double), (void**)&base));
+  double* dZ = base; double* dW = dZ + (size_t)K * zld; double* dTh = dW + K; double* dV = dTh + d; double* dG = dV + 1; double* dH = dG + d;
+  if (K > 0) {
+    CK(cudaMemcpyAsync(dZ, Z, (size_t)K * zld * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dW, w, (size_t)K * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  CK(cudaMemcpyAsync(dTh, theta, (size_t)d * sizeof(double), cudaMemcpyHostToDevice, st));
+  GlmJointArgs a;
+  a.Z = dZ; a.w = dW; a.theta = dTh; a.value = dV; a.grad = dG; a.hess = dH; a.K = (int32_t)K; a.zld = zld; a.d = d; a.model = model;
+  CK(cudaFuncSetAttribute(glm_joint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  glm_joint_kernel<<<1, 256, smem, st>>>(a);
+  CK(cudaGetLastError());
+  if (value) CK(cudaMemcpyAsync(value, dV, sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (grad) CK(cudaMemcpyAsync(grad, dG, (size_t)d * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (hess) CK(cudaMemcpyAsync(hess, dH, dd * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return BCG_OK;
+}
+
 // Projection straight from a HOST array, chunked and software-pipelined: while chunk c is being projected on
 // `stream`, chunk c+1 is staged (multi-threaded memcpy into pinned memory) and copied on `copy_stream`.  The
 // data are not kept on the device (HilbertCoreset projects once).  thetaT: d x S, coff: S or null (host).

@@ -124,3 +124,88 @@ __global__ void gauss_post_sample_kernel(const GaussPostArgs a) {
 }
 
 }  // namespace bcg
+
+namespace bcg {
+
+// Weighted log-joint of the GLM example models over the K coreset points, with its gradient and Hessian in theta -- the
+// reductions of the Laplace sampler (examples/logistic_poisson_regression/main.py:16-41 `get_laplace`, which minimises
+// -log_joint with its gradient and factorises -hess at the optimum):
+//   model_lr.py:25-32, 34-39, 41-48, 59-80       log_joint / grad_th_log_joint / hess_th_log_joint (logistic regression)
+//   model_poiss.py:32-38, 40-45, 47-56, 69-93    the same for Poisson regression with the softplus rate
+// value = sum_k w_k ll_k - d/2 log(2 pi) - |theta|^2 / 2 ; grad = -theta + sum_k w_k g_k x_k ; hess = -I + sum_k w_k h_k x_k x_k^T
+// One CTA: per-point scalars (ll, g, h) into shared memory, then one thread per gradient / Hessian entry.
+struct GlmJointArgs {
+  const double* Z;        // K x zld  (LR: z = y x; Poisson: [x, y])
+  const double* w;        // K
+  const double* theta;    // d
+  double* value;          // 1
+  double* grad;           // d
+  double* hess;           // d x d
+  int32_t K, zld, d, model;
+};
+
+__global__ void __launch_bounds__(256) glm_joint_kernel(const GlmJointArgs a) {
+  extern __shared__ double gj_smem[];           // theta[d], then (w ll, w g, w h)[K]
+  double* th = gj_smem;
+  double* sl = gj_smem + a.d;
+  double* sg = sl + a.K;
+  double* sh = sg + a.K;
+  __shared__ double s_red[8];
+  const int t = threadIdx.x, nt = blockDim.x, d = a.d, K = a.K;
+  for (int i = t; i < d; i += nt) th[i] = a.theta[i];
+  __syncthreads();
+  double part = 0.;
+  for (int k = t; k < K; k += nt) {
+    const double* x = a.Z + (size_t)k * a.zld;
+    double lin = 0.;
+    for (int i = 0; i < d; ++i) lin = fma(x[i], th[i], lin);
+    double ll, g, h;
+    if (a.model == BCG_MODEL_LR) {
+      const double m = -lin;                                             // model_lr.py:28-31, 44-47, 63-66
+      if (m < 100.) {
+        const double e = exp(m);
+        ll = -log1p(e); g = e / (1. + e); h = -(e / ((1. + e) * (1. + e)));
+      } else {
+        ll = -m; g = 1.; h = -0.;
+      }
+    } else {
+      const double y = x[d];
+      double s = lin;                                                    // model_poiss.py:25-30
+      if (s > -100.) s = log(fmax(s, 0.) + log1p(exp(-fabs(s))));
+      const double es = exp(s);
+      ll = y * s - lgamma(y + 1.) - es;                                  // model_poiss.py:38
+      g = y - es;                                                        // model_poiss.py:53-55
+      h = -(1. + y) * es;                                                // model_poiss.py:82-84
+      if (es > 1e-15) {
+        g = (y * exp(-s) - 1.) * (1. - exp(-es));
+        h = (y * exp(-s) * (1. - exp(-s + es) + exp(-s)) - 1.) * (exp(-es) - exp(-2. * es));
+      }
+    }
+    const double wk = a.w[k];
+    sl[k] = wk * ll; sg[k] = wk * g; sh[k] = wk * h;
+    part += wk * ll;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+  if ((t & 31) == 0) s_red[t >> 5] = part;
+  __syncthreads();
+  if (t == 0) {
+    double v = 0., n2 = 0.;
+    for (int wv = 0; wv < (nt >> 5); ++wv) v += s_red[wv];
+    for (int i = 0; i < d; ++i) n2 += th[i] * th[i];
+    *a.value = v - 0.5 * d * log(2. * 3.14159265358979323846) - 0.5 * n2;   // + log_prior (model_lr.py:34-36)
+  }
+  for (int j = t; j < d; j += nt) {
+    double acc = 0.;
+    for (int k = 0; k < K; ++k) acc = fma(sg[k], a.Z[(size_t)k * a.zld + j], acc);
+    a.grad[j] = acc - th[j];
+  }
+  for (int q = t; q < d * d; q += nt) {
+    const int i = q / d, j = q - i * d;
+    double acc = 0.;
+    for (int k = 0; k < K; ++k) acc = fma(sh[k] * a.Z[(size_t)k * a.zld + i], a.Z[(size_t)k * a.zld + j], acc);
+    a.hess[q] = acc - (i == j ? 1. : 0.);
+  }
+}
+
+}  // namespace bcg

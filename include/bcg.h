@@ -16,6 +16,7 @@
  *   bcg_vecs_project_gaussian  projector.py:19-21 with examples/common/model_gaussian.py:4-10
  *   bcg_vecs_project_poisson   projector.py:19-21 with examples/common/model_poiss.py:25-38
  *   bcg_vecs_colsum / _rows    hilbert.py:24 / the ndarray returned by Projector.project
+ *   bcg_glm_joint              examples/common/model_lr.py:38-80 / model_poiss.py:44-93 (log_joint, grad, hess: Laplace sampler reductions)
  *   bcg_sampler_gaussian_post  examples/common/model_gaussian.py:23-30 + examples/gaussian/main.py:107-113 (sampler feeding Projector.update)
  *   bcg_pseudo_grad            projector.py:23-28 + model_lr.py:50-57 / model_poiss.py:58-67 / model_gaussian.py:12-15, bpsvi.py:53
  *   bcg_dataset_project_lazy   the same projection without storing it (norms, b only); rows re-evaluated per selection pass
@@ -165,6 +166,12 @@ int  bcg_pseudo_grad(bcg_ctx* ctx, int32_t model, const double* pts, int64_t K, 
 int  bcg_sampler_gaussian_post(bcg_ctx* ctx, int32_t d, const double* th0, const double* Sig0inv, const double* Siginv,
                                const double* pts, const double* w, int64_t K, const double* E, int32_t S, double* theta,
                                double* mup, double* U);
+/* Reductions of the LAPLACE sampler (examples/logistic_poisson_regression/main.py:16-41) over the K coreset points, on the
+ * device: value = log_joint(Z, theta, w), grad = grad_th_log_joint, hess = hess_th_log_joint of examples/common/model_lr.py:
+ * 25-80 (BCG_MODEL_LR) or model_poiss.py:32-93 (BCG_MODEL_POISSON), standard normal prior.  Z: host K x zld; outputs host,
+ * any may be null. */
+int  bcg_glm_joint(bcg_ctx* ctx, int32_t model, const double* Z, const double* w, int64_t K, int32_t zld, int32_t d,
+                   const double* theta, double* value, double* grad, double* hess);
 /* ll_ns = x_n . A_s + coff_s : the Gaussian model with A = theta Siginv (host S x d) and
  * coff_s = -0.5 theta_s Siginv theta_s precomputed by the caller */
 int  bcg_dataset_project_linear(bcg_dataset* ds, const int64_t* rowidx, int64_t nsel, int32_t d, const double* A,

@@ -194,6 +194,18 @@ def main():
   save('gaussian_weighted_post', mu0=mu0, Sig0inv=S0inv, Siginv=S1inv, pts=ptsw, wts=ww, mup=mup, USigp=USigp, draw_seed=21,
        draw=draw, mup_empty=mup0, USigp_empty=USigp0)
 
+  # ---- log-joint / gradient / Hessian of the GLM models over weighted points (the Laplace sampler's reductions:
+  #      examples/logistic_poisson_regression/main.py:16-41 with model_lr.py:34-80, model_poiss.py:40-93)
+  rng = np.random.RandomState(14)
+  Zl, thl = lr_problem(15, 40, 5, 3)
+  wl = rng.uniform(0., 4., size=40)
+  wl[::7] = 0.
+  Zq = np.hstack((rng.randn(40, 5), rng.poisson(3., size=(40, 1)).astype(np.float64)))
+  thq = 0.4*rng.randn(3, 5)
+  save('glm_joint', Z_lr=Zl, th_lr=thl, w=wl, lr_value=model_lr.log_joint(Zl, thl, wl), lr_grad=model_lr.grad_th_log_joint(Zl, thl, wl),
+       lr_hess=model_lr.hess_th_log_joint(Zl, thl, wl), Z_poiss=Zq, th_poiss=thq, poiss_value=model_poiss.log_joint(Zq, thq, wl),
+       poiss_grad=model_poiss.grad_th_log_joint(Zq, thq, wl), poiss_hess=model_poiss.hess_th_log_joint(Zq, thq, wl))
+
 
 if __name__ == '__main__':
   main()

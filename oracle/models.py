@@ -74,6 +74,45 @@ def gaussian_sampler_w(th0, Sig0inv, Siginv):
   return sampler_w
 
 
+def lr_log_joint(z, th, wts):
+  """model_lr.py:34-39"""
+  th = np.atleast_2d(th)
+  return (wts[:, np.newaxis]*lr_loglik(z, th)).sum(axis=0) - 0.5*th.shape[1]*np.log(2.*np.pi) - 0.5*(th**2).sum(axis=1)
+
+
+def lr_grad_th_log_joint(z, th, wts):
+  """model_lr.py:41-48, 59-64"""
+  z, th = np.atleast_2d(z), np.atleast_2d(th)
+  m = -z.dot(th.T)
+  idcs = m < 100
+  m[idcs] = np.exp(m[idcs])/(1.+np.exp(m[idcs]))
+  m[np.logical_not(idcs)] = 1.
+  return -th + (wts[:, np.newaxis, np.newaxis]*(m[:, :, np.newaxis]*z[:, np.newaxis, :])).sum(axis=0)
+
+
+def lr_hess_th_log_joint(z, th, wts):
+  """model_lr.py:66-80"""
+  z, th = np.atleast_2d(z), np.atleast_2d(th)
+  m = -z.dot(th.T)
+  idcs = m < 100
+  m[idcs] = np.exp(m[idcs])/(1.+np.exp(m[idcs]))**2
+  m[np.logical_not(idcs)] = 0.
+  hl = -m[:, :, np.newaxis, np.newaxis]*z[:, np.newaxis, :, np.newaxis]*z[:, np.newaxis, np.newaxis, :]
+  return np.tile(-np.eye(th.shape[1]), (th.shape[0], 1, 1)) + (wts[:, np.newaxis, np.newaxis, np.newaxis]*hl).sum(axis=0)
+
+
+def get_laplace(wts, Z, mu0, log_joint, grad_log_joint, hess_log_joint):
+  """examples/logistic_poisson_regression/main.py:16-41 (diag = False, no retries needed in the tests)"""
+  from scipy.optimize import minimize
+  from scipy.linalg import solve_triangular
+  Zw, ww = Z[wts > 0, :], wts[wts > 0]
+  res = minimize(lambda mu: -log_joint(Zw, mu, ww)[0], mu0, jac=lambda mu: -grad_log_joint(Zw, mu, ww)[0, :])
+  mu = res.x
+  LSigInv = np.linalg.cholesky(-hess_log_joint(Zw, mu, ww)[0, :, :])
+  LSig = solve_triangular(LSigInv, np.eye(LSigInv.shape[0]), lower=True, overwrite_b=True, check_finite=False)
+  return mu, LSig, LSigInv
+
+
 # ---------------------------------------------------------------- Poisson regression
 def poisson_log_rate(th, x):
   """model_poiss.py:25-30: s = log(softplus(x.th)), with s ~= x.th when x.th <= -100."""
@@ -144,3 +183,34 @@ class OracleProjector(object):
         raise ValueError('grad_loglikelihood was requested but not initialized')
       return project(self.loglik, pts, self.samples, self.grad_loglik)
     return project(self.loglik, pts, self.samples)
+
+
+def poisson_log_joint(z, th, wts):
+  """model_poiss.py:40-45"""
+  th = np.atleast_2d(th)
+  return (wts[:, np.newaxis]*poisson_loglik(z, th)).sum(axis=0) - 0.5*th.shape[1]*np.log(2.*np.pi) - 0.5*(th**2).sum(axis=1)
+
+
+def poisson_grad_th_log_joint(z, th, wts):
+  """model_poiss.py:47-56, 69-74"""
+  th, z = np.atleast_2d(th), np.atleast_2d(z)
+  x = z[:, :-1]
+  y = np.tile(z[:, -1][:, np.newaxis], (1, th.shape[0]))
+  s = poisson_log_rate(th, x)
+  g = y - np.exp(s)
+  idcs = np.exp(s) > 1e-15
+  g[idcs] = (y[idcs]*np.exp(-s[idcs]) - 1.)*(1. - np.exp(-np.exp(s[idcs])))
+  return -th + (wts[:, np.newaxis, np.newaxis]*(g[:, :, np.newaxis]*x[:, np.newaxis, :])).sum(axis=0)
+
+
+def poisson_hess_th_log_joint(z, th, wts):
+  """model_poiss.py:76-93"""
+  th, z = np.atleast_2d(th), np.atleast_2d(z)
+  x = z[:, :-1]
+  y = np.tile(z[:, -1][:, np.newaxis], (1, th.shape[0]))
+  s = poisson_log_rate(th, x)
+  h = -(1.+y)*np.exp(s)
+  idcs = np.exp(s) > 1e-15
+  h[idcs] = (y[idcs]*np.exp(-s[idcs])*(1.-np.exp(-s[idcs]+np.exp(s[idcs]))+np.exp(-s[idcs])) - 1.)*(np.exp(-np.exp(s[idcs]))-np.exp(-2*np.exp(s[idcs])))
+  hl = h[:, :, np.newaxis, np.newaxis]*x[:, np.newaxis, :, np.newaxis]*x[:, np.newaxis, np.newaxis, :]
+  return np.tile(-np.eye(th.shape[1]), (th.shape[0], 1, 1)) + (wts[:, np.newaxis, np.newaxis, np.newaxis]*hl).sum(axis=0)

@@ -1086,3 +1086,40 @@ def test_gaussian_posterior_sampler_on_the_device(bc):
   np.testing.assert_allclose(svi.wts, g['raw_wts'], rtol=1e-6, atol=1e-9)
   with pytest.raises(bc.BcgError):
     bc.GaussianPosteriorSampler(np.zeros(3), -np.eye(3), np.eye(3))(4, np.zeros(1), np.zeros((1, 3)))
+
+
+def test_laplace_sampler_reductions_on_the_device(bc):
+  """bcg_glm_joint against the reference-generated fixture (log_joint / grad / hess of model_lr.py and model_poiss.py), and
+  bc.LaplaceSampler (= sampler_w of examples/logistic_poisson_regression/main.py:153-160) against the oracle's get_laplace"""
+  import bayesiancoresets_b200._native as nat
+  g = load_golden('glm_joint')
+  for name, model, Z, th in (('lr', nat.MODEL_LR, g['Z_lr'], g['th_lr']), ('poiss', nat.MODEL_POISSON, g['Z_poiss'], g['th_poiss'])):
+    for s in range(th.shape[0]):
+      v, gr, H = nat.glm_joint(model, Z, g['w'], th[s], hess=True)
+      assert v == pytest.approx(g[name + '_value'][s], rel=1e-12)
+      np.testing.assert_allclose(gr, g[name + '_grad'][s], rtol=1e-11, atol=1e-12)
+      np.testing.assert_allclose(H, g[name + '_hess'][s], rtol=1e-11, atol=1e-12)
+  Z, theta = lr_problem(3, 400, 6, 4)
+  rng = np.random.RandomState(5)
+  idx = rng.choice(400, size=60, replace=False)
+  w = rng.uniform(1., 12., size=60)
+  mu, LSig, _ = models.get_laplace(w, Z[idx], np.zeros(6), models.lr_log_joint, models.lr_grad_th_log_joint, models.lr_hess_th_log_joint)
+  smp = bc.LaplaceSampler('lr', 6)
+  mu_d, LSig_d, _ = smp.get_laplace(w, Z[idx], np.zeros(6))
+  np.testing.assert_allclose(mu_d, mu, rtol=1e-4, atol=1e-6)             # two runs of SciPy's BFGS to its gradient tolerance
+  np.testing.assert_allclose(LSig_d, LSig, rtol=1e-4, atol=1e-7)
+  np.random.seed(2)
+  a = smp(50, w, Z[idx])
+  np.random.seed(2)
+  b = mu + np.random.randn(50, 6).dot(LSig.T)
+  np.testing.assert_allclose(a, b, rtol=1e-3, atol=1e-5)
+  np.random.seed(4)
+  c = smp(5, None, None)                                                   # no coreset yet: prior (main.py:154-156)
+  np.random.seed(4)
+  assert np.array_equal(c, np.random.randn(5, 6))
+  # and as the sampler of a device projector inside SparseVI (runs end to end)
+  prj = bc.LogisticRegressionProjector(bc.LaplaceSampler('lr', 6), 32)
+  np.random.seed(1)
+  svi = bc.SparseVICoreset(Z, prj, opt_itrs=4)
+  svi.build(3)
+  assert 1 <= svi.size() <= 3 and np.all(svi.wts >= 0)
