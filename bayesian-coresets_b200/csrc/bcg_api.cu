@@ -151,7 +151,8 @@ struct bcg_solver {
   SolverState h;      // host mirror (valid after every synchronising call)
   SolverState* d;
   ScanConfig sc;
-  bool use_loop;            // persistent cooperative kernel available for this shape
+  bool use_loop;            // persistent cooperative kernel available for this shape (GIGA / FW: greedy_loop_kernel)
+  bool use_omp_loop;        // persistent OrthoPursuit kernel available (omp_loop_kernel)
   LoopCtl* d_ctl;
   ScanCand* d_cta_cands;
   float* d_cta_lost;
@@ -1336,12 +1337,19 @@ static int choose_scan_config(bcg_solver* s) {
   c.grid = s->ctx->sm_count;
   CK(scan_set_smem(c));
   s->use_loop = false;
-  if (env_int("BCG_ENGINE", 2) >= 2 && s->h.alg != BCG_ALG_OMP && loop_variant_exists(c.ch, c.lpr)) {
+  s->use_omp_loop = false;
+  if (env_int("BCG_ENGINE", 2) >= 2 && loop_variant_exists(c.ch, c.lpr)) {
     int coop = 0, nbm = 0;
     CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, s->ctx->device));
-    CK(loop_set_smem(c));
-    CK(loop_max_blocks_per_sm(c, &nbm));
-    s->use_loop = coop && nbm >= 1;
+    if (s->h.alg != BCG_ALG_OMP) {
+      CK(loop_set_smem(c));
+      CK(loop_max_blocks_per_sm(c, &nbm));
+      s->use_loop = coop && nbm >= 1;
+    } else if (env_int("BCG_OMP_LOOP", 1) && c.grid >= 2) {
+      CK(omp_loop_set_smem(c));
+      CK(omp_loop_max_blocks_per_sm(c, &nbm));
+      s->use_omp_loop = coop && nbm >= 1;
+    }
   }
   return BCG_OK;
 }
@@ -1453,7 +1461,7 @@ static int solver_init(bcg_solver* s, bcg_ctx* ctx, bcg_vecs* v, int32_t alg, co
   h.lazy = (v->n > 0 && !v->An) ? 1 : 0;
   h.n_exact_cands = h.lazy ? ctx->sm_count * 8 : ctx->sm_count;
   h.fused_row = -1;
-  if (h.lazy) s->use_loop = false;                       // the persistent kernel streams the resident matrix
+  if (h.lazy) s->use_loop = s->use_omp_loop = false;     // the persistent kernels stream the resident matrix
   h.check_monotone = 1;
   cudaStream_t st = ctx->stream;
   std::vector<double> bn(S);
@@ -1511,6 +1519,7 @@ extern "C" int bcg_solver_create(bcg_ctx* ctx, bcg_vecs* v, int32_t alg, const d
   s->v = v;
   s->peers_open = false;
   s->use_loop = false;
+  s->use_omp_loop = false;
   s->d_ctl = nullptr;
   s->d_cta_cands = nullptr;
   s->d_cta_lost = nullptr;
@@ -1705,6 +1714,77 @@ extern "C" int bcg_solver_nnls(bcg_solver* s, int32_t from_scratch) {
   return BCG_OK;
 }
 
+static int run_persistent(bcg_solver* s, int32_t itrs, bool omp) {
+  cudaStream_t st = s->ctx->stream;
+  SolverState& h = s->h;
+// The whole build call as ONE persistent cooperative kernel (loop_kernel.cuh / omp_loop_kernel.cuh).  Rare exception: when the control
+  // warp finds the float32 candidate set ambiguous (an unpublished score inside the near-tie window) it stops before
+  // that iteration; the selection is redone exactly in float64 (exact_scan_kernel) and the loop is relaunched for the
+  // remaining iterations with that result.
+  LoopArgs la;
+  la.st = s->d;
+  la.ctl = s->d_ctl;
+  la.cta_cands = s->d_cta_cands;
+  la.cta_lost = s->d_cta_lost;
+  la.g.An = s->v->An;
+  la.g.n_rows = s->v->n;
+  la.g.ld = s->v->ld;
+  la.g.rps = s->sc.rps;
+  la.g.stages = s->sc.stages;
+  la.g.evict_first = s->sc.evict_first;
+  la.wpb = s->sc.wpb;
+  if (s->claims_cap < itrs) {
+    if (s->d_claims) CK(cudaFree(s->d_claims));
+    s->d_claims = nullptr;
+    CK(cudaMalloc(&s->d_claims, (size_t)itrs * sizeof(unsigned int)));
+    s->claims_cap = itrs;
+  }
+  la.claims = s->d_claims;
+  la.static_frac = (float)env_int("BCG_STATIC_PCT", 100) / 100.f;   // measured: a larger dynamic share only costs (atomics); the grid is HBM-bound either way
+  la.trace = nullptr;
+  s->trace_n = 0;
+  if (s->trace_on) {
+    if (s->trace_cap < itrs) {
+      if (s->d_trace) CK(cudaFree(s->d_trace));
+      s->d_trace = nullptr;
+      CK(cudaMalloc(&s->d_trace, (size_t)itrs * 8 * sizeof(unsigned long long)));
+      s->trace_cap = itrs;
+    }
+    CK(cudaMemsetAsync(s->d_trace, 0, (size_t)itrs * 8 * sizeof(unsigned long long), st));
+    s->trace_n = itrs;
+  }
+  CK(cudaEventRecord(s->ev0, st));
+  int done = 0;
+  s->loop_launches = 0;
+  s->scan_launches = 0;
+  la.cont = 0;
+  la.use_pre = 0;
+  for (;;) {
+    la.itrs = itrs - done;
+    la.trace = s->trace_on ? s->d_trace + (size_t)done * 8 : nullptr;
+    CK(cudaMemsetAsync(s->d_claims, 0, (size_t)la.itrs * sizeof(unsigned int), st));
+    CK(cudaMemsetAsync(s->d_ctl, 0, sizeof(LoopCtl), st));
+    if (omp) CK(omp_loop_launch(s->sc, la, s->d_nw, env_int("BCG_OMP_WIDE", 1), st));
+    else CK(loop_launch(s->sc, la, st));
+    CK(cudaEventRecord(s->ev1, st));                                 // (re-recorded per launch: the last one counts)
+    s->loop_launches += 1;
+    RET(pull_state(s));
+    if (!h.need_exact || h.halted || h.comm_error) break;
+    done += h.iters_done;
+    if (done >= itrs) break;                                         // (cannot happen: the stop precedes an iteration)
+    step_kernel<<<1, kStepThreads, 0, st>>>(s->d, 0, 1, 0);          // float64 direction of the pending iteration
+    CK(exact_scan_launch(h.n_exact_cands, s->d, 1, st));
+    CK(cudaGetLastError());
+    s->scan_launches += 1;
+    la.cont = 1;
+    la.use_pre = 1;
+  }
+  CK(cudaEventElapsedTime(&s->build_ms, s->ev0, s->ev1));
+  s->step_launches = s->scan_launches;
+  s->scan_ms = 0.f;
+  return BCG_OK;
+}
+
 extern "C" int bcg_solver_build(bcg_solver* s, int32_t itrs, double tol, bcg_iter_event* events, int32_t* n_events) {
   if (!s) return fail(BCG_ERR_ARG, "null solver");
   RET(use_device(s->ctx));
@@ -1727,9 +1807,18 @@ extern "C" int bcg_solver_build(bcg_solver* s, int32_t itrs, double tol, bcg_ite
   h.comm_error = 0;
   RET(push_state(s));
   const bool loop = s->use_loop && !s->profiling;
-  if (h.alg == BCG_ALG_OMP) {
-    // OrthoPursuit: selection scan + on-device NNLS per iteration (two launches), no host round trip inside the loop
+  if (h.alg == BCG_ALG_OMP && s->use_omp_loop && !s->profiling && !env_int("BCG_OMP_TRACE", 0)) {
+    // OrthoPursuit as one persistent kernel: CTA 0 runs the selection / NNLS logic, the other CTAs scan (omp_loop_kernel.cuh)
     RET(ensure_nnls(s));
+    h.n_cands = 2 * (s->sc.grid - 1);
+    RET(push_state(s));
+    RET(run_persistent(s, itrs, true));
+  } else if (h.alg == BCG_ALG_OMP) {
+    // OrthoPursuit, launch per iteration (profiling, tracing, S > 512, never-materialising solver): selection scan +
+    // on-device NNLS, no host round trip inside the loop
+    RET(ensure_nnls(s));
+    h.n_cands = s->sc.grid * s->sc.wpb;
+    RET(push_state(s));
     const int wide = env_int("BCG_OMP_WIDE", 1);
     DevBuf<unsigned long long> d_omp_trace;
     struct TraceGuard {                       // the state must not keep a pointer to the trace buffer once it is freed
@@ -1801,70 +1890,7 @@ extern "C" int bcg_solver_build(bcg_solver* s, int32_t itrs, double tol, bcg_ite
       }
     }
   } else if (loop) {
-    // the whole build call is ONE persistent cooperative kernel (loop_kernel.cuh).  Rare exception: when the control
-    // warp finds the float32 candidate set ambiguous (an unpublished score inside the near-tie window) it stops before
-    // that iteration; the selection is redone exactly in float64 (exact_scan_kernel) and the loop is relaunched for the
-    // remaining iterations with that result.
-    LoopArgs la;
-    la.st = s->d;
-    la.ctl = s->d_ctl;
-    la.cta_cands = s->d_cta_cands;
-    la.cta_lost = s->d_cta_lost;
-    la.g.An = s->v->An;
-    la.g.n_rows = s->v->n;
-    la.g.ld = s->v->ld;
-    la.g.rps = s->sc.rps;
-    la.g.stages = s->sc.stages;
-    la.g.evict_first = s->sc.evict_first;
-    la.wpb = s->sc.wpb;
-    if (s->claims_cap < itrs) {
-      if (s->d_claims) CK(cudaFree(s->d_claims));
-      s->d_claims = nullptr;
-      CK(cudaMalloc(&s->d_claims, (size_t)itrs * sizeof(unsigned int)));
-      s->claims_cap = itrs;
-    }
-    la.claims = s->d_claims;
-    la.static_frac = (float)env_int("BCG_STATIC_PCT", 100) / 100.f;   // measured: a larger dynamic share only costs (atomics); the grid is HBM-bound either way
-    la.trace = nullptr;
-    s->trace_n = 0;
-    if (s->trace_on) {
-      if (s->trace_cap < itrs) {
-        if (s->d_trace) CK(cudaFree(s->d_trace));
-        s->d_trace = nullptr;
-        CK(cudaMalloc(&s->d_trace, (size_t)itrs * 8 * sizeof(unsigned long long)));
-        s->trace_cap = itrs;
-      }
-      CK(cudaMemsetAsync(s->d_trace, 0, (size_t)itrs * 8 * sizeof(unsigned long long), st));
-      s->trace_n = itrs;
-    }
-    CK(cudaEventRecord(s->ev0, st));
-    int done = 0;
-    s->loop_launches = 0;
-    s->scan_launches = 0;
-    la.cont = 0;
-    la.use_pre = 0;
-    for (;;) {
-      la.itrs = itrs - done;
-      la.trace = s->trace_on ? s->d_trace + (size_t)done * 8 : nullptr;
-      CK(cudaMemsetAsync(s->d_claims, 0, (size_t)la.itrs * sizeof(unsigned int), st));
-      CK(cudaMemsetAsync(s->d_ctl, 0, sizeof(LoopCtl), st));
-      CK(loop_launch(s->sc, la, st));
-      CK(cudaEventRecord(s->ev1, st));                                 // (re-recorded per launch: the last one counts)
-      s->loop_launches += 1;
-      RET(pull_state(s));
-      if (!h.need_exact || h.halted || h.comm_error) break;
-      done += h.iters_done;
-      if (done >= itrs) break;                                         // (cannot happen: the stop precedes an iteration)
-      step_kernel<<<1, kStepThreads, 0, st>>>(s->d, 0, 1, 0);          // float64 direction of the pending iteration
-      CK(exact_scan_launch(h.n_exact_cands, s->d, 1, st));
-      CK(cudaGetLastError());
-      s->scan_launches += 1;
-      la.cont = 1;
-      la.use_pre = 1;
-    }
-    CK(cudaEventElapsedTime(&s->build_ms, s->ev0, s->ev1));
-    s->step_launches = s->scan_launches;
-    s->scan_ms = 0.f;
+    RET(run_persistent(s, itrs, false));
   } else {
     if (s->profiling) {
       while ((int)s->scan_ev.size() < 2 * itrs) {

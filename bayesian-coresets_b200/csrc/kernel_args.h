@@ -79,5 +79,9 @@ bool loop_variant_exists(int ch, int lpr);
 cudaError_t loop_set_smem(const ScanConfig& c);
 cudaError_t loop_max_blocks_per_sm(const ScanConfig& c, int* nb);
 cudaError_t loop_launch(const ScanConfig& c, const LoopArgs& a, cudaStream_t st);
+struct NnlsWork;
+cudaError_t omp_loop_set_smem(const ScanConfig& c);
+cudaError_t omp_loop_max_blocks_per_sm(const ScanConfig& c, int* nb);
+cudaError_t omp_loop_launch(const ScanConfig& c, const LoopArgs& a, NnlsWork* W, int wide, cudaStream_t st);
 
 }  // namespace bcg

@@ -1,5 +1,6 @@
 // Instantiations + launcher of the persistent greedy-loop kernel (see loop_kernel.cuh).
 #include "loop_kernel.cuh"
+#include "omp_loop_kernel.cuh"
 
 namespace bcg {
 
@@ -51,6 +52,41 @@ cudaError_t loop_launch(const ScanConfig& c, const LoopArgs& a, cudaStream_t st)
     return cudaLaunchCooperativeKernel((const void*)greedy_loop_kernel<CH, 1, LPR, R, J>, grid, block, args,    \
                                        c.loop_smem, st);                                                         \
   }
+  BCG_LOOP_VARIANTS(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+
+// ---- persistent OrthoPursuit kernel (omp_loop_kernel.cuh): same (CH, LPR, R) variants, one direction ----------------
+static size_t omp_loop_smem(const ScanConfig& c) {
+  const size_t control = (256 + (size_t)(kOmpLoopThreads / 32) * kWideCols) * sizeof(double);
+  return c.loop_smem > control ? c.loop_smem : control;
+}
+
+cudaError_t omp_loop_set_smem(const ScanConfig& c) {
+#define X(CH, LPR, R, J)                                                                                        \
+  if (c.ch == CH && c.lpr == LPR)                                                                               \
+    return cudaFuncSetAttribute(omp_loop_kernel<CH, LPR, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)omp_loop_smem(c));
+  BCG_LOOP_VARIANTS(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t omp_loop_max_blocks_per_sm(const ScanConfig& c, int* nb) {
+#define X(CH, LPR, R, J)                                                                                        \
+  if (c.ch == CH && c.lpr == LPR)                                                                               \
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, omp_loop_kernel<CH, LPR, R>, kOmpLoopThreads, omp_loop_smem(c));
+  BCG_LOOP_VARIANTS(X)
+#undef X
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t omp_loop_launch(const ScanConfig& c, const LoopArgs& a, NnlsWork* W, int wide, cudaStream_t st) {
+  void* args[] = {const_cast<LoopArgs*>(&a), &W, &wide};
+  const dim3 grid(c.grid), block(kOmpLoopThreads);
+#define X(CH, LPR, R, J)                                                                                        \
+  if (c.ch == CH && c.lpr == LPR)                                                                               \
+    return cudaLaunchCooperativeKernel((const void*)omp_loop_kernel<CH, LPR, R>, grid, block, args, omp_loop_smem(c), st);
   BCG_LOOP_VARIANTS(X)
 #undef X
   return cudaErrorInvalidValue;

@@ -637,10 +637,14 @@ __device__ void control_loop(const LoopArgs& a, double* sb, double* sbn, double*
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <int CH, int NDIR, int LPR, int R, int J>
-__global__ void __launch_bounds__(384, 1) greedy_loop_kernel(const LoopArgs a) {
+// ---------------------------------------------------------------------------------------------
+// the scan warps of one CTA: stream this CTA's share of the matrix once per iteration, publish the CTA's two best
+// candidates + its lost score, arrive.  cta_rank / n_ctas: position among the SCANNING CTAs (the OrthoPursuit kernel
+// reserves CTA 0 for the control path).  Shared memory: rings | barriers | 64 candidate slots | ... | slot records.
+// ---------------------------------------------------------------------------------------------
+template <int CH, int NDIR, int LPR, int R>
+__device__ __forceinline__ void scan_cta_body(const LoopArgs& a, unsigned char* smem_raw, int cta_rank, int n_ctas) {
   using Core = ScanCore<CH, NDIR, LPR, R>;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int wpb = a.wpb;
@@ -649,21 +653,10 @@ __global__ void __launch_bounds__(384, 1) greedy_loop_kernel(const LoopArgs a) {
   const size_t ring_bytes = (size_t)wpb * q.stages * stage_floats * sizeof(float);
   uint64_t* bars_all = reinterpret_cast<uint64_t*>(smem_raw + ring_bytes);
   ScanCand* cta_c = reinterpret_cast<ScanCand*>(bars_all + wpb * q.stages);   // 64 slots (see the end of the scan loop)
-  double* sb = reinterpret_cast<double*>(cta_c + 64);
-  double* sbn = sb + a.st->S;
-
-  // shared memory after the rings: barriers | per-warp candidates | b, bn (2 S) | float64 directions (2 S) |
-  // peer mailbox pointers (8) | ring slot records
-  double* sdir = sbn + a.st->S;
-  unsigned char** speers = reinterpret_cast<unsigned char**>(sdir + 2 * a.st->S);
-  if (warp == wpb) {                    // control warp (only CTA 0's does anything)
-    if (blockIdx.x == 0) control_loop<J>(a, sb, sbn, sdir, speers);
-    return;
-  }
-
+  unsigned char** speers = reinterpret_cast<unsigned char**>(reinterpret_cast<double*>(cta_c + 64) + 4 * a.st->S);
   LoopCtl* ctl = a.ctl;
-  const int64_t gw = (int64_t)blockIdx.x * wpb + warp;
-  const int64_t GW = (int64_t)gridDim.x * wpb;
+  const int64_t gw = (int64_t)cta_rank * wpb + warp;
+  const int64_t GW = (int64_t)n_ctas * wpb;
   float* wbuf = reinterpret_cast<float*>(smem_raw) + (size_t)warp * q.stages * stage_floats;
   uint64_t* bars = bars_all + warp * q.stages;
   if (lane == 0) {
@@ -797,9 +790,9 @@ __global__ void __launch_bounds__(384, 1) greedy_loop_kernel(const LoopArgs a) {
       if (lane == 0) {
         ScanCand c0; c0.score = bs; c0.row = br;
         ScanCand c1; c1.score = ss; c1.row = sr;
-        a.cta_cands[2 * blockIdx.x] = c0;
-        a.cta_cands[2 * blockIdx.x + 1] = c1;
-        a.cta_lost[blockIdx.x] = l1;
+        a.cta_cands[2 * cta_rank] = c0;
+        a.cta_cands[2 * cta_rank + 1] = c1;
+        a.cta_lost[cta_rank] = l1;
         __threadfence();
         red_release_gpu_add(&ctl->arrive, 1u);
       }
@@ -812,6 +805,32 @@ __global__ void __launch_bounds__(384, 1) greedy_loop_kernel(const LoopArgs a) {
       if (++slot == q.stages) { slot = 0; parity ^= 1u; }
     }
   }
+}
+
+template <int CH, int NDIR, int LPR, int R, int J>
+__global__ void __launch_bounds__(384, 1) greedy_loop_kernel(const LoopArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int wpb = a.wpb;
+  const ScanGeom& q = a.g;
+  const uint32_t stage_floats = (uint32_t)q.rps * (uint32_t)q.ld;
+  const size_t ring_bytes = (size_t)wpb * q.stages * stage_floats * sizeof(float);
+  uint64_t* bars_all = reinterpret_cast<uint64_t*>(smem_raw + ring_bytes);
+  ScanCand* cta_c = reinterpret_cast<ScanCand*>(bars_all + wpb * q.stages);   // 64 slots (see the end of the scan loop)
+  double* sb = reinterpret_cast<double*>(cta_c + 64);
+  double* sbn = sb + a.st->S;
+
+  // shared memory after the rings: barriers | per-warp candidates | b, bn (2 S) | float64 directions (2 S) |
+  // peer mailbox pointers (8) | ring slot records
+  double* sdir = sbn + a.st->S;
+  unsigned char** speers = reinterpret_cast<unsigned char**>(sdir + 2 * a.st->S);
+  if (warp == wpb) {                    // control warp (only CTA 0's does anything)
+    if (blockIdx.x == 0) control_loop<J>(a, sb, sbn, sdir, speers);
+    return;
+  }
+
+  scan_cta_body<CH, NDIR, LPR, R>(a, smem_raw, (int)blockIdx.x, (int)gridDim.x);
 }
 
 }  // namespace bcg

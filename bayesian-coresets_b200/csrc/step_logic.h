@@ -326,7 +326,7 @@ BCG_HD void pick_local(const Blk& B, SolverState* st, bool force_rescore, uint32
 
 #ifdef __CUDA_ARCH__
 // all-to-all candidate exchange over NVLink peer memory (defined in kernels.cuh)
-__device__ void mail_exchange(const Blk& B, SolverState* st, uint32_t lrow, double lscore, int64_t* f,
+__device__ inline void mail_exchange(const Blk& B, SolverState* st, uint32_t lrow, double lscore, int64_t* f,
                               double* norm, const float** row);
 #endif
 

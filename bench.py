@@ -366,9 +366,9 @@ def main():
     ok_steps = sum(1 for e in cs.snnls.last_events if e.code == 0)
     build_ms = max_over_ranks(tm['build_ms'])
     if tm['scan_launches'] == 0:
-      # persistent engine: the whole timed region is ONE launch of greedy_loop_kernel, which streams the
+      # persistent engine: the whole timed region is ONE launch of greedy_loop_kernel / omp_loop_kernel, which streams the
       # matrix `steps` times; its duration is the CUDA-event time of that launch on the library's stream
-      kernel, launches_per_step, kernel_ms = 'greedy_loop_kernel', 1.0 / steps, build_ms
+      kernel, launches_per_step, kernel_ms = ('omp_loop_kernel' if alg == 'OrthoPursuit' else 'greedy_loop_kernel'), 1.0 / steps, build_ms
       bytes_per_launch = 4.0 * (hi - lo) * S * steps
     else:
       # launch-per-iteration engine (OMP; GIGA / FW after an exact-selection stop): same loop continued with CUDA
