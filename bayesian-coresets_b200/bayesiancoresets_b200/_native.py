@@ -44,6 +44,7 @@ _PROTOTYPES = {
   'bcg_ctx_info': (_c.c_int, [_P, _c.c_char_p, _c.c_int, _c.POINTER(_c.c_int), _c.POINTER(_c.c_int),
                               _c.POINTER(_c.c_int), _c.POINTER(_c.c_int64)]),
   'bcg_ctx_synchronize': (_c.c_int, [_P]),
+  'bcg_ctx_trim': (_c.c_int, [_P]),
   'bcg_ctx_mem_info': (_c.c_int, [_P, _c.POINTER(_c.c_int64), _c.POINTER(_c.c_int64)]),
   'bcg_ctx_flush_l2': (_c.c_int, [_P, _c.c_int64]),
   'bcg_host_alloc': (_c.c_int, [_c.c_int64, _PP]),
@@ -197,6 +198,10 @@ class Context(object):
 
   def synchronize(self):
     check(lib().bcg_ctx_synchronize(self.handle))
+
+  def trim(self):
+    """release the cached matrix buffers of destroyed DeviceVecs"""
+    check(lib().bcg_ctx_trim(self.handle))
 
   def mem_info(self):
     f, t = ctypes.c_int64(), ctypes.c_int64()

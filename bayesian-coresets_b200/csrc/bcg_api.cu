@@ -129,6 +129,13 @@ struct bcg_ctx {
                                    // so a value left in a slot by an earlier solver never matches (ranks connect in
                                    // the same order, SPMD, hence agree on the epoch)
   std::vector<std::pair<std::array<unsigned char, 64>, void*>> peer_cache;
+  // one-slot cache of the last released matrix buffers: a cudaMalloc of gigabytes costs milliseconds -- far more once peer
+  // access is enabled and the allocation has to be mapped for 7 peers -- and SparseVI / repeated coreset constructions
+  // allocate a matrix of the same size again and again.  bcg_ctx_trim() releases it.
+  float* pool_An;
+  size_t pool_An_bytes;
+  double* pool_norms;
+  size_t pool_norms_bytes;
 };
 
 struct bcg_vecs {
@@ -137,6 +144,7 @@ struct bcg_vecs {
   int32_t S, ld;
   float* An;
   double* norms;
+  size_t An_bytes, norms_bytes; // requested sizes (the buffers may be larger: they come from the context's one-slot cache)
   std::vector<double> colsum;   // S sums + [S] = sum of norms
   uint64_t zero_rows;
   // never-materialising form (bcg_dataset_project_lazy): An == null, rows are re-evaluated from the dataset on demand
@@ -234,6 +242,8 @@ extern "C" int bcg_ctx_create(int device, bcg_ctx** out) {
   c->mail_bytes = 0;
   c->mail_epoch = 0;
   c->sp_tab = nullptr;
+  c->pool_An = nullptr; c->pool_An_bytes = 0;
+  c->pool_norms = nullptr; c->pool_norms_bytes = 0;
   auto body = [&]() -> int {
     CK(cudaSetDevice(device));
     CK(cudaGetDeviceProperties(&c->prop, device));
@@ -262,6 +272,8 @@ extern "C" int bcg_ctx_destroy(bcg_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);
   if (ctx->sp_tab) cudaFree(ctx->sp_tab);
+  if (ctx->pool_An) cudaFree(ctx->pool_An);
+  if (ctx->pool_norms) cudaFree(ctx->pool_norms);
   for (auto& pc : ctx->peer_cache) cudaIpcCloseMemHandle(pc.second);
   if (ctx->mail) cudaFree(ctx->mail);
   for (int i = 0; i < 8; ++i)
@@ -295,6 +307,39 @@ extern "C" int bcg_ctx_mem_info(bcg_ctx* ctx, int64_t* free_bytes, int64_t* tota
   if (free_bytes) *free_bytes = (int64_t)f;
   if (total_bytes) *total_bytes = (int64_t)t;
   return BCG_OK;
+}
+
+extern "C" int bcg_ctx_trim(bcg_ctx* ctx) {
+  RET(use_device(ctx));
+  if (ctx->pool_An) CK(cudaFree(ctx->pool_An));
+  if (ctx->pool_norms) CK(cudaFree(ctx->pool_norms));
+  ctx->pool_An = nullptr; ctx->pool_An_bytes = 0;
+  ctx->pool_norms = nullptr; ctx->pool_norms_bytes = 0;
+  return BCG_OK;
+}
+
+// take a buffer of at least `bytes` from the one-slot cache when it fits without wasting more than half of it
+template <typename T>
+static int pool_take(T** slot, size_t* slot_bytes, size_t bytes, T** out) {
+  if (*slot && *slot_bytes >= bytes && *slot_bytes <= 2 * bytes + (1 << 20)) {
+    *out = *slot;
+    *slot = nullptr;
+    *slot_bytes = 0;
+    return BCG_OK;
+  }
+  CK(cudaMalloc(out, bytes));
+  return BCG_OK;
+}
+template <typename T>
+static void pool_give(T** slot, size_t* slot_bytes, T* p, size_t bytes) {
+  if (!p) return;
+  if (bytes > *slot_bytes) {
+    if (*slot) cudaFree(*slot);
+    *slot = p;
+    *slot_bytes = bytes;
+  } else {
+    cudaFree(p);
+  }
 }
 
 extern "C" int bcg_ctx_synchronize(bcg_ctx* ctx) {
@@ -423,9 +468,14 @@ static int vecs_alloc(bcg_ctx* ctx, int64_t n, int32_t S, bcg_vecs** out, bool l
   v->lazy_ds = nullptr;
   v->lazy_model = v->lazy_d = 0;
   v->lazy_thetaT = v->lazy_tt = v->lazy_Siginv = nullptr;
+  v->An_bytes = v->norms_bytes = 0;
   if (n > 0) {
-    if (!lazy) CK(cudaMalloc(&v->An, (size_t)n * v->ld * sizeof(float)));
-    CK(cudaMalloc(&v->norms, (size_t)n * sizeof(double)));
+    if (!lazy) {
+      v->An_bytes = (size_t)n * v->ld * sizeof(float);
+      RET(pool_take(&ctx->pool_An, &ctx->pool_An_bytes, v->An_bytes, &v->An));
+    }
+    v->norms_bytes = (size_t)n * sizeof(double);
+    RET(pool_take(&ctx->pool_norms, &ctx->pool_norms_bytes, v->norms_bytes, &v->norms));
   }
   *out = v;
   return BCG_OK;
@@ -1293,8 +1343,9 @@ extern "C" int bcg_vecs_rows_f64(bcg_vecs* v, int64_t row0, int64_t nrows, doubl
 extern "C" int bcg_vecs_destroy(bcg_vecs* v) {
   if (!v) return BCG_OK;
   cudaSetDevice(v->ctx->device);
-  if (v->An) cudaFree(v->An);
-  if (v->norms) cudaFree(v->norms);
+  cudaStreamSynchronize(v->ctx->stream);
+  pool_give(&v->ctx->pool_An, &v->ctx->pool_An_bytes, v->An, v->An_bytes);
+  pool_give(&v->ctx->pool_norms, &v->ctx->pool_norms_bytes, v->norms, v->norms_bytes);
   if (v->lazy_thetaT) cudaFree(v->lazy_thetaT);
   if (v->lazy_tt) cudaFree(v->lazy_tt);
   if (v->lazy_Siginv) cudaFree(v->lazy_Siginv);

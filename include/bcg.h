@@ -96,6 +96,8 @@ int  bcg_ctx_destroy(bcg_ctx* ctx);
 int  bcg_ctx_info(bcg_ctx* ctx, char* name, int name_cap, int* sm_count, int* cc_major, int* cc_minor,
                   int64_t* total_mem_bytes);
 int  bcg_ctx_synchronize(bcg_ctx* ctx);
+/* release the context's one-slot cache of matrix buffers (a destroyed bcg_vecs leaves its buffers there for the next one) */
+int  bcg_ctx_trim(bcg_ctx* ctx);
 int  bcg_ctx_mem_info(bcg_ctx* ctx, int64_t* free_bytes, int64_t* total_bytes);
 /* Page-locked host memory for the caller's input arrays.  Every host -> device upload of this library checks
  * whether its source is page-locked (allocated here, or registered by the caller with the CUDA runtime): such a
