@@ -10,8 +10,8 @@ import sys
 
 rep, out_path = sys.argv[1], sys.argv[2]
 # (kernel substring, S, algorithmic bytes per launch) in launch order of tools/ncu_traffic_case.py
-EXPECT = [('greedy_loop_kernel', 512, 4.*10_000_000*512*5), ('scan_kernel', 512, 4.*10_000_000*512), ('scan_kernel', 512, 4.*10_000_000*512),
-          ('greedy_loop_kernel', 256, 4.*1_000_000*256*5)]
+EXPECT = [('greedy_loop_kernel', 512, 4.*10_000_000*512*5), ('omp_loop_kernel', 512, 4.*10_000_000*512*2), ('scan_kernel', 512, 4.*10_000_000*512),
+          ('scan_kernel', 512, 4.*10_000_000*512), ('greedy_loop_kernel', 256, 4.*1_000_000*256*5)]
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units, data = rows[0], rows[1], [r for r in rows[2:] if 'exact_scan_kernel' not in r[rows[0].index('Kernel Name')]]
@@ -36,6 +36,6 @@ for r, (kern, S, alg) in zip(data, EXPECT):
   c['ratio'] = c['dram_bytes']/alg
   c['dram_GBps_under_ncu'] = c['dram_bytes']/(c['duration_ms']*1e-3)/1e9
   caps.append(c)
-json.dump({'captures': caps, 'command': 'ncu --set full --clock-control none -k regex:greedy_loop_kernel|scan_kernel python tools/ncu_traffic_case.py'},
+json.dump({'captures': caps, 'command': 'ncu --set full --clock-control none -k regex:greedy_loop_kernel|omp_loop_kernel|scan_kernel python tools/ncu_traffic_case.py'},
           open(out_path, 'w'), indent=1)
 print(json.dumps(caps, indent=1))
