@@ -330,16 +330,13 @@ static int pool_take(T** slot, size_t* slot_bytes, size_t bytes, T** out) {
   CK(cudaMalloc(out, bytes));
   return BCG_OK;
 }
+// the most recently released buffer stays (repeated constructions ask for the size they just released)
 template <typename T>
 static void pool_give(T** slot, size_t* slot_bytes, T* p, size_t bytes) {
   if (!p) return;
-  if (bytes > *slot_bytes) {
-    if (*slot) cudaFree(*slot);
-    *slot = p;
-    *slot_bytes = bytes;
-  } else {
-    cudaFree(p);
-  }
+  if (*slot) cudaFree(*slot);
+  *slot = p;
+  *slot_bytes = bytes;
 }
 
 extern "C" int bcg_ctx_synchronize(bcg_ctx* ctx) {

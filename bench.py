@@ -118,6 +118,9 @@ class ClockSampler(object):
       time.sleep(0.005)
 
   def start(self):
+    if os.environ.get('BCG_BENCH_NO_CLOCKS'):
+      self.proc = None
+      return
     try:
       import pynvml as nv
       nv.nvmlInit()
@@ -534,11 +537,12 @@ def main():
     prj = bc.GaussianProjector(sampler_w, S3, Siginv, ctx=ctx)
     prj.project_sum(x)                                           # one-off upload of x + warm-up
     ctx.synchronize()
-    reps = 10
-    t0 = time.perf_counter()
-    for _ in range(reps):
+    ts = []
+    for _ in range(10):
+      t0 = time.perf_counter()
       prj.project_sum(x)
-    t_sum = (time.perf_counter() - t0) / reps
+      ts.append(time.perf_counter() - t0)
+    t_sum = float(np.median(ts))                                 # host-driven calls on a shared box: medians, not means
     v = prj.project_device(x, cache=True)                        # warm-up (first use of the streamed DMMA projection kernel)
     del v
     ctx.synchronize()
@@ -549,14 +553,16 @@ def main():
     del v
     svi = bc.SparseVICoreset(x, prj, opt_itrs=opt_itrs)
     svi.build(1)
-    nb = 2
-    t0 = time.perf_counter()
-    svi.build(nb)
-    t_iter = (time.perf_counter() - t0) / nb
+    ts = []
+    for _ in range(3):
+      t0 = time.perf_counter()
+      svi.build(1)
+      ts.append(time.perf_counter() - t0)
+    t_iter = float(np.median(ts))
     extra['c3_gaussian_sparsevi_N1e6_d200_S512'] = {
       'metric': 'sparsevi_build_iter_seconds', 'value': t_iter, 'unit': 's/iter', 'higher_is_better': False,
       'config': {'N': n3, 'd': d3, 'S': S3, 'opt_itrs': opt_itrs, 'coreset_size': int(svi.size()),
-                 'colsum_pass_s': t_sum, 'materialising_pass_s': t_full,
+                 'colsum_pass_s': t_sum, 'materialising_pass_s': t_full, 'build_iter_s_runs': [round(t, 4) for t in ts],
                  'note': 'one build iteration = 1 materialising projection + correlation arg-max + opt_itrs column-sum passes '
                          '(sparsevi.py:16-76); whole C-ABI calls, wall clock'},
       'roofline': k3b_roofline(n3, d3, d3, S3, t_sum, 'project_sum_mma_kernel<LINEAR> (whole bcg_dataset_project call)')}
@@ -582,16 +588,18 @@ def main():
     bp.gradient(x0.copy(), sz, d5 + 1)                           # one-off upload of Z + warm-up
     ctx.synchronize()
     barrier()
-    reps = 5
-    t0 = time.perf_counter()
-    for _ in range(reps):
+    tg = []
+    for _ in range(5):
+      barrier()
+      t0 = time.perf_counter()
       g = bp.gradient(x0.copy(), sz, d5 + 1)
-    ctx.synchronize()
-    barrier()
-    dt = max_over_ranks((time.perf_counter() - t0) / reps)
+      ctx.synchronize()
+      barrier()
+      tg.append(max_over_ranks(time.perf_counter() - t0))
+    dt = float(np.median(tg))
     extra['c5_poisson_bpsvi_grad_N1e7_d128_S512'] = {
       'metric': 'bpsvi_gradient_seconds', 'value': dt, 'unit': 's/grad', 'higher_is_better': False, 'n_gpus': world,
-      'config': {'N': n5, 'rows_local': hi - lo, 'd': d5, 'S': S5, 'K': sz, 'grad_norm': float(np.linalg.norm(g)),
+      'config': {'N': n5, 'rows_local': hi - lo, 'd': d5, 'S': S5, 'K': sz, 'grad_norm': float(np.linalg.norm(g)), 's_per_grad_runs': [round(t, 4) for t in tg],
                  'note': 'one grd() evaluation of bpsvi.py:46-55: column-sum projection of the local shard, S-vector all-reduce '
                          'over the ranks, K pseudo-point projection + gradient contraction; wall clock, max over ranks'},
       'roofline': k3b_roofline(hi - lo, d5, d5 + 1, S5, dt, 'project_sum_mma_kernel<POISSON> (whole gradient evaluation)')}
