@@ -16,7 +16,12 @@ theta = lr_samples(0, th, S)
 prj = bc.LogisticRegressionProjector(lambda n, w, p: theta, S, ctx=ctx)
 kw = {'comm': comm} if world > 1 else {}
 # the same prelude as bench.py: one resident solver first
-cs = bc.HilbertCoreset(Z, prj, **kw); cs.build(5); cs.build(steps); ctx.synchronize(); comm.barrier()
+from bench import ClockSampler
+cs = bc.HilbertCoreset(Z, prj, **kw); cs.build(5)
+smp = ClockSampler(int(os.environ.get('LOCAL_RANK', '0')))
+if len(sys.argv) > 2 and sys.argv[2] == 'sampler' and rank == 0: smp.start()
+cs.build(steps); ctx.synchronize(); comm.barrier()
+if len(sys.argv) > 2 and sys.argv[2] == 'sampler' and rank == 0: print('clocks', smp.stop(), flush=True)
 del cs
 mode = sys.argv[1] if len(sys.argv) > 1 else 'pinned'
 src = bc.pinned_copy(Z) if mode == 'pinned' else Z
