@@ -288,13 +288,15 @@ extern "C" int hostcheck_run_omp(const float* An, const double* norms, const dou
 // ---- table-driven link functions of the projection kernels (csrc/softplus_table.h), host build ----------------
 #include "../../bayesian-coresets_b200/csrc/softplus_table.h"
 
-// model: 0 softplus_neg(t = lin), 1 LR link, 2 Poisson link
+// model: 0 softplus_neg(t = lin), 1 LR link, 2 Poisson link, 3 / 4 the branch-free LR / Poisson forms (|lin| <= 37)
 extern "C" int hostcheck_link(int model, const double* lin, const double* y, int64_t n, double* out) {
   static std::vector<double> tab;
   if (tab.empty()) { tab.resize(kSpTableDoubles); softplus_table_build(tab.data()); }
   for (int64_t i = 0; i < n; ++i) {
     if (model == 0) out[i] = softplus_neg(tab.data(), lin[i]);
     else if (model == 1) out[i] = lr_link_fast(tab.data(), lin[i]);
+    else if (model == 3) out[i] = lr_link_nb(tab.data(), lin[i]);
+    else if (model == 4) out[i] = poisson_link_nb(tab.data(), lin[i], y[i]);
     else out[i] = poisson_link_fast(tab.data(), lin[i], y[i]);
   }
   return 0;

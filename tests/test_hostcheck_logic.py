@@ -281,6 +281,23 @@ def test_fast_links_match_reference_formulas(lib):
     np.testing.assert_allclose(got, ref, rtol=1e-13, atol=5e-14)
 
 
+def test_branch_free_links_match_reference_formulas(lib):
+  """the *_nb forms used inside the projection kernels (no tail branch; the two highest Taylor orders in float32): exact to
+  2e-15 wherever link_needs_tail() is false (|lin| <= 37)"""
+  from oracle import models
+  from scipy.special import gammaln
+  rng = np.random.RandomState(2)
+  lin = np.concatenate([rng.randn(200000)*6., rng.uniform(-37., 37., size=100000), [0., -0., 36.99, -36.99, 37., -37., 1e-300, -1e-9]])
+  lin = lin[np.abs(lin) <= 37.]
+  ref = models.lr_loglik(np.ones((1, 1)), lin[:, None])[0]
+  np.testing.assert_allclose(_link(lib, 3, lin), ref, rtol=2e-15, atol=0.)
+  Z = np.array([[1., 0.]])
+  for yy in (0., 2., 9.):
+    Z[0, 1] = yy
+    ref = models.poisson_loglik(Z, lin[:, None])[0] + gammaln(yy + 1.)
+    np.testing.assert_allclose(_link(lib, 4, lin, np.full(lin.size, yy)), ref, rtol=1e-13, atol=5e-14)
+
+
 def test_nnls_givens_removal_stress(lib):
   """many removals (more candidate columns than dimensions, strongly correlated columns): the Givens column
   removal keeps the warm-started factorisation consistent with scipy.optimize.nnls over a long sequence"""

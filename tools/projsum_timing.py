@@ -1,19 +1,19 @@
-"""diagnostic: time the column-sum-only projection kernel alone (Gaussian = pure GEMM, Poisson = GEMM + link)"""
+"""device+call time of the column-sum-only projection passes (K3b), N=1e6 d=200 S=512, three models, and LR/Poisson at d=128"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, 'bayesian-coresets_b200')); sys.path.insert(0, ROOT)
 import numpy as np
-import bayesiancoresets_b200 as bc
-N, d, S = int(float(sys.argv[1])), int(sys.argv[2]), int(sys.argv[3])
+from bayesiancoresets_b200 import _native as nat
 rng = np.random.RandomState(0)
-X = rng.randn(N, d)
-th = rng.randn(S, d)/np.sqrt(d)
-for name, prj, data in (('gaussian', bc.GaussianProjector(lambda n, w, p: th, S, np.eye(d)), X),
-                        ('lr', bc.LogisticRegressionProjector(lambda n, w, p: th, S), X),
-                        ('poisson', bc.PoissonProjector(lambda n, w, p: th, S), np.hstack((X, rng.poisson(1., (N, 1)).astype(float))))):
-  prj.project_sum(data)
-  t0 = time.perf_counter()
-  for _ in range(3):
-    prj.project_sum(data)
-  dt = (time.perf_counter() - t0)/3
-  print('%s N=%d d=%d S=%d: %.2f ms per pass, %.2f TFLOP/s (GEMM flops only)' % (name, N, d, S, dt*1e3, 2.*N*d*S/dt/1e12), flush=True)
+for N, d, S in ((1_000_000, 200, 512), (2_000_000, 128, 512)):
+  X = rng.randn(N, d)/np.sqrt(d)*3.
+  Zp = np.hstack((X, rng.poisson(2., size=(N, 1)).astype(float)))
+  th = rng.randn(S, d)
+  for name, model, Z, si in (('gauss', nat.MODEL_GAUSSIAN, X, np.eye(d)), ('lr', nat.MODEL_LR, X, None), ('poisson', nat.MODEL_POISSON, Zp, None)):
+    ds = nat.Dataset(Z)
+    ds.project(model, th, si, colsum=True)
+    ts = []
+    for _ in range(7):
+      t0 = time.perf_counter(); ds.project(model, th, si, colsum=True); ts.append(time.perf_counter() - t0)
+    print('%-8s N=%d d=%d S=%d: %.2f ms per pass (median of 7), %.1f TFLOP/s' % (name, N, d, S, np.median(ts)*1e3, 2.*N*d*S/np.median(ts)/1e12), flush=True)
+    del ds
