@@ -1140,3 +1140,42 @@ def test_laplace_sampler_reductions_on_the_device(bc):
   svi = bc.SparseVICoreset(Z, prj, opt_itrs=4)
   svi.build(3)
   assert 1 <= svi.size() <= 3 and np.all(svi.wts >= 0)
+
+
+@pytest.mark.parametrize('model,alg', [('gaussian', 'fw'), ('poisson', 'giga')])
+def test_full_size_audit_other_models(bc, model, alg):
+  """the Gaussian and Poisson projections at N = 1e6 against the replay oracle + independent float64 audit (the LR model
+  is covered at N = 1e6 and N = 1e7 by test_full_size_selection_equals_float64_audit)"""
+  import bayesiancoresets_b200._native as nat
+  from oracle import replay
+  N, S, itrs = 1000000, 256, 25
+  rng = np.random.RandomState(7)
+  if model == 'gaussian':
+    d = 20
+    Z = rng.randn(N, d) + 1.
+    theta = 1. + 0.3*rng.randn(S, d)
+    Si = np.eye(d) + 0.05*np.ones((d, d))
+    prj = bc.GaussianProjector(lambda n, w, p: theta, S, Si)
+    mid, f = nat.MODEL_GAUSSIAN, (lambda x, t: models.gaussian_loglik(x, t, Si, 0.))
+  else:
+    d = 8
+    th_true = rng.randn(d)/np.sqrt(d)
+    X = np.hstack((rng.randn(N, d - 1), np.ones((N, 1))))
+    Z = np.hstack((X, rng.poisson(np.log1p(np.exp(X.dot(th_true)))).astype(np.float64)[:, None]))
+    theta = th_true + 0.1*rng.randn(S, d)
+    Si = None
+    prj = bc.PoissonProjector(lambda n, w, p: theta, S)
+    mid, f = nat.MODEL_POISSON, models.poisson_loglik
+  cs = bc.HilbertCoreset(Z, prj, snnls=algs(bc)[alg])
+  cs.build(itrs)
+  ev = cs.snnls.last_events
+  ds = nat.Dataset(Z)
+  _, norms, b = ds.audit(mid, theta, Si, norms=True, colsum=True)
+  np.testing.assert_allclose(cs.snnls.b, b, rtol=1e-9, atol=1e-9*np.abs(b).max())
+  kw = {'norm_sum': norms.sum()} if alg == 'fw' else {}
+  r = replay.REPLAYS[alg](N, b, audit_score_fn(nat, ds, mid, theta, Si), lambda idx: models.project(f, Z[idx], theta), **kw)
+  rev = r.build(itrs)
+  assert [(e.code, e.f) for e in ev] == [(e[0], e[1]) for e in rev]
+  assert_weights_close(cs.snnls.weights(), r.w)
+  atol = 2.**-24*float(np.abs(r.wa).dot(norms[r.idx])) + 1e-300
+  np.testing.assert_allclose([e.error for e in ev], [e[2] for e in rev], rtol=W_RTOL, atol=atol)
