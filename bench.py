@@ -296,7 +296,7 @@ def run_reference(args):
   if rank != 0:
     return
   steps = min(args.steps, 40)
-  warmup = min(args.warmup, 3)
+  warmup = min(args.warmup, 5)
   N, d, S = WORKLOADS[args.workload]
   cb = cpu_greedy_run(N, d, S, 'GIGA', steps, warmup, min(N, args.ref_rows))
   line = {'impl': 'reference', 'metric': METRIC, 'value': cb['value'], 'unit': UNIT, 'n_gpus': args.gpus,
