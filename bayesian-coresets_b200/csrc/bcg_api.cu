@@ -13,7 +13,10 @@
 #include <algorithm>
 #include <array>
 #include <utility>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
+#include <unistd.h>
 #include <vector>
 
 #include "../../include/bcg.h"
@@ -367,20 +370,60 @@ extern "C" int bcg_ctx_flush_l2(bcg_ctx* ctx, int64_t bytes) {
 // ------------------------------------------------------------------------------------------
 static const size_t kPinChunk = (size_t)32 << 20;
 
+// Host worker threads for the staging copies of pageable sources, started on first use and kept (one staging copy per
+// 16 - 32 MB chunk: spawning threads per chunk cost as much as the copy itself).  Process-wide; re-created after a fork.
+struct HostWorkers {
+  std::vector<std::thread> th;
+  std::mutex m;
+  std::condition_variable cv_go, cv_done;
+  const char* src = nullptr;
+  char* dst = nullptr;
+  size_t bytes = 0, per = 0;
+  uint64_t gen = 0;
+  int pending = 0;
+  explicit HostWorkers(int n) {
+    for (int t = 0; t < n; ++t) th.emplace_back([this, t]() { loop(t); });
+  }
+  void loop(int t) {
+    uint64_t seen = 0;
+    for (;;) {
+      std::unique_lock<std::mutex> lk(m);
+      cv_go.wait(lk, [&]() { return gen != seen; });
+      seen = gen;
+      const size_t off = (size_t)t * per;
+      const size_t len = off < bytes ? std::min(per, bytes - off) : 0;
+      const char* s = src;
+      char* d = dst;
+      lk.unlock();
+      if (len) memcpy(d + off, s + off, len);
+      lk.lock();
+      if (--pending == 0) cv_done.notify_one();
+    }
+  }
+  void copy(void* d, const void* s, size_t n) {
+    std::unique_lock<std::mutex> lk(m);
+    dst = (char*)d; src = (const char*)s; bytes = n;
+    per = (n / th.size() + 4095) / 4096 * 4096;
+    pending = (int)th.size();
+    ++gen;
+    cv_go.notify_all();
+    cv_done.wait(lk, [&]() { return pending == 0; });
+  }
+};
+static HostWorkers* g_workers = nullptr;
+static pid_t g_workers_pid = 0;
+static std::mutex g_workers_mu;
+
 static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
   unsigned hw = std::thread::hardware_concurrency();
-  int nt = (int)std::max(1u, std::min(8u, hw ? hw / 2 : 1u));
-  if (bytes < ((size_t)4 << 20)) nt = 1;
-  if (nt == 1) { memcpy(dst, src, bytes); return; }
-  std::vector<std::thread> th;
-  const size_t per = (bytes / nt + 4095) / 4096 * 4096;
-  for (int t = 0; t < nt; ++t) {
-    const size_t off = (size_t)t * per;
-    if (off >= bytes) break;
-    const size_t len = std::min(per, bytes - off);
-    th.emplace_back([=]() { memcpy((char*)dst + off, (const char*)src + off, len); });
+  const int nt = (int)std::max(1u, std::min(8u, hw ? hw / 2 : 1u));
+  if (nt == 1 || bytes < ((size_t)4 << 20)) { memcpy(dst, src, bytes); return; }
+  std::lock_guard<std::mutex> g(g_workers_mu);
+  if (!g_workers || g_workers_pid != getpid()) {          // (a forked child inherits the pointer but not the threads)
+    g_workers = new HostWorkers(nt);
+    g_workers_pid = getpid();
   }
-  for (auto& x : th) x.join();
+  g_workers->copy(dst, src, bytes);
 }
 
 extern "C" int bcg_host_alloc(int64_t bytes, void** out) {
@@ -1224,8 +1267,11 @@ static int project_host_pipelined(bcg_ctx* ctx, int kmodel, const double* Z, int
       const int i = c & 1;
       const int64_t r0 = (int64_t)c * chunk_rows;
       const int64_t nr = std::min<int64_t>(chunk_rows, n - r0);
-      if (c >= 2) CK(cudaEventSynchronize(kdone.e[i]));            // staging + device buffer i are free again
       const double* src = Z + r0 * zld;
+      if (c >= 2) {
+        CK(cudaStreamWaitEvent(cs, kdone.e[i], 0));                  // device buffer i is free again: ordered on the
+        if (!direct) CK(cudaEventSynchronize(copied.e[i]));          // device; the host waits only for ITS staging buffer
+      }
       if (!direct) { parallel_memcpy(pin[i], src, (size_t)nr * zld * sizeof(double)); src = pin[i]; }
       CK(cudaMemcpyAsync(dev[i], src, (size_t)nr * zld * sizeof(double), cudaMemcpyHostToDevice, cs));
       CK(cudaEventRecord(copied.e[i], cs));
