@@ -80,16 +80,6 @@ struct DevBuf {
   cudaError_t alloc(size_t n) { return cudaMalloc(&p, (n ? n : 1) * sizeof(T)); }
   operator T*() const { return p; }
 };
-template <typename T>
-struct PinBuf {
-  T* p = nullptr;
-  PinBuf() {}
-  PinBuf(const PinBuf&) = delete;
-  PinBuf& operator=(const PinBuf&) = delete;
-  ~PinBuf() { if (p) cudaFreeHost(p); }
-  cudaError_t alloc(size_t n) { return cudaMallocHost(&p, (n ? n : 1) * sizeof(T)); }
-  operator T*() const { return p; }
-};
 struct EventPair {
   cudaEvent_t e[2] = {nullptr, nullptr};
   ~EventPair() { for (auto x : e) if (x) cudaEventDestroy(x); }
@@ -561,40 +551,49 @@ static int dispatch_ingest(bcg_ctx* ctx, const double* src, int64_t src_ld, int6
   }
 }
 
-// double-buffered pinned staging: host memcpy of chunk c+1 overlaps H2D + ingest of chunk c
+// double-buffered staging through the context's pinned buffers: the host memcpy of chunk c+1 overlaps H2D + ingest of
+// chunk c; the host waits only for its staging buffer (copy of chunk c-2 done), the device buffer is ordered by events
 static int ingest_host_rows(bcg_ctx* ctx, const double* rows, int64_t n, int32_t S, int64_t ld_host, bcg_vecs* v) {
-  const int64_t chunk_rows = std::max<int64_t>(1, std::min<int64_t>(n, (32ll << 20) / ((int64_t)S * 8)));
+  const int64_t chunk_rows = std::max<int64_t>(1, std::min<int64_t>(n, (int64_t)kPinChunk / ((int64_t)S * 8)));
   const int nchunks = (int)((n + chunk_rows - 1) / chunk_rows);
   const int grid = (int)std::min<int64_t>((chunk_rows + kProjWarps - 1) / kProjWarps, (int64_t)ctx->sm_count * 2);
-  PinBuf<double> pin[2];
-  DevBuf<double> dev[2];
-  EventPair done;
+  cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
+  RET(ensure_pins(ctx));
+  double* pin[2] = {reinterpret_cast<double*>(ctx->pin[0]), reinterpret_cast<double*>(ctx->pin[1])};
+  double* dev[2] = {nullptr, nullptr};
+  EventPair copied, kdone;
   DevBuf<double> d_partial;
   DevBuf<unsigned long long> d_zero;
   const size_t celems = (size_t)chunk_rows * S;
   for (int i = 0; i < 2; ++i) {
-    CK(pin[i].alloc(celems));
-    CK(dev[i].alloc(celems));
-    CK(cudaEventCreateWithFlags(&done.e[i], cudaEventDisableTiming));
+    RET(ctx_scratch(ctx, 6 + i, celems * sizeof(double), (void**)&dev[i]));
+    CK(cudaEventCreateWithFlags(&copied.e[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&kdone.e[i], cudaEventDisableTiming));
   }
   CK(d_partial.alloc((size_t)nchunks * grid * (S + 1)));
   CK(d_zero.alloc(1));
-  CK(cudaMemsetAsync(d_zero, 0, sizeof(unsigned long long), ctx->stream));
+  CK(cudaMemsetAsync(d_zero, 0, sizeof(unsigned long long), st));
   for (int c = 0; c < nchunks; ++c) {
     const int i = c & 1;
     const int64_t r0 = (int64_t)c * chunk_rows;
     const int64_t nr = std::min<int64_t>(chunk_rows, n - r0);
-    if (c >= 2) CK(cudaEventSynchronize(done.e[i]));
+    if (c >= 2) {
+      CK(cudaStreamWaitEvent(cs, kdone.e[i], 0));
+      CK(cudaEventSynchronize(copied.e[i]));
+    }
     if (ld_host == S) {
       parallel_memcpy(pin[i], rows + r0 * ld_host, (size_t)nr * S * sizeof(double));
     } else {
-      for (int64_t r = 0; r < nr; ++r) memcpy(pin[i].p + r * S, rows + (r0 + r) * ld_host, (size_t)S * sizeof(double));
+      for (int64_t r = 0; r < nr; ++r) memcpy(pin[i] + r * S, rows + (r0 + r) * ld_host, (size_t)S * sizeof(double));
     }
-    CK(cudaMemcpyAsync(dev[i], pin[i], (size_t)nr * S * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dev[i], pin[i], (size_t)nr * S * sizeof(double), cudaMemcpyHostToDevice, cs));
+    CK(cudaEventRecord(copied.e[i], cs));
+    CK(cudaStreamWaitEvent(st, copied.e[i], 0));
     RET(dispatch_ingest(ctx, dev[i], S, nr, v, r0, d_partial.p + (size_t)c * grid * (S + 1), grid, d_zero));
-    CK(cudaEventRecord(done.e[i], ctx->stream));
+    CK(cudaEventRecord(kdone.e[i], st));
   }
   RET(finish_colsum(v, d_partial, nchunks * grid, d_zero));
+  CK(cudaStreamSynchronize(cs));
   return BCG_OK;
 }
 
