@@ -92,6 +92,8 @@ _PROTOTYPES = {
   'bcg_solver_set_check_monotone': (_c.c_int, [_P, _c.c_int32]),
   'bcg_solver_set_force_exact': (_c.c_int, [_P, _c.c_int32]),
   'bcg_solver_exact_count': (_c.c_int, [_P, _c.POINTER(_c.c_int64)]),
+  'bcg_solver_set_filter16': (_c.c_int, [_P, _c.c_int32]),
+  'bcg_solver_filter16_stats': (_c.c_int, [_P, _c.POINTER(_c.c_int32), _c.POINTER(_c.c_int64)]),
   'bcg_solver_set_profiling': (_c.c_int, [_P, _c.c_int32]),
   'bcg_solver_set_trace': (_c.c_int, [_P, _c.c_int32]),
   'bcg_solver_get_trace': (_c.c_int, [_P, _c.c_int32, _P, _c.POINTER(_c.c_int32)]),
@@ -558,6 +560,16 @@ class NativeSolver(object):
     v = ctypes.c_int64()
     check(lib().bcg_solver_exact_count(self.handle, ctypes.byref(v)))
     return v.value
+
+  def set_filter16(self, on):
+    """float16 pre-filter of the persistent greedy kernels (bcg.h: bcg_solver_set_filter16); selections are unchanged"""
+    check(lib().bcg_solver_set_filter16(self.handle, 1 if on else 0))
+
+  def filter16_stats(self):
+    """(enabled, rows re-scanned in float32 so far)"""
+    e, r = ctypes.c_int32(), ctypes.c_int64()
+    check(lib().bcg_solver_filter16_stats(self.handle, ctypes.byref(e), ctypes.byref(r)))
+    return bool(e.value), int(r.value)
 
   def set_profiling(self, on):
     check(lib().bcg_solver_set_profiling(self.handle, 1 if on else 0))

@@ -1,6 +1,7 @@
 // C-ABI implementation (include/bcg.h) of the B200-native coreset engine.
 // Host side: handle management, uploads, kernel launches on a private stream.  There is no CPU
 // compute path: without a CUDA device every entry point fails with BCG_ERR_NO_DEVICE.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <chrono>
 #include <math.h>
@@ -21,6 +22,7 @@
 
 #include "../../include/bcg.h"
 #include "bcg_state.h"
+#include "filter_bounds.h"
 #include "kernel_args.h"
 #include "project_kernels.cuh"
 #include "project_fast_kernel.cuh"
@@ -129,6 +131,8 @@ struct bcg_ctx {
   size_t pool_An_bytes;
   double* pool_norms;
   size_t pool_norms_bytes;
+  uint16_t* pool_An16;
+  size_t pool_An16_bytes;
 };
 
 struct bcg_vecs {
@@ -137,6 +141,9 @@ struct bcg_vecs {
   int32_t S, ld;
   float* An;
   double* norms;
+  uint16_t* An16;               // float16 copy of An for the pre-filter of the persistent scan (made on demand; may stay null)
+  int32_t ld16;                 // halves per row of An16 (multiple of 8)
+  size_t An16_bytes;
   size_t An_bytes, norms_bytes; // requested sizes (the buffers may be larger: they come from the context's one-slot cache)
   std::vector<double> colsum;   // S sums + [S] = sum of norms
   uint64_t zero_rows;
@@ -154,6 +161,7 @@ struct bcg_solver {
   ScanConfig sc;
   bool use_loop;            // persistent cooperative kernel available for this shape (GIGA / FW: greedy_loop_kernel)
   bool use_omp_loop;        // persistent OrthoPursuit kernel available (omp_loop_kernel)
+  bool filter16;            // the persistent kernel streams the float16 copy and re-scans by bounds (filter_bounds.h)
   LoopCtl* d_ctl;
   ScanCand* d_cta_cands;
   float* d_cta_lost;
@@ -237,6 +245,7 @@ extern "C" int bcg_ctx_create(int device, bcg_ctx** out) {
   c->sp_tab = nullptr;
   c->pool_An = nullptr; c->pool_An_bytes = 0;
   c->pool_norms = nullptr; c->pool_norms_bytes = 0;
+  c->pool_An16 = nullptr; c->pool_An16_bytes = 0;
   auto body = [&]() -> int {
     CK(cudaSetDevice(device));
     CK(cudaGetDeviceProperties(&c->prop, device));
@@ -267,6 +276,7 @@ extern "C" int bcg_ctx_destroy(bcg_ctx* ctx) {
   if (ctx->sp_tab) cudaFree(ctx->sp_tab);
   if (ctx->pool_An) cudaFree(ctx->pool_An);
   if (ctx->pool_norms) cudaFree(ctx->pool_norms);
+  if (ctx->pool_An16) cudaFree(ctx->pool_An16);
   for (auto& pc : ctx->peer_cache) cudaIpcCloseMemHandle(pc.second);
   if (ctx->mail) cudaFree(ctx->mail);
   for (int i = 0; i < 8; ++i)
@@ -306,8 +316,10 @@ extern "C" int bcg_ctx_trim(bcg_ctx* ctx) {
   RET(use_device(ctx));
   if (ctx->pool_An) CK(cudaFree(ctx->pool_An));
   if (ctx->pool_norms) CK(cudaFree(ctx->pool_norms));
+  if (ctx->pool_An16) CK(cudaFree(ctx->pool_An16));
   ctx->pool_An = nullptr; ctx->pool_An_bytes = 0;
   ctx->pool_norms = nullptr; ctx->pool_norms_bytes = 0;
+  ctx->pool_An16 = nullptr; ctx->pool_An16_bytes = 0;
   return BCG_OK;
 }
 
@@ -482,6 +494,9 @@ static int j_for_ld(int ld) {
   return j;
 }
 
+// rows of padding behind An: the float32 re-scan of the filtered persistent kernel reads whole row batches from global memory
+static const int64_t kRowPad = 64;
+
 static int vecs_alloc(bcg_ctx* ctx, int64_t n, int32_t S, bcg_vecs** out, bool lazy = false) {
   if (n < 0 || S <= 0) return fail(BCG_ERR_ARG, "bad shape n=%lld S=%d", (long long)n, S);
   if (S > 1024) return fail(BCG_ERR_UNSUPPORTED, "S=%d > 1024 is not supported", S);
@@ -493,6 +508,9 @@ static int vecs_alloc(bcg_ctx* ctx, int64_t n, int32_t S, bcg_vecs** out, bool l
   v->ld = (S + 3) / 4 * 4;
   v->An = nullptr;
   v->norms = nullptr;
+  v->An16 = nullptr;
+  v->ld16 = (S + 7) / 8 * 8;
+  v->An16_bytes = 0;
   v->zero_rows = 0;
   v->colsum.assign(S + 1, 0.);
   v->lazy_ds = nullptr;
@@ -501,7 +519,7 @@ static int vecs_alloc(bcg_ctx* ctx, int64_t n, int32_t S, bcg_vecs** out, bool l
   v->An_bytes = v->norms_bytes = 0;
   if (n > 0) {
     if (!lazy) {
-      v->An_bytes = (size_t)n * v->ld * sizeof(float);
+      v->An_bytes = (size_t)(n + kRowPad) * v->ld * sizeof(float);   // (padding: see kRowPad)
       RET(pool_take(&ctx->pool_An, &ctx->pool_An_bytes, v->An_bytes, &v->An));
     }
     v->norms_bytes = (size_t)n * sizeof(double);
@@ -1388,10 +1406,61 @@ extern "C" int bcg_vecs_destroy(bcg_vecs* v) {
   cudaStreamSynchronize(v->ctx->stream);
   pool_give(&v->ctx->pool_An, &v->ctx->pool_An_bytes, v->An, v->An_bytes);
   pool_give(&v->ctx->pool_norms, &v->ctx->pool_norms_bytes, v->norms, v->norms_bytes);
+  pool_give(&v->ctx->pool_An16, &v->ctx->pool_An16_bytes, v->An16, v->An16_bytes);
   if (v->lazy_thetaT) cudaFree(v->lazy_thetaT);
   if (v->lazy_tt) cudaFree(v->lazy_tt);
   if (v->lazy_Siginv) cudaFree(v->lazy_Siginv);
   delete v;
+  return BCG_OK;
+}
+
+// float16 copy of the unit rows for the pre-filter of the persistent scan (filter_bounds.h): round to nearest, padding zero
+__global__ void __launch_bounds__(256) half_copy_kernel(const float* __restrict__ An, int64_t n, int ld, uint16_t* __restrict__ out,
+                                                        int ld16) {
+  const int gpr = ld16 >> 3;                                  // 8-element groups per row
+  const int64_t total = n * gpr;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / gpr;
+    const int e0 = (int)(i - row * gpr) * 8;
+    const float* src = An + row * ld + e0;
+    float x[8];
+#pragma unroll
+    for (int k = 0; k < 8; k += 4) {
+      if (e0 + k < ld) {                                      // ld is a multiple of 4: whole float4 inside or outside the row
+        const float4 t = __ldcs(reinterpret_cast<const float4*>(src + k));
+        x[k] = t.x; x[k + 1] = t.y; x[k + 2] = t.z; x[k + 3] = t.w;
+      } else {
+        x[k] = x[k + 1] = x[k + 2] = x[k + 3] = 0.f;
+      }
+    }
+    uint4 o;
+    __half2 h;
+    h = __floats2half2_rn(x[0], x[1]); o.x = *reinterpret_cast<unsigned int*>(&h);
+    h = __floats2half2_rn(x[2], x[3]); o.y = *reinterpret_cast<unsigned int*>(&h);
+    h = __floats2half2_rn(x[4], x[5]); o.z = *reinterpret_cast<unsigned int*>(&h);
+    h = __floats2half2_rn(x[6], x[7]); o.w = *reinterpret_cast<unsigned int*>(&h);
+    *reinterpret_cast<uint4*>(out + row * ld16 + e0) = o;
+  }
+}
+
+// make v->An16 (idempotent).  Not an error when the memory is not there: the solver then streams the float32 rows.
+static int vecs_ensure_half(bcg_vecs* v) {
+  if (v->An16 || !v->An || v->n == 0) return BCG_OK;
+  bcg_ctx* ctx = v->ctx;
+  const size_t bytes = (size_t)v->n * v->ld16 * sizeof(uint16_t);
+  uint16_t* p = nullptr;
+  if (ctx->pool_An16 && ctx->pool_An16_bytes >= bytes && ctx->pool_An16_bytes <= 2 * bytes + (1 << 20)) {
+    p = ctx->pool_An16;
+    ctx->pool_An16 = nullptr;
+    ctx->pool_An16_bytes = 0;
+  } else if (cudaMalloc(&p, bytes) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return BCG_OK;
+  }
+  v->An16 = p;
+  v->An16_bytes = bytes;
+  half_copy_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(v->An, v->n, v->ld, v->An16, v->ld16);
+  CK(cudaGetLastError());
   return BCG_OK;
 }
 
@@ -1418,7 +1487,8 @@ static int choose_scan_config(bcg_solver* s) {
   c.stages = std::max(1, env_int("BCG_SCAN_STAGES", 2));
   c.evict_first = env_int("BCG_SCAN_EVICT_FIRST", 0);
   const size_t budget = (size_t)(200 * 1024);
-  const size_t extra = 64 * sizeof(ScanCand) + 4 * (size_t)s->v->S * sizeof(double) + 64 + 16 * 8 * 12 + 128;   // loop kernel only
+  const size_t extra = 64 * sizeof(ScanCand) + 4 * (size_t)s->v->S * sizeof(double) + 64 + 16 * 8 * 12 + 128 +
+                       11 * 32 * 8;                                  // loop kernel only (last term: re-scan slots of the float16 pre-filter)
   auto ring = [&](int stages, int rps) { return (size_t)c.wpb * stages * rps * row_bytes + (size_t)c.wpb * stages * 8; };
   while (c.stages > 2 && ring(c.stages, c.rps) + extra > budget) --c.stages;
   while (c.rps > c.rb && ring(c.stages, c.rps) + extra > budget) c.rps -= c.rb;
@@ -1428,6 +1498,10 @@ static int choose_scan_config(bcg_solver* s) {
   c.loop_smem = c.smem + extra;
   if (c.loop_smem > 227 * 1024) return fail(BCG_ERR_UNSUPPORTED, "scan tile does not fit shared memory (ld=%d)", ld);
   c.grid = s->ctx->sm_count;
+  // float16 pre-filter of the persistent kernels: rows per ring stage in the float16 pass (multiple of its batch of 4 rows)
+  c.ch16 = env_int("BCG_FILTER16", 1) ? loop_variant_ch16(c.ch, c.lpr) : 0;
+  c.rps16 = (int)((size_t)c.rps * row_bytes / ((size_t)s->v->ld16 * 2)) / 4 * 4;
+  if (c.rps16 < 4 || s->h.lazy) c.ch16 = 0;
   CK(scan_set_smem(c));
   s->use_loop = false;
   s->use_omp_loop = false;
@@ -1444,6 +1518,8 @@ static int choose_scan_config(bcg_solver* s) {
       s->use_omp_loop = coop && nbm >= 1;
     }
   }
+  s->filter16 = (s->use_loop || s->use_omp_loop) && c.ch16 > 0;
+  if (s->filter16) RET(vecs_ensure_half(s->v));
   return BCG_OK;
 }
 
@@ -1613,6 +1689,7 @@ extern "C" int bcg_solver_create(bcg_ctx* ctx, bcg_vecs* v, int32_t alg, const d
   s->peers_open = false;
   s->use_loop = false;
   s->use_omp_loop = false;
+  s->filter16 = false;
   s->d_ctl = nullptr;
   s->d_cta_cands = nullptr;
   s->d_cta_lost = nullptr;
@@ -1825,6 +1902,11 @@ static int run_persistent(bcg_solver* s, int32_t itrs, bool omp) {
   la.g.rps = s->sc.rps;
   la.g.stages = s->sc.stages;
   la.g.evict_first = s->sc.evict_first;
+  const bool f16 = s->filter16 && s->v->An16 != nullptr;
+  la.g.An16 = f16 ? s->v->An16 : nullptr;
+  la.g.ld16 = s->v->ld16;
+  la.g.rps16 = s->sc.rps16;
+  la.g.eps16 = filter_eps_unit(s->v->S);
   la.wpb = s->sc.wpb;
   if (s->claims_cap < itrs) {
     if (s->d_claims) CK(cudaFree(s->d_claims));
@@ -1862,6 +1944,10 @@ static int run_persistent(bcg_solver* s, int32_t itrs, bool omp) {
     CK(cudaEventRecord(s->ev1, st));                                 // (re-recorded per launch: the last one counts)
     s->loop_launches += 1;
     RET(pull_state(s));
+    if (h.filt_overflow) {                                           // more near-maximal row groups than re-scan slots (e.g. many
+      s->filter16 = false;                                           // duplicated rows): this solver goes back to the float32 stream
+      la.g.An16 = nullptr;
+    }
     if (!h.need_exact || h.halted || h.comm_error) break;
     done += h.iters_done;
     if (done >= itrs) break;                                         // (cannot happen: the stop precedes an iteration)
@@ -2243,6 +2329,27 @@ extern "C" int bcg_solver_set_force_exact(bcg_solver* s, int32_t on) {
 extern "C" int bcg_solver_exact_count(bcg_solver* s, int64_t* n_exact) {
   if (!s || !n_exact) return fail(BCG_ERR_ARG, "null argument");
   *n_exact = s->h.n_exact;
+  return BCG_OK;
+}
+
+// float16 pre-filter of the persistent kernels: switch it off / on for this solver (on only where it is available)
+extern "C" int bcg_solver_set_filter16(bcg_solver* s, int32_t on) {
+  if (!s) return fail(BCG_ERR_ARG, "null solver");
+  RET(use_device(s->ctx));
+  if (!on) { s->filter16 = false; return BCG_OK; }
+  if ((s->use_loop || s->use_omp_loop) && s->sc.ch16 > 0) {
+    RET(vecs_ensure_half(s->v));
+    s->filter16 = s->v->An16 != nullptr;
+    s->h.filt_overflow = 0;
+  }
+  return BCG_OK;
+}
+
+// enabled: the next persistent launch streams the float16 copy; rows_rescanned: rows re-scanned in float32 so far
+extern "C" int bcg_solver_filter16_stats(bcg_solver* s, int32_t* enabled, int64_t* rows_rescanned) {
+  if (!s) return fail(BCG_ERR_ARG, "null solver");
+  if (enabled) *enabled = (s->filter16 && s->v->An16) ? 1 : 0;
+  if (rows_rescanned) *rows_rescanned = (int64_t)s->h.filt_rows;
   return BCG_OK;
 }
 

@@ -95,6 +95,9 @@ struct SolverState {
   unsigned char* mail_local;        // this rank's mailbox: [2][world] slots
   unsigned char* mail_peer[kMaxWorld];  // mapped mailboxes of all ranks (self included)
   int64_t mail_slot_bytes;
+  // ---- float16 pre-filter of the persistent scan (filter_bounds.h) --------------------------------
+  unsigned long long filt_rows;     // rows re-scanned in float32 so far (diagnostics; all other rows were excluded by bounds)
+  int32_t filt_overflow;            // a scan warp ran out of re-scan slots (the iteration was resolved by the exact pass)
   // ---- diagnostics ---------------------------------------------------------------------------
   unsigned long long* omp_trace;    // null, or 16 device timestamps per OMP iteration (BCG_OMP_TRACE=1)
 };

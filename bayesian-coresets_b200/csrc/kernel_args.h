@@ -16,6 +16,11 @@ struct ScanGeom {
   int32_t rps;          // rows per stage (multiple of the batch size R * 32/LPR)
   int32_t stages;
   int32_t evict_first;  // L2 policy of the streaming loads
+  // float16 pre-filter (persistent kernels only; null = off): the ring streams this copy instead of An
+  const uint16_t* An16; // n_rows x ld16 halves (IEEE binary16, round to nearest of An; padding zero)
+  int32_t ld16;         // halves per row (multiple of 8)
+  int32_t rps16;        // rows per ring stage in the float16 pass
+  float eps16;          // filter_eps_unit(S)
 };
 
 struct ScanArgs {
@@ -64,6 +69,7 @@ struct ScanConfig {
   int ch, ndir, lpr, r;      // template parameters of the scan core
   int rb;                    // rows per batch = r * 32 / lpr
   int rps, stages, wpb, grid, evict_first;
+  int ch16, rps16;           // float16 pre-filter: 16-byte groups per lane (0 = not available for this row length)
   size_t smem;               // dynamic shared memory of scan_kernel
   size_t loop_smem;          // dynamic shared memory of greedy_loop_kernel
 };
@@ -76,6 +82,7 @@ cudaError_t scan_launch(const ScanConfig& c, const ScanArgs& a, cudaStream_t st)
 cudaError_t exact_scan_launch(int grid, SolverState* st, int force, cudaStream_t s);
 // kernels_loop.cu
 bool loop_variant_exists(int ch, int lpr);
+int loop_variant_ch16(int ch, int lpr);   // 16-byte groups per lane of the float16 pre-filter (0: none)
 cudaError_t loop_set_smem(const ScanConfig& c);
 cudaError_t loop_max_blocks_per_sm(const ScanConfig& c, int* nb);
 cudaError_t loop_launch(const ScanConfig& c, const LoopArgs& a, cudaStream_t st);

@@ -642,9 +642,20 @@ __device__ void control_loop(const LoopArgs& a, double* sb, double* sbn, double*
 // candidates + its lost score, arrive.  cta_rank / n_ctas: position among the SCANNING CTAs (the OrthoPursuit kernel
 // reserves CTA 0 for the control path).  Shared memory: rings | barriers | 64 candidate slots | ... | slot records.
 // ---------------------------------------------------------------------------------------------
-template <int CH, int NDIR, int LPR, int R>
+constexpr int kFiltCap = 32;       // re-scan slots per scan warp and iteration (one per lane)
+
+// CH16 > 0: float16 pre-filter (filter_bounds.h).  The ring streams the float16 copy (half the bytes); every ring stage
+// yields an upper bound of the float32 scores of its rows and raises the warp's lower bound L of the float32 maximum;
+// stages whose upper bound reaches filter_threshold(L) are remembered (kFiltCap slots, compacted against the rising L)
+// and re-scanned afterwards from the float32 rows in global memory with the unchanged Core::batch.  Rows that are not
+// re-scanned provably score below (float32 maximum - near-tie window), so best / runner-up / lost -- and with them the
+// selection, the near-tie re-scoring and the ambiguity test -- are exactly those of the plain float32 scan.  A warp
+// that runs out of slots reports lost = +inf, which sends the iteration to the exact float64 pass.
+template <int CH, int NDIR, int LPR, int R, int CH16>
 __device__ __forceinline__ void scan_cta_body(const LoopArgs& a, unsigned char* smem_raw, int cta_rank, int n_ctas) {
   using Core = ScanCore<CH, NDIR, LPR, R>;
+  constexpr bool F16 = CH16 > 0;
+  using FCore = Filter16Core<(F16 ? CH16 : 1), NDIR, 4>;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int wpb = a.wpb;
@@ -669,7 +680,11 @@ __device__ __forceinline__ void scan_cta_body(const LoopArgs& a, unsigned char* 
   const int g = lane & (LPR - 1);
   const int grp = lane / LPR;
   const int nchunk = q.ld >> 2;
-  const int64_t n_chunks = (q.n_rows + q.rps - 1) / q.rps;
+  // what the ring streams: the float32 rows, or their float16 copy
+  const int rps = F16 ? q.rps16 : q.rps;
+  const uint32_t row_bytes = F16 ? (uint32_t)q.ld16 * 2u : (uint32_t)q.ld * 4u;
+  const unsigned char* src = F16 ? reinterpret_cast<const unsigned char*>(q.An16) : reinterpret_cast<const unsigned char*>(q.An);
+  const int64_t n_chunks = (q.n_rows + rps - 1) / rps;
   // Work split per iteration: the first n_s chunks of every warp are STATIC (chunk gw + k GW, interleaved so
   // that neighbouring warps stream neighbouring rows); the remaining chunks [n_static, n_chunks) are claimed
   // DYNAMICALLY with one atomic per chunk from a per-iteration counter, so SMs that the memory system serves
@@ -685,6 +700,10 @@ __device__ __forceinline__ void scan_cta_body(const LoopArgs& a, unsigned char* 
   const bool leader = lane == 0;
   int64_t* sm_row0 = reinterpret_cast<int64_t*>(speers + kMaxWorld) + warp * q.stages;
   int* sm_it = reinterpret_cast<int*>(reinterpret_cast<int64_t*>(speers + kMaxWorld) + wpb * q.stages) + warp * q.stages;
+  // re-scan slots of this warp (float16 pre-filter): first row and upper bound of a remembered stage
+  uint32_t* fl_base = reinterpret_cast<uint32_t*>(sm_it - warp * q.stages + wpb * q.stages);
+  uint32_t* fl_row = fl_base + warp * kFiltCap;
+  float* fl_ub = reinterpret_cast<float*>(fl_base + wpb * kFiltCap) + warp * kFiltCap;
   int issue_slot = 0;
   int64_t issue_k = 0;         // static chunks of iteration issue_it issued so far
   int issue_it = 0;            // iteration the next issue belongs to
@@ -718,11 +737,11 @@ __device__ __forceinline__ void scan_cta_body(const LoopArgs& a, unsigned char* 
           continue;
         }
       }
-      const int64_t row0 = c * q.rps;
+      const int64_t row0 = c * rps;
       const int64_t left = q.n_rows - row0;
-      const uint32_t nr = (uint32_t)(left < q.rps ? left : q.rps);
-      tma_load_rows(&bars[issue_slot], wbuf + (size_t)issue_slot * stage_floats, q.An + (size_t)row0 * q.ld,
-                    nr * (uint32_t)q.ld * 4u, policy, leader);
+      const uint32_t nr = (uint32_t)(left < rps ? left : rps);
+      tma_load_rows(&bars[issue_slot], wbuf + (size_t)issue_slot * stage_floats,
+                    reinterpret_cast<const float*>(src + (size_t)row0 * row_bytes), nr * row_bytes, policy, leader);
       if (leader) { sm_row0[issue_slot] = row0; sm_it[issue_slot] = issue_it; }
       if (++issue_slot == q.stages) issue_slot = 0;
       ++outstanding;
@@ -741,25 +760,98 @@ __device__ __forceinline__ void scan_cta_body(const LoopArgs& a, unsigned char* 
     if (a.trace && gw == 0 && lane == 0) a.trace[(size_t)it * 8 + 2] = globaltimer_ns();
     __syncwarp();
 
-    float4 d0[CH];
-    float4 d1[CH];
-    Core::load_dirs(a.st->dir32, q.ld, nchunk, g, d0, d1);
-
     float best = -INFINITY, lost = -INFINITY;
     uint32_t brow = kNoRowU;
-    while (outstanding > 0 && sm_it[slot] == it) {   // uniform: shared-memory broadcast reads
-      mbar_wait(&bars[slot], parity);
-      const int64_t row0 = sm_row0[slot];
-      const int64_t left = q.n_rows - row0;
-      const int nr = (int)(left < q.rps ? left : q.rps);
-      const float* tile = wbuf + (size_t)slot * stage_floats;
-      for (int b0 = 0; b0 < nr; b0 += Core::RB)
-        Core::batch(tile + (size_t)b0 * q.ld, q.ld, nchunk, g, grp, nr - b0, (uint32_t)(row0 + b0), d0, d1, best, brow, lost);
-      __syncwarp();   // every lane's shared-memory reads of this stage (and of its slot record) are complete
-      --outstanding;
-      issue_next();
-      __syncwarp();   // the leader's slot record is visible to all lanes
-      if (++slot == q.stages) { slot = 0; parity ^= 1u; }
+    if constexpr (!F16) {
+      float4 d0[CH];
+      float4 d1[CH];
+      Core::load_dirs(a.st->dir32, q.ld, nchunk, g, d0, d1);
+      while (outstanding > 0 && sm_it[slot] == it) {   // uniform: shared-memory broadcast reads
+        mbar_wait(&bars[slot], parity);
+        const int64_t row0 = sm_row0[slot];
+        const int64_t left = q.n_rows - row0;
+        const int nr = (int)(left < rps ? left : rps);
+        const float* tile = wbuf + (size_t)slot * stage_floats;
+        for (int b0 = 0; b0 < nr; b0 += Core::RB)
+          Core::batch(tile + (size_t)b0 * q.ld, q.ld, nchunk, g, grp, nr - b0, (uint32_t)(row0 + b0), d0, d1, best, brow, lost);
+        __syncwarp();   // every lane's shared-memory reads of this stage (and of its slot record) are complete
+        --outstanding;
+        issue_next();
+        __syncwarp();   // the leader's slot record is visible to all lanes
+        if (++slot == q.stages) { slot = 0; parity ^= 1u; }
+      }
+    } else {
+      // ---- pass A: bounds from the float16 copy ----------------------------------------------------------------
+      float Lw = -INFINITY;                            // lower bound of this warp's float32 maximum (warp-uniform)
+      int nlist = 0;
+      bool overflow = false;
+      {
+        float dh0[F16 ? CH16 : 1][8];
+        float dh1[F16 ? CH16 : 1][8];
+        float dn0, dn1;
+        FCore::load_dirs(a.st->dir32, q.ld, a.st->S, lane, dh0, dh1, &dn0, &dn1);
+        const float e0 = q.eps16 * dn0, e1 = q.eps16 * dn1;
+        const int ngroups = q.ld16 >> 3;
+        while (outstanding > 0 && sm_it[slot] == it) {
+          mbar_wait(&bars[slot], parity);
+          const int64_t row0 = sm_row0[slot];
+          const int64_t left = q.n_rows - row0;
+          const int nr = (int)(left < rps ? left : rps);
+          const __half* tile = reinterpret_cast<const __half*>(wbuf + (size_t)slot * stage_floats);
+          float ubm = -INFINITY, lbm = -INFINITY;
+          for (int b0 = 0; b0 < nr; b0 += FCore::RB)
+            FCore::batch(tile + (size_t)b0 * q.ld16, q.ld16, ngroups, lane, nr - b0, dh0, dh1, e0, e1, ubm, lbm);
+          ubm = warp_max_f(ubm);
+          Lw = fmaxf(Lw, warp_max_f(lbm));
+          if (ubm >= filter_threshold(Lw)) {           // warp-uniform
+            if (nlist == kFiltCap) {                   // compact the slots against the risen bound
+              const uint32_t r_i = fl_row[lane];
+              const float u_i = fl_ub[lane];
+              const bool keep = u_i >= filter_threshold(Lw);
+              const unsigned int m = __ballot_sync(0xffffffffu, keep);
+              __syncwarp();
+              if (keep) { const int pos = __popc(m & ((1u << lane) - 1u)); fl_row[pos] = r_i; fl_ub[pos] = u_i; }
+              nlist = __popc(m);
+              __syncwarp();
+            }
+            if (nlist < kFiltCap) {
+              if (lane == 0) { fl_row[nlist] = (uint32_t)row0; fl_ub[nlist] = ubm; }
+              ++nlist;
+            } else {
+              overflow = true;
+            }
+          }
+          __syncwarp();
+          --outstanding;
+          issue_next();
+          __syncwarp();
+          if (++slot == q.stages) { slot = 0; parity ^= 1u; }
+        }
+      }
+      // ---- pass B: the remembered stages again, float32 rows straight from global memory -------------------------------
+      {
+        float4 d0[CH];
+        float4 d1[CH];
+        Core::load_dirs(a.st->dir32, q.ld, nchunk, g, d0, d1);
+        const float thr = filter_threshold(Lw);
+        unsigned int nres = 0;
+        for (int i = 0; i < nlist; ++i) {
+          if (!(fl_ub[i] >= thr)) continue;            // uniform (shared-memory broadcast)
+          const int64_t row0 = (int64_t)fl_row[i];
+          const int64_t left = q.n_rows - row0;
+          const int nr = (int)(left < rps ? left : rps);
+          for (int b0 = 0; b0 < nr; b0 += Core::RB)    // (the last batch may read up to RB - 1 rows of padding: kRowPad)
+            Core::batch(q.An + (size_t)(row0 + b0) * q.ld, q.ld, nchunk, g, grp, nr - b0, (uint32_t)(row0 + b0), d0, d1, best,
+                        brow, lost);
+          nres += (unsigned int)nr;
+        }
+        if (overflow) lost = INFINITY;
+        if (lane == 0) {
+          if (nres) atomicAdd(&a.st->filt_rows, (unsigned long long)nres);
+          if (overflow) a.st->filt_overflow = 1;
+        }
+        __syncwarp();
+      }
     }
 
     if (a.trace && gw == 0 && lane == 0) a.trace[(size_t)it * 8 + 3] = globaltimer_ns();
@@ -807,7 +899,7 @@ __device__ __forceinline__ void scan_cta_body(const LoopArgs& a, unsigned char* 
   }
 }
 
-template <int CH, int NDIR, int LPR, int R, int J>
+template <int CH, int NDIR, int LPR, int R, int J, int CH16>
 __global__ void __launch_bounds__(384, 1) greedy_loop_kernel(const LoopArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
@@ -830,7 +922,7 @@ __global__ void __launch_bounds__(384, 1) greedy_loop_kernel(const LoopArgs a) {
     return;
   }
 
-  scan_cta_body<CH, NDIR, LPR, R>(a, smem_raw, (int)blockIdx.x, (int)gridDim.x);
+  scan_cta_body<CH, NDIR, LPR, R, CH16>(a, smem_raw, (int)blockIdx.x, (int)gridDim.x);
 }
 
 }  // namespace bcg

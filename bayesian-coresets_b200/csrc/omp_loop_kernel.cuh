@@ -113,7 +113,7 @@ __device__ void omp_control_cta(const LoopArgs& a, NnlsWork* W, int wide, unsign
   if (B.tid == 0) st->iters_done = stop_exact ? it : a.itrs;
 }
 
-template <int CH, int LPR, int R>
+template <int CH, int LPR, int R, int CH16>
 __global__ void __launch_bounds__(kOmpLoopThreads, 1) omp_loop_kernel(const LoopArgs a, NnlsWork* W, int wide) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   if (blockIdx.x == 0) {
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(kOmpLoopThreads, 1) omp_loop_kernel(const Loop
     return;
   }
   if ((int)(threadIdx.x >> 5) >= a.wpb) return;                // the scanning CTAs use wpb warps
-  scan_cta_body<CH, 1, LPR, R>(a, smem_raw, (int)blockIdx.x - 1, (int)gridDim.x - 1);
+  scan_cta_body<CH, 1, LPR, R, CH16>(a, smem_raw, (int)blockIdx.x - 1, (int)gridDim.x - 1);
 }
 
 }  // namespace bcg

@@ -19,9 +19,11 @@
 // executed 150 warp-instructions per 1 KB row and was issue-bound at 55 % of HBM bandwidth
 // (profiles/r01_v1_scan_N1e6_S256_full.csv).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "bcg_state.h"
+#include "filter_bounds.h"
 #include "kernel_args.h"
 
 namespace bcg {
@@ -202,6 +204,105 @@ struct ScanCore {
       const float s2 = __shfl_xor_sync(0xffffffffu, best, off);
       const uint32_t r2 = __shfl_xor_sync(0xffffffffu, brow, off);
       if (cand_better(s2, r2, best, brow)) { best = s2; brow = r2; }
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// float16 pre-filter pass (filter_bounds.h): the same register-tiled row batch over a float16 copy of the rows.
+// All 32 lanes cooperate on one row (lane g owns the 8-element groups g, g + 32, ...; one 16-byte shared-memory load
+// each); R rows run side by side.  Instead of a running arg-max the pass keeps, per row group (= ring stage), the largest
+// upper bound of the float32 score, and per warp the largest lower bound.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int float_sortable(float x) {          // monotone float -> int (no NaN)
+  const int i = __float_as_int(x);
+  return i ^ ((i >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float sortable_float(int i) {
+  return __int_as_float(i ^ ((i >> 31) & 0x7fffffff));
+}
+__device__ __forceinline__ float warp_max_f(float x) {
+  return sortable_float(__reduce_max_sync(0xffffffffu, float_sortable(x)));
+}
+
+template <int CH16, int NDIR, int R>
+struct Filter16Core {
+  static constexpr int RB = R;                                   // rows per batch (LPR = 32)
+  static constexpr int HALVINGS = cmin(ilog2c(R), 5);
+  static constexpr int VREM = R >> HALVINGS;
+
+  // direction registers for this lane's element groups + |d|_2 of each direction (warp-uniform)
+  static __device__ __forceinline__ void load_dirs(const float* dir, int ld, int S, int g, float (&d0)[CH16][8],
+                                                   float (&d1)[CH16][8], float* n0, float* n1) {
+    float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < CH16; ++j) {
+      const int e0 = 8 * (g + 32 * j);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int e = e0 + k;
+        d0[j][k] = (e < S) ? __ldcg(dir + e) : 0.f;
+        d1[j][k] = (NDIR == 2 && e < S) ? __ldcg(dir + ld + e) : 0.f;
+        q0 = fmaf(d0[j][k], d0[j][k], q0);
+        q1 = fmaf(d1[j][k], d1[j][k], q1);
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      q0 += __shfl_xor_sync(0xffffffffu, q0, off);
+      q1 += __shfl_xor_sync(0xffffffffu, q1, off);
+    }
+    *n0 = sqrtf(q0);
+    *n1 = sqrtf(q1);
+  }
+
+  // one batch of R rows of `tile` (stride ld16 halves); folds the rows' bounds into ub_max / lb_max (per lane)
+  static __device__ __forceinline__ void batch(const __half* tile, int ld16, int ngroups, int g, int nvalid,
+                                               const float (&d0)[CH16][8], const float (&d1)[CH16][8], float e0, float e1,
+                                               float& ub_max, float& lb_max) {
+    float a0[R];
+    float a1[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) { a0[r] = 0.f; a1[r] = 0.f; }
+    const uint4* base = reinterpret_cast<const uint4*>(tile);
+    const int rstride = ld16 >> 3;                               // uint4 stride between rows
+#pragma unroll
+    for (int j = 0; j < CH16; ++j) {
+      const int c = g + 32 * j;
+      if (c < ngroups) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const uint4 x = base[(size_t)r * rstride + c];
+          const float2 p0 = __half22float2(*reinterpret_cast<const __half2*>(&x.x));
+          const float2 p1 = __half22float2(*reinterpret_cast<const __half2*>(&x.y));
+          const float2 p2 = __half22float2(*reinterpret_cast<const __half2*>(&x.z));
+          const float2 p3 = __half22float2(*reinterpret_cast<const __half2*>(&x.w));
+          a0[r] = fmaf(p0.x, d0[j][0], a0[r]); a0[r] = fmaf(p0.y, d0[j][1], a0[r]);
+          a0[r] = fmaf(p1.x, d0[j][2], a0[r]); a0[r] = fmaf(p1.y, d0[j][3], a0[r]);
+          a0[r] = fmaf(p2.x, d0[j][4], a0[r]); a0[r] = fmaf(p2.y, d0[j][5], a0[r]);
+          a0[r] = fmaf(p3.x, d0[j][6], a0[r]); a0[r] = fmaf(p3.y, d0[j][7], a0[r]);
+          if (NDIR == 2) {
+            a1[r] = fmaf(p0.x, d1[j][0], a1[r]); a1[r] = fmaf(p0.y, d1[j][1], a1[r]);
+            a1[r] = fmaf(p1.x, d1[j][2], a1[r]); a1[r] = fmaf(p1.y, d1[j][3], a1[r]);
+            a1[r] = fmaf(p2.x, d1[j][4], a1[r]); a1[r] = fmaf(p2.y, d1[j][5], a1[r]);
+            a1[r] = fmaf(p3.x, d1[j][6], a1[r]); a1[r] = fmaf(p3.y, d1[j][7], a1[r]);
+          }
+        }
+      }
+    }
+    int rid = 0;
+    HalvingReduce<R, 16>::run(a0, g, rid);
+    if (NDIR == 2) { int rid2 = 0; HalvingReduce<R, 16>::run(a1, g, rid2); }
+#pragma unroll
+    for (int t = 0; t < VREM; ++t) {
+      const int rin = rid + t;
+      float lb, ub;
+      if (NDIR == 2) filter_bounds_giga(a0[t], a1[t], e0, e1, &lb, &ub);
+      else filter_bounds_lin(a0[t], e0, &lb, &ub);
+      if (rin < nvalid) {
+        if (ub == ub) ub_max = fmaxf(ub_max, ub);                // a NaN score is ignored by the float32 scan as well
+        if (lb == lb) lb_max = fmaxf(lb_max, lb);
+      }
     }
   }
 };

@@ -238,6 +238,14 @@ int  bcg_solver_set_check_monotone(bcg_solver* s, int32_t check);
  * exact_count: selections resolved that way so far.  set_force_exact(1): every selection takes the exact pass (tests). */
 int  bcg_solver_exact_count(bcg_solver* s, int64_t* n_exact);
 int  bcg_solver_set_force_exact(bcg_solver* s, int32_t on);
+/* float16 pre-filter of the persistent greedy kernels (row lengths 129..512).  The loop streams a float16 copy of the unit
+ * rows (2 N S bytes per iteration instead of 4 N S), bounds every row's float32 score from it with a rigorous error bound,
+ * and re-scans in float32 only the row groups whose bound reaches the float32 maximum's near-tie window -- the selection
+ * (giga.py:38, frankwolfe.py:17, orthopursuit.py:19) is bit-identical to the plain float32 scan.  On by default where the
+ * copy fits in device memory (env BCG_FILTER16=0 disables it); filter16_stats: whether the next build uses it, and the
+ * number of rows re-scanned in float32 so far. */
+int  bcg_solver_set_filter16(bcg_solver* s, int32_t on);
+int  bcg_solver_filter16_stats(bcg_solver* s, int32_t* enabled, int64_t* rows_rescanned);
 /* device time of the last bcg_solver_build: total, and summed over the scan kernel launches */
 int  bcg_solver_timing(bcg_solver* s, float* build_ms, float* scan_ms, int32_t* scan_launches,
                        int32_t* step_launches);

@@ -301,3 +301,48 @@ extern "C" int hostcheck_link(int model, const double* lin, const double* y, int
   }
   return 0;
 }
+
+// ---- bounds of the float16 pre-filter (csrc/filter_bounds.h), host build ------------------------------------------
+#include "../../bayesian-coresets_b200/csrc/filter_bounds.h"
+
+// For every row: the float32 score exactly as scan_core.cuh evaluates it (two summation orders: `order` 0 = left to
+// right, 1 = 32 interleaved partial sums added pairwise -- the kernel's lane layout), and [lb, ub] from the float16-rounded
+// row.  1.f / sqrtf stands in for rsqrtf (2 ulp on the device; covered by kScoreRel).
+extern "C" int hostcheck_filter_bounds(const float* An, int64_t n, int ld, int S, const float* d0, const float* d1, int giga,
+                                       int order, float* score32, float* lb, float* ub) {
+  auto dot = [&](const float* x, const float* d, bool half) {
+    float part[32];
+    for (int i = 0; i < 32; ++i) part[i] = 0.f;
+    float seq = 0.f;
+    for (int s = 0; s < S; ++s) {
+      float v = x[s];
+      if (half) v = (float)(_Float16)v;                   // round to nearest even, as __floats2half2_rn
+      if (order == 0) seq = fmaf(v, d[s], seq);
+      else part[(s / 4) % 32] = fmaf(v, d[s], part[(s / 4) % 32]);
+    }
+    if (order == 0) return seq;
+    for (int off = 16; off > 0; off >>= 1)
+      for (int i = 0; i < off; ++i) part[i] += part[i + off];
+    return part[0];
+  };
+  double q0 = 0., q1 = 0.;
+  for (int s = 0; s < S; ++s) { q0 += (double)d0[s] * d0[s]; if (giga) q1 += (double)d1[s] * d1[s]; }
+  const float eu = bcg::filter_eps_unit(S);
+  const float e0 = eu * (float)sqrt(q0), e1 = eu * (float)sqrt(q1);
+  for (int64_t r = 0; r < n; ++r) {
+    const float* x = An + r * ld;
+    const float s0 = dot(x, d0, false), t0 = dot(x, d0, true);
+    if (giga) {
+      const float s1 = dot(x, d1, false), t1 = dot(x, d1, true);
+      const float den = 1.f - s1 * s1;
+      score32[r] = (s1 > -1.f && den > 0.f) ? s0 * (1.f / sqrtf(den)) : 0.f;
+      bcg::filter_bounds_giga(t0, t1, e0, e1, &lb[r], &ub[r]);
+    } else {
+      score32[r] = s0;
+      bcg::filter_bounds_lin(t0, e0, &lb[r], &ub[r]);
+    }
+  }
+  return 0;
+}
+
+extern "C" float hostcheck_filter_threshold(float L) { return bcg::filter_threshold(L); }

@@ -1179,3 +1179,75 @@ def test_full_size_audit_other_models(bc, model, alg):
   assert_weights_close(cs.snnls.weights(), r.w)
   atol = 2.**-24*float(np.abs(r.wa).dot(norms[r.idx])) + 1e-300
   np.testing.assert_allclose([e.error for e in ev], [e[2] for e in rev], rtol=W_RTOL, atol=atol)
+
+
+# ---------------------------------------------------------------- float16 pre-filter of the persistent kernels
+def _events(s):
+  return [(e.code, e.nact, e.f, e.error, e.aux0, e.aux1) for e in s.last_events]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('alg', ['giga', 'fw', 'omp'])
+@pytest.mark.parametrize('N,d,S', [(60000, 6, 130), (200000, 8, 256), (50001, 5, 300), (150000, 10, 512)])
+def test_filter16_changes_nothing_but_the_bytes(bc, alg, N, d, S):
+  """the persistent kernel that streams the float16 copy and re-scans by bounds (csrc/filter_bounds.h) produces the SAME
+  event log, bit for bit, as the one that streams the float32 rows -- selections, errors, weights, float64 scores"""
+  Z, theta = lr_problem(5 + S, N, d, S)
+  prj = bc.LogisticRegressionProjector(lambda n, w, p: theta, S)
+  a = bc.HilbertCoreset(Z, prj, snnls=algs(bc)[alg])
+  b = bc.HilbertCoreset(Z, prj, snnls=algs(bc)[alg])
+  on, _ = a.snnls._native.filter16_stats()
+  assert on, 'the float16 pre-filter should be available for S = %d' % S
+  b.snnls._native.set_filter16(False)
+  assert b.snnls._native.filter16_stats()[0] is False
+  for itrs in (1, 30, 9):                                    # incremental builds: the state survives relaunches
+    a.build(itrs)
+    b.build(itrs)
+    assert _events(a.snnls) == _events(b.snnls)
+  np.testing.assert_array_equal(a.snnls.weights(), b.snnls.weights())
+  assert a.error() == b.error()
+  on, rows = a.snnls._native.filter16_stats()
+  assert on and 0 < rows < 0.02*N*40, rows                   # almost every row is excluded by its bound
+  assert b.snnls._native.filter16_stats()[1] == 0
+
+
+@pytest.mark.gpu
+def test_filter16_near_ties_duplicates_and_slot_overflow(bc):
+  """(a) near ties inside one warp's rows still reach the exact pass; (b) exact duplicates resolve to the lowest index;
+  (c) a matrix made of 8 distinct rows repeated 90000 times puts a copy of the maximum into EVERY ring stage (16 rows)
+  and gives every scan warp more stages than it has re-scan slots (32): the slots overflow, the iteration goes to the exact pass, the solver falls back to the float32 stream -- same result as
+  with the filter off"""
+  rng = np.random.RandomState(4)
+  N, S = 40000, 256
+  X = rng.randn(N, S)
+  f0 = greedy.GigaOracle(X.T, X.sum(axis=0)).select()
+  r = X[f0].copy()
+  b = X.sum(axis=0)
+  bh, rh = b/np.linalg.norm(b), r/np.linalg.norm(r)
+  p = bh - bh.dot(rh)*rh
+  p /= np.linalg.norm(p)
+  for k in range(12):
+    X[20000 + k] = np.linalg.norm(r)*(rh + 1e-6*(k + 1)*p)
+  for alg in ('giga', 'fw'):
+    oev = greedy.ORACLES[alg](X.T, X.sum(axis=0)).build(6)
+    s = algs(bc)[alg](X.T, X.sum(axis=0))
+    assert s._native.filter16_stats()[0]
+    s.build(6)
+    assert [e.f for e in s.last_events] == [e[1] for e in oev]
+    assert s._native.exact_count() >= 1
+  base = rng.randn(6000, 200)
+  D = np.vstack((base, base[::-1].copy()))
+  oev = greedy.GigaOracle(D.T, D.sum(axis=0)).build(30)
+  s = algs(bc)['giga'](D.T, D.sum(axis=0))
+  s.build(30)
+  assert [e.f for e in s.last_events] == [e[1] for e in oev]
+  R = np.tile(rng.randn(8, 160), (90000, 1))
+  res = []
+  for filt in (True, False):
+    s = algs(bc)['fw'](R.T, R.sum(axis=0))
+    s._native.set_filter16(filt)
+    s.build(8)
+    res.append((_events(s), s._native.filter16_stats()[0], s._native.exact_count()))
+  assert res[0][0] == res[1][0]
+  assert all(e[2] < 8 for e in res[0][0])                    # lowest index among the 90000 copies
+  assert res[0][1] is False and res[0][2] >= 1               # overflowed -> exact pass -> float32 stream from then on

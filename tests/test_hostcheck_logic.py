@@ -347,3 +347,59 @@ def test_nnls_dependent_columns_keep_the_optimal_residual(lib):
       assert np.all(out[t] >= 0) and np.all(out[t][~active] == 0)
       assert res_got <= res_ref*(1. + 1e-8) + 1e-9, (downdate, t, res_got, res_ref)
       active = out[t] > 0                                  # continue from OUR active set (what the device loop does)
+
+
+# ---- float16 pre-filter of the persistent scan: the proof obligation of csrc/filter_bounds.h ---------------------------
+def _filter_case(lib, An, d0, d1, giga, order):
+  n, ld = An.shape
+  S = d0.shape[0]
+  sc, lb, ub = (np.empty(n, np.float32) for _ in range(3))
+  f32p = ctypes.POINTER(ctypes.c_float)
+  lib.hostcheck_filter_bounds(An.ctypes.data_as(f32p), ctypes.c_int64(n), ld, S, d0.ctypes.data_as(f32p),
+                              d1.ctypes.data_as(f32p), giga, order, sc.ctypes.data_as(f32p), lb.ctypes.data_as(f32p),
+                              ub.ctypes.data_as(f32p))
+  return sc, lb, ub
+
+
+@pytest.mark.parametrize('S', [130, 256, 500, 512])
+@pytest.mark.parametrize('giga', [0, 1])
+def test_filter16_bounds_contain_the_float32_score(lib, S, giga):
+  """every float32 score lies inside [lb, ub] computed from the float16-rounded row, for random rows, rows (anti)parallel
+  to the directions, sparse rows, rows of tiny (float16-subnormal) entries and zero rows; both summation orders"""
+  rng = np.random.RandomState(S + giga)
+  ld = (S + 3)//4*4
+  n = 4000
+  X = rng.randn(n, S)
+  X[100:200] *= rng.rand(100, S) < 0.02                     # sparse rows
+  X[200:300] = rng.randn(100, 1)*np.ones(S) + 1e-3*rng.randn(100, S)   # nearly constant rows
+  X[300:400] *= 10.**rng.uniform(-8, 0, size=(100, S))      # wide dynamic range: many float16 subnormals after scaling
+  d0 = rng.randn(S); d0 /= np.linalg.norm(d0)
+  d1 = rng.randn(S); d1 -= d1.dot(d0)*d0; d1 /= np.linalg.norm(d1)
+  X[400:450] = d1 + 10.**rng.uniform(-7, -1, size=(50, 1))*rng.randn(50, S)    # nearly parallel to the iterate (den -> 0)
+  X[450:500] = -d1 + 10.**rng.uniform(-7, -1, size=(50, 1))*rng.randn(50, S)
+  X[500:550] = d0 + 10.**rng.uniform(-7, -1, size=(50, 1))*rng.randn(50, S)
+  X[550] = d1; X[551] = -d1; X[552] = d0
+  nrm = np.linalg.norm(X, axis=1)
+  nrm[nrm == 0] = 1.
+  An = np.zeros((n, ld), np.float32)
+  An[:, :S] = (X/nrm[:, None]).astype(np.float32)
+  An[600:610] = 0.                                          # zero rows
+  d0f, d1f = d0.astype(np.float32), d1.astype(np.float32)
+  for order in (0, 1):
+    sc, lb, ub = _filter_case(lib, An, d0f, d1f, giga, order)
+    assert np.all(lb <= sc) and np.all(sc <= ub), (np.flatnonzero(~((lb <= sc) & (sc <= ub)))[:10])
+    # the bound is tight where it is finite: a few 1e-4 around the score for well-conditioned rows
+    fin = np.isfinite(lb) & np.isfinite(ub)
+    assert fin[:100].all()
+    assert np.max((ub - lb)[:100]) < 4e-3
+  # the threshold keeps every row inside the near-tie window of ANY maximum >= L
+  for L in (-0.5, -1e-3, 0., 1e-3, 0.2, 1., 50.):
+    thr = lib_threshold(lib, L)
+    for top in (L, L + 1e-6, L + 0.5*abs(L) + 1e-3, L + 10.):
+      assert thr <= np.float32(top) - (np.float32(2e-5) + np.float32(1e-5)*abs(np.float32(top)))
+  assert lib_threshold(lib, np.inf) >= 3e38 and lib_threshold(lib, -np.inf) == -np.inf
+
+
+def lib_threshold(lib, L):
+  lib.hostcheck_filter_threshold.restype = ctypes.c_float
+  return lib.hostcheck_filter_threshold(ctypes.c_float(L))
