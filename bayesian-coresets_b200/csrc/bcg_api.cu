@@ -1483,7 +1483,12 @@ static int choose_scan_config(bcg_solver* s) {
   const int stage_bytes = env_int("BCG_SCAN_STAGE_BYTES", 8192);
   const int nb = std::max(1, stage_bytes / batch_bytes);
   c.rps = nb * c.rb;
-  c.wpb = std::max(1, std::min(11, env_int("BCG_SCAN_WARPS", 8)));   // loop kernel: <= 11 scan warps + 1 control warp
+  // float16 pre-filter of the persistent kernels (filter_bounds.h): available for 128 < S <= 512
+  c.ch16 = (env_int("BCG_FILTER16", 1) && s->v->An) ? loop_variant_ch16(c.ch, c.lpr) : 0;
+  // loop kernel: <= 11 scan warps + 1 control warp.  The float16 pass executes 2.6 x the instructions per byte of the
+  // float32 scan and needs the extra warps to stay HBM-bound (measured at N = 1e7, S = 512: 1.63 / 1.51 / 1.455 ms per
+  // iteration with 8 / 10 / 11 warps; float32 stream: 2.78 ms)
+  c.wpb = std::max(1, std::min(11, env_int("BCG_SCAN_WARPS", c.ch16 ? 11 : 8)));
   c.stages = std::max(1, env_int("BCG_SCAN_STAGES", 2));
   c.evict_first = env_int("BCG_SCAN_EVICT_FIRST", 0);
   const size_t budget = (size_t)(200 * 1024);
@@ -1498,10 +1503,9 @@ static int choose_scan_config(bcg_solver* s) {
   c.loop_smem = c.smem + extra;
   if (c.loop_smem > 227 * 1024) return fail(BCG_ERR_UNSUPPORTED, "scan tile does not fit shared memory (ld=%d)", ld);
   c.grid = s->ctx->sm_count;
-  // float16 pre-filter of the persistent kernels: rows per ring stage in the float16 pass (multiple of its batch of 4 rows)
-  c.ch16 = env_int("BCG_FILTER16", 1) ? loop_variant_ch16(c.ch, c.lpr) : 0;
+  // rows per ring stage in the float16 pass (multiple of its batch of 4 rows)
   c.rps16 = (int)((size_t)c.rps * row_bytes / ((size_t)s->v->ld16 * 2)) / 4 * 4;
-  if (c.rps16 < 4 || s->h.lazy) c.ch16 = 0;
+  if (c.rps16 < 4) c.ch16 = 0;
   CK(scan_set_smem(c));
   s->use_loop = false;
   s->use_omp_loop = false;

@@ -68,7 +68,11 @@ BCG_HD void filter_bounds_giga(float t0, float t1, float e0, float e1, float* lb
     *lb = -INFINITY;
     return;
   }
+#if defined(__CUDA_ARCH__)
+  const float rmin = rsqrtf(dmax), rmax = rsqrtf(dmin);                // 2 ulp; inside kScoreRel together with the float32
+#else                                                                  // evaluation of dmin / dmax (<= 1.3e-4 relative)
   const float rmin = 1.f / sqrtf(dmax), rmax = 1.f / sqrtf(dmin);      // rmin <= 1/sqrt(den) <= rmax
+#endif
   const float u = (u0 > 0.f) ? u0 * rmax : u0 * rmin;
   const float l = (l0 > 0.f) ? l0 * rmin : l0 * rmax;
   *ub = u + (kScoreRel * fabsf(u) + kScoreAbs);
