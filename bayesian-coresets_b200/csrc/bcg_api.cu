@@ -1503,9 +1503,10 @@ static int choose_scan_config(bcg_solver* s) {
   c.loop_smem = c.smem + extra;
   if (c.loop_smem > 227 * 1024) return fail(BCG_ERR_UNSUPPORTED, "scan tile does not fit shared memory (ld=%d)", ld);
   c.grid = s->ctx->sm_count;
-  // rows per ring stage in the float16 pass (multiple of its batch of 4 rows)
-  c.rps16 = (int)((size_t)c.rps * row_bytes / ((size_t)s->v->ld16 * 2)) / 4 * 4;
-  if (c.rps16 < 4) c.ch16 = 0;
+  // rows per ring stage in the float16 pass (multiple of its batch: 8 rows when a lane owns one 16-byte group per row, else 4)
+  const int fr = c.ch16 == 1 ? 8 : 4;
+  c.rps16 = (int)((size_t)c.rps * row_bytes / ((size_t)s->v->ld16 * 2)) / fr * fr;
+  if (c.rps16 < fr) c.ch16 = 0;
   CK(scan_set_smem(c));
   s->use_loop = false;
   s->use_omp_loop = false;
@@ -1915,10 +1916,11 @@ static int run_persistent(bcg_solver* s, int32_t itrs, bool omp) {
   if (s->claims_cap < itrs) {
     if (s->d_claims) CK(cudaFree(s->d_claims));
     s->d_claims = nullptr;
-    CK(cudaMalloc(&s->d_claims, (size_t)itrs * sizeof(unsigned int)));
+    CK(cudaMalloc(&s->d_claims, 2 * (size_t)itrs * sizeof(unsigned int)));   // claim counters | filter bounds
     s->claims_cap = itrs;
   }
   la.claims = s->d_claims;
+  la.filt_L = reinterpret_cast<int*>(s->d_claims + s->claims_cap);
   la.static_frac = (float)env_int("BCG_STATIC_PCT", 100) / 100.f;   // measured: a larger dynamic share only costs (atomics); the grid is HBM-bound either way
   la.trace = nullptr;
   s->trace_n = 0;
@@ -1942,6 +1944,7 @@ static int run_persistent(bcg_solver* s, int32_t itrs, bool omp) {
     la.itrs = itrs - done;
     la.trace = s->trace_on ? s->d_trace + (size_t)done * 8 : nullptr;
     CK(cudaMemsetAsync(s->d_claims, 0, (size_t)la.itrs * sizeof(unsigned int), st));
+    CK(cudaMemsetAsync(la.filt_L, 0x80, (size_t)la.itrs * sizeof(int), st));
     CK(cudaMemsetAsync(s->d_ctl, 0, sizeof(LoopCtl), st));
     if (omp) CK(omp_loop_launch(s->sc, la, s->d_nw, env_int("BCG_OMP_WIDE", 1), st));
     else CK(loop_launch(s->sc, la, st));

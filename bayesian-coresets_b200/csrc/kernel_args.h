@@ -57,6 +57,8 @@ struct LoopArgs {
   int32_t wpb;           // scan warps per CTA (blockDim.x = (wpb + 1) * 32)
   unsigned int* claims;  // itrs zero-initialised counters: dynamically claimed chunks per iteration
   float static_frac;     // share of the chunks that is statically assigned (rest: dynamic tail)
+  int* filt_L;           // itrs words preset to 0x80808080: GPU-wide lower bound of the float32 maximum per iteration (float16
+                         // pre-filter; monotone int image of the float, raised with atomicMax)
   // optional device timestamps (globaltimer ns), null when tracing is off:
   //   trace[it*8 + 0] control: grid arrived      trace[it*8 + 1] control: next direction published
   //   trace[it*8 + 2] CTA 0 warp 0: go observed   trace[it*8 + 3] CTA 0 warp 0: its scan finished

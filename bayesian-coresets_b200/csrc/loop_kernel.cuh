@@ -655,7 +655,7 @@ template <int CH, int NDIR, int LPR, int R, int CH16>
 __device__ __forceinline__ void scan_cta_body(const LoopArgs& a, unsigned char* smem_raw, int cta_rank, int n_ctas) {
   using Core = ScanCore<CH, NDIR, LPR, R>;
   constexpr bool F16 = CH16 > 0;
-  using FCore = Filter16Core<(F16 ? CH16 : 1), NDIR, 4>;
+  using FCore = Filter16Core<(F16 ? CH16 : 1), NDIR, (CH16 == 1 ? 8 : 4)>;   // short rows: 8 per batch amortise the reduce + bounds
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int wpb = a.wpb;
@@ -782,7 +782,14 @@ __device__ __forceinline__ void scan_cta_body(const LoopArgs& a, unsigned char* 
       }
     } else {
       // ---- pass A: bounds from the float16 copy ----------------------------------------------------------------
-      float Lw = -INFINITY;                            // lower bound of this warp's float32 maximum (warp-uniform)
+      // lower bound L of the float32 maximum (warp-uniform): the rows this warp has seen, and -- through one word of global
+      // memory per iteration, raised with atomicMax and polled every 8th stage one stage ahead of its use -- the rows every
+      // other warp of the GPU has seen.  Any valid lower bound may be used at any time, so the exchange needs no ordering.
+      float Lw = -INFINITY;
+      int* Lslot = a.filt_L + it;
+      float Lpub = -INFINITY;                          // what the global word is known to hold at least
+      int Lpend = (int)0x80808080;
+      int nstage = 0;
       int nlist = 0;
       bool overflow = false;
       {
@@ -803,6 +810,13 @@ __device__ __forceinline__ void scan_cta_body(const LoopArgs& a, unsigned char* 
             FCore::batch(tile + (size_t)b0 * q.ld16, q.ld16, ngroups, lane, nr - b0, dh0, dh1, e0, e1, ubm, lbm);
           ubm = warp_max_f(ubm);
           Lw = fmaxf(Lw, warp_max_f(lbm));
+          if ((nstage & 7) == 1) { const float Lg = sortable_float(Lpend); Lw = fmaxf(Lw, Lg); Lpub = fmaxf(Lpub, Lg); }
+          if ((nstage & 7) == 0) Lpend = __ldcg(Lslot);
+          ++nstage;
+          if (Lw > Lpub) {                             // this warp raises the GPU-wide bound
+            if (lane == 0) atomicMax(Lslot, float_sortable(Lw));
+            Lpub = Lw;
+          }
           if (ubm >= filter_threshold(Lw)) {           // warp-uniform
             if (nlist == kFiltCap) {                   // compact the slots against the risen bound
               const uint32_t r_i = fl_row[lane];
@@ -833,6 +847,7 @@ __device__ __forceinline__ void scan_cta_body(const LoopArgs& a, unsigned char* 
         float4 d0[CH];
         float4 d1[CH];
         Core::load_dirs(a.st->dir32, q.ld, nchunk, g, d0, d1);
+        if (nlist > 0) Lw = fmaxf(Lw, sortable_float(__ldcg(Lslot)));
         const float thr = filter_threshold(Lw);
         unsigned int nres = 0;
         for (int i = 0; i < nlist; ++i) {

@@ -204,21 +204,21 @@ def measured_f64_peak(device):
     return F64_NOMINAL_TFLOPS, 'nominal (B200 data sheet FP64 40 TFLOP/s; dgemm measurement unavailable)'
 
 
-def measured_traffic_ratio(kernel, S):
+def measured_traffic_ratio(kernel, S, filter16=False):
   """DRAM bytes / algorithmic bytes of the dominant kernel from the committed `ncu --set full` capture
   (profiles/r02_loop_traffic.json, written by profiles/extract_traffic.py from tools/ncu_traffic_case.py; the round-1
   capture as a fallback); None when there is no capture of this kernel at this S"""
   try:
     with open(os.path.join(ROOT, 'profiles', 'r02_loop_traffic.json')) as f:
       for c in json.load(f)['captures']:
-        if c['kernel'] == kernel and int(c['S']) == int(S):
+        if c['kernel'] == kernel and int(c['S']) == int(S) and bool(c.get('filter16', False)) == bool(filter16):
           return float(c['dram_bytes'])/float(c['algorithmic_bytes']), 'r02_loop_traffic.json'
   except Exception:
     pass
   try:
     with open(os.path.join(ROOT, 'profiles', 'r01_loop_traffic.json')) as f:
       t = json.load(f)
-    if t.get('kernel') == kernel and int(t.get('S', -1)) == int(S):
+    if t.get('kernel') == kernel and int(t.get('S', -1)) == int(S) and not filter16:
       return float(t['dram_bytes'])/float(t['algorithmic_bytes']), 'r01_loop_traffic.json'
   except Exception:
     pass
@@ -399,10 +399,12 @@ def main():
     clocks = ClockSampler(local_rank)
     if rank == 0:
       clocks.start()
+    f16_on, f16_rows0 = nat.filter16_stats()
     cs.snnls.build(steps)                                   # timed: K iterations, one device-side loop
     ctx.synchronize()
     barrier()
     tm = nat.timing()
+    f16_rows = nat.filter16_stats()[1] - f16_rows0          # rows re-scanned in float32 inside the timed region (this rank)
     clk = clocks.stop() if rank == 0 else None
     ev_all += list(cs.snnls.last_events)
     ok_steps = sum(1 for e in cs.snnls.last_events if e.code == 0)
@@ -425,7 +427,8 @@ def main():
       kernel_ms = max_over_ranks(tp['scan_ms'] / max(tp['scan_launches'], 1))
       bytes_per_launch = 4.0 * (hi - lo) * S
     achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
-    ratio, ratio_src = measured_traffic_ratio(kernel, S)
+    f16 = bool(f16_on) and tm['scan_launches'] == 0
+    ratio, ratio_src = measured_traffic_ratio(kernel, S, f16)
     res = {'N': N, 'd': d, 'S': S, 'alg': alg, 'build_ms': build_ms, 'rows_local': hi - lo, 'clocks': clk,
            'ok_steps': ok_steps, 'launches': tm['scan_launches'] + tm['step_launches'], 'error': cs.error(),
            'size': int(cs.snnls.size()), 'sel_hash': sel_hash(ev_all), 'exact_selections': nat.exact_count(),
@@ -437,6 +440,18 @@ def main():
                         'peak_source': peak_src,
                         'kernel_share_of_step': kernel_ms * launches_per_step * steps / build_ms},
            'keep': (Z, theta, prj)}
+    if f16:
+      # float16 pre-filter (csrc/filter_bounds.h): `achieved` keeps SURVEY 8(d)'s algorithmic figure (4 N S bytes per iteration,
+      # one float32 read of the matrix), which this kernel no longer has to move -- it streams a float16 copy (2 bytes per
+      # element) and re-reads in float32 only the row groups whose bound reaches the maximum.  `moved` is the roofline of the
+      # bytes it does move.
+      ld16 = (S + 7)//8*8
+      moved = 2.0*(hi - lo)*ld16*steps + 4.0*S*f16_rows
+      res['roofline']['filter16'] = {
+        'moved_bytes_per_launch': moved, 'achieved': moved/(kernel_ms*1e-3)/1e9, 'unit': 'GB/s',
+        'frac': moved/(kernel_ms*1e-3)/1e9/peak, 'rows_rescanned_float32_per_step': f16_rows/float(steps),
+        'note': 'selection bit-identical to the float32 stream (config.sel_hash; tests/test_gpu_parity.py::test_filter16_*); '
+                'roofline.achieved / frac above use the 4 N S algorithmic bytes of SURVEY 8(d) and therefore exceed the HBM peak'}
     if with_e2e:
       # end to end through the public API from HOST buffers: upload Z and theta, project on the device,
       # build(steps), read the coreset back -- everything inside the timed region.  Timed twice: from a page-locked
