@@ -494,6 +494,31 @@ static int j_for_ld(int ld) {
   return j;
 }
 
+// is the float16 pre-filter available for rows of ld floats (same rule as choose_scan_config)
+static bool filter16_shape_ok(int ld) {
+  if (!env_int("BCG_FILTER16", 1)) return false;
+  const int nchunk = ld / 4;
+  const int lpr = std::min(32, pow2ceil(nchunk));
+  const int ch = pow2ceil((nchunk + lpr - 1) / lpr);
+  return loop_variant_exists(ch, lpr) && loop_variant_ch16(ch, lpr) > 0;
+}
+
+// buffer for a float16 copy from the context's one-slot cache or the device; false (no error) when there is no memory
+static bool half_take(bcg_ctx* ctx, size_t bytes, uint16_t** out) {
+  if (ctx->pool_An16 && ctx->pool_An16_bytes >= bytes && ctx->pool_An16_bytes <= 2 * bytes + (1 << 20)) {
+    *out = ctx->pool_An16;
+    ctx->pool_An16 = nullptr;
+    ctx->pool_An16_bytes = 0;
+    return true;
+  }
+  if (cudaMalloc(out, bytes) != cudaSuccess) {
+    (void)cudaGetLastError();
+    *out = nullptr;
+    return false;
+  }
+  return true;
+}
+
 // rows of padding behind An: the float32 re-scan of the filtered persistent kernel reads whole row batches from global memory
 static const int64_t kRowPad = 64;
 
@@ -720,6 +745,14 @@ static int project_grid(bcg_ctx* ctx, const ProjectArgs& a) {
   return (int)std::min<int64_t>((a.n + kProjWarps - 1) / kProjWarps, (int64_t)ctx->sm_count);
 }
 
+// the warp-per-row specialised kernel applies (BCG_PROJ_FAST=0 forces the general kernel)
+static bool project_fast_ok(const ProjectArgs& a) {
+  if (project_mma_ok(a)) return false;
+  const int fast = env_int("BCG_PROJ_FAST", 1);
+  return fast && !a.out64 && a.ld == a.S && a.d <= 32 && a.ktile >= a.d && (a.model == MODEL_LINEAR || a.sp_tab != nullptr) &&
+         (a.S == 64 || a.S == 128 || a.S == 256 || a.S == 512);
+}
+
 // K3 launch: the specialised kernels (project_fast_kernel.cuh) for S in {64, 128, 256, 512} with the whole sample tile
 // in shared memory and table links, the general kernel otherwise (BCG_PROJ_FAST=0 forces the general kernel)
 static int dispatch_project(bcg_ctx* ctx, const ProjectArgs& a, int grid, size_t smem) {
@@ -728,11 +761,7 @@ static int dispatch_project(bcg_ctx* ctx, const ProjectArgs& a, int grid, size_t
     if (a.d <= kPjKT) return launch_project_mma_model<1>(ctx, a, grid);
     return launch_project_mma_model<4>(ctx, a, grid);
   }
-  // BCG_PROJ_FAST=0 forces the general kernel
-  const int fast = env_int("BCG_PROJ_FAST", 1);
-  const bool fast_ok = fast && !a.out64 && a.ld == a.S && a.d <= 32 && a.ktile >= a.d &&
-                       (a.model == MODEL_LINEAR || a.sp_tab != nullptr);
-  if (fast_ok) {
+  if (project_fast_ok(a)) {
     switch (a.S) {
       case 64: return launch_project_fast_model<1>(ctx, a, grid, smem);
       case 128: return launch_project_fast_model<2>(ctx, a, grid, smem);
@@ -1239,6 +1268,7 @@ static int project_host_pipelined(bcg_ctx* ctx, int kmodel, const double* Z, int
   bcg_vecs* v = nullptr;
   RET(vecs_alloc(ctx, n, S, &v));
   if (n == 0) { *out = v; return BCG_OK; }
+  uint16_t* an16 = nullptr;
   auto body = [&]() -> int {
     cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
     const int ld = v->ld;
@@ -1255,8 +1285,14 @@ static int project_host_pipelined(bcg_ctx* ctx, int kmodel, const double* Z, int
     const int nchunks = (int)((n + chunk_rows - 1) / chunk_rows);
     ProjectArgs proto;                                                   // what decides the kernel and its grid
     proto.An = v->An; proto.out64 = nullptr; proto.n = chunk_rows; proto.d = d; proto.S = S; proto.ld = ld; proto.model = kmodel;
-    proto.sp_tab = ctx->sp_tab;
+    proto.sp_tab = ctx->sp_tab; proto.ktile = ktile;
     const int grid = project_grid(ctx, proto);
+    // float16 copy for the pre-filter of the persistent greedy kernels, written by the projection itself where the kernel
+    // supports it (otherwise the solver makes it with one more pass: vecs_ensure_half)
+    if (project_fast_ok(proto) && filter16_shape_ok(ld)) {
+      const size_t bytes = (size_t)n * v->ld16 * sizeof(uint16_t);
+      if (half_take(ctx, bytes, &an16)) v->An16_bytes = bytes;
+    }
     // staging and chunk buffers are context-owned (no cudaMallocHost / cudaMalloc / cudaFree per call)
     const bool direct = is_pinned(Z);                                    // page-locked source: no staging copy
     if (!direct) RET(ensure_pins(ctx));
@@ -1297,15 +1333,22 @@ static int project_host_pipelined(bcg_ctx* ctx, int kmodel, const double* Z, int
       a.Z = dev[i]; a.rowidx = nullptr; a.theta = dT; a.coff = dC; a.An = v->An + (size_t)r0 * ld; a.norms = v->norms + r0;
       a.out64 = nullptr; a.partial = d_partial.p + (size_t)c * grid * (S + 1); a.zero_rows = d_zero; a.n = nr; a.zld = zld;
       a.d = d; a.S = S; a.ld = ld; a.model = kmodel; a.ktile = ktile; a.sp_tab = ctx->sp_tab;
+      a.An16 = an16 ? an16 + (size_t)r0 * v->ld16 : nullptr; a.ld16 = v->ld16;
       RET(dispatch_project(ctx, a, grid, smem));
       CK(cudaEventRecord(kdone.e[i], st));
     }
     RET(finish_colsum(v, d_partial, nchunks * grid, d_zero));
     CK(cudaStreamSynchronize(cs));
+    v->An16 = an16;
+    an16 = nullptr;
     return BCG_OK;
   };
   const int rc = body();
-  if (rc != BCG_OK) { bcg_vecs_destroy(v); return rc; }
+  if (rc != BCG_OK) {
+    if (an16) { cudaStreamSynchronize(ctx->stream); cudaFree(an16); v->An16_bytes = 0; }
+    bcg_vecs_destroy(v);
+    return rc;
+  }
   *out = v;
   return BCG_OK;
 }
@@ -1449,14 +1492,7 @@ static int vecs_ensure_half(bcg_vecs* v) {
   bcg_ctx* ctx = v->ctx;
   const size_t bytes = (size_t)v->n * v->ld16 * sizeof(uint16_t);
   uint16_t* p = nullptr;
-  if (ctx->pool_An16 && ctx->pool_An16_bytes >= bytes && ctx->pool_An16_bytes <= 2 * bytes + (1 << 20)) {
-    p = ctx->pool_An16;
-    ctx->pool_An16 = nullptr;
-    ctx->pool_An16_bytes = 0;
-  } else if (cudaMalloc(&p, bytes) != cudaSuccess) {
-    (void)cudaGetLastError();
-    return BCG_OK;
-  }
+  if (!half_take(ctx, bytes, &p)) return BCG_OK;
   v->An16 = p;
   v->An16_bytes = bytes;
   half_copy_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(v->An, v->n, v->ld, v->An16, v->ld16);

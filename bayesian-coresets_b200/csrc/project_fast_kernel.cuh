@@ -14,6 +14,7 @@
 //     to hide behind)
 // Bytes per row: 8 d_in read + 4 S + 8 written; bound: float64 pipe + issue (about 50 instructions per element), not HBM.
 #pragma once
+#include <cuda_fp16.h>
 #include "project_kernels.cuh"
 
 namespace bcg {
@@ -123,6 +124,11 @@ __global__ void __launch_bounds__(kProjWarps * 32, 1) project_fast_kernel(const 
       float2* out = reinterpret_cast<float2*>(a.An + (size_t)row * S) + lane;
 #pragma unroll
       for (int j = 0; j < J2; ++j) out[32 * j] = make_float2((float)(acc[j][0] * inv), (float)(acc[j][1] * inv));
+      if (a.An16) {                              // the pre-filter's copy: fl16 of the float32 value just stored
+        __half2* o16 = reinterpret_cast<__half2*>(a.An16 + (size_t)row * a.ld16) + lane;
+#pragma unroll
+        for (int j = 0; j < J2; ++j) o16[32 * j] = __floats2half2_rn((float)(acc[j][0] * inv), (float)(acc[j][1] * inv));
+      }
       if (lane == 0) a.norms[row] = norm;
     }
     if (lane == 0) {

@@ -139,6 +139,8 @@ struct ProjectArgs {
   const double* theta;   // d x S, TRANSPOSED samples (LINEAR: Siginv theta^T)
   const double* coff;    // S        per-column offset (LINEAR: -0.5 theta Siginv theta) or null
   float* An;             // unit float32 rows (null: not materialised)
+  uint16_t* An16 = nullptr;  // optional float16 copy of the unit rows (fl16 of the float32 value; project_fast_kernel only)
+  int32_t ld16 = 0;          // halves per row of An16
   double* norms;         // row norms (null with An)
   double* out64;         // n x S float64 centred rows (null unless requested)
   double* partial;
