@@ -431,7 +431,7 @@ def main():
     ratio, ratio_src = measured_traffic_ratio(kernel, S, f16)
     res = {'N': N, 'd': d, 'S': S, 'alg': alg, 'build_ms': build_ms, 'rows_local': hi - lo, 'clocks': clk,
            'ok_steps': ok_steps, 'launches': tm['scan_launches'] + tm['step_launches'], 'error': cs.error(),
-           'size': int(cs.snnls.size()), 'sel_hash': sel_hash(ev_all), 'exact_selections': nat.exact_count(),
+           'size': int(cs.snnls.size()), 'sel_hash': sel_hash(ev_all), 'exact_selections': nat.exact_count(), 'filter16': bool(f16),
            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                         'traffic': None if ratio is None else ratio * bytes_per_launch,
                         'traffic_source': None if ratio is None else
@@ -499,7 +499,7 @@ def main():
                'sharding': 'N axis over %d GPU(s), %d rows/GPU' % (world, r['rows_local']),
                'l2': 'inputs larger than L2 (%.2f GB scanned per GPU per step)' % (4e-9 * r['rows_local'] * S),
                'ok_steps': r['ok_steps'], 'final_error': r['error'], 'coreset_size': r['size'], 'sel_hash': r['sel_hash'],
-               'exact_selections': r['exact_selections']},
+               'exact_selections': r['exact_selections'], 'filter16': r['filter16']},
     'gpu_launches': r['launches'], 'clocks': r['clocks'], 'roofline': r['roofline'],
   }
   if 'e2e' in r:
