@@ -291,9 +291,9 @@ BCG_HD void nnls_solve(const Blk& B, SolverState* st, NnlsWork* W, int from_scra
         wmax = fmax(wmax, w);
       }
       { int64_t i2 = 0; int p2 = 0; double k2 = wmax; blk_argbest(B, &k2, &i2, &p2); wmax = k2; }
+      const int p_before = W->nP;          // read by every thread BEFORE the barrier: thread 0 rewrites W->nP right behind it
       B.sync();
       // drop the columns that reached zero (to the zero set) and compact P
-      const int p_before = W->nP;
       if (B.tid == 0) {
         int keep = 0, first = -1, nrem = 0;
         for (int p = 0; p < W->nP; ++p) {

@@ -594,9 +594,10 @@ BCG_HD int64_t omp_select(const Blk& B, SolverState* st) {
     }
   }
   if (!nonempty || neg_decided) omp_mark(B, st, 3);
+  const int nact0 = st->nact;              // read by every thread BEFORE the barriers of find_slot: thread 0 writes st->nact below
   int slot = find_slot(B, st, f);
   if (slot < 0) {
-    slot = st->nact;
+    slot = nact0;
     for (int s = B.tid; s < ld; s += B.nthr) st->act_rows[(size_t)slot * ld + s] = frow[s];
     if (B.tid == 0) { st->act_idx[slot] = f; st->act_norm[slot] = nf_stored; st->nact = slot + 1; }
   }

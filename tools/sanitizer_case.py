@@ -7,7 +7,7 @@ import numpy as np
 import bayesiancoresets_b200 as bc
 from conftest import lr_problem
 N, d = int(sys.argv[1]) if len(sys.argv) > 1 else 3000, 6
-for S in (256, 96):
+for S in (512, 256, 96):                  # 512 / 256: float16 pre-filter variants CH16 = 2 / 1 (512: the projection writes the copy)
   Z, theta = lr_problem(1, N, d, S)
   for mma, fast in (('2', '1'), ('0', '1'), ('0', '0')):            # DMMA / warp-per-row / general projection kernels
     os.environ['BCG_PROJ_MMA'], os.environ['BCG_PROJ_FAST'] = mma, fast
