@@ -392,6 +392,16 @@ def test_filter16_bounds_contain_the_float32_score(lib, S, giga):
     fin = np.isfinite(lb) & np.isfinite(ub)
     assert fin[:100].all()
     assert np.max((ub - lb)[:100]) < 4e-3
+    # the filter's decision, as the kernel takes it: L = the largest lower bound; every row that can matter to the selection
+    # (the float32 arg-max and everything inside its near-tie window) has an upper bound that reaches filter_threshold(L)
+    fin_lb = lb[np.isfinite(lb)]
+    L = fin_lb.max() if fin_lb.size else -np.inf
+    thr = lib_threshold(lib, L)
+    top = sc.max()
+    window = np.float32(2e-5) + np.float32(1e-5)*abs(top)
+    must = sc >= top - window
+    assert np.all(ub[must] >= thr)
+    assert L <= top
   # the threshold keeps every row inside the near-tie window of ANY maximum >= L
   for L in (-0.5, -1e-3, 0., 1e-3, 0.2, 1., 50.):
     thr = lib_threshold(lib, L)
