@@ -497,7 +497,9 @@ def main():
     'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
     'config': {'workload': args.workload, 'N': N, 'd': d, 'S': S, 'alg': 'GIGA',
                'sharding': 'N axis over %d GPU(s), %d rows/GPU' % (world, r['rows_local']),
-               'l2': 'inputs larger than L2 (%.2f GB scanned per GPU per step)' % (4e-9 * r['rows_local'] * S),
+               'l2': ('inputs larger than L2 (%.2f GB float16 copy of the %.2f GB matrix scanned per GPU per step)' %
+                      (2e-9*r['rows_local']*((S + 7)//8*8), 4e-9*r['rows_local']*S)) if r['filter16'] else
+                     'inputs larger than L2 (%.2f GB scanned per GPU per step)' % (4e-9 * r['rows_local'] * S),
                'ok_steps': r['ok_steps'], 'final_error': r['error'], 'coreset_size': r['size'], 'sel_hash': r['sel_hash'],
                'exact_selections': r['exact_selections'], 'filter16': r['filter16']},
     'gpu_launches': r['launches'], 'clocks': r['clocks'], 'roofline': r['roofline'],
