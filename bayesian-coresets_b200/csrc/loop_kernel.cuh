@@ -14,6 +14,10 @@
 //     bookkeeping (weights rescale, active-set append, event log) while the grid is already
 //     scanning again;
 //   * grid-wide ordering is two monotonic counters in global memory (arrive / go).
+//   * for 128 < S <= 512 the scan warps stream a float16 COPY of the rows (half the bytes) and bound every row's float32
+//     score from it; only ring stages whose bound reaches the near-tie window of the maximum are re-scanned from the
+//     float32 rows, so the selection is bit-identical to the float32 stream (scan_cta_body<..., CH16 > 0>,
+//     filter_bounds.h: the error bound and its proof obligation).
 // Semantics are those of step_logic.h (snnls.py:41-78, giga.py:20-64, frankwolfe.py:15-40);
 // A w is updated incrementally (A w' = alpha A w + (w_f' - alpha w_f) a_f) and re-summed exactly
 // from the active set every kRefreshEvery iterations, off the critical path.
