@@ -413,3 +413,41 @@ def test_filter16_bounds_contain_the_float32_score(lib, S, giga):
 def lib_threshold(lib, L):
   lib.hostcheck_filter_threshold.restype = ctypes.c_float
   return lib.hostcheck_filter_threshold(ctypes.c_float(L))
+
+
+@pytest.mark.parametrize('S', [256, 512])
+def test_filter16_bounds_hold_in_the_aligned_worst_case(lib, S):
+  """the adversarial row for the Cauchy-Schwarz step of the bound: |a_i| proportional to |d_i|, every element on a float16
+  rounding MIDPOINT with an even lower neighbour (round-to-nearest-even moves all of them the same way, by the full half
+  ulp), signs aligned with the direction -- the quantisation errors add up coherently to ~2^-11 |a||d|, 90 % of the bound"""
+  rng = np.random.RandomState(S)
+  ld = S
+  d0 = rng.randn(S); d0 /= np.linalg.norm(d0)
+  d1 = rng.randn(S); d1 -= d1.dot(d0)*d0; d1 /= np.linalg.norm(d1)
+  rows = []
+  for sgn in (1., -1.):
+    for dirv in (d0, d1):
+      m = 0.999*np.abs(dirv)
+      e = np.floor(np.log2(np.maximum(m, 2.**-14)))          # float16 exponent (normal range)
+      ulp = 2.**(e - 10)
+      k = np.floor(m/ulp)
+      k -= (k % 2)                                           # even lower neighbour: the tie rounds DOWN
+      a = (k + 0.5)*ulp                                      # exactly representable in float32
+      a[m < 2.**-14] = 0.
+      rows.append(sgn*np.sign(dirv)*a)
+  An = np.ascontiguousarray(np.array(rows), dtype=np.float32)
+  assert np.array_equal(An.astype(np.float64), np.array(rows))                 # no float32 rounding of the construction
+  assert np.all(np.linalg.norm(An.astype(np.float64), axis=1) <= 1.0001)
+  d0f, d1f = d0.astype(np.float32), d1.astype(np.float32)
+  worst, half = 0., 0.
+  for giga in (0, 1):
+    for order in (0, 1):
+      sc, lb, ub = _filter_case(lib, An, d0f, d1f, giga, order)
+      assert np.all(lb <= sc) and np.all(sc <= ub), (giga, order, sc, lb, ub)
+      if not giga:
+        mid = 0.5*(lb.astype(np.float64) + ub)                # = the float16 inner product t
+        worst = max(worst, float(np.max(np.abs(mid - sc))))
+        half = 0.5*float((ub - lb)[0])                        # = E, the bound on |t - s|
+  # the construction really stresses the bound: a half ulp is 2^-11 of the value only at the bottom of a binade, ~0.7 of
+  # that on average, so the coherent sum reaches ~0.6 E
+  assert 0.5*half < worst <= half, (worst, half)
