@@ -29,6 +29,13 @@
 
 namespace bcg {
 
+// Budget of kScoreRel (all relative to the score, den >= kDenFloor = 1e-3):
+//   the scan's own evaluation      den_f32 = fl(1 - s1^2) is off by <= 1.2e-7 absolute = 1.2e-4 relative  -> 0.60e-4 on rsqrt
+//                                  rsqrtf: 2 ulp = 2.4e-7;  the product s0 * rsqrtf(den): 0.6e-7           -> 0.62e-4 in total
+//   this header's evaluation       dmin / dmax carry the same 1.2e-7 absolute error                         -> 0.60e-4 on rmin / rmax
+//                                  (rsqrtf / the product again 3e-7; the rounding of |t1| +- e1 and of t0 +- e0 is covered by
+//                                   the 0.1 % by which filter_eps_unit inflates E: 5e-7 >> 6e-8)
+//   sum 1.25e-4 < kScoreRel = 2e-4.  kScoreAbs covers scores near zero.
 constexpr float kDenFloor = 1e-3f;
 constexpr float kScoreRel = 2e-4f;     // relative slack of the float32 score evaluation when den >= kDenFloor
 constexpr float kScoreAbs = 1e-7f;
