@@ -451,3 +451,54 @@ def test_filter16_bounds_hold_in_the_aligned_worst_case(lib, S):
   # the construction really stresses the bound: a half ulp is 2^-11 of the value only at the bottom of a binade, ~0.7 of
   # that on average, so the coherent sum reaches ~0.6 E
   assert 0.5*half < worst <= half, (worst, half)
+
+
+def test_filter16_slot_policy_simulation(lib):
+  """the bookkeeping of the pre-filter, simulated: stages arrive at the warps in arbitrary order, the shared lower bound L is
+  seen with arbitrary delay, every warp has a handful of slots which it compacts against its current L.  Invariant: a warp
+  either reports overflow or ends with every stage that holds a row inside the near-tie window of the true maximum still in
+  its slots -- a dropped entry was dropped against a threshold that only rises (loop_kernel.cuh: scan_cta_body, pass A / B)."""
+  rng = np.random.RandomState(11)
+  S, n, rows_per_stage, cap = 256, 6000, 8, 4
+  d0 = rng.randn(S); d0 /= np.linalg.norm(d0)
+  X = rng.randn(n, S)
+  X[::97] = d0 + 0.3*rng.randn(len(X[::97]), S)              # a population of high scorers, some of them close together
+  X[1000:1003] = X[1000]                                     # exact duplicates of one of them
+  An = (X/np.linalg.norm(X, axis=1)[:, None]).astype(np.float32)
+  d0f = d0.astype(np.float32)
+  sc, lb, ub = _filter_case(lib, An, d0f, d0f, 0, 1)
+  top = sc.max()
+  must_rows = sc >= top - (np.float32(2e-5) + np.float32(1e-5)*abs(top))
+  nst = n//rows_per_stage
+  st_ub = ub.reshape(nst, rows_per_stage).max(1)
+  st_lb = lb.reshape(nst, rows_per_stage).max(1)
+  st_must = must_rows.reshape(nst, rows_per_stage).any(1)
+  for trial in range(20):
+    W = int(rng.choice([1, 3, 16, 64]))
+    owner = rng.randint(0, W, size=nst)
+    order = rng.permutation(nst)                             # global arrival order of the stages
+    Lglob = -np.inf                                          # the atomicMax word
+    Lw = np.full(W, -np.inf); Lseen = np.full(W, -np.inf)
+    slots = [[] for _ in range(W)]
+    overflow = np.zeros(W, bool)
+    for s_ in order:
+      w = owner[s_]
+      Lw[w] = max(Lw[w], st_lb[s_])
+      if rng.rand() < 0.3:                                   # a delayed look at the shared word
+        Lseen[w] = Lglob
+      Lw[w] = max(Lw[w], Lseen[w])
+      Lglob = max(Lglob, Lw[w])                              # publish
+      thr = lib_threshold(lib, Lw[w])
+      if st_ub[s_] >= thr:
+        if len(slots[w]) == cap:
+          slots[w] = [e for e in slots[w] if st_ub[e] >= thr]
+        if len(slots[w]) < cap:
+          slots[w].append(s_)
+        else:
+          overflow[w] = True
+    for w in range(W):
+      thr = lib_threshold(lib, max(Lw[w], Lglob if rng.rand() < 0.5 else -np.inf))
+      kept = {e for e in slots[w] if st_ub[e] >= thr}
+      mine_must = {int(e) for e in np.flatnonzero(st_must & (owner == w))}
+      assert overflow[w] or mine_must <= kept, (trial, w)
+    assert Lglob <= top
